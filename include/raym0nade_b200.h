@@ -1,0 +1,183 @@
+/* raym0nade_b200.h — C ABI of the B200-native path-tracing hot path.
+ *
+ * The reference (lemonchu/Raym0nade) has no plugin / FFI layer; its seams are ordinary
+ * C++ calls.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference tree).  Conventions: plain C structs, POD only,
+ * no exceptions across the boundary; every call returns RM_OK (0) or a negative error
+ * and leaves a message for rm_last_error(); one context per CUDA device; calls on one
+ * context are serialised by the caller; all buffers are caller-owned.  Pointers named
+ * `d_*` are DEVICE pointers, all others are host pointers.
+ *
+ * There is no CPU fallback: every compute entry point fails with RM_ERR_CUDA when no
+ * sm_100 device is present.
+ */
+#ifndef RAYM0NADE_B200_H
+#define RAYM0NADE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "rm_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_OK 0
+#define RM_ERR_INVALID (-1)
+#define RM_ERR_CUDA (-2)
+#define RM_ERR_STATE (-3)
+
+/* ---------------------------------------------------------------------------------
+ * Post-load scene: exactly what a loaded reference `Model` holds (include/model.h:31-37)
+ * after Model::Model has run (src/model.cpp:172-215).  An integration fills this from
+ * its own Model; rm_prepare_scene() below builds it from a raw scene.
+ * ------------------------------------------------------------------------------- */
+
+/* ImageData with its mip chain (include/material.h:12-25; generateMipmaps src/material.cpp:113-148). */
+typedef struct RmTextureDesc {
+    int32_t width, height, channels, map_depth;
+    const uint8_t *levels[8];          /* level l: (width>>l)*(height>>l)*channels bytes */
+} RmTextureDesc;
+
+/* Material (include/material.h:30-51). tex[]: 0 diffuse, 1 specular, 2 emissive, 3 normals; -1 = empty. */
+typedef struct RmMaterialDesc {
+    int32_t tex[4];
+    float opacity, ior, roughness;
+    float transmitting_color[3];
+    int32_t has_fully_transparent_part;
+    int32_t _pad;
+} RmMaterialDesc;
+
+/* LightObject (include/component.h:42-50; built by checkLightObject src/model.cpp:44-82). */
+typedef struct RmLightDesc {
+    float center[3], color[3];
+    float power;
+    int32_t n_faces;
+    const float *face_positions;       /* [n_faces][3][3] */
+    const float *face_normals;         /* [n_faces][3][3] vertex normals of those faces */
+    const float *face_cdf;             /* [n_faces] RandomDistribution prefix sums (src/component.cpp:12-18) */
+} RmLightDesc;
+
+typedef struct RmSceneDesc {
+    int32_t n_faces, n_nodes, n_materials, n_textures, n_lights;
+    int32_t sky_width, sky_height;     /* 0 = no sky */
+    int32_t _pad;
+    const RmBvhNode *nodes;            /* BVH::node, heap-indexed from 1 (src/bvh.cpp:18-54); never-written slots zero */
+    const float *positions;            /* [n_faces][3][3] Model::faces in POST-BUILD order (BVH::build permutes, bvh.cpp:38) */
+    const float *uvs;                  /* [n_faces][3][2] */
+    const float *normals;              /* [n_faces][3][3] */
+    const int32_t *face_material;      /* [n_faces] Material::id */
+    const RmMaterialDesc *materials;
+    const RmTextureDesc *textures;
+    const RmLightDesc *lights;
+    const float *sky_data;             /* [h][w][3] SkyBox::data AFTER SkyBox::Init premultiplied it (src/component.cpp:54-67) */
+    const float *sky_cdf;              /* [h*w] SkyBox::dist prefix sums */
+} RmSceneDesc;
+
+/* ---------------------------------------------------------------------------------
+ * Host-side scene preparation — the load-time derivations of Model::Model that the
+ * north star keeps on the host: BVH::build (src/bvh.cpp:18-54), generateMipmaps
+ * (src/material.cpp:113-148), checkLightObject (src/model.cpp:23-82), SkyBox::Init
+ * (src/component.cpp:54-67), hasTransparentPart (src/material.cpp:102-107,330-333).
+ * Pure host C++, no CUDA.
+ * ------------------------------------------------------------------------------- */
+typedef struct RmPrepared RmPrepared;
+int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out);
+const RmSceneDesc *rm_prepared_desc(const RmPrepared *p);
+const int32_t *rm_prepared_permutation(const RmPrepared *p); /* perm[i] = raw face index stored at post-build slot i */
+void rm_prepared_free(RmPrepared *p);
+
+/* ---------------------------------------------------------------------------------
+ * Context and scene upload
+ * ------------------------------------------------------------------------------- */
+typedef struct RmContext RmContext;
+
+const char *rm_last_error(void);
+const char *rm_version(void);
+
+/* One context per CUDA device.  stream = a cudaStream_t the caller owns (0 = default
+ * stream); every kernel and copy of this context is issued on it. */
+int rm_context_create(int device, void *stream, RmContext **out);
+void rm_context_destroy(RmContext *ctx);
+int rm_context_synchronize(RmContext *ctx);
+
+/* Flatten a post-load scene into the SoA device layout and stage it to HBM.
+ * Replaces nothing in the reference (it has no device); it is what `const Model&`
+ * is to render_multiThread (src/render.cpp:593). */
+int rm_scene_upload(RmContext *ctx, const RmSceneDesc *scene);
+/* bytes of HBM the staged scene occupies */
+int64_t rm_scene_device_bytes(const RmContext *ctx);
+
+/* ---------------------------------------------------------------------------------
+ * Per-ray seam: Model::rayHit / Model::rayHit_test (include/model.h:41-42,
+ * src/model.cpp:332-354) over batches of rays.
+ * ------------------------------------------------------------------------------- */
+/* Closest hit.  org/dir: [n][3].  tri_idx: post-build face index or -1; t: hit.t_max (INF on miss). */
+int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *dir, int32_t *tri_idx, float *t);
+/* Occlusion test, rayHit_test semantics: out[i] = 1 iff something blocks the ray before aim[i]. */
+int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *dir, const float *aim, uint8_t *out);
+
+/* ---------------------------------------------------------------------------------
+ * Per-pixel seam: renderPixel (src/render.cpp:448-551) split into its stages.
+ * ------------------------------------------------------------------------------- */
+/* Primary rays exactly as renderPixel forms them (466-479) + Model::rayHit.
+ * Leaves {tri_idx, t} in the context and, if non-NULL, copies them to the host. */
+int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx, float *t);
+
+/* G-buffer: getHitInfo (src/render.cpp:62-79) at the primary hit, sky emission on a
+ * miss (480-485).  Requires rm_trace_primary for the same args.  gbuffer (host, may be
+ * NULL) receives width*height HitInfo records in the reference's AoS layout with the
+ * restored baseColor (550). */
+int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer);
+
+/* Sample loops of renderPixel (498-547): the direct-light samples s with
+ * s = sample_begin + k*sample_stride < spp_direct and the indirect samples likewise
+ * below spp_indirect, each weighted with the GLOBAL 1/spp factors, accumulated into the
+ * context's fp32 accumulators.  sample_begin = rank, sample_stride = world size shards a
+ * render across GPUs by interleaved sample index.  Resets the accumulators first when
+ * `reset` is non-zero.  Requires rm_gbuffer. */
+int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_begin, int32_t sample_stride,
+                      uint64_t seed, int32_t reset);
+
+/* Device view of the accumulators for the multi-GPU reduction (caller runs
+ * ncclReduce/ncclAllReduce or torch.distributed on them): `d_sum` = floats to be
+ * SUMMED across ranks, `d_max` = floats to be MAX-reduced across ranks (firefly-clamp
+ * side data, render.cpp:534-547).  Sizes in floats. */
+int rm_accum_view(RmContext *ctx, float **d_sum, int64_t *n_sum, float **d_max, int64_t *n_max);
+/* After a cross-rank reduction: tell the context which rank's held-back sample owns the
+ * global per-pixel maximum (see DESIGN.md "firefly clamp"); no-op on one GPU. */
+int rm_accum_after_reduce(RmContext *ctx, int32_t rank, int32_t world);
+
+/* Resolve: firefly clamp + diffuse/specular split + exposure/variance finalise
+ * (render.cpp:510-549) -> the four RadianceData planes (host, reference AoS layout). */
+int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);
+
+/* Whole render_multiThread pixel loop (src/render.cpp:593-626) on one GPU:
+ * primary + G-buffer + all samples + resolve, results to host buffers (any may be NULL). */
+int rm_render(RmContext *ctx, const RmRenderArgs *args, uint64_t seed,
+              RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);
+
+/* ---------------------------------------------------------------------------------
+ * Post pass
+ * ------------------------------------------------------------------------------- */
+/* Photo::FXAA (include/image.h:54, src/image.cpp:363-452): fp32 RGB in -> fp32 RGB out, host buffers. */
+int rm_fxaa(RmContext *ctx, const float *rgb_in, float *rgb_out, int32_t width, int32_t height);
+/* Same on device buffers (no copies): d_rgb_in/d_rgb_out [h][w][3]. */
+int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int32_t width, int32_t height);
+/* Photo::shade (src/image.cpp:215-246) + gammaCorrection (454-468) [+ FXAA when
+ * shade_options has DoFXAA = 512] on the context's resolved planes -> host RGB. */
+int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_options, float *rgb_out);
+
+/* ---------------------------------------------------------------------------------
+ * Work counters (device-side), reset by rm_stats_reset:
+ *   [0] rays = BVH::rayHit invocations   [1] box tests (rayInBox)   [2] triangle tests
+ *   [3] kernel launches issued by this context
+ * Box/triangle counts are only collected when rm_set_option("count_tests", 1). */
+int rm_stats_reset(RmContext *ctx);
+int rm_stats_read(RmContext *ctx, uint64_t out[4]);
+int rm_set_option(RmContext *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYM0NADE_B200_H */

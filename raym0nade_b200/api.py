@@ -1,0 +1,306 @@
+"""Python host side over the C ABI (include/raym0nade_b200.h).
+
+Mirrors the reference's host interface for the hot path: a `Model` that is prepared once
+(BVH build, mip chains, light objects, sky CDF - what `Model::Model` does, src/model.cpp:172-215)
+and a `render_multiThread(model, args)` that runs the pixel loop (src/render.cpp:593-626) -
+here on one B200 through libraym0nade_b200.so.  There is no CPU fallback: if the CUDA
+library is missing or no device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .ctypes_defs import (BVHNODE_DTYPE, HITINFO_DTYPE, RADIANCE_DTYPE, RmRawScene, RmRenderArgs)
+from .scenes import RawScene, RenderArgs
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libraym0nade_b200.so")
+_LIB = None
+
+
+class RmError(RuntimeError):
+    pass
+
+
+class RmTextureDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("map_depth", C.c_int32),
+                ("levels", C.c_void_p * 8)]
+
+
+class RmMaterialDesc(C.Structure):
+    _fields_ = [("tex", C.c_int32 * 4), ("opacity", C.c_float), ("ior", C.c_float), ("roughness", C.c_float),
+                ("transmitting_color", C.c_float * 3), ("has_fully_transparent_part", C.c_int32), ("_pad", C.c_int32)]
+
+
+class RmLightDesc(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("color", C.c_float * 3), ("power", C.c_float), ("n_faces", C.c_int32),
+                ("face_positions", C.c_void_p), ("face_normals", C.c_void_p), ("face_cdf", C.c_void_p)]
+
+
+class RmSceneDesc(C.Structure):
+    _fields_ = [("n_faces", C.c_int32), ("n_nodes", C.c_int32), ("n_materials", C.c_int32), ("n_textures", C.c_int32),
+                ("n_lights", C.c_int32), ("sky_width", C.c_int32), ("sky_height", C.c_int32), ("_pad", C.c_int32),
+                ("nodes", C.c_void_p), ("positions", C.c_void_p), ("uvs", C.c_void_p), ("normals", C.c_void_p),
+                ("face_material", C.c_void_p), ("materials", C.POINTER(RmMaterialDesc)),
+                ("textures", C.POINTER(RmTextureDesc)), ("lights", C.POINTER(RmLightDesc)),
+                ("sky_data", C.c_void_p), ("sky_cdf", C.c_void_p)]
+
+
+# every symbol include/raym0nade_b200.h declares
+EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
+           "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
+           "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
+           "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_resolve", "rm_render", "rm_fxaa",
+           "rm_fxaa_device", "rm_postprocess", "rm_stats_reset", "rm_stats_read", "rm_set_option"]
+
+
+def lib():
+    """Load libraym0nade_b200.so (built in-tree by raym0nade_b200.build).  Fails loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RmError("%s is missing - run `python -m raym0nade_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    ARGS = C.POINTER(RmRenderArgs)
+    L.rm_last_error.restype = C.c_char_p
+    L.rm_version.restype = C.c_char_p
+    L.rm_prepare_scene.argtypes = [C.POINTER(RmRawScene), C.POINTER(vp)]
+    L.rm_prepared_desc.restype = C.POINTER(RmSceneDesc)
+    L.rm_prepared_desc.argtypes = [vp]
+    L.rm_prepared_permutation.restype = C.POINTER(C.c_int32)
+    L.rm_prepared_permutation.argtypes = [vp]
+    L.rm_prepared_free.argtypes = [vp]
+    L.rm_context_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.rm_context_destroy.argtypes = [vp]
+    L.rm_context_synchronize.argtypes = [vp]
+    L.rm_scene_upload.argtypes = [vp, C.POINTER(RmSceneDesc)]
+    L.rm_scene_device_bytes.restype = i64
+    L.rm_scene_device_bytes.argtypes = [vp]
+    L.rm_trace_closest.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.rm_trace_occluded.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.rm_trace_primary.argtypes = [vp, ARGS, vp, vp]
+    L.rm_gbuffer.argtypes = [vp, ARGS, vp]
+    L.rm_render_samples.argtypes = [vp, ARGS, i32, i32, u64, i32]
+    L.rm_accum_view.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
+    L.rm_accum_after_reduce.argtypes = [vp, i32, i32]
+    L.rm_resolve.argtypes = [vp, ARGS, vp, vp, vp, vp]
+    L.rm_render.argtypes = [vp, ARGS, u64, vp, vp, vp, vp, vp]
+    L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
+    L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
+    L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
+    L.rm_stats_reset.argtypes = [vp]
+    L.rm_stats_read.argtypes = [vp, vp]
+    L.rm_set_option.argtypes = [vp, C.c_char_p, i64]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RmError("raym0nade_b200 error %d: %s" % (rc, lib().rm_last_error().decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Model:
+    """Host-side prepared scene = the reference's loaded `Model` (include/model.h:25-43)."""
+
+    def __init__(self, raw: RawScene):
+        self.raw = raw
+        self._c = raw.to_c()
+        h = C.c_void_p()
+        _check(lib().rm_prepare_scene(C.byref(self._c), C.byref(h)))
+        self.h = h
+        self.desc = lib().rm_prepared_desc(h).contents
+
+    @property
+    def n_faces(self):
+        return self.desc.n_faces
+
+    def permutation(self) -> np.ndarray:
+        return np.ctypeslib.as_array(lib().rm_prepared_permutation(self.h), (self.desc.n_faces,)).copy()
+
+    def nodes(self) -> np.ndarray:
+        buf = (C.c_char * (32 * self.desc.n_nodes)).from_address(self.desc.nodes)
+        return np.frombuffer(buf, BVHNODE_DTYPE).copy()
+
+    def _f32_view(self, addr, n):
+        if not addr or n == 0:
+            return np.zeros(0, np.float32)
+        return np.frombuffer((C.c_char * (4 * n)).from_address(addr), np.float32).copy()
+
+    def lights(self):
+        out = []
+        for i in range(self.desc.n_lights):
+            l = self.desc.lights[i]
+            out.append(dict(center=np.array(l.center[:], np.float32), color=np.array(l.color[:], np.float32),
+                            power=float(l.power), faces=self._f32_view(l.face_positions, l.n_faces * 9).reshape(-1, 3, 3),
+                            cdf=self._f32_view(l.face_cdf, l.n_faces)))
+        return out
+
+    def sky(self):
+        n = self.desc.sky_width * self.desc.sky_height
+        return (self._f32_view(self.desc.sky_data, n * 3).reshape(self.desc.sky_height, self.desc.sky_width, 3),
+                self._f32_view(self.desc.sky_cdf, n))
+
+    def texture_levels(self, tex_index):
+        t = self.desc.textures[tex_index]
+        out = []
+        for l in range(t.map_depth):
+            nbytes = (t.width >> l) * (t.height >> l) * t.channels
+            out.append(np.frombuffer((C.c_char * nbytes).from_address(t.levels[l]), np.uint8).copy())
+        return out, t.map_depth
+
+    def material(self, i):
+        return self.desc.materials[i]
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rm_prepared_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA device + one staged scene.  `stream` = a raw cudaStream_t (int) or None."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        h = C.c_void_p()
+        _check(lib().rm_context_create(device, C.c_void_p(stream or 0), C.byref(h)))
+        self.h = h
+        self.model = None
+
+    def upload(self, model: Model):
+        _check(lib().rm_scene_upload(self.h, C.byref(model.desc)))
+        self.model = model
+        return self
+
+    def scene_bytes(self):
+        return lib().rm_scene_device_bytes(self.h)
+
+    def set_option(self, name, value):
+        _check(lib().rm_set_option(self.h, name.encode(), int(value)))
+
+    def synchronize(self):
+        _check(lib().rm_context_synchronize(self.h))
+
+    def stats_reset(self):
+        _check(lib().rm_stats_reset(self.h))
+
+    def stats(self):
+        out = np.zeros(4, np.uint64)
+        _check(lib().rm_stats_read(self.h, _p(out)))
+        return dict(rays=int(out[0]), box=int(out[1]), tri=int(out[2]), launches=int(out[3]))
+
+    # ---- per-ray seam
+    def trace_closest(self, org, dirs):
+        org, dirs = _f32(org), _f32(dirs)
+        n = org.shape[0]
+        tri, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        _check(lib().rm_trace_closest(self.h, n, _p(org), _p(dirs), _p(tri), _p(t)))
+        return tri, t
+
+    def trace_occluded(self, org, dirs, aim):
+        org, dirs, aim = _f32(org), _f32(dirs), _f32(aim)
+        out = np.zeros(org.shape[0], np.uint8)
+        _check(lib().rm_trace_occluded(self.h, org.shape[0], _p(org), _p(dirs), _p(aim), _p(out)))
+        return out
+
+    # ---- per-pixel stages
+    def trace_primary(self, args: RenderArgs, download=True):
+        a = args.to_c()
+        n = args.width * args.height
+        tri = np.zeros(n, np.int32) if download else None
+        t = np.zeros(n, np.float32) if download else None
+        _check(lib().rm_trace_primary(self.h, C.byref(a), _p(tri), _p(t)))
+        return tri, t
+
+    def gbuffer(self, args: RenderArgs, download=True):
+        a = args.to_c()
+        g = np.zeros(args.width * args.height, HITINFO_DTYPE) if download else None
+        _check(lib().rm_gbuffer(self.h, C.byref(a), _p(g)))
+        return g
+
+    def render_samples(self, args: RenderArgs, sample_begin=0, sample_stride=1, seed=0, reset=True):
+        a = args.to_c()
+        _check(lib().rm_render_samples(self.h, C.byref(a), sample_begin, sample_stride, seed, int(reset)))
+
+    def accum_view(self):
+        ps, ns, pm, nm = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        _check(lib().rm_accum_view(self.h, C.byref(ps), C.byref(ns), C.byref(pm), C.byref(nm)))
+        return ps.value, ns.value, pm.value, nm.value
+
+    def accum_after_reduce(self, rank, world):
+        _check(lib().rm_accum_after_reduce(self.h, rank, world))
+
+    def resolve(self, args: RenderArgs):
+        a = args.to_c()
+        n = args.width * args.height
+        planes = [np.zeros(n, RADIANCE_DTYPE) for _ in range(4)]
+        _check(lib().rm_resolve(self.h, C.byref(a), *[_p(p) for p in planes]))
+        return dict(Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
+
+    def render(self, args: RenderArgs, seed=0, download=True):
+        """The whole render_multiThread pixel loop on this GPU; returns gbuffer + 4 planes."""
+        a = args.to_c()
+        n = args.width * args.height
+        g = np.zeros(n, HITINFO_DTYPE) if download else None
+        planes = [np.zeros(n, RADIANCE_DTYPE) if download else None for _ in range(4)]
+        _check(lib().rm_render(self.h, C.byref(a), seed, _p(g), *[_p(p) for p in planes]))
+        return dict(gbuffer=g, Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
+
+    # ---- post pass
+    def fxaa(self, rgb):
+        rgb = _f32(rgb)
+        h, w = rgb.shape[:2]
+        out = np.zeros_like(rgb)
+        _check(lib().rm_fxaa(self.h, _p(rgb), _p(out), w, h))
+        return out
+
+    def fxaa_device(self, d_in: int, d_out: int, width: int, height: int):
+        _check(lib().rm_fxaa_device(self.h, C.c_void_p(d_in), C.c_void_p(d_out), width, height))
+
+    def postprocess(self, args: RenderArgs, shade_options: int):
+        a = args.to_c()
+        out = np.zeros((args.height, args.width, 3), np.float32)
+        _check(lib().rm_postprocess(self.h, C.byref(a), shade_options, _p(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rm_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render_multiThread(model: Model, args: RenderArgs, device: int = 0, seed: int = 0):
+    """Drop-in for the reference's `render_multiThread(Model&, const RenderArgs&)`
+    (include/render.h:43): runs the pixel loop and returns the Photo buffers
+    (G-buffer + the four RadianceData planes) instead of writing PNGs."""
+    ctx = Context(device).upload(model)
+    try:
+        return ctx.render(args, seed=seed)
+    finally:
+        ctx.close()

@@ -1,0 +1,65 @@
+// dev_scene.cuh — the scene as it lies in HBM (see DESIGN.md "Data layout").
+//
+// Everything is flattened from the post-load RmSceneDesc by rm_scene_upload:
+//   nodes    2 x float4 per BVH_Node, heap-indexed exactly like BVH::node (src/bvh.cpp:18-54):
+//            the two children of u are nodes 2u, 2u+1 = one 64-byte aligned 64-byte block.
+//            float4 a = {v0.x v0.y v0.z v1.x}, float4 b = {v1.y v1.z faceL faceR} (ints as bits).
+//   tri      3 x float4 per face for traversal only: {v0.xyz e1.x} {e1.yz e2.xy} {e2.z |e1| cutout 0}
+//            where e1 = v1-v0, e2 = v2-v0, |e1| = length(e1): the fp32 values
+//            RayTriangleIntersection recomputes per test (src/geometry.cpp:65-70), hoisted.
+//   shade    7 x float4 per face for shading: positions[9] uv[6] normals[9] material(int) pad[3]
+//   texels   all mip levels of all textures in one byte blob, 16-byte aligned per level
+#pragma once
+#include <cstdint>
+#include "dev_math.cuh"
+
+namespace rm {
+
+struct DevTexture {
+    int32_t width, height, channels, map_depth;
+    uint32_t offset[8];             // byte offset of each level in the texel blob
+};
+
+struct DevMaterial {
+    int32_t tex[4];                 // diffuse, specular, emissive, normals; -1 = empty
+    float opacity, ior, roughness;
+    float tc[3];                    // transmittingColor
+    int32_t cutout;                 // hasFullyTransparentPart
+    int32_t _pad;
+};
+
+struct DevLight {
+    float center[3], color[3];
+    float power;
+    int32_t n_faces;
+    int32_t face_offset;            // into light_pos / light_nrm (faces), light_cdf (floats)
+    int32_t _pad[3];
+};
+
+struct DevScene {
+    const float4 *nodes;
+    const float4 *tri;
+    const float4 *shade;
+    const DevMaterial *materials;
+    const DevTexture *textures;
+    const uint8_t *texels;
+    const DevLight *lights;
+    const float *light_pos;         // [total light faces][9]
+    const float *light_nrm;         // [total light faces][9]
+    const float *light_cdf;         // [total light faces]
+    const float *sky_data;          // [h*w][3], premultiplied by texel solid angle
+    const float *sky_cdf;           // [h*w]
+    int32_t n_faces, n_nodes, n_materials, n_lights;
+    int32_t sky_width, sky_height;
+    int32_t any_cutout;             // some material has hasFullyTransparentPart
+    int32_t root_is_leaf;
+};
+
+// Camera / render arguments in device form (RenderArgs, include/render.h:8-15).
+struct DevArgs {
+    V3 position, direction, up, right;
+    float accuracy, exposure, P_Direct;
+    int32_t width, height, spp;
+};
+
+} // namespace rm

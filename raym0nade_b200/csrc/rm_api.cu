@@ -1,0 +1,325 @@
+// rm_api.cu — C ABI: context, scene staging, the per-ray seam and the primary-ray stage.
+//
+// No CPU fallback: every entry point that computes needs an sm_100 device and fails with
+// RM_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <new>
+
+#include "rm_context.cuh"
+#include "kernels_trace.cuh"
+
+using namespace rm;
+
+rm::DevArgs to_dev_args(const RmRenderArgs *a) {
+    DevArgs d;
+    d.position = {a->position[0], a->position[1], a->position[2]};
+    d.direction = {a->direction[0], a->direction[1], a->direction[2]};
+    d.up = {a->up[0], a->up[1], a->up[2]};
+    d.right = {a->right[0], a->right[1], a->right[2]};
+    d.accuracy = a->accuracy;
+    d.exposure = a->exposure;
+    d.P_Direct = a->P_Direct;
+    d.width = a->width;
+    d.height = a->height;
+    d.spp = a->spp;
+    return d;
+}
+
+int rm_check_args(const RmRenderArgs *a) {
+    if (!a) return rm_fail(RM_ERR_INVALID, "render args are NULL");
+    if (a->width <= 0 || a->height <= 0 || (int64_t)a->width * a->height > (int64_t)1 << 28)
+        return rm_fail(RM_ERR_INVALID, "render args: bad image size %d x %d", a->width, a->height);
+    if (a->spp < 0) return rm_fail(RM_ERR_INVALID, "render args: negative spp");
+    return RM_OK;
+}
+
+static int upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st, int64_t &total) {
+    int rc = b.alloc(bytes);
+    if (rc) return rc;
+    if (bytes) RM_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    total += (int64_t)bytes;
+    return RM_OK;
+}
+
+extern "C" {
+
+int rm_context_create(int device, void *stream, RmContext **out) {
+    if (!out) return rm_fail(RM_ERR_INVALID, "rm_context_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return rm_fail(RM_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return rm_fail(RM_ERR_INVALID, "rm_context_create: device %d out of range (have %d)", device, n);
+    RM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return rm_fail(RM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    RmContext *ctx = new (std::nothrow) RmContext();
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    int rc = ctx->b_counters.alloc(8 * sizeof(unsigned long long));
+    if (rc) { delete ctx; return rc; }
+    cudaMemsetAsync(ctx->b_counters.p, 0, ctx->b_counters.bytes, ctx->stream);
+    *out = ctx;
+    return RM_OK;
+}
+
+void rm_context_destroy(RmContext *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    rm_render_state_free(ctx);
+    delete ctx;
+}
+
+int rm_context_synchronize(RmContext *ctx) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RM_OK;
+}
+
+int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
+    if (!ctx || !sc) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: null argument");
+    if (sc->n_faces <= 0 || sc->n_nodes < 2 || !sc->nodes || !sc->positions || !sc->uvs || !sc->normals || !sc->face_material)
+        return rm_fail(RM_ERR_INVALID, "rm_scene_upload: scene is missing geometry");
+    if ((int64_t)sc->n_faces >= ((int64_t)1 << 27)) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: more than 2^27 faces");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int64_t total = 0;
+    int rc;
+    const int n = sc->n_faces;
+
+    // nodes: same 32-byte images, heap-indexed; the array is padded to an even count so that
+    // every child pair (2u, 2u+1) is a whole 64-byte block
+    std::vector<RmBvhNode> nodes(size_t(sc->n_nodes + 2) & ~size_t(1));
+    std::memcpy(nodes.data(), sc->nodes, sizeof(RmBvhNode) * sc->n_nodes);
+    if ((rc = upload(ctx->b_nodes, nodes.data(), nodes.size() * sizeof(RmBvhNode), st, total))) return rc;
+
+    // materials (needed first for the per-triangle cut-out flag)
+    std::vector<DevMaterial> mats(std::max(sc->n_materials, 1));
+    bool any_cutout = false;
+    for (int i = 0; i < sc->n_materials; i++) {
+        const RmMaterialDesc &m = sc->materials[i];
+        DevMaterial &d = mats[i];
+        for (int k = 0; k < 4; k++) {
+            if (m.tex[k] >= sc->n_textures) return rm_fail(RM_ERR_INVALID, "material %d: texture index out of range", i);
+            d.tex[k] = m.tex[k] < 0 ? -1 : m.tex[k];
+        }
+        d.opacity = m.opacity; d.ior = m.ior; d.roughness = m.roughness;
+        for (int k = 0; k < 3; k++) d.tc[k] = m.transmitting_color[k];
+        d.cutout = m.has_fully_transparent_part ? 1 : 0;
+        d._pad = 0;
+        any_cutout |= d.cutout != 0;
+    }
+    if ((rc = upload(ctx->b_mats, mats.data(), mats.size() * sizeof(DevMaterial), st, total))) return rc;
+
+    // traversal records (48 B) and shading records (112 B)
+    std::vector<float> tri(size_t(n) * 12), shade(size_t(n) * 28, 0.0f);
+    for (int i = 0; i < n; i++) {
+        const float *p = sc->positions + size_t(i) * 9;
+        int mat = sc->face_material[i];
+        if (mat < 0 || mat >= sc->n_materials) return rm_fail(RM_ERR_INVALID, "face %d: material index out of range", i);
+        float e1[3], e2[3];
+        for (int k = 0; k < 3; k++) { e1[k] = p[3 + k] - p[k]; e2[k] = p[6 + k] - p[k]; }
+        float len = std::sqrt((e1[0] * e1[0] + e1[1] * e1[1]) + e1[2] * e1[2]);   // glm::length(edge1)
+        float *t = &tri[size_t(i) * 12];
+        t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = e1[0];
+        t[4] = e1[1]; t[5] = e1[2]; t[6] = e2[0]; t[7] = e2[1];
+        t[8] = e2[2]; t[9] = len; t[10] = mats[mat].cutout ? 1.0f : 0.0f; t[11] = 0.0f;
+        float *s = &shade[size_t(i) * 28];
+        std::memcpy(s, p, 36);
+        std::memcpy(s + 9, sc->uvs + size_t(i) * 6, 24);
+        std::memcpy(s + 15, sc->normals + size_t(i) * 9, 36);
+        std::memcpy(s + 24, &mat, 4);
+    }
+    if ((rc = upload(ctx->b_tri, tri.data(), tri.size() * 4, st, total))) return rc;
+    if ((rc = upload(ctx->b_shade, shade.data(), shade.size() * 4, st, total))) return rc;
+
+    // textures: one blob, each level 16-byte aligned
+    std::vector<DevTexture> texs(std::max(sc->n_textures, 1));
+    std::vector<uint8_t> blob;
+    for (int i = 0; i < sc->n_textures; i++) {
+        const RmTextureDesc &t = sc->textures[i];
+        if (t.map_depth < 1 || t.map_depth > 8 || (t.channels != 3 && t.channels != 4))
+            return rm_fail(RM_ERR_INVALID, "texture %d: bad map_depth/channels", i);
+        DevTexture &d = texs[i];
+        d.width = t.width; d.height = t.height; d.channels = t.channels; d.map_depth = t.map_depth;
+        for (int l = 0; l < 8; l++) {
+            d.offset[l] = 0;
+            if (l >= t.map_depth) continue;
+            size_t bytes = size_t(t.width >> l) * (t.height >> l) * t.channels;
+            size_t off = (blob.size() + 15) & ~size_t(15);
+            if (off + bytes > 0xFFFFFFFFull) return rm_fail(RM_ERR_INVALID, "texture data exceeds 4 GiB");
+            blob.resize(off + bytes);
+            std::memcpy(blob.data() + off, t.levels[l], bytes);
+            d.offset[l] = uint32_t(off);
+        }
+    }
+    blob.resize((blob.size() + 15) & ~size_t(15));
+    if ((rc = upload(ctx->b_texs, texs.data(), texs.size() * sizeof(DevTexture), st, total))) return rc;
+    if ((rc = upload(ctx->b_texels, blob.data(), blob.size(), st, total))) return rc;
+
+    // lights
+    std::vector<DevLight> lights(std::max(sc->n_lights, 1));
+    std::vector<float> lpos, lnrm, lcdf;
+    for (int i = 0; i < sc->n_lights; i++) {
+        const RmLightDesc &L = sc->lights[i];
+        DevLight &d = lights[i];
+        for (int k = 0; k < 3; k++) { d.center[k] = L.center[k]; d.color[k] = L.color[k]; }
+        d.power = L.power;
+        d.n_faces = L.n_faces;
+        d.face_offset = int32_t(lcdf.size());
+        lpos.insert(lpos.end(), L.face_positions, L.face_positions + size_t(L.n_faces) * 9);
+        lnrm.insert(lnrm.end(), L.face_normals, L.face_normals + size_t(L.n_faces) * 9);
+        lcdf.insert(lcdf.end(), L.face_cdf, L.face_cdf + L.n_faces);
+    }
+    if ((rc = upload(ctx->b_lights, lights.data(), lights.size() * sizeof(DevLight), st, total))) return rc;
+    if ((rc = upload(ctx->b_lpos, lpos.data(), lpos.size() * 4, st, total))) return rc;
+    if ((rc = upload(ctx->b_lnrm, lnrm.data(), lnrm.size() * 4, st, total))) return rc;
+    if ((rc = upload(ctx->b_lcdf, lcdf.data(), lcdf.size() * 4, st, total))) return rc;
+
+    // sky
+    size_t nsky = size_t(sc->sky_width) * sc->sky_height;
+    if (nsky && (!sc->sky_data || !sc->sky_cdf)) return rm_fail(RM_ERR_INVALID, "sky size set but sky_data/sky_cdf missing");
+    if ((rc = upload(ctx->b_sky, sc->sky_data, nsky * 12, st, total))) return rc;
+    if ((rc = upload(ctx->b_skycdf, sc->sky_cdf, nsky * 4, st, total))) return rc;
+    RM_CUDA(cudaStreamSynchronize(st));    // host staging vectors die at scope exit
+
+    DevScene &S = ctx->scene;
+    S.nodes = ctx->b_nodes.as<float4>();
+    S.tri = ctx->b_tri.as<float4>();
+    S.shade = ctx->b_shade.as<float4>();
+    S.materials = ctx->b_mats.as<DevMaterial>();
+    S.textures = ctx->b_texs.as<DevTexture>();
+    S.texels = ctx->b_texels.as<uint8_t>();
+    S.lights = ctx->b_lights.as<DevLight>();
+    S.light_pos = ctx->b_lpos.as<float>();
+    S.light_nrm = ctx->b_lnrm.as<float>();
+    S.light_cdf = ctx->b_lcdf.as<float>();
+    S.sky_data = ctx->b_sky.as<float>();
+    S.sky_cdf = ctx->b_skycdf.as<float>();
+    S.n_faces = n;
+    S.n_nodes = sc->n_nodes;
+    S.n_materials = sc->n_materials;
+    S.n_lights = sc->n_lights;
+    S.sky_width = sc->sky_width;
+    S.sky_height = sc->sky_height;
+    S.any_cutout = any_cutout ? 1 : 0;
+    S.root_is_leaf = sc->nodes[1].faceR != 0;
+    ctx->scene_bytes = total;
+    ctx->has_scene = true;
+    ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
+    return RM_OK;
+}
+
+int64_t rm_scene_device_bytes(const RmContext *ctx) { return ctx ? ctx->scene_bytes : 0; }
+
+// ------------------------------------------------------------------------ per-ray seam
+int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *dir, int32_t *tri_idx, float *t) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_trace_closest: no scene uploaded");
+    if (n < 0 || (n > 0 && (!org || !dir || !tri_idx || !t))) return rm_fail(RM_ERR_INVALID, "rm_trace_closest: bad arguments");
+    if (n == 0) return RM_OK;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->b_io[0].alloc(n * 12)) || (rc = ctx->b_io[1].alloc(n * 12)) || (rc = ctx->b_io[2].alloc(n * 4)) || (rc = ctx->b_io[3].alloc(n * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    RM_CUDA(cudaMemcpyAsync(ctx->b_io[0].p, org, n * 12, cudaMemcpyHostToDevice, st));
+    RM_CUDA(cudaMemcpyAsync(ctx->b_io[1].p, dir, n * 12, cudaMemcpyHostToDevice, st));
+    unsigned blocks = unsigned((n + kTraceBlock - 1) / kTraceBlock);
+    auto *cnt = ctx->b_counters.as<unsigned long long>();
+    if (ctx->count_tests)
+        k_trace_closest<true><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<int>(), ctx->b_io[3].as<float>(), cnt);
+    else
+        k_trace_closest<false><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<int>(), ctx->b_io[3].as<float>(), cnt);
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaMemcpyAsync(t, ctx->b_io[3].p, n * 4, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    return RM_OK;
+}
+
+int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *dir, const float *aim, uint8_t *out) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_trace_occluded: no scene uploaded");
+    if (n < 0 || (n > 0 && (!org || !dir || !aim || !out))) return rm_fail(RM_ERR_INVALID, "rm_trace_occluded: bad arguments");
+    if (n == 0) return RM_OK;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->b_io[0].alloc(n * 12)) || (rc = ctx->b_io[1].alloc(n * 12)) || (rc = ctx->b_io[2].alloc(n * 4)) || (rc = ctx->b_io[3].alloc(n * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    RM_CUDA(cudaMemcpyAsync(ctx->b_io[0].p, org, n * 12, cudaMemcpyHostToDevice, st));
+    RM_CUDA(cudaMemcpyAsync(ctx->b_io[1].p, dir, n * 12, cudaMemcpyHostToDevice, st));
+    RM_CUDA(cudaMemcpyAsync(ctx->b_io[2].p, aim, n * 4, cudaMemcpyHostToDevice, st));
+    unsigned blocks = unsigned((n + kTraceBlock - 1) / kTraceBlock);
+    auto *cnt = ctx->b_counters.as<unsigned long long>();
+    if (ctx->count_tests)
+        k_trace_occluded<true><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<float>(), ctx->b_io[3].as<unsigned char>(), cnt);
+    else
+        k_trace_occluded<false><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<float>(), ctx->b_io[3].as<unsigned char>(), cnt);
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    return RM_OK;
+}
+
+// ------------------------------------------------------------------------ primary rays (K1)
+int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx, float *t) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_trace_primary: no scene uploaded");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = size_t(args->width) * args->height;
+    if ((rc = ctx->b_tri_idx.alloc(npix * 4)) || (rc = ctx->b_t.alloc(npix * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    dim3 grid((args->width + 15) / 16, (args->height + 7) / 8);
+    auto *cnt = ctx->b_counters.as<unsigned long long>();
+    DevArgs A = to_dev_args(args);
+    if (ctx->count_tests)
+        k_trace_primary<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
+    else
+        k_trace_primary<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    ctx->width = args->width;
+    ctx->height = args->height;
+    ctx->frame_args = *args;
+    ctx->have_primary = true;
+    ctx->have_gbuffer = ctx->have_resolved = false;
+    if (tri_idx) RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_tri_idx.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (t) RM_CUDA(cudaMemcpyAsync(t, ctx->b_t.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (tri_idx || t) RM_CUDA(cudaStreamSynchronize(st));
+    return RM_OK;
+}
+
+// ------------------------------------------------------------------------ counters / options
+int rm_stats_reset(RmContext *ctx) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    RM_CUDA(cudaMemsetAsync(ctx->b_counters.p, 0, ctx->b_counters.bytes, ctx->stream));
+    ctx->launches = 0;
+    return RM_OK;
+}
+
+int rm_stats_read(RmContext *ctx, uint64_t out[4]) {
+    if (!ctx || !out) return rm_fail(RM_ERR_INVALID, "rm_stats_read: null argument");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long h[3];
+    RM_CUDA(cudaMemcpyAsync(h, ctx->b_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    out[3] = ctx->launches;
+    return RM_OK;
+}
+
+int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return rm_fail(RM_ERR_INVALID, "rm_set_option: null argument");
+    if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
+    return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
+}
+
+} // extern "C"

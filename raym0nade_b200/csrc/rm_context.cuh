@@ -1,0 +1,72 @@
+// rm_context.cuh — the context object behind the C ABI (host side, CUDA runtime).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "raym0nade_b200.h"
+#include "rm_internal.h"
+#include "dev_scene.cuh"
+
+#define RM_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return rm_fail(RM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Owning device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        if (n <= bytes && p) return RM_OK;
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; bytes = 0; return rm_fail(RM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); }
+        bytes = n;
+        return RM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct RmContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool has_scene = false;
+    bool count_tests = false;
+    bool exact_secondary = true;
+    uint64_t launches = 0;
+
+    // scene
+    rm::DevScene scene{};
+    DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf;
+    int64_t scene_bytes = 0;
+
+    // counters: rays, box, tri (device)
+    DevBuf b_counters;
+
+    // per-frame state
+    int width = 0, height = 0;
+    bool have_primary = false, have_gbuffer = false, have_resolved = false;
+    RmRenderArgs frame_args{};
+    DevBuf b_tri_idx, b_t;                 // primary hits
+    DevBuf b_gbuffer;                      // RmHitInfo AoS [npix]
+    DevBuf b_io[4];                        // staging for the batched per-ray seam / fxaa
+    // wavefront + accumulators live in rm_render.cu's state
+    void *render_state = nullptr;
+
+    ~RmContext() {
+        for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
+                          &b_sky, &b_skycdf, &b_counters, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+            b->release();
+    }
+};
+
+rm::DevArgs to_dev_args(const RmRenderArgs *a);
+int rm_check_args(const RmRenderArgs *a);
+// implemented in rm_render.cu
+void rm_render_state_free(RmContext *ctx);

@@ -1,0 +1,111 @@
+"""GPU parity, stage K1 and the per-ray seam: CUDA traversal vs the reference oracle.
+
+Bar (BASELINE.json north_star): the primary-ray triangle index must match the reference
+exactly and the hit distance t within 1e-5 relative (we expect and assert bit equality).
+"""
+import numpy as np
+import pytest
+
+from raym0nade_b200 import scenes
+from raym0nade_b200.api import Context, Model
+
+pytestmark = pytest.mark.gpu
+
+T_REL_TOL = 1e-5   # the north star's stated tolerance; asserted in addition to bit equality
+
+
+def _compare_primary(ref, scene, args):
+    model = Model(scene)
+    R = ref.RefScene(scene)
+    ctx = Context(0).upload(model)
+    tri, t = ctx.trace_primary(args)
+    rtri, rt = R.trace_primary(args)
+    assert np.array_equal(tri, rtri), "tri_idx mismatches: %d of %d" % ((tri != rtri).sum(), tri.size)
+    hit = rtri >= 0
+    assert np.all(np.isinf(t[~hit])) and np.all(np.isinf(rt[~hit]))
+    rel = np.abs(t[hit] - rt[hit]) / rt[hit]
+    assert rel.max(initial=0.0) <= T_REL_TOL
+    assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)), "t not bit-equal"
+    ctx.close()
+    return hit.mean()
+
+
+def test_primary_cornell(ref):
+    scene, args = scenes.cornell_box(512, 512, 0)
+    assert _compare_primary(ref, scene, args) > 0.9
+
+
+def test_primary_heightfield_20k(ref):
+    scene, args = scenes.heightfield_scene(20_000, 480, 270)
+    assert _compare_primary(ref, scene, args) > 0.3
+
+
+def test_primary_sponza_scale_260k(ref):
+    scene, args = scenes.sponza_scale(260_000, 960, 540, tex_size=64, sky_size=(256, 128))
+    assert _compare_primary(ref, scene, args) > 0.3
+
+
+def test_primary_cutout_materials(ref):
+    """alpha cut-outs exercise the <=8 re-trace loop of Model::rayHit (src/model.cpp:332-341)"""
+    scene, args = scenes.texture_heavy(40_000, 320, 180, tex_size=64, n_materials=8)
+    assert _compare_primary(ref, scene, args) > 0.3
+
+
+def _random_rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene.positions.reshape(-1, 3).min(0), scene.positions.reshape(-1, 3).max(0)
+    org = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    org[:, 1] = hi[1] * (0.3 + rng.random(n)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    # a share of axis-parallel directions: exercises the |d| < 1e-4 "parallel" branch of rayInBox
+    d[: n // 16, 0] = 0.0
+    d[n // 16: n // 8, 2] = 5e-5
+    return org, d
+
+
+@pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout"])
+def test_closest_and_occluded_random_rays(ref, which):
+    if which == "cornell":
+        scene, _ = scenes.cornell_box()
+    elif which == "heightfield":
+        scene, _ = scenes.heightfield_scene(20_000)
+    else:
+        scene, _ = scenes.texture_heavy(40_000, tex_size=64, n_materials=8)
+    model = Model(scene)
+    R = ref.RefScene(scene)
+    ctx = Context(0).upload(model)
+    org, d = _random_rays(scene, 20_000, 11)
+    tri, t = ctx.trace_closest(org, d)
+    rtri, rt = R.trace_closest(org, d)
+    assert np.array_equal(tri, rtri)
+    assert np.array_equal(t.view(np.uint32), rt.view(np.uint32))
+    # occlusion: aim at, just before and just behind the closest hit, and at infinity
+    hit = rtri >= 0
+    aim = np.full(org.shape[0], np.inf, np.float32)
+    aim[hit] = rt[hit] * np.where(np.arange(hit.sum()) % 3 == 0, 0.5, np.where(np.arange(hit.sum()) % 3 == 1, 1.0, 1.5)).astype(np.float32)
+    occ = ctx.trace_occluded(org, d, aim)
+    rocc = R.trace_occluded(org, d, aim)
+    assert np.array_equal(occ, rocc)
+    assert 0 < occ.sum() < occ.size
+    ctx.close()
+
+
+def test_work_counters_match_reference_traversal(ref):
+    """box / triangle test counts come out identical because the traversal order is identical
+    (these are the B and T of the bytes-per-ray roofline figure)"""
+    from oracle import refbind
+    if not refbind.available("count"):
+        pytest.skip("counting oracle not built")
+    scene, args = scenes.heightfield_scene(20_000, 160, 90)
+    model = Model(scene)
+    R = refbind.RefScene(scene, flavour="count")
+    ctx = Context(0).upload(model)
+    ctx.set_option("count_tests", 1)
+    ctx.stats_reset()
+    ctx.trace_primary(args)
+    s = ctx.stats()
+    _, _, cnt = R.trace_primary(args, counters=True)
+    assert (s["rays"], s["box"], s["tri"]) == (int(cnt[0]), int(cnt[1]), int(cnt[2]))
+    ctx.close()
