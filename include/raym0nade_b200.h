@@ -139,14 +139,20 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer);
 int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_begin, int32_t sample_stride,
                       uint64_t seed, int32_t reset);
 
-/* Device view of the accumulators for the multi-GPU reduction (caller runs
- * ncclReduce/ncclAllReduce or torch.distributed on them): `d_sum` = floats to be
- * SUMMED across ranks, `d_max` = floats to be MAX-reduced across ranks (firefly-clamp
- * side data, render.cpp:534-547).  Sizes in floats. */
+/* Multi-GPU reduction of a sharded render, in three steps (single-GPU callers skip all of
+ * this: rm_resolve does the local equivalent).  The caller owns the collective
+ * (ncclAllReduce / torch.distributed) and runs it on the context's stream:
+ *   1. rm_accum_view: firefly-clamp side data (render.cpp:534-547).  `d_sum` = 2 floats per
+ *      pixel {sum of sample luminances, number of indirect samples} to be SUMMED across
+ *      ranks; `d_max` = 1 float per pixel (luminance of the rank's held-back sample) to be
+ *      MAX-reduced across ranks.  Sizes in floats.
+ *   2. rm_accum_after_reduce: every rank commits its held-back sample against the global
+ *      totals (only the rank owning the global maximum can drop it).
+ *   3. rm_accum_radiance: `d_rad` = 16 floats per pixel (Dd, Ds, Id, Is as {rgb, second
+ *      moment}) to be SUMMED across ranks; then rm_resolve on the rank(s) holding the sum. */
 int rm_accum_view(RmContext *ctx, float **d_sum, int64_t *n_sum, float **d_max, int64_t *n_max);
-/* After a cross-rank reduction: tell the context which rank's held-back sample owns the
- * global per-pixel maximum (see DESIGN.md "firefly clamp"); no-op on one GPU. */
 int rm_accum_after_reduce(RmContext *ctx, int32_t rank, int32_t world);
+int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad);
 
 /* Resolve: firefly clamp + diffuse/specular split + exposure/variance finalise
  * (render.cpp:510-549) -> the four RadianceData planes (host, reference AoS layout). */

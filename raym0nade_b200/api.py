@@ -54,7 +54,7 @@ class RmSceneDesc(C.Structure):
 EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
-           "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_resolve", "rm_render", "rm_fxaa",
+           "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_stats_reset", "rm_stats_read", "rm_set_option"]
 
 
@@ -89,6 +89,7 @@ def lib():
     L.rm_render_samples.argtypes = [vp, ARGS, i32, i32, u64, i32]
     L.rm_accum_view.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
     L.rm_accum_after_reduce.argtypes = [vp, i32, i32]
+    L.rm_accum_radiance.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.rm_resolve.argtypes = [vp, ARGS, vp, vp, vp, vp]
     L.rm_render.argtypes = [vp, ARGS, u64, vp, vp, vp, vp, vp]
     L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
@@ -249,6 +250,11 @@ class Context:
 
     def accum_after_reduce(self, rank, world):
         _check(lib().rm_accum_after_reduce(self.h, rank, world))
+
+    def accum_radiance(self):
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().rm_accum_radiance(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def resolve(self, args: RenderArgs):
         a = args.to_c()

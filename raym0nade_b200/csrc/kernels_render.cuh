@@ -1,0 +1,651 @@
+// kernels_render.cuh — the per-pixel estimator as a wavefront pipeline.
+//
+// renderPixel (src/render.cpp:448-551) is split into stages; every stage restates the
+// reference's procedure (including its idiosyncrasies) per sample:
+//   k_gbuffer        466-495   primary hit -> HitInfo, sky emission on a miss, red nudge
+//   k_direct_gen     425-437 + sampleDirectLight (src/sampling.cpp:467-527): one NEE sample -> shadow queue
+//   k_indirect_gen   314-423   first vertex of an indirect path from the cached primary hit
+//   k_trace_paths    Model::rayHit over the path queue (closest hit)
+//   k_shade          121-312   one sampleRay level: miss/emission/NEE-termination/continue
+//   k_trace_shadow   Model::rayHit_test over the shadow queue + accumulateInwardRadiance
+//   k_resolve        510-549   firefly clamp (top-1 hold-back), exposure, variance finalise
+// Recursion is unrolled into a linear chain: a path carries the product of the per-level
+// bsdfPdf*absorb (T), the first-vertex bsdfPdf (B0, kept apart because
+// accumulateInwardRadiance splits on it, src/image.cpp:630-659) and the product of the
+// 1/(1+fails) re-weights (W).
+#pragma once
+#include "dev_bsdf.cuh"
+#include "kernels_trace.cuh"
+
+namespace rm {
+
+constexpr int kMediumSlots = 6;     // nested-dielectric entries kept per path besides the air base entry
+constexpr int kMaxRayDepth = 16;    // maxRayDepth, src/render.cpp:125
+
+// ------------------------------------------------------------------ path queue (SoA)
+struct PathQueue {
+    int cap;
+    int *pixel;
+    unsigned *sample, *drawn;
+    float *o, *d;            // [3][cap]
+    float *diff;             // [12][cap]
+    float *T, *B0;           // [3][cap]
+    float *W, *rough;
+    int *flags;              // depth | exclude << 8 | n_medium << 16
+    int *med_id;             // [kMediumSlots][cap]
+    float *med;              // [4][kMediumSlots][cap]  ior, absorb rgb
+    float *hit_t;
+    int *hit_face;
+};
+
+// one NEE / terminal sample waiting for its visibility test
+struct __align__(16) ShadowItem {
+    float o[3], aim;
+    float d[3];
+    int pixel;               // bit 31: direct-light sample (goes to Dd/Ds, no firefly hold-back)
+    float b[3], weight;      // LightSample::bsdfPdf, weight (final)
+    float l[3], _pad;        // LightSample::light (final)
+};
+
+// per-pixel accumulators
+struct Accum {
+    float *rad;              // [npix][16]  Dd{rgb,Var} Ds Id Is   (summed across GPUs)
+    float *clum_sum;         // [npix][2]   sum of Clum, number of indirect LightSamples (summed across GPUs)
+    float *clum_max;         // [npix]      luminance of the held-back sample (max-reduced across GPUs)
+    float *hold_clum;        // [npix]      local held-back luminance (-1 = none)
+    float *hold;             // [npix][8]   held-back sample: bsdfPdf rgb, light rgb, weight
+    int *lock;               // [npix]
+};
+
+struct FrameBuffers {
+    RmHitInfo *gbuffer;      // AoS, baseColor = nudged value the samplers use
+    float *sav_base;         // [npix][3] un-nudged baseColor (restored at resolve, src/render.cpp:550)
+    int *n_ind;              // [npix] spp_indirect of the pixel (0 when nothing is sampled)
+};
+
+struct Medium {
+    int n;
+    int id[kMediumSlots];
+    float ior[kMediumSlots];
+    V3 ab[kMediumSlots];
+};
+
+RM_DI float medium_ior(const Medium &m) {          // Medium::ior, src/render.cpp:26-31
+    float v = 1.0f;
+    for (int i = 0; i < m.n; i++) v = fmaxf(v, m.ior[i]);
+    return v;
+}
+RM_DI V3 medium_absorb(const Medium &m) {          // Medium::absorb, 33-38
+    V3 a = splat3(1.0f);
+    for (int i = 0; i < m.n; i++) a = a * m.ab[i];
+    return a;
+}
+RM_DI void medium_insert(Medium &m, int id, float ior, V3 ab) {
+    if (m.n < kMediumSlots) { m.id[m.n] = id; m.ior[m.n] = ior; m.ab[m.n] = ab; m.n++; }
+}
+RM_DI void medium_erase(Medium &m, int id) {       // multimap::erase(key): every entry with that id
+    int k = 0;
+    for (int i = 0; i < m.n; i++)
+        if (m.id[i] != id) { m.id[k] = m.id[i]; m.ior[k] = m.ior[i]; m.ab[k] = m.ab[i]; k++; }
+    m.n = k;
+}
+
+// getAbsorb (src/render.cpp:83-87); pow_s lives in geometry.cpp where pow resolves to the double version
+RM_DI V3 get_absorb(V3 absorb, float dis) {
+    float C = lum(absorb);
+    if (!(C < fsub(1.0f, kEps))) return splat3(1.0f);
+    float k = fmul(32.0f, dis);
+    V3 a = absorb;
+    if (a.x < 0.0f) a.x = 0.0f;
+    if (a.y < 0.0f) a.y = 0.0f;
+    if (a.z < 0.0f) a.z = 0.0f;
+    return mk3((float)pow((double)a.x, (double)k), (float)pow((double)a.y, (double)k), (float)pow((double)a.z, (double)k));
+}
+
+// warp-aggregated slot allocation
+RM_DI int alloc_slot(int *counter, bool want) {
+    unsigned mask = __ballot_sync(0xffffffffu, want);   // every lane of the warp calls this (loops are padded to whole warps)
+    if (!want) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+}
+
+// ------------------------------------------------------------------ accumulation
+RM_DI void accum_basic(float *r4, V3 inrad, float weight) {          // accumulateInwardRadiance_basic, src/image.cpp:615-628
+    if (!isfinite_any(inrad)) return;
+    if (!isfinite(weight)) return;
+    atomicAdd(r4 + 0, fmul(inrad.x, weight));
+    atomicAdd(r4 + 1, fmul(inrad.y, weight));
+    atomicAdd(r4 + 2, fmul(inrad.z, weight));
+    atomicAdd(r4 + 3, fmul(dot(inrad, inrad), weight));
+}
+
+// accumulateInwardRadiance (src/image.cpp:630-659): split into demodulated diffuse + specular
+RM_DI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) {
+    if (length(l) < kEps) return;
+    V3 base0 = normalize(baseColor);
+    if (length(baseColor) < kEps) { accum_basic(rs, l * b, w); return; }
+    const V3 White = normalize(splat3(1.0f));
+    float XdotY = dot(base0, White);
+    if (XdotY > 0.99f) { accum_basic(rd, div_true(l * b, baseColor), w); return; }
+    V3 perp = normalize(cross(base0, White));
+    V3 bp = b - perp * dot(perp, b);
+    float d1 = dot(bp, White), d2 = dot(bp, base0);
+    float AplusB = fdiv(fadd(d1, d2), fadd(1.0f, XdotY));
+    float AminusB = fdiv(fsub(d1, d2), fsub(1.0f, XdotY));
+    float Bc = fdiv(fsub(AplusB, AminusB), 2.0f);
+    V3 base_part = Bc * base0;
+    accum_basic(rd, div_recip(l * Bc, length(baseColor)), w);
+    accum_basic(rs, l * (b - base_part), w);
+}
+
+// One finished indirect LightSample of pixel p.  The reference drops a sample when it alone
+// exceeds 16/17 of the pixel's total luminance (src/render.cpp:534-547); at most one sample per
+// pixel can qualify, so the running maximum is held back un-accumulated (exact, single pass).
+RM_DI void add_indirect(const Accum &A, const FrameBuffers &Fb, int p, V3 b, V3 l, float w) {
+    const RmHitInfo *g = Fb.gbuffer + p;
+    const float *gf = reinterpret_cast<const float *>(g);
+    V3 base = gf[18] < kEps ? splat3(0.0f) : mk3(gf[9], gf[10], gf[11]);
+    float clum = fmul(lum(b * l), w);
+    atomicAdd(A.clum_sum + 2 * p, clum);
+    atomicAdd(A.clum_sum + 2 * p + 1, 1.0f);
+    volatile float *hc = A.hold_clum + p;
+    if (!(clum > *hc)) { accum_split(A.rad + 16 * p + 8, A.rad + 16 * p + 12, base, b, l, w); return; }
+    bool done = false, spill = false;
+    V3 ob = b, ol = l;
+    float ow = w;
+    while (!done) {
+        if (atomicCAS(A.lock + p, 0, 1) == 0) {
+            __threadfence();
+            float cur = *hc;
+            volatile float *h = A.hold + 8 * p;
+            if (clum > cur) {
+                if (cur >= 0.0f) { ob = mk3(h[0], h[1], h[2]); ol = mk3(h[3], h[4], h[5]); ow = h[6]; spill = true; }
+                h[0] = b.x; h[1] = b.y; h[2] = b.z; h[3] = l.x; h[4] = l.y; h[5] = l.z; h[6] = w;
+                *hc = clum;
+            } else spill = true;
+            __threadfence();
+            atomicExch(A.lock + p, 0);
+            done = true;
+        }
+    }
+    if (spill) accum_split(A.rad + 16 * p + 8, A.rad + 16 * p + 12, base, ob, ol, ow);
+}
+
+RM_DI void add_direct(const Accum &A, const FrameBuffers &Fb, int p, V3 b, V3 l, float w) {
+    const float *gf = reinterpret_cast<const float *>(Fb.gbuffer + p);
+    accum_split(A.rad + 16 * p, A.rad + 16 * p + 4, mk3(gf[9], gf[10], gf[11]), b, l, w);
+}
+
+// ------------------------------------------------------------------ K2: G-buffer
+__global__ void __launch_bounds__(128) k_gbuffer(DevScene S, DevArgs A, const int *__restrict__ tri_idx, const float *__restrict__ t_in,
+                                                 FrameBuffers Fb, int spp_direct, int spp_indirect_base, int *glass_count) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.width * A.height) return;
+    int x = p % A.width, y = p / A.width;
+    V3 d = primary_d(A, x, y);
+    V3 Dir = normalize(d);
+    Surface s = default_surface();
+    int face = tri_idx[p];
+    int n_ind = 0;
+    V3 sav = splat3(0.0f);
+    if (face < 0) {
+        s.position = splat3(CUDART_NAN_F);
+        if (S.sky_width) s.emission = sky_get(S, Dir);
+    } else {
+        float t = t_in[p];
+        s.position = A.position + t * Dir;
+        RayDiff bd = init_ray_diff(d, A);
+        V3 dPdx, dPdy;
+        get_hit_info(S, face, t, Dir, bd, dPdx, dPdy, s);
+        bool opaque = s.opacity > fsub(1.0f, kEps);
+        sav = s.baseColor;
+        // near-black / near-grey base colours get +0.04 red so that baseColor and white stay
+        // separable (src/render.cpp:492-495; the literals there are doubles)
+        float C0 = lum(s.baseColor);
+        bool nudge = (double)C0 < 2e-2;
+        if (!nudge && C0 < 0.8f) nudge = (double)length(div_recip(s.baseColor, C0) - splat3(1.0f)) < 2e-2;
+        if (nudge) s.baseColor.x = (float)((double)s.baseColor.x + 4e-2);
+        n_ind = spp_indirect_base * (opaque ? 1 : 16);
+        if (!opaque && spp_indirect_base > 0) atomicAdd(glass_count, 1);
+    }
+    store_hitinfo(Fb.gbuffer + p, s);
+    Fb.sav_base[3 * p] = sav.x; Fb.sav_base[3 * p + 1] = sav.y; Fb.sav_base[3 * p + 2] = sav.z;
+    Fb.n_ind[p] = n_ind;
+}
+
+// ------------------------------------------------------------------ NEE (sampleDirectLight for ONE sample)
+// Emits at most one ShadowItem.  scale multiplies bsdfPdf (the `scaling` step of sampleRay);
+// chain: light is multiplied by the path's carried throughput when `indirect`.
+struct NeeOut { bool valid; V3 dir; float aim; V3 bsdf, light; float weight; };
+
+RM_DI NeeOut nee_sample(const DevScene &S, const Bsdf &B, Rng &gen, const float *lw, float total, int sampleCnt) {
+    NeeOut o;
+    o.valid = false;
+    const V3 pos = B.s.position;
+    if (S.sky_width == 0) {
+        int li = pick_light(lw, S.n_lights, fmul(total, gen()));
+        if (li < 0) return o;
+        float P_light = fdiv(lw[li], total);
+        const DevLight &L = S.lights[li];
+        V3 lightPos;
+        int fails = 0;
+        sample_light_face(S, L, pos, gen, lightPos, fails);
+        if (!isfinite_any(lightPos)) return o;
+        o.dir = normalize(lightPos - pos);
+        float distance = length(lightPos - pos);
+        o.aim = fsub(distance, kEps);
+        o.bsdf = get_bsdf(B, o.dir);
+        clamp_lum(o.bsdf);
+        V3 color = mk3(L.color[0], L.color[1], L.color[2]);
+        V3 li3 = fmul(fmul(2.0f, kPi), L.power) * color;
+        o.light = div_recip(div_recip(li3, fadd(fmul(distance, distance), 1e-3f)), P_light);
+        o.weight = fdiv(1.0f, float(sampleCnt * (fails + 1)));
+        o.valid = true;
+    } else {
+        V3 light;
+        sample_sky(S, B.s.surfaceNormal, gen, o.dir, light);
+        if (!isfinite_any(o.dir)) return o;
+        o.aim = CUDART_INF_F;
+        o.bsdf = get_bsdf(B, o.dir);
+        clamp_lum(o.bsdf);
+        o.light = light;
+        o.weight = fdiv(1.0f, float(sampleCnt));
+        o.valid = true;
+    }
+    return o;
+}
+
+RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool want, int pixel_tag, V3 org, const NeeOut &n, V3 b, V3 l, float w) {
+    int slot = alloc_slot(count, want);
+    if (!want) return;
+    if (slot >= cap) { atomicExch(overflow, 1); return; }
+    ShadowItem it;
+    it.o[0] = org.x; it.o[1] = org.y; it.o[2] = org.z; it.aim = n.aim;
+    it.d[0] = n.dir.x; it.d[1] = n.dir.y; it.d[2] = n.dir.z; it.pixel = pixel_tag;
+    it.b[0] = b.x; it.b[1] = b.y; it.b[2] = b.z; it.weight = w;
+    it.l[0] = l.x; it.l[1] = l.y; it.l[2] = l.z; it._pad = 0.0f;
+    float4 *dst = reinterpret_cast<float4 *>(q + slot);
+    const float4 *src = reinterpret_cast<const float4 *>(&it);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
+// ------------------------------------------------------------------ direct light at the primary hit
+// item = (pixel, k-th direct sample of this wave); sample index s = s_begin + k*s_stride
+__global__ void __launch_bounds__(128) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, int npix, int s_begin,
+                                                    int s_stride, int spp_direct, unsigned long long seed,
+                                                    ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        bool want = false;
+        NeeOut n;
+        int p = 0;
+        V3 org = splat3(0.0f);
+        if (i < n_items) {
+            p = int(i % npix);
+            int s = s_begin + int(i / npix) * s_stride;
+            Surface g = load_hitinfo(Fb.gbuffer + p);
+            if (s < spp_direct && isfinite_any(g.position) && !(length(g.emission) > 0.0f)) {
+                V3 inDir = normalize(g.position - A.position);
+                Bsdf B;
+                B.inDir = -inDir;
+                B.s = g;
+                float lw[kMaxLights];
+                float total = 0.0f;
+                bool go = true;
+                if (S.sky_width == 0) { total = light_weights(S, B, lw); if (total == 0.0f) go = false; }
+                if (go) {
+                    Rng gen;
+                    gen.init(seed, (unsigned)p, (unsigned)s, kStreamDirect);
+                    n = nee_sample(S, B, gen, lw, total, spp_direct);
+                    want = n.valid;
+                    org = g.position;
+                }
+            }
+        }
+        push_shadow(sq, s_count, s_cap, overflow, want, p | 0x80000000, org, n, n.bsdf, n.light, n.weight);
+    }
+}
+
+// ------------------------------------------------------------------ path state I/O
+RM_DI void store_path(const PathQueue &Q, int i, int pixel, unsigned sample, unsigned drawn, V3 o, V3 d, const RayDiff &df,
+                      V3 T, V3 B0, float W, float rough, int depth, bool exclude, const Medium &m) {
+    const int c = Q.cap;
+    Q.pixel[i] = pixel; Q.sample[i] = sample; Q.drawn[i] = drawn;
+    Q.o[i] = o.x; Q.o[c + i] = o.y; Q.o[2 * c + i] = o.z;
+    Q.d[i] = d.x; Q.d[c + i] = d.y; Q.d[2 * c + i] = d.z;
+    const V3 *dv = &df.dPdx;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { Q.diff[(3 * k) * c + i] = dv[k].x; Q.diff[(3 * k + 1) * c + i] = dv[k].y; Q.diff[(3 * k + 2) * c + i] = dv[k].z; }
+    Q.T[i] = T.x; Q.T[c + i] = T.y; Q.T[2 * c + i] = T.z;
+    Q.B0[i] = B0.x; Q.B0[c + i] = B0.y; Q.B0[2 * c + i] = B0.z;
+    Q.W[i] = W; Q.rough[i] = rough;
+    Q.flags[i] = depth | (exclude ? 256 : 0) | (m.n << 16);
+    for (int k = 0; k < m.n; k++) {
+        Q.med_id[k * c + i] = m.id[k];
+        Q.med[(4 * k) * c + i] = m.ior[k];
+        Q.med[(4 * k + 1) * c + i] = m.ab[k].x; Q.med[(4 * k + 2) * c + i] = m.ab[k].y; Q.med[(4 * k + 3) * c + i] = m.ab[k].z;
+    }
+}
+
+// ------------------------------------------------------------------ first vertex of an indirect path
+// sampleIndirectLightFromFirstIntersection (src/render.cpp:314-423) up to the new ray.
+__global__ void __launch_bounds__(128) k_indirect_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, const int *__restrict__ pix_list,
+                                                      int npix_list, int s_begin, int s_stride, unsigned long long seed,
+                                                      PathQueue Q, int *q_count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        bool want = false;
+        int p = 0;
+        unsigned s = 0;
+        Rng gen;
+        V3 newDir = splat3(0.0f), bsdfPdf = splat3(CUDART_NAN_F), pos = splat3(0.0f);
+        RayDiff next;
+        float W = 1.0f, rough = 0.0f;
+        Medium med;
+        med.n = 0;
+        if (i < n_items) {
+            int li = int(i % npix_list);
+            p = pix_list ? pix_list[li] : li;
+            s = unsigned(s_begin + int(i / npix_list) * s_stride);
+            int n_ind = Fb.n_ind[p];
+            Surface g = load_hitinfo(Fb.gbuffer + p);
+            if ((int)s < n_ind && !(length(g.emission) > 0.0f)) {
+                gen.init(seed, (unsigned)p, s, kStreamIndirect);
+                int x = p % A.width, y = p / A.width;
+                RayDiff bd = init_ray_diff(primary_d(A, x, y), A);
+                V3 inDir = normalize(g.position - A.position);
+                float hit_t = length(g.position - A.position);
+                Bsdf B;
+                B.inDir = -inDir;
+                B.s = g;
+                rough = fmul(g.roughness, 1.0f);
+                float ior = B.s.eta;
+                B.s.eta = fdiv(1.0f, B.s.eta);
+                float P_reflect = 1.0f, F = 0.0f;
+                V3 refr;
+                if (B.s.opacity < kEps) {
+                    precise_refraction(B, refr, F);
+                    P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
+                }
+                int fails = 0;
+                if (gen() < P_reflect) {
+                    V3 dPdx, dPdy, dDdx, dDdy;
+                    calc_dPdxy(inDir, hit_t, B.s.shapeNormal, bd, dPdx, dPdy);
+                    calc_dDdxy(inDir, B.s.surfaceNormal, bd, dDdx, dDdy);
+                    next.dPdx = dPdx; next.dPdy = dPdy; next.dDdx = dDdx; next.dDdy = dDdy;
+                    sample_reflection(B, gen, newDir, bsdfPdf, fails);
+                    bsdfPdf = div_true(bsdfPdf, P_reflect);
+                } else {
+                    sample_btdf(B, gen, newDir, bsdfPdf, fails);
+                    bsdfPdf = bsdfPdf * fsub(1.0f, F);
+                    bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
+                    next = bd;
+                    if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
+                    else medium_erase(med, B.s.id);
+                }
+                if (isfinite_any(newDir)) {
+                    want = true;
+                    pos = B.s.position;
+                    if (fails > 0) W = fdiv(1.0f, float(1 + fails));
+                }
+            }
+        }
+        int slot = alloc_slot(q_count, want);
+        if (want && slot < Q.cap)
+            store_path(Q, slot, p, s, gen.drawn, pos, newDir, next, splat3(1.0f), bsdfPdf, W, rough, 1, true, med);
+    }
+}
+
+// ------------------------------------------------------------------ closest hit over the path queue
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_paths(DevScene S, PathQueue Q, const int *__restrict__ q_count, unsigned long long *counters) {
+    __shared__ int2 stack[kStackDepth * kTraceBlock];
+    const int n = min(*q_count, Q.cap);
+    TraceCounters cnt = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = Q.cap;
+        RaySetup r = setup_ray(mk3(Q.o[i], Q.o[c + i], Q.o[2 * c + i]), mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]));
+        float t;
+        int face;
+        ray_hit<COUNT>(S, r, t, face, stack + threadIdx.x, kTraceBlock, cnt);
+        Q.hit_t[i] = t;
+        Q.hit_face[i] = face;
+    }
+    flush_counters(cnt, counters, COUNT);
+}
+
+// ------------------------------------------------------------------ one sampleRay level
+__constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6};
+
+__global__ void __launch_bounds__(128) k_shade(DevScene S, FrameBuffers Fb, Accum Ac, unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
+                                               PathQueue Qout, int *out_count, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+    const int n = min(*in_count, Qin.cap);
+    const int n_pad = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        bool cont = false;            // continue the path
+        int n_nee = 0;                // NEE samples to emit (terminating vertex)
+        bool alive = i < n;
+        const int c = Qin.cap;
+        int p = 0, depth = 0;
+        unsigned sample = 0;
+        bool exclude = false;
+        Rng gen;
+        V3 dir = splat3(0.0f), T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), bsdfPdf = splat3(CUDART_NAN_F), absorb = splat3(1.0f);
+        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f, inv_spp = 0.0f;
+        bool nee_pass_absorb = false, doDirect = false;
+        RayDiff bd, next;
+        Medium med;
+        med.n = 0;
+        Bsdf B;
+        B.s = default_surface();
+        B.inDir = splat3(0.0f);
+        float lw[kMaxLights];
+        float lw_total = 0.0f;
+        if (alive) {
+            p = Qin.pixel[i];
+            sample = Qin.sample[i];
+            int fl = Qin.flags[i];
+            depth = fl & 255;
+            exclude = (fl & 256) != 0;
+            med.n = fl >> 16;
+            for (int k = 0; k < med.n; k++) {
+                med.id[k] = Qin.med_id[k * c + i];
+                med.ior[k] = Qin.med[(4 * k) * c + i];
+                med.ab[k] = mk3(Qin.med[(4 * k + 1) * c + i], Qin.med[(4 * k + 2) * c + i], Qin.med[(4 * k + 3) * c + i]);
+            }
+            V3 org = mk3(Qin.o[i], Qin.o[c + i], Qin.o[2 * c + i]);
+            dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
+            T = mk3(Qin.T[i], Qin.T[c + i], Qin.T[2 * c + i]);
+            B0 = mk3(Qin.B0[i], Qin.B0[c + i], Qin.B0[2 * c + i]);
+            W = Qin.W[i];
+            rough = Qin.rough[i];
+            inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));
+            gen.init(seed, (unsigned)p, sample, kStreamIndirect, Qin.drawn[i]);
+            V3 *dv = &bd.dPdx;
+#pragma unroll
+            for (int k = 0; k < 4; k++) dv[k] = mk3(Qin.diff[(3 * k) * c + i], Qin.diff[(3 * k + 1) * c + i], Qin.diff[(3 * k + 2) * c + i]);
+            const float t = Qin.hit_t[i];
+            const int face = Qin.hit_face[i];
+            if (t == CUDART_INF_F) {
+                // miss (src/render.cpp:129-133)
+                if (!(exclude || S.sky_width == 0)) {
+                    V3 l = (sky_get(S, dir) * splat3(1.0f)) * T;
+                    add_indirect(Ac, Fb, p, B0, l, fmul(fmul(1.0f, W), inv_spp));
+                }
+            } else {
+                B.inDir = -dir;
+                B.s.position = org + dir * t;
+                V3 dPdx, dPdy;
+                get_hit_info(S, face, t, dir, bd, dPdx, dPdy, B.s);
+                const float ior = B.s.eta;
+                rough = fmaxf(rough, fmul(1.0f, B.s.roughness));
+                B.s.roughness = fmaxf(B.s.roughness, rough);
+                const float P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
+                doDirect = P_RR < 0.9f;
+                absorb = get_absorb(medium_absorb(med), t);
+                if (length(B.s.emission) > kEps) {
+                    if (!exclude) {
+                        V3 l = (B.s.emission * absorb) * T;
+                        add_indirect(Ac, Fb, p, B0, l, fmul(fmul(1.0f, W), inv_spp));
+                    }
+                } else {
+                    float P_reflect = 1.0f, F = 0.0f;
+                    V3 refr;
+                    if (B.s.opacity < kEps) {
+                        // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
+                        float eta1 = medium_ior(med), eta2;
+                        if (B.s.entering) eta2 = fmaxf(eta1, B.s.eta);
+                        else {
+                            medium_erase(med, B.s.id);
+                            eta2 = medium_ior(med);
+                            medium_insert(med, B.s.id, B.s.eta, B.s.baseColor);
+                        }
+                        B.s.eta = fdiv(eta1, eta2);
+                        precise_refraction(B, refr, F);
+                        if (med.n == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
+                        else P_reflect = F;
+                        P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
+                    }
+                    int fails = 0;
+                    bool terminate = false;
+                    if (gen() <= P_reflect) {
+                        doDirect = doDirect && B.s.entering && med.n == 0;
+                        if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                            terminate = true;
+                            nee_factor = fdiv(1.0f, P_reflect);
+                            if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
+                        } else {
+                            sample_reflection(B, gen, newDir, bsdfPdf, fails);
+                            bsdfPdf = div_true(bsdfPdf, P_reflect);
+                            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+                            V3 dDdx, dDdy;
+                            calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
+                            next.dPdx = dPdx; next.dPdy = dPdy; next.dDdx = dDdx; next.dDdy = dDdy;
+                        }
+                    } else {
+                        doDirect = doDirect && !B.s.entering && med.n == 1;
+                        if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                            terminate = true;
+                            nee_pass_absorb = true;
+                            nee_factor = fdiv(1.0f, fsub(1.0f, P_reflect));
+                            if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
+                        } else {
+                            if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
+                            else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
+                            next = bd;
+                            bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
+                            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+                            if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
+                            else medium_erase(med, B.s.id);
+                        }
+                    }
+                    if (terminate) {
+                        n_nee = c_sampleCount[depth];
+                        if (S.sky_width == 0) { lw_total = light_weights(S, B, lw); if (lw_total == 0.0f) n_nee = 0; }
+                    } else if (isfinite_any(newDir) && depth != kMaxRayDepth) {
+                        cont = true;
+                        bsdfPdf = bsdfPdf * absorb;
+                        T = T * bsdfPdf;
+                        if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
+                    }
+                }
+            }
+        }
+        // NEE samples of a terminating vertex: sampleDirectLight(bsdf, model, gen, sampleCount[depth])
+        const int cnt = n_nee;
+        int max_nee = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_nee = max(max_nee, __shfl_xor_sync(0xffffffffu, max_nee, o));
+        for (int k = 0; k < max_nee; k++) {
+            NeeOut ne;
+            ne.valid = false;
+            V3 b = splat3(0.0f), l = splat3(0.0f);
+            float w = 0.0f;
+            if (k < cnt) {
+                ne = nee_sample(S, B, gen, lw, lw_total, cnt);
+                if (ne.valid) {
+                    V3 sb = ne.bsdf * nee_factor;                 // scaling()
+                    V3 lt = ne.light * sb;                        // passBsdf: light *= bsdfPdf
+                    if (nee_pass_absorb) lt = lt * absorb;        // refract branch: passBsdf(samples, absorb) then one more level
+                    l = lt * T;
+                    b = B0;
+                    w = fmul(fmul(ne.weight, W), inv_spp);
+                }
+            }
+            push_shadow(sq, s_count, s_cap, overflow, ne.valid, p, B.s.position, ne, b, l, w);
+        }
+        int slot = alloc_slot(out_count, cont);
+        if (cont && slot < Qout.cap)
+            store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
+    }
+}
+
+// ------------------------------------------------------------------ visibility + accumulation
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(DevScene S, FrameBuffers Fb, Accum Ac, const ShadowItem *__restrict__ sq,
+                                                              const int *__restrict__ s_count, int s_cap, unsigned long long *counters) {
+    __shared__ int2 stack[kStackDepth * kTraceBlock];
+    const int n = min(*s_count, s_cap);
+    TraceCounters cnt = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(sq + i);
+        float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+        RaySetup r = setup_ray(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z));
+        if (ray_occluded<COUNT>(S, r, a.w, stack + threadIdx.x, kTraceBlock, cnt)) continue;
+        int tag = __float_as_int(b.w);
+        V3 bs = mk3(c.x, c.y, c.z), li = mk3(d.x, d.y, d.z);
+        if (tag < 0) add_direct(Ac, Fb, tag & 0x7fffffff, bs, li, c.w);
+        else add_indirect(Ac, Fb, tag, bs, li, c.w);
+    }
+    flush_counters(cnt, counters, COUNT);
+}
+
+// ------------------------------------------------------------------ resolve
+// Commit the held-back sample against the (cross-GPU) totals, then calcVar (src/render.cpp:510-516).
+__global__ void k_commit_hold(Accum Ac, FrameBuffers Fb, int npix, bool never_drop) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float hc = Ac.hold_clum[p];
+    if (!(hc >= 0.0f)) return;
+    float total = Ac.clum_sum[2 * p], gmax = Ac.clum_max[p];
+    bool drop = false;
+    if (hc == gmax && !never_drop) drop = fdiv(hc, fadd(fsub(total, hc), kEps)) > 16.0f;      // clampThreshold
+    if (!drop) {
+        const float *h = Ac.hold + 8 * p;
+        const float *gf = reinterpret_cast<const float *>(Fb.gbuffer + p);
+        V3 base = gf[18] < kEps ? splat3(0.0f) : mk3(gf[9], gf[10], gf[11]);
+        accum_split(Ac.rad + 16 * p + 8, Ac.rad + 16 * p + 12, base, mk3(h[0], h[1], h[2]), mk3(h[3], h[4], h[5]), h[6]);
+    }
+    Ac.hold_clum[p] = -1.0f;
+}
+
+__global__ void k_publish_max(Accum Ac, int npix) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) Ac.clum_max[p] = Ac.hold_clum[p];
+}
+
+__global__ void k_finalise(Accum Ac, FrameBuffers Fb, int npix, float exposure, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is,
+                           RmHitInfo *g_out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    RmRadiance *planes[4] = {Dd, Ds, Id, Is};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float *r = Ac.rad + 16 * p + 4 * k;
+        V3 rad = mk3(r[0], r[1], r[2]) * exposure;
+        float var = fmul(r[3], fmul(exposure, exposure));
+        var = fsub(var, dot(rad, rad));
+        if (var < 0.0f) var = 0.0f;
+        planes[k][p].radiance[0] = rad.x; planes[k][p].radiance[1] = rad.y; planes[k][p].radiance[2] = rad.z;
+        planes[k][p].Var = var;
+    }
+    // the reference restores the un-nudged baseColor only when the pixel produced indirect samples (529-530, 550)
+    RmHitInfo g = Fb.gbuffer[p];
+    if (Ac.clum_sum[2 * p + 1] > 0.0f) { g.baseColor[0] = Fb.sav_base[3 * p]; g.baseColor[1] = Fb.sav_base[3 * p + 1]; g.baseColor[2] = Fb.sav_base[3 * p + 2]; }
+    g_out[p] = g;
+}
+
+} // namespace rm

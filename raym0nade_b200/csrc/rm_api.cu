@@ -319,6 +319,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return rm_fail(RM_ERR_INVALID, "rm_set_option: null argument");
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
 }
 

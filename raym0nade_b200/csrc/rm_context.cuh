@@ -39,6 +39,7 @@ struct RmContext {
     bool has_scene = false;
     bool count_tests = false;
     bool exact_secondary = true;
+    bool disable_clamp = false;        // debugging aid: never drop the held-back sample
     uint64_t launches = 0;
 
     // scene

@@ -1,20 +1,412 @@
-// rm_render.cu — G-buffer, sample loops, resolve and post pass (C ABI).
+// rm_render.cu — C ABI for the per-pixel stages: G-buffer, sample loops (wavefront), resolve, post pass.
+//
+// Host orchestration only; the kernels are in kernels_render.cuh / kernels_post.cuh.  The
+// whole render is issued asynchronously on the context's stream: queue lengths live in
+// device memory and every kernel is a grid-stride loop over them, so the host never waits
+// between waves or bounces.
+#include <algorithm>
+#include <new>
+
 #include "rm_context.cuh"
+#include "kernels_render.cuh"
+#include "kernels_post.cuh"
 
 using namespace rm;
 
-void rm_render_state_free(RmContext *ctx) { (void)ctx; }
+namespace {
+
+struct RenderState {
+    int npix = 0;
+    // frame
+    DevBuf gbuffer, sav_base, n_ind, glass_list;
+    // accumulators
+    DevBuf rad, clum_sum, clum_max, hold_clum, hold, lock;
+    bool accum_valid = false, hold_committed = false;
+    // queues
+    int q_cap = 0, s_cap = 0;
+    DevBuf q[2][16];
+    DevBuf shadow;
+    DevBuf counts;            // int[8]: 0,1 path queue lengths; 2 shadow length; 3 overflow; 4 glass count; 5 glass list length
+    // resolved planes + output images
+    DevBuf planes[4], g_out, rgb[2];
+    int n_glass = 0;
+    int sm_count = 148;
+    int wave_paths = 1 << 22;
+};
+
+RenderState *state(RmContext *ctx) {
+    if (!ctx->render_state) {
+        auto *s = new (std::nothrow) RenderState();
+        if (s) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+        }
+        ctx->render_state = s;
+    }
+    return static_cast<RenderState *>(ctx->render_state);
+}
+
+PathQueue make_queue(RenderState *R, int which) {
+    PathQueue Q;
+    DevBuf *b = R->q[which];
+    Q.cap = R->q_cap;
+    Q.pixel = b[0].as<int>(); Q.sample = b[1].as<unsigned>(); Q.drawn = b[2].as<unsigned>();
+    Q.o = b[3].as<float>(); Q.d = b[4].as<float>(); Q.diff = b[5].as<float>();
+    Q.T = b[6].as<float>(); Q.B0 = b[7].as<float>(); Q.W = b[8].as<float>(); Q.rough = b[9].as<float>();
+    Q.flags = b[10].as<int>(); Q.med_id = b[11].as<int>(); Q.med = b[12].as<float>();
+    Q.hit_t = b[13].as<float>(); Q.hit_face = b[14].as<int>();
+    return Q;
+}
+
+int alloc_queues(RenderState *R, int q_cap, int s_cap) {
+    int rc;
+    if (q_cap > R->q_cap) {
+        const size_t c = size_t(q_cap);
+        const size_t words[15] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1};
+        for (int w = 0; w < 2; w++)
+            for (int k = 0; k < 15; k++)
+                if ((rc = R->q[w][k].alloc(c * words[k] * 4))) return rc;
+        R->q_cap = q_cap;
+    }
+    if (s_cap > R->s_cap) {
+        if ((rc = R->shadow.alloc(size_t(s_cap) * sizeof(ShadowItem)))) return rc;
+        R->s_cap = s_cap;
+    }
+    return RM_OK;
+}
+
+FrameBuffers frame(RenderState *R) {
+    FrameBuffers F;
+    F.gbuffer = R->gbuffer.as<RmHitInfo>();
+    F.sav_base = R->sav_base.as<float>();
+    F.n_ind = R->n_ind.as<int>();
+    return F;
+}
+
+Accum accum(RenderState *R) {
+    Accum A;
+    A.rad = R->rad.as<float>();
+    A.clum_sum = R->clum_sum.as<float>();
+    A.clum_max = R->clum_max.as<float>();
+    A.hold_clum = R->hold_clum.as<float>();
+    A.hold = R->hold.as<float>();
+    A.lock = R->lock.as<int>();
+    return A;
+}
+
+__global__ void k_fill(float *p, float v, size_t n) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+__global__ void k_glass_list(const int *__restrict__ n_ind, int npix, int base, int *list, int *count) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool glass = p < npix && base > 0 && n_ind[p] > base;
+    int slot = alloc_slot(count, glass);
+    if (glass) list[slot] = p;
+}
+
+bool same_args(const RmRenderArgs &a, const RmRenderArgs &b) { return std::memcmp(&a, &b, sizeof(RmRenderArgs)) == 0; }
+
+int spp_direct_of(const RmRenderArgs *a) { return int(float(a->spp) * a->P_Direct); }        // src/render.cpp:500
+
+} // namespace
+
+void rm_render_state_free(RmContext *ctx) {
+    auto *R = static_cast<RenderState *>(ctx->render_state);
+    if (!R) return;
+    for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
+                      &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1]})
+        b->release();
+    for (int w = 0; w < 2; w++)
+        for (int k = 0; k < 16; k++) R->q[w][k].release();
+    delete R;
+    ctx->render_state = nullptr;
+}
 
 extern "C" {
 
-int rm_gbuffer(RmContext *, const RmRenderArgs *, RmHitInfo *) { return rm_fail(RM_ERR_STATE, "rm_gbuffer: not built yet"); }
-int rm_render_samples(RmContext *, const RmRenderArgs *, int32_t, int32_t, uint64_t, int32_t) { return rm_fail(RM_ERR_STATE, "rm_render_samples: not built yet"); }
-int rm_accum_view(RmContext *, float **, int64_t *, float **, int64_t *) { return rm_fail(RM_ERR_STATE, "rm_accum_view: not built yet"); }
-int rm_accum_after_reduce(RmContext *, int32_t, int32_t) { return rm_fail(RM_ERR_STATE, "rm_accum_after_reduce: not built yet"); }
-int rm_resolve(RmContext *, const RmRenderArgs *, RmRadiance *, RmRadiance *, RmRadiance *, RmRadiance *) { return rm_fail(RM_ERR_STATE, "rm_resolve: not built yet"); }
-int rm_render(RmContext *, const RmRenderArgs *, uint64_t, RmHitInfo *, RmRadiance *, RmRadiance *, RmRadiance *, RmRadiance *) { return rm_fail(RM_ERR_STATE, "rm_render: not built yet"); }
-int rm_fxaa(RmContext *, const float *, float *, int32_t, int32_t) { return rm_fail(RM_ERR_STATE, "rm_fxaa: not built yet"); }
-int rm_fxaa_device(RmContext *, const float *, float *, int32_t, int32_t) { return rm_fail(RM_ERR_STATE, "rm_fxaa_device: not built yet"); }
-int rm_postprocess(RmContext *, const RmRenderArgs *, int32_t, float *) { return rm_fail(RM_ERR_STATE, "rm_postprocess: not built yet"); }
+// ------------------------------------------------------------------------ G-buffer (K2)
+int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_gbuffer: no scene uploaded");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->have_primary || !same_args(ctx->frame_args, *args))
+        if ((rc = rm_trace_primary(ctx, args, nullptr, nullptr))) return rc;
+    RenderState *R = state(ctx);
+    if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    const int npix = args->width * args->height;
+    if ((rc = R->gbuffer.alloc(size_t(npix) * sizeof(RmHitInfo))) || (rc = R->sav_base.alloc(size_t(npix) * 12)) ||
+        (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(64)))
+        return rc;
+    R->npix = npix;
+    cudaStream_t st = ctx->stream;
+    RM_CUDA(cudaMemsetAsync(R->counts.p, 0, 64, st));
+    const int spp_d = spp_direct_of(args), base = args->spp - spp_d;
+    int *counts = R->counts.as<int>();
+    k_gbuffer<<<(npix + 127) / 128, 128, 0, st>>>(ctx->scene, to_dev_args(args), ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), frame(R), spp_d, base, counts + 4);
+    k_glass_list<<<(npix + 127) / 128, 128, 0, st>>>(R->n_ind.as<int>(), npix, base, R->glass_list.as<int>(), counts + 5);
+    ctx->launches += 2;
+    RM_CUDA(cudaGetLastError());
+    int h[8];
+    RM_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    if (gbuffer) RM_CUDA(cudaMemcpyAsync(gbuffer, R->gbuffer.p, size_t(npix) * sizeof(RmHitInfo), cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    R->n_glass = h[5];
+    ctx->have_gbuffer = true;
+    ctx->have_resolved = false;
+    R->accum_valid = false;
+    return RM_OK;
+}
+
+// ------------------------------------------------------------------------ sample loops
+static int reset_accum(RmContext *ctx, RenderState *R) {
+    const size_t n = size_t(R->npix);
+    int rc;
+    if ((rc = R->rad.alloc(n * 64)) || (rc = R->clum_sum.alloc(n * 8)) || (rc = R->clum_max.alloc(n * 4)) || (rc = R->hold_clum.alloc(n * 4)) ||
+        (rc = R->hold.alloc(n * 32)) || (rc = R->lock.alloc(n * 4)))
+        return rc;
+    cudaStream_t st = ctx->stream;
+    RM_CUDA(cudaMemsetAsync(R->rad.p, 0, n * 64, st));
+    RM_CUDA(cudaMemsetAsync(R->clum_sum.p, 0, n * 8, st));
+    RM_CUDA(cudaMemsetAsync(R->clum_max.p, 0, n * 4, st));
+    RM_CUDA(cudaMemsetAsync(R->hold.p, 0, n * 32, st));
+    RM_CUDA(cudaMemsetAsync(R->lock.p, 0, n * 4, st));
+    k_fill<<<R->sm_count * 4, 256, 0, st>>>(R->hold_clum.as<float>(), -1.0f, n);
+    ctx->launches++;
+    R->accum_valid = true;
+    R->hold_committed = false;
+    return RM_OK;
+}
+
+int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_begin, int32_t sample_stride, uint64_t seed, int32_t reset) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_render_samples: no scene uploaded");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    if (sample_begin < 0 || sample_stride < 1) return rm_fail(RM_ERR_INVALID, "rm_render_samples: bad sample range");
+    if (ctx->scene.sky_width == 0 && ctx->scene.n_lights > kMaxLights)
+        return rm_fail(RM_ERR_INVALID, "rm_render_samples: %d light objects, at most %d supported", ctx->scene.n_lights, kMaxLights);
+    RM_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->have_gbuffer || !same_args(ctx->frame_args, *args))
+        if ((rc = rm_gbuffer(ctx, args, nullptr))) return rc;
+    RenderState *R = state(ctx);
+    if (reset || !R->accum_valid)
+        if ((rc = reset_accum(ctx, R))) return rc;
+    if (R->hold_committed) return rm_fail(RM_ERR_STATE, "rm_render_samples: accumulators were already resolved; pass reset=1");
+    const int npix = R->npix;
+    const int spp_d = spp_direct_of(args), base = args->spp - spp_d;
+    auto local_count = [&](int total) { return total > sample_begin ? (total - sample_begin + sample_stride - 1) / sample_stride : 0; };
+    const int n_d = local_count(spp_d), n_a = local_count(base);
+    const int n_b_total = (R->n_glass > 0) ? local_count(16 * base) : 0;     // local samples below 16*base; the first n_a are phase A's
+
+    // wave sizes
+    const long long target = R->wave_paths;
+    const int S_all = int(std::max(1LL, target / npix));
+    const int S_glass = R->n_glass > 0 ? int(std::max(1LL, target / R->n_glass)) : 1;
+    long long max_paths = 0, max_direct = 0;
+    if (n_a > 0) max_paths = (long long)npix * std::min(S_all, n_a);
+    if (n_b_total > n_a) max_paths = std::max(max_paths, (long long)R->n_glass * std::min(S_glass, n_b_total - n_a));
+    if (n_d > 0) max_direct = (long long)npix * std::min(S_all, n_d);
+    if (max_paths > 0x7fffffffLL / 8 || max_direct > 0x7fffffffLL / 2) return rm_fail(RM_ERR_INVALID, "rm_render_samples: wave too large");
+    if ((rc = alloc_queues(R, int(std::max(max_paths, 1LL)), int(std::max({max_direct, 6 * max_paths, 1LL}))))) return rc;
+
+    cudaStream_t st = ctx->stream;
+    int *counts = R->counts.as<int>();
+    auto *cnt = ctx->b_counters.as<unsigned long long>();
+    const DevArgs A = to_dev_args(args);
+    const FrameBuffers Fb = frame(R);
+    const Accum Ac = accum(R);
+    ShadowItem *sq = R->shadow.as<ShadowItem>();
+    const int grid = R->sm_count * 8;
+    const bool ct = ctx->count_tests;
+
+    auto trace_shadow = [&]() {
+        if (ct) k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt);
+        else k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt);
+        ctx->launches++;
+    };
+
+    // ---- direct light at the primary hit
+    for (int k0 = 0; k0 < n_d; k0 += S_all) {
+        const int S = std::min(S_all, n_d - k0);
+        RM_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
+        k_direct_gen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, (long long)npix * S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+                                           seed, sq, counts + 2, R->s_cap, counts + 3);
+        ctx->launches++;
+        trace_shadow();
+    }
+
+    // ---- indirect paths: phase A = every pixel, samples below `base`; phase B = glass pixels, samples in [base, 16*base)
+    auto run_wave = [&](const int *pix_list, int n_list, int k0, int S) {
+        cudaMemsetAsync(counts, 0, 12, st);
+        k_indirect_gen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, (long long)n_list * S, pix_list, n_list, sample_begin + k0 * sample_stride,
+                                             sample_stride, seed, make_queue(R, 0), counts);
+        ctx->launches++;
+        int cur = 0;
+        for (int depth = 1; depth <= kMaxRayDepth; depth++) {
+            PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
+            if (ct) k_trace_paths<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt);
+            else k_trace_paths<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt);
+            cudaMemsetAsync(counts + (cur ^ 1), 0, 4, st);
+            cudaMemsetAsync(counts + 2, 0, 4, st);
+            k_shade<<<grid, 128, 0, st>>>(ctx->scene, Fb, Ac, seed, Qin, counts + cur, Qout, counts + (cur ^ 1), sq, counts + 2, R->s_cap, counts + 3);
+            ctx->launches += 2;
+            trace_shadow();
+            cur ^= 1;
+        }
+    };
+    for (int k0 = 0; k0 < n_a; k0 += S_all) run_wave(nullptr, npix, k0, std::min(S_all, n_a - k0));
+    for (int k0 = n_a; k0 < n_b_total; k0 += S_glass) run_wave(R->glass_list.as<int>(), R->n_glass, k0, std::min(S_glass, n_b_total - k0));
+    RM_CUDA(cudaGetLastError());
+    ctx->have_resolved = false;
+    return RM_OK;
+}
+
+int rm_accum_view(RmContext *ctx, float **d_sum, int64_t *n_sum, float **d_max, int64_t *n_max) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_accum_view: nothing rendered yet");
+    RenderState *R = state(ctx);
+    if (!R->accum_valid) return rm_fail(RM_ERR_STATE, "rm_accum_view: nothing rendered yet");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    // publish the local held-back luminance into the max-reduced plane
+    if (!R->hold_committed) {
+        k_publish_max<<<(R->npix + 255) / 256, 256, 0, ctx->stream>>>(accum(R), R->npix);
+        ctx->launches++;
+    }
+    if (d_sum) *d_sum = R->clum_sum.as<float>();
+    if (n_sum) *n_sum = int64_t(R->npix) * 2;
+    if (d_max) *d_max = R->clum_max.as<float>();
+    if (n_max) *n_max = R->npix;
+    return RM_OK;
+}
+
+// After the firefly side data {clum_sum (sum), clum_max (max)} has been reduced across ranks:
+// commit every rank's held-back sample against the global totals.  Afterwards the 16-float
+// radiance accumulators (returned through d_sum/n_sum of a second rm_accum_view call... see
+// rm_accum_radiance) can be summed across ranks.
+int rm_accum_after_reduce(RmContext *ctx, int32_t rank, int32_t world) {
+    (void)rank; (void)world;
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_accum_after_reduce: nothing rendered yet");
+    RenderState *R = state(ctx);
+    if (!R->accum_valid) return rm_fail(RM_ERR_STATE, "rm_accum_after_reduce: nothing rendered yet");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    if (!R->hold_committed) {
+        k_commit_hold<<<(R->npix + 255) / 256, 256, 0, ctx->stream>>>(accum(R), frame(R), R->npix, ctx->disable_clamp);
+        ctx->launches++;
+        R->hold_committed = true;
+    }
+    return RM_OK;
+}
+
+int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_accum_radiance: nothing rendered yet");
+    RenderState *R = state(ctx);
+    if (!R->accum_valid || !R->hold_committed) return rm_fail(RM_ERR_STATE, "rm_accum_radiance: call rm_accum_after_reduce first");
+    if (d_rad) *d_rad = R->rad.as<float>();
+    if (n_rad) *n_rad = int64_t(R->npix) * 16;
+    return RM_OK;
+}
+
+int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_resolve: nothing rendered yet");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RenderState *R = state(ctx);
+    if (!R->accum_valid || R->npix != args->width * args->height) return rm_fail(RM_ERR_STATE, "rm_resolve: accumulators do not match these args");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int npix = R->npix;
+    if (!R->hold_committed) {          // single-GPU path: local totals are the global totals
+        k_publish_max<<<(npix + 255) / 256, 256, 0, st>>>(accum(R), npix);
+        k_commit_hold<<<(npix + 255) / 256, 256, 0, st>>>(accum(R), frame(R), npix, ctx->disable_clamp);
+        ctx->launches += 2;
+        R->hold_committed = true;
+    }
+    for (int k = 0; k < 4; k++)
+        if ((rc = R->planes[k].alloc(size_t(npix) * sizeof(RmRadiance)))) return rc;
+    if ((rc = R->g_out.alloc(size_t(npix) * sizeof(RmHitInfo)))) return rc;
+    k_finalise<<<(npix + 127) / 128, 128, 0, st>>>(accum(R), frame(R), npix, args->exposure, R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
+                                                   R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), R->g_out.as<RmHitInfo>());
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    RmRadiance *host[4] = {Dd, Ds, Id, Is};
+    for (int k = 0; k < 4; k++)
+        if (host[k]) { RM_CUDA(cudaMemcpyAsync(host[k], R->planes[k].p, size_t(npix) * sizeof(RmRadiance), cudaMemcpyDeviceToHost, st)); }
+    int h[8];
+    RM_CUDA(cudaMemcpyAsync(h, R->counts.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    if (h[3]) return rm_fail(RM_ERR_STATE, "rm_resolve: a shadow queue overflowed during rendering (results incomplete)");
+    ctx->have_resolved = true;
+    return RM_OK;
+}
+
+int rm_render(RmContext *ctx, const RmRenderArgs *args, uint64_t seed, RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is) {
+    int rc;
+    if ((rc = rm_trace_primary(ctx, args, nullptr, nullptr))) return rc;
+    if ((rc = rm_gbuffer(ctx, args, nullptr))) return rc;
+    if ((rc = rm_render_samples(ctx, args, 0, 1, seed, 1))) return rc;
+    if ((rc = rm_resolve(ctx, args, Dd, Ds, Id, Is))) return rc;
+    if (gbuffer) {
+        RenderState *R = state(ctx);
+        RM_CUDA(cudaMemcpyAsync(gbuffer, R->g_out.p, size_t(R->npix) * sizeof(RmHitInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return RM_OK;
+}
+
+// ------------------------------------------------------------------------ post pass
+int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int32_t width, int32_t height) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    if (!d_rgb_in || !d_rgb_out || width <= 0 || height <= 0) return rm_fail(RM_ERR_INVALID, "rm_fxaa_device: bad arguments");
+    if (d_rgb_in == d_rgb_out) return rm_fail(RM_ERR_INVALID, "rm_fxaa_device: in-place operation is not supported");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    dim3 grid((width + kFxTileW - 1) / kFxTileW, (height + kFxTileH - 1) / kFxTileH), block(kFxTileW, kFxTileH);
+    k_fxaa<<<grid, block, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height);
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    return RM_OK;
+}
+
+int rm_fxaa(RmContext *ctx, const float *rgb_in, float *rgb_out, int32_t width, int32_t height) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    if (!rgb_in || !rgb_out || width <= 0 || height <= 0) return rm_fail(RM_ERR_INVALID, "rm_fxaa: bad arguments");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    RenderState *R = state(ctx);
+    if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    const size_t bytes = size_t(width) * height * 12;
+    int rc;
+    if ((rc = R->rgb[0].alloc(bytes)) || (rc = R->rgb[1].alloc(bytes))) return rc;
+    RM_CUDA(cudaMemcpyAsync(R->rgb[0].p, rgb_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = rm_fxaa_device(ctx, R->rgb[0].as<float>(), R->rgb[1].as<float>(), width, height))) return rc;
+    RM_CUDA(cudaMemcpyAsync(rgb_out, R->rgb[1].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RM_OK;
+}
+
+int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_options, float *rgb_out) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_postprocess: nothing resolved yet");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RenderState *R = state(ctx);
+    if (!ctx->have_resolved || R->npix != args->width * args->height) return rm_fail(RM_ERR_STATE, "rm_postprocess: call rm_resolve for these args first");
+    if (!rgb_out) return rm_fail(RM_ERR_INVALID, "rm_postprocess: rgb_out is NULL");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    const int npix = R->npix;
+    const size_t bytes = size_t(npix) * 12;
+    if ((rc = R->rgb[0].alloc(bytes)) || (rc = R->rgb[1].alloc(bytes))) return rc;
+    cudaStream_t st = ctx->stream;
+    k_shade_gamma<<<(npix + 255) / 256, 256, 0, st>>>(R->g_out.as<RmHitInfo>(), R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
+                                                       R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), npix, args->exposure, shade_options,
+                                                       R->rgb[0].as<float>());
+    ctx->launches++;
+    int out = 0;
+    if (shade_options & 512) {          // DoFXAA
+        if ((rc = rm_fxaa_device(ctx, R->rgb[0].as<float>(), R->rgb[1].as<float>(), args->width, args->height))) return rc;
+        out = 1;
+    }
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaMemcpyAsync(rgb_out, R->rgb[out].p, bytes, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    return RM_OK;
+}
 
 } // extern "C"
