@@ -158,6 +158,9 @@ int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad);
  * (render.cpp:510-549) -> the four RadianceData planes (host, reference AoS layout). */
 int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);
 
+/* Copy the resolved Photo buffers (restored G-buffer + the four planes) to host memory; any may be NULL. */
+int rm_download_resolved(RmContext *ctx, RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);
+
 /* Whole render_multiThread pixel loop (src/render.cpp:593-626) on one GPU:
  * primary + G-buffer + all samples + resolve, results to host buffers (any may be NULL). */
 int rm_render(RmContext *ctx, const RmRenderArgs *args, uint64_t seed,
@@ -182,6 +185,12 @@ int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_optio
 int rm_stats_reset(RmContext *ctx);
 int rm_stats_read(RmContext *ctx, uint64_t out[4]);
 int rm_set_option(RmContext *ctx, const char *name, int64_t value);
+/* Per-kernel-kind breakdown.  Kinds: 0 primary / batched per-ray kernels, 1 closest hit over the
+ * path queue, 2 occlusion over the shadow queue, 3 shading.  counters[3*kind + {0,1,2}] =
+ * {rays, box tests, triangle tests} for kinds 0..2.  ms / timed_launches: device time (cudaEvent
+ * pairs on the context's stream) and launch count per kind since the last call, collected only
+ * while rm_set_option("time_kernels", 1).  Synchronises the stream. */
+int rm_stats_kernels(RmContext *ctx, uint64_t counters[9], double ms[4], uint64_t timed_launches[4]);
 
 #ifdef __cplusplus
 }

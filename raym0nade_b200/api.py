@@ -54,8 +54,8 @@ class RmSceneDesc(C.Structure):
 EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
-           "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_render", "rm_fxaa",
-           "rm_fxaa_device", "rm_postprocess", "rm_stats_reset", "rm_stats_read", "rm_set_option"]
+           "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
+           "rm_fxaa_device", "rm_postprocess", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -92,12 +92,14 @@ def lib():
     L.rm_accum_radiance.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.rm_resolve.argtypes = [vp, ARGS, vp, vp, vp, vp]
     L.rm_render.argtypes = [vp, ARGS, u64, vp, vp, vp, vp, vp]
+    L.rm_download_resolved.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
     L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
     L.rm_stats_reset.argtypes = [vp]
     L.rm_stats_read.argtypes = [vp, vp]
     L.rm_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.rm_stats_kernels.argtypes = [vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -210,6 +212,14 @@ class Context:
         _check(lib().rm_stats_read(self.h, _p(out)))
         return dict(rays=int(out[0]), box=int(out[1]), tri=int(out[2]), launches=int(out[3]))
 
+    def stats_kernels(self):
+        """per kernel kind (primary, paths, shadow, shade): rays/box/tri counters, device ms, launches"""
+        cnt, ms, n = np.zeros(9, np.uint64), np.zeros(4, np.float64), np.zeros(4, np.uint64)
+        _check(lib().rm_stats_kernels(self.h, _p(cnt), _p(ms), _p(n)))
+        kinds = ["primary", "paths", "shadow", "shade"]
+        return {k: dict(rays=int(cnt[3 * i]) if i < 3 else 0, box=int(cnt[3 * i + 1]) if i < 3 else 0,
+                        tri=int(cnt[3 * i + 2]) if i < 3 else 0, ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(kinds)}
+
     # ---- per-ray seam
     def trace_closest(self, org, dirs):
         org, dirs = _f32(org), _f32(dirs)
@@ -256,12 +266,21 @@ class Context:
         _check(lib().rm_accum_radiance(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def resolve(self, args: RenderArgs):
+    def resolve(self, args: RenderArgs, download=True):
         a = args.to_c()
         n = args.width * args.height
-        planes = [np.zeros(n, RADIANCE_DTYPE) for _ in range(4)]
+        planes = [np.zeros(n, RADIANCE_DTYPE) if download else None for _ in range(4)]
         _check(lib().rm_resolve(self.h, C.byref(a), *[_p(p) for p in planes]))
         return dict(Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
+
+    def download_resolved(self, gbuffer, planes):
+        """copy the resolved G-buffer + [Dd, Ds, Id, Is] into caller-owned (e.g. pinned) arrays"""
+        _check(lib().rm_download_resolved(self.h, _p(gbuffer), *[_p(p) for p in planes]))
+
+    def render_into(self, args: RenderArgs, seed, gbuffer, planes):
+        """rm_render with caller-owned host output arrays"""
+        a = args.to_c()
+        _check(lib().rm_render(self.h, C.byref(a), seed, _p(gbuffer), *[_p(p) for p in planes]))
 
     def render(self, args: RenderArgs, seed=0, download=True):
         """The whole render_multiThread pixel loop on this GPU; returns gbuffer + 4 planes."""

@@ -60,7 +60,7 @@ int rm_context_create(int device, void *stream, RmContext **out) {
     if (!ctx) return rm_fail(RM_ERR_INVALID, "out of host memory");
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(stream);
-    int rc = ctx->b_counters.alloc(8 * sizeof(unsigned long long));
+    int rc = ctx->b_counters.alloc(16 * sizeof(unsigned long long));   // 3 kernel kinds x {rays, box, tri}
     if (rc) { delete ctx; return rc; }
     cudaMemsetAsync(ctx->b_counters.p, 0, ctx->b_counters.bytes, ctx->stream);
     *out = ctx;
@@ -278,10 +278,12 @@ int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx,
     dim3 grid((args->width + 15) / 16, (args->height + 7) / 8);
     auto *cnt = ctx->b_counters.as<unsigned long long>();
     DevArgs A = to_dev_args(args);
+    ctx->timed_begin(RM_KIND_PRIMARY);
     if (ctx->count_tests)
         k_trace_primary<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
     else
         k_trace_primary<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
+    ctx->timed_end();
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     ctx->width = args->width;
@@ -301,17 +303,36 @@ int rm_stats_reset(RmContext *ctx) {
     RM_CUDA(cudaSetDevice(ctx->device));
     RM_CUDA(cudaMemsetAsync(ctx->b_counters.p, 0, ctx->b_counters.bytes, ctx->stream));
     ctx->launches = 0;
+    ctx->ev_kind.clear();
     return RM_OK;
 }
 
 int rm_stats_read(RmContext *ctx, uint64_t out[4]) {
     if (!ctx || !out) return rm_fail(RM_ERR_INVALID, "rm_stats_read: null argument");
     RM_CUDA(cudaSetDevice(ctx->device));
-    unsigned long long h[3];
+    unsigned long long h[9];
     RM_CUDA(cudaMemcpyAsync(h, ctx->b_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     RM_CUDA(cudaStreamSynchronize(ctx->stream));
-    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    for (int k = 0; k < 3; k++) out[k] = h[k] + h[3 + k] + h[6 + k];
     out[3] = ctx->launches;
+    return RM_OK;
+}
+
+int rm_stats_kernels(RmContext *ctx, uint64_t counters[9], double ms[4], uint64_t timed_launches[4]) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "rm_stats_kernels: null argument");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long h[9];
+    RM_CUDA(cudaMemcpyAsync(h, ctx->b_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (counters) for (int k = 0; k < 9; k++) counters[k] = h[k];
+    double t[4] = {0, 0, 0, 0};
+    uint64_t n[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < ctx->ev_kind.size(); i++) {
+        float e = 0.0f;
+        if (cudaEventElapsedTime(&e, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) == cudaSuccess) { t[ctx->ev_kind[i]] += e; n[ctx->ev_kind[i]]++; }
+    }
+    ctx->ev_kind.clear();
+    for (int k = 0; k < 4; k++) { if (ms) ms[k] = t[k]; if (timed_launches) timed_launches[k] = n[k]; }
     return RM_OK;
 }
 
@@ -319,6 +340,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return rm_fail(RM_ERR_INVALID, "rm_set_option: null argument");
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
 }

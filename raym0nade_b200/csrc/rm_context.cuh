@@ -42,6 +42,22 @@ struct RmContext {
     bool disable_clamp = false;        // debugging aid: never drop the held-back sample
     uint64_t launches = 0;
 
+    // optional per-kernel-kind device timing (cudaEvent pairs on the context's stream)
+    bool time_kernels = false;
+    std::vector<cudaEvent_t> ev_pool;      // [2*i], [2*i+1] = begin / end of timed launch i
+    std::vector<int> ev_kind;
+    void timed_begin(int kind) {
+        if (!time_kernels) return;
+        size_t i = ev_kind.size();
+        while (ev_pool.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        ev_kind.push_back(kind);
+        cudaEventRecord(ev_pool[2 * i], stream);
+    }
+    void timed_end() {
+        if (!time_kernels) return;
+        cudaEventRecord(ev_pool[2 * (ev_kind.size() - 1) + 1], stream);
+    }
+
     // scene
     rm::DevScene scene{};
     DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf;
@@ -61,12 +77,14 @@ struct RmContext {
     void *render_state = nullptr;
 
     ~RmContext() {
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
                           &b_sky, &b_skycdf, &b_counters, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };
 
+enum { RM_KIND_PRIMARY = 0, RM_KIND_PATHS = 1, RM_KIND_SHADOW = 2, RM_KIND_SHADE = 3 };
 rm::DevArgs to_dev_args(const RmRenderArgs *a);
 int rm_check_args(const RmRenderArgs *a);
 // implemented in rm_render.cu

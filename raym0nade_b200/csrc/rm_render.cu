@@ -221,8 +221,10 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const bool ct = ctx->count_tests;
 
     auto trace_shadow = [&]() {
-        if (ct) k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt);
-        else k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt);
+        ctx->timed_begin(RM_KIND_SHADOW);
+        if (ct) k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt + 6);
+        else k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt + 6);
+        ctx->timed_end();
         ctx->launches++;
     };
 
@@ -245,11 +247,15 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         int cur = 0;
         for (int depth = 1; depth <= kMaxRayDepth; depth++) {
             PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
-            if (ct) k_trace_paths<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt);
-            else k_trace_paths<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt);
+            ctx->timed_begin(RM_KIND_PATHS);
+            if (ct) k_trace_paths<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt + 3);
+            else k_trace_paths<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt + 3);
+            ctx->timed_end();
             cudaMemsetAsync(counts + (cur ^ 1), 0, 4, st);
             cudaMemsetAsync(counts + 2, 0, 4, st);
+            ctx->timed_begin(RM_KIND_SHADE);
             k_shade<<<grid, 128, 0, st>>>(ctx->scene, Fb, Ac, seed, Qin, counts + cur, Qout, counts + (cur ^ 1), sq, counts + 2, R->s_cap, counts + 3);
+            ctx->timed_end();
             ctx->launches += 2;
             trace_shadow();
             cur ^= 1;
@@ -336,6 +342,19 @@ int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadia
     RM_CUDA(cudaStreamSynchronize(st));
     if (h[3]) return rm_fail(RM_ERR_STATE, "rm_resolve: a shadow queue overflowed during rendering (results incomplete)");
     ctx->have_resolved = true;
+    return RM_OK;
+}
+
+int rm_download_resolved(RmContext *ctx, RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is) {
+    if (!ctx || !ctx->render_state || !ctx->have_resolved) return rm_fail(RM_ERR_STATE, "rm_download_resolved: call rm_resolve first");
+    RenderState *R = state(ctx);
+    RM_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = size_t(R->npix);
+    RmRadiance *host[4] = {Dd, Ds, Id, Is};
+    for (int k = 0; k < 4; k++)
+        if (host[k]) RM_CUDA(cudaMemcpyAsync(host[k], R->planes[k].p, npix * sizeof(RmRadiance), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gbuffer) RM_CUDA(cudaMemcpyAsync(gbuffer, R->g_out.p, npix * sizeof(RmHitInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
     return RM_OK;
 }
 

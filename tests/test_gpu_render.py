@@ -1,0 +1,249 @@
+"""GPU parity for the per-pixel stages: G-buffer, per-sample replay, full renders, FXAA, post pass.
+
+Three kinds of evidence, strongest first:
+  * bit / ulp-level equality where the arithmetic is deterministic (G-buffer geometry, FXAA);
+  * per-sample REPLAY: the GPU's counter-based random stream of one (pixel, sample) is fed to
+    the reference's own sampleIndirectLightFromFirstIntersection / sampleDirectLight by
+    pre-loading its mt19937 (oracle/ref_harness.cpp), so the two must agree sample by sample
+    up to libm ulps;
+  * statistical agreement of converged means against the reference at equal spp, with the
+    CPU-vs-CPU noise floor (two reference runs with different seeds) as the yardstick.
+"""
+import numpy as np
+import pytest
+
+from raym0nade_b200 import rng, scenes
+from raym0nade_b200.api import Context, Model
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _setup(ref, scene):
+    model = Model(scene)
+    return ref.RefScene(scene), Context(0).upload(model)
+
+
+# --------------------------------------------------------------------------- G-buffer
+def _check_gbuffer(ref, scene, args):
+    R, ctx = _setup(ref, scene)
+    g = ctx.gbuffer(args.replace(spp=0))
+    rg = R.gbuffer(args.replace(spp=0), threads=8)
+    hit = ~np.isnan(rg["position"][:, 0])
+    assert np.array_equal(hit, ~np.isnan(g["position"][:, 0]))
+    # pure + - * / sqrt chains: bit-equal
+    for k in ["position", "shapeNormal"]:
+        assert np.array_equal(g[k][hit].view(np.uint32), rg[k][hit].view(np.uint32)), k
+    for k in ["opacity", "eta", "specular", "id", "entering"]:
+        assert np.array_equal(g[k][hit], rg[k][hit]), k
+    # texture-driven fields go through powf / log2f, which differ from glibc by <= 2 ulp
+    for k, tol in [("surfaceNormal", 2e-5), ("baseColor", 2e-5), ("emission", 2e-5), ("roughness", 1e-6), ("metallic", 1e-6)]:
+        a, b = g[k][hit].astype(np.float64), rg[k][hit].astype(np.float64)
+        bad = np.abs(a - b) > tol * (1.0 + np.abs(b))
+        assert bad.mean() < 2e-3, (k, bad.mean(), np.abs(a - b).max())
+    # misses carry the sky emission
+    if scene.sky is not None and (~hit).any():
+        a, b = g["emission"][~hit].astype(np.float64), rg["emission"][~hit].astype(np.float64)
+        assert (np.abs(a - b) > 1e-4 * (1 + np.abs(b))).mean() < 2e-3
+    ctx.close()
+
+
+def test_gbuffer_cornell(ref):
+    _check_gbuffer(ref, *scenes.cornell_box(256, 256, 0))
+
+
+def test_gbuffer_sky_smooth_normals(ref):
+    _check_gbuffer(ref, *scenes.heightfield_scene(20_000, 320, 180, with_sky=True))
+
+
+def test_gbuffer_textures_normal_maps_mips(ref):
+    _check_gbuffer(ref, *scenes.texture_heavy(40_000, 320, 180, tex_size=128, n_materials=8))
+
+
+def test_gbuffer_glass(ref):
+    _check_gbuffer(ref, *scenes.glossy_dielectric(60_000, 320, 180))
+
+
+# --------------------------------------------------------------------------- per-sample replay
+def _calc_var(rad, var, exposure):
+    """calcVar lambda of renderPixel (src/render.cpp:510-516), fp32"""
+    rad = (rad * f32(exposure)).astype(f32)
+    var = (var * f32(exposure * exposure)).astype(f32)
+    var = var - ((rad[0] * rad[0] + rad[1] * rad[1]) + rad[2] * rad[2])
+    return rad, max(f32(var), f32(0))
+
+
+def _replay_scene(ref, scene, args, seed, direct):
+    """Render ONE sample per pixel on the GPU (clamp off), replay every pixel through the
+    reference with the same draws, return (gpu planes, ref planes) as float64 arrays [npix, 2, 4]."""
+    R, ctx = _setup(ref, scene)
+    a = args.replace(spp=1, P_Direct=1.0 if direct else 0.0)
+    ctx.set_option("disable_clamp", 1)
+    out = ctx.render(a, seed=seed)
+    rg = R.gbuffer(a.replace(spp=0), threads=8)
+    npix = a.width * a.height
+    keys = ("Dd", "Ds") if direct else ("Id", "Is")
+    gpu = np.zeros((npix, 2, 4))
+    refv = np.zeros((npix, 2, 4))
+    exhausted = 0
+    for p in range(npix):
+        for j, k in enumerate(keys):
+            gpu[p, j, :3] = out[k]["radiance"][p]
+            gpu[p, j, 3] = out[k]["Var"][p]
+        g = rg[p]
+        if np.isnan(g["position"][0]):
+            continue
+        if direct:
+            u32 = rng.stream_u32(seed, p, 0, rng.STREAM_DIRECT, 624)
+            s, used = R.replay_direct(a, g, u32)
+            samples = [] if s is None else [s]
+            base = g["baseColor"]
+            n_s = 1
+        else:
+            n_s = 1 if g["opacity"] > 1 - 1e-4 else 16
+            samples = []
+            for si in range(n_s):
+                u32 = rng.stream_u32(seed, p, si, rng.STREAM_INDIRECT, 624)
+                ss, used = R.replay_indirect(a, p % a.width, p // a.width, g, u32)
+                exhausted += used >= 624
+                samples += list(ss)
+            base = np.zeros(3, f32) if g["opacity"] < 1e-4 else g["baseColor"]
+        acc = np.zeros(8, f32)
+        for s in samples:
+            s = s.copy()
+            if not direct:
+                s[6] = f32(s[6]) * (f32(1.0) / f32(n_s))          # mulWeight(samples, 1/spp_indirect)
+            acc = acc + ref.accumulate(base[None], s[None])[0]
+        for j in range(2):
+            rad, var = _calc_var(acc[4 * j:4 * j + 3], acc[4 * j + 3], a.exposure)
+            refv[p, j, :3] = rad
+            refv[p, j, 3] = var
+    ctx.close()
+    return gpu, refv, exhausted
+
+
+def _assert_replay(gpu, refv, min_match):
+    rad_g, rad_r = gpu[:, :, :3], refv[:, :, :3]
+    scale = np.abs(rad_r).max(axis=(1, 2)) + 1e-6
+    err = np.abs(rad_g - rad_r).max(axis=(1, 2)) / scale
+    match = err < 2e-3
+    assert match.mean() >= min_match, "only %.4f of pixels replay identically" % match.mean()
+    # and the images agree in the mean far better than Monte-Carlo noise would allow
+    assert abs(rad_g.sum() - rad_r.sum()) <= 0.02 * abs(rad_r.sum()) + 1e-6
+    return match.mean()
+
+
+@pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
+def test_replay_indirect_sample_by_sample(ref, which):
+    if which == "cornell":
+        scene, args = scenes.cornell_box(64, 64, 1)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(8_000, 80, 45, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(30_000, 80, 45)
+    gpu, refv, exhausted = _replay_scene(ref, scene, args, seed=1234, direct=False)
+    assert exhausted == 0
+    _assert_replay(gpu, refv, 0.97)
+
+
+@pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
+def test_replay_direct_sample_by_sample(ref, which):
+    if which == "cornell":
+        scene, args = scenes.cornell_box(64, 64, 1)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(8_000, 80, 45, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(30_000, 80, 45)
+    gpu, refv, _ = _replay_scene(ref, scene, args, seed=77, direct=True)
+    _assert_replay(gpu, refv, 0.99)
+
+
+# --------------------------------------------------------------------------- converged means
+def _planes(out):
+    return {k: out[k]["radiance"].astype(np.float64) for k in ("Dd", "Ds", "Id", "Is")}
+
+
+def _rel_mse(a, b, trim=0.01):
+    """per-pixel relative squared error, mean over all but the worst `trim` share of pixels:
+    the specular planes are heavy-tailed (single fireflies dominate an untrimmed mean, for the
+    CPU-vs-CPU floor just as much as for GPU-vs-CPU)"""
+    e = np.sort(((a - b) ** 2).sum(1) / ((b ** 2).sum(1) + 1e-2))
+    return float(e[: max(1, int(len(e) * (1.0 - trim)))].mean())
+
+
+@pytest.mark.parametrize("which,spp", [("cornell", 128), ("sky", 64), ("glossy", 32)])
+def test_render_matches_reference_statistically(ref, which, spp):
+    """relMSE(GPU, CPU seed A) <= 1.5 x relMSE(CPU seed A, CPU seed B) per plane; energy within 1.5 %."""
+    if which == "cornell":
+        scene, args = scenes.cornell_box(96, 96, spp)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(20_000, 128, 72, spp, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(60_000, 128, 72, spp)
+    R, ctx = _setup(ref, scene)
+    gpu = _planes(ctx.render(args, seed=5))
+    ca = _planes(R.render(args, threads=8, seed_base=100))
+    cb = _planes(R.render(args, threads=8, seed_base=200))
+    for k in ("Dd", "Ds", "Id", "Is"):
+        floor = _rel_mse(ca[k], cb[k])
+        got = _rel_mse(gpu[k], ca[k])
+        assert got <= 1.5 * floor + 1e-6, (k, got, floor)
+    tot = lambda P: sum(P[k].sum() for k in P)
+    e_gpu, e_a, e_b = tot(gpu), tot(ca), tot(cb)
+    assert abs(e_gpu - e_a) <= max(0.015 * e_a, 3 * abs(e_a - e_b)), (e_gpu, e_a, e_b)
+    ctx.close()
+
+
+def test_gbuffer_basecolor_restore_quirk(ref):
+    """baseColor comes back un-nudged only for pixels that produced indirect samples
+    (src/render.cpp:492-495,529-530,550)"""
+    scene, args = scenes.cornell_box(64, 64, 16)
+    R, ctx = _setup(ref, scene)
+    g = ctx.render(args, seed=3)["gbuffer"]
+    rg = R.render(args, threads=4)["gbuffer"]
+    hit = ~np.isnan(rg["position"][:, 0])
+    a, b = g["baseColor"][hit].astype(np.float64), rg["baseColor"][hit].astype(np.float64)
+    # a pixel whose few samples all died keeps the nudge in one implementation and not in the other
+    # only if its sample set differs - rare at 16 spp; everything else must agree to powf precision
+    assert (np.abs(a - b).max(1) > 1e-4).mean() < 0.02
+    ctx.close()
+
+
+# --------------------------------------------------------------------------- FXAA + post pass
+def test_fxaa_bit_exact_random_and_edges(ref):
+    ctx = Context(0)
+    rs = np.random.default_rng(0)
+    for (h, w) in [(37, 53), (64, 64), (1, 40), (40, 1), (8, 32)]:
+        img = rs.random((h, w, 3), dtype=np.float32)
+        img[h // 3: h // 2, :, :] *= 0.05          # strong horizontal edges
+        img[:, w // 3: w // 2, :] *= 0.2
+        got = ctx.fxaa(img)
+        want = ref.fxaa(img)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (h, w)
+    flat = np.full((16, 16, 3), 0.5, np.float32)
+    assert np.array_equal(ctx.fxaa(flat), flat)    # below the edge threshold: identity
+    ctx.close()
+
+
+def test_postprocess_shade_gamma_fxaa(ref):
+    scene, args = scenes.cornell_box(96, 96, 16)
+    R, ctx = _setup(ref, scene)
+    out = ctx.render(args, seed=9)
+    for opts in [ref.SHADE["Full"], ref.SHADE["Full"] | ref.SHADE["DoFXAA"], ref.SHADE["BaseColor"], ref.SHADE["shapeNormal"],
+                 ref.SHADE["DirectLight"] | ref.SHADE["Diffuse"]]:
+        got = ctx.postprocess(args, opts)
+        want = ref.postprocess(out["gbuffer"], out["Dd"], out["Ds"], out["Id"], out["Is"], args.width, args.height, args.exposure, opts)
+        ok = np.isfinite(want)
+        if opts & ref.SHADE["DoFXAA"]:
+            # a 1-ulp powf difference can flip an FXAA tap choice on a handful of pixels
+            assert (np.abs(got[ok] - want[ok]) > 1e-5).mean() < 5e-3
+        else:
+            assert np.abs(got[ok] - want[ok]).max() <= 2e-6, opts
+    ctx.close()
+
+
+def test_no_cuda_path_fails_loudly_not_silently():
+    """there is no CPU fallback: asking for a device that does not exist is an error"""
+    from raym0nade_b200.api import RmError
+    with pytest.raises(RmError):
+        Context(99)
