@@ -88,11 +88,6 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-class _DevPtr:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
-
-
 def cpu_reference_run(scene, args, threads):
     """The reference's own renderPixel loop (oracle/_ref) on a bounded sample of the workload."""
     from oracle import refbind
@@ -149,12 +144,9 @@ def run_ours(opt, rank, world, local_rank):
     ctx = Context(local_rank, stream=stream).upload(model)
 
     def reduce_across_ranks():
-        ps, ns, pm, nm = ctx.accum_view()
-        dist.all_reduce(torch.as_tensor(_DevPtr(ps, ns), device=dev), op=dist.ReduceOp.SUM)
-        dist.all_reduce(torch.as_tensor(_DevPtr(pm, nm), device=dev), op=dist.ReduceOp.MAX)
-        ctx.accum_after_reduce(rank, world)
-        pr, nr = ctx.accum_radiance()
-        dist.reduce(torch.as_tensor(_DevPtr(pr, nr), device=dev), dst=0, op=dist.ReduceOp.SUM)
+        from raym0nade_b200 import multi_gpu
+        multi_gpu.reduce_frame(multi_gpu.ContextAccum(ctx), dist, rank, world,
+                               lambda buf: torch.as_tensor(multi_gpu.DevPtr(buf), device=dev))
 
     def step(seed):
         ctx.trace_primary(args, download=False)

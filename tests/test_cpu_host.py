@@ -1,0 +1,196 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what the header declares,
+host-side scene preparation reproduces the reference's load-time derivations bit for bit,
+argument parsing follows the reference console, errors are loud, and the multi-GPU reduction
+protocol is exact (world_size 2 over gloo)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from raym0nade_b200 import api, multi_gpu, rng, scenes
+from raym0nade_b200.api import Model, RmError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "raym0nade_b200.h")).read()
+    declared = set(re.findall(r"\b(rm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    L = api.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.rm_version()
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RmError) as e:
+        api.Context(0)
+    assert "no CPU path" in str(e.value) or "CUDA" in str(e.value)
+
+
+@pytest.mark.parametrize("name", ["cornell", "hf", "tex"])
+def test_host_prepare_matches_reference_vectors(name):
+    scene, _ = {"cornell": lambda: scenes.cornell_box(64, 64, 0), "hf": lambda: scenes.heightfield_scene(3000, 96, 54, 0, with_sky=True),
+                "tex": lambda: scenes.texture_heavy(6000, 96, 54, 0, tex_size=32, n_materials=8)}[name]()
+    m = Model(scene)
+    assert np.array_equal(m.permutation(), G[name + "_perm"])
+    assert m.nodes().tobytes() == G[name + "_nodes"].tobytes()
+    if name == "hf":
+        _, cdf = m.sky()
+        assert np.array_equal(cdf[-16:], G["sky_cdf_tail"])
+
+
+def test_host_prepare_matches_reference_directly(ref):
+    for scene in [scenes.cornell_box()[0], scenes.texture_heavy(20_000, tex_size=64, n_materials=8)[0],
+                  scenes.heightfield_scene(20_000, with_sky=True)[0], scenes.glossy_dielectric(120_000)[0]]:
+        m, R = Model(scene), ref.RefScene(scene)
+        rn, rp = R.bvh()
+        assert np.array_equal(m.permutation(), rp) and m.nodes().tobytes() == rn.tobytes(), scene.name
+        for a, b in zip(m.lights(), R.lights()):
+            assert np.array_equal(a["center"], b["center"]) and np.array_equal(a["color"], b["color"])
+            assert np.float32(a["power"]) == np.float32(b["power"]) and np.array_equal(a["cdf"], b["cdf"])
+            assert np.array_equal(a["faces"], b["faces"])
+        assert len(m.lights()) == len(R.lights())
+        sd, sc = m.sky()
+        rd, rc = R.sky()
+        assert np.array_equal(sd, rd) and np.array_equal(sc, rc)
+        # mip chains of every texture slot
+        slots = [ref.SLOT_DIFFUSE, ref.SLOT_SPECULAR, ref.SLOT_EMISSIVE, ref.SLOT_NORMALS]
+        for mi in range(m.desc.n_materials):
+            md = m.material(mi)
+            for k in range(4):
+                if md.tex[k] < 0:
+                    continue
+                mine, depth = m.texture_levels(md.tex[k])
+                theirs, rdepth = R.texture_levels(mi, slots[k])
+                assert depth == rdepth and len(mine) == len(theirs)
+                assert all(np.array_equal(x, y) for x, y in zip(mine, theirs))
+            assert bool(md.has_fully_transparent_part) == any(
+                (scene.textures[scene.materials[mi].tex_diffuse][..., 3] < 255).any() for _ in [0] if scene.materials[mi].tex_diffuse >= 0)
+        R.close()
+
+
+def test_prepare_rejects_bad_input():
+    scene, _ = scenes.cornell_box()
+    bad = scenes.RawScene(positions=scene.positions, uvs=scene.uvs, normals=scene.normals,
+                          meshes=[(0, scene.n_faces + 5, 0)], materials=scene.materials, textures=scene.textures)
+    with pytest.raises(RmError):
+        Model(bad)
+    rgb_as_diffuse = scenes.RawScene(positions=scene.positions, uvs=scene.uvs, normals=scene.normals, meshes=scene.meshes,
+                                     materials=scene.materials, textures=[t[..., :3].copy() for t in scene.textures])
+    with pytest.raises(RmError):
+        Model(rgb_as_diffuse)      # the reference would stride an RGB8 diffuse texture by 4 (src/material.cpp:58)
+
+
+def test_render_args_follow_the_reference_console():
+    txt = """0.987117 -0.16 0
+             0 0 1
+             -0.16 -0.987117 0
+             6.9 -0.2 -3.5
+             0.00048 0.0 0.0 512.0
+             2048 1152
+             320 12 0.7
+             output/Bistro"""                      # docs/renderArguments.txt, arg_interior_table
+    a = scenes.RenderArgs.from_console(txt)
+    assert (a.width, a.height, a.spp, a.threads) == (2048, 1152, 320, 12)
+    d, r, u = np.float32([0.987117, -0.16, 0]), np.float32([0, 0, 1]), np.float32([-0.16, -0.987117, 0])
+    want = np.float32(6.9) * d + np.float32(-0.2) * r + np.float32(-3.5) * u       # position = D*direction + R*right + U*up
+    assert np.allclose(a.position, want, rtol=0, atol=1e-6)
+    assert abs(a.P_Direct - 0.7) < 1e-6 and a.savePath == "output/Bistro"
+    c = a.to_c()
+    assert c.width == 2048 and abs(c.exposure - 512.0) < 1e-6
+    with pytest.raises(ValueError):
+        scenes.RenderArgs.from_console("1 2 3")
+
+
+def test_rng_stream_statement_matches_reference_mapping():
+    got = rng.uniform_from_u32(G["rng_u32"])
+    assert np.array_equal(got.view(np.uint32), G["rng_out"].view(np.uint32))
+    # Philox4x32-10 known answers (Random123 kat_vectors): zero key/counter and all-ones
+    z = rng.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(x) for x in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    o = rng.philox4x32_10(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(x) for x in o] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    a = rng.stream_u32(7, 11, 3, rng.STREAM_INDIRECT, 10)
+    b = rng.stream_u32(7, 11, 3, rng.STREAM_DIRECT, 10)
+    assert len(a) == 10 and not np.array_equal(a, b)
+
+
+def test_sample_sharding_partitions_every_index_once():
+    for total in [0, 1, 7, 44, 1024]:
+        for world in [1, 2, 4, 8]:
+            counts = [multi_gpu.local_sample_count(total, r, world) for r in range(world)]
+            assert sum(counts) == total
+            seen = sorted(r + k * world for r in range(world) for k in range(counts[r]))
+            assert seen == list(range(total))
+
+
+# --------------------------------------------------------------------------- world_size 2 over gloo
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    npix, n_samples = 64, 40
+    rs = np.random.default_rng(5)
+    clum = rs.random((n_samples, npix)).astype(np.float32)
+    clum[3, ::4] = 500.0          # fireflies owned by rank 1 (sample 3): must be dropped in a quarter of the pixels
+    clum[8, 1::4] = 3.0           # large but below 16/17 of the total: must survive
+
+    class Acc:                     # numpy stand-in for the CUDA accumulators, same protocol
+        def __init__(self):
+            mine = clum[rank::world]
+            self.sum = np.zeros((npix, 2), np.float32)
+            self.sum[:, 0], self.sum[:, 1] = mine.sum(0), mine.shape[0]
+            self.hold = mine.max(0)
+            self.max = self.hold.copy()
+            self.rad = np.zeros((npix, 16), np.float32)
+            self.rad[:, 8] = mine.sum(0) - self.hold          # everything but the held-back sample
+
+        def accum_view(self):
+            return self.sum, self.max
+
+        def accum_after_reduce(self, rank, world):
+            total, gmax = self.sum[:, 0], self.max
+            drop = (self.hold == gmax) & (self.hold / (total - self.hold + np.float32(1e-4)) > 16.0)
+            self.rad[:, 8] += np.where(drop, 0.0, self.hold).astype(np.float32)
+
+        def accum_radiance(self):
+            return self.rad
+
+    acc = Acc()
+    multi_gpu.reduce_frame(acc, dist, rank, world, torch.from_numpy)
+    if rank == 0:
+        q.put(acc.rad[:, 8].copy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_equals_single_process_clamp():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process statement of src/render.cpp:534-547 on the same samples
+    rs = np.random.default_rng(5)
+    clum = rs.random((40, 64)).astype(np.float32)
+    clum[3, ::4] = 500.0
+    clum[8, 1::4] = 3.0
+    total = clum.sum(0)
+    keep = ~(clum / (total - clum + np.float32(1e-4)) > 16.0)
+    want = (clum * keep).sum(0)
+    assert keep[3, ::4].sum() == 0 and keep[8].all()
+    assert np.allclose(got, want, rtol=1e-5)
