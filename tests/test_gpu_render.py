@@ -196,16 +196,33 @@ def test_render_matches_reference_statistically(ref, which, spp):
 
 def test_gbuffer_basecolor_restore_quirk(ref):
     """baseColor comes back un-nudged only for pixels that produced indirect samples
-    (src/render.cpp:492-495,529-530,550)"""
+    (src/render.cpp:492-495,529-530,550).  Which pixels end up with an empty sample set depends
+    on the random stream, so the per-pixel outcome is compared structurally: every pixel holds
+    either the nudged or the restored value, a pixel with indirect radiance is always restored,
+    and the restored share matches the reference's."""
     scene, args = scenes.cornell_box(64, 64, 16)
     R, ctx = _setup(ref, scene)
-    g = ctx.render(args, seed=3)["gbuffer"]
-    rg = R.render(args, threads=4)["gbuffer"]
-    hit = ~np.isnan(rg["position"][:, 0])
-    a, b = g["baseColor"][hit].astype(np.float64), rg["baseColor"][hit].astype(np.float64)
-    # a pixel whose few samples all died keeps the nudge in one implementation and not in the other
-    # only if its sample set differs - rare at 16 spp; everything else must agree to powf precision
-    assert (np.abs(a - b).max(1) > 1e-4).mean() < 0.02
+    nudged = ctx.gbuffer(args.replace(spp=0))["baseColor"].copy()         # spp 0: nothing is restored
+    rn = R.gbuffer(args.replace(spp=0), threads=4)["baseColor"]
+    out = ctx.render(args, seed=3)
+    rout = R.render(args, threads=4)
+    g, rg = out["gbuffer"]["baseColor"], rout["gbuffer"]["baseColor"]
+    hit = ~np.isnan(rout["gbuffer"]["position"][:, 0])
+    assert np.abs(nudged[hit] - rn[hit]).max() <= 2e-5
+
+    def restored_mask(after, before):
+        d = before.astype(np.float64) - after.astype(np.float64)
+        assert np.abs(d[:, 1:]).max() == 0.0                                # only the red channel ever moves
+        is_restored = np.abs(d[:, 0] - 4e-2) < 1e-6
+        assert (is_restored | (d[:, 0] == 0.0)).all()                       # exactly two possible states
+        return is_restored
+
+    m_gpu, m_ref = restored_mask(g[hit], nudged[hit]), restored_mask(rg[hit], rn[hit])
+    assert m_gpu.any() and m_ref.any()
+    lit = (np.abs(out["Id"]["radiance"][hit]).sum(1) + np.abs(out["Is"]["radiance"][hit]).sum(1)) > 0
+    grey = np.abs(nudged[hit][:, 0] - nudged[hit][:, 1] - 4e-2) < 1e-4      # grey walls: the pixels that were nudged
+    assert m_gpu[lit & grey].all()                                          # samples present => restored
+    assert abs(m_gpu.mean() - m_ref.mean()) < 0.03, (m_gpu.mean(), m_ref.mean())
     ctx.close()
 
 
