@@ -16,48 +16,48 @@
 
 namespace rm {
 
-constexpr int kStackDepth = 32;   // tree depth is <= 20 for 5 M triangles
+constexpr int kStackDepth = 24;   // one deferred child per tree level; depth is <= 20 for 5 M triangles
 
 struct TraceCounters { unsigned long long rays, box, tri; };
 
 // A reference to a BVH child: inner node index u >= 1, or a leaf encoded as ~(faceL<<4 | count).
 RM_DI int leaf_ref(int faceL, int faceR) { return ~((faceL << 4) | (faceR - faceL)); }
+constexpr int kTraceDone = int(0x80000000u);     // "stack empty": never a valid leaf ref (faceL < 2^27)
 
 struct RaySetup {
     V3 o, d;
     float inv[3];      // 1.0f / d[i]                    (src/geometry.cpp:48)
-    bool par[3];       // |d[i]| < eps_zero              (src/geometry.cpp:42)
+    unsigned flags;    // bit i: |d[i]| < eps_zero (src/geometry.cpp:42); bit 4+i: !(inv[i] >= 0)
 };
 
+// __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the reference's 1.0f / x
 RM_DI RaySetup setup_ray(V3 o, V3 d) {
     RaySetup r;
     r.o = o; r.d = d;
-    r.par[0] = fabsf(d.x) < kEps; r.par[1] = fabsf(d.y) < kEps; r.par[2] = fabsf(d.z) < kEps;
-    r.inv[0] = frcp(d.x); r.inv[1] = frcp(d.y); r.inv[2] = frcp(d.z);
+    r.inv[0] = __frcp_rn(d.x); r.inv[1] = __frcp_rn(d.y); r.inv[2] = __frcp_rn(d.z);
+    r.flags = (fabsf(d.x) < kEps ? 1u : 0u) | (fabsf(d.y) < kEps ? 2u : 0u) | (fabsf(d.z) < kEps ? 4u : 0u) |
+              (r.inv[0] >= 0.0f ? 0u : 16u) | (r.inv[1] >= 0.0f ? 0u : 32u) | (r.inv[2] >= 0.0f ? 0u : 64u);
     return r;
 }
 
-// One axis of rayInBox; `live` carries the early-return state.
-RM_DI void slab_axis(bool par, float o, float inv, float b0, float b1, float &tL, float &tR, bool &live) {
-    if (!live) return;
-    if (par) {
-        if (o < b0 || o > b1) { tR = -1.0f; live = false; }
-    } else {
-        float tn, tf;
-        if (inv >= 0.0f) { tn = fmul(fsub(b0, o), inv); tf = fmul(fsub(b1, o), inv); }
-        else { tn = fmul(fsub(b1, o), inv); tf = fmul(fsub(b0, o), inv); }
-        tL = fmaxf(tL, tn);
-        tR = fminf(tR, tf);
-        tR = fadd(tR, kEps);
-        if (tL > tR) live = false;
-    }
+// One axis of rayInBox, branch-free; `live` carries the early-return state.
+RM_DI void slab_axis(bool par, bool neg, float o, float inv, float b0, float b1, float &tL, float &tR, bool &live) {
+    float t0 = fmul(fsub(b0, o), inv), t1 = fmul(fsub(b1, o), inv);
+    float nL = fmaxf(tL, neg ? t1 : t0);
+    float nR = fadd(fminf(tR, neg ? t0 : t1), kEps);
+    bool outside = o < b0 || o > b1;
+    bool upd = live && !par;
+    bool kill = live && par && outside;
+    tL = upd ? nL : tL;
+    tR = upd ? nR : (kill ? -1.0f : tR);
+    live = live && (par ? !outside : !(nL > nR));
 }
 
 RM_DI void ray_in_box(const RaySetup &r, float4 a, float4 b, float &tL, float &tR) {
     bool live = true;
-    slab_axis(r.par[0], r.o.x, r.inv[0], a.x, a.w, tL, tR, live);
-    slab_axis(r.par[1], r.o.y, r.inv[1], a.y, b.x, tL, tR, live);
-    slab_axis(r.par[2], r.o.z, r.inv[2], a.z, b.y, tL, tR, live);
+    slab_axis(r.flags & 1u, r.flags & 16u, r.o.x, r.inv[0], a.x, a.w, tL, tR, live);
+    slab_axis(r.flags & 2u, r.flags & 32u, r.o.y, r.inv[1], a.y, b.x, tL, tR, live);
+    slab_axis(r.flags & 4u, r.flags & 64u, r.o.z, r.inv[2], a.z, b.y, tL, tR, live);
 }
 
 // returns t or +INF
@@ -67,8 +67,12 @@ RM_DI float ray_triangle(const RaySetup &r, float4 q0, float4 q1, float4 q2) {
     V3 e2 = mk3(q1.z, q1.w, q2.x);
     V3 h = cross(r.d, e2);
     float a = dot(e1, h);
-    if (fdiv(fabsf(a), q2.y) < kEps) return CUDART_INF_F;
-    float f = frcp(a);
+    // degenerate test |a| / |e1| < eps_zero.  The correctly rounded quotient can only fall below
+    // eps_zero when |a| < 1.0001e-4 * |e1| (rounding moves either side by < 1e-7 relative), so the
+    // division is evaluated only in that sliver; NaN / zero |e1| take the same side as the reference.
+    float aa = fabsf(a);
+    if (aa < fmul(1.0001e-4f, q2.y) && fdiv(aa, q2.y) < kEps) return CUDART_INF_F;
+    float f = __frcp_rn(a);
     V3 s = r.o - v0;
     float u = fmul(f, dot(s, h));
     if (u < 0.0f || u > 1.0f) return CUDART_INF_F;
@@ -76,66 +80,6 @@ RM_DI float ray_triangle(const RaySetup &r, float4 q0, float4 q1, float4 q2) {
     float v = fmul(f, dot(r.d, q));
     if (v < 0.0f || fadd(u, v) > 1.0f) return CUDART_INF_F;
     return fmul(f, dot(e2, q));
-}
-
-// BVH::rayHit: closest hit in (t_min, t_max).  `stack` is this thread's column of a shared-memory
-// array, entries strided by `stride` (conflict-free).  ANYHIT: stop at the first accepted
-// triangle - used only where that cannot change the caller's answer (see ray_occluded).
-template <bool COUNT, bool ANYHIT>
-RM_DI void bvh_ray_hit(const DevScene &S, const RaySetup &r, float t_min, float &t_max, int &face,
-                       int2 *stack, int stride, TraceCounters &cnt, float any_limit = 0.0f) {
-    cnt.rays++;                      // rays are always counted; COUNT adds box / triangle tests
-    int sp = 0;
-    int cur;
-    if (S.root_is_leaf) {
-        float4 rb = __ldg(S.nodes + 3);
-        cur = leaf_ref(__float_as_int(rb.z), __float_as_int(rb.w));
-    } else cur = 1;
-    for (;;) {
-        if (cur >= 0) {
-            const float4 *n = S.nodes + (size_t(cur) << 2);        // children 2u, 2u+1: one 64-byte block
-            float4 a0 = __ldg(n), b0 = __ldg(n + 1), a1 = __ldg(n + 2), b1 = __ldg(n + 3);
-            float tL0 = t_min, tR0 = t_max, tL1 = t_min, tR1 = t_max;
-            ray_in_box(r, a0, b0, tL0, tR0);
-            ray_in_box(r, a1, b1, tL1, tR1);
-            if (COUNT) cnt.box += 2;
-            int fr0 = __float_as_int(b0.w), fr1 = __float_as_int(b1.w);
-            int ref0 = fr0 ? leaf_ref(__float_as_int(b0.z), fr0) : (cur << 1);
-            int ref1 = fr1 ? leaf_ref(__float_as_int(b1.z), fr1) : (cur << 1 | 1);
-            bool ok0 = tL0 < tR0, ok1 = tL1 < tR1;
-            int first, second;
-            bool okF, okS;
-            float tLS;
-            if (tL0 < tL1) { first = ref0; okF = ok0; second = ref1; okS = ok1; tLS = tL1; }
-            else { first = ref1; okF = ok1; second = ref0; okS = ok0; tLS = tL0; }
-            if (okF) {
-                if (okS) { stack[sp * stride] = make_int2(second, __float_as_int(tLS)); sp++; }
-                cur = first;
-                continue;
-            }
-            if (okS && tLS < t_max) { cur = second; continue; }
-        } else {
-            int x = ~cur;
-            int f0 = x >> 4, f1 = f0 + (x & 15);
-            for (int i = f0; i < f1; i++) {
-                const float4 *q = S.tri + size_t(i) * 3;
-                float t = ray_triangle(r, __ldg(q), __ldg(q + 1), __ldg(q + 2));
-                if (t_min < t && t < t_max) {
-                    t_max = t;
-                    face = i;
-                    if (ANYHIT && t < any_limit) { if (COUNT) cnt.tri += unsigned(i - f0 + 1); return; }
-                }
-            }
-            if (COUNT) cnt.tri += unsigned(f1 - f0);
-        }
-        // pop: a deferred child is entered only if its tL is still below the current t_max
-        for (;;) {
-            if (sp == 0) return;
-            sp--;
-            int2 e = stack[sp * stride];
-            if (__int_as_float(e.y) < t_max) { cur = e.x; break; }
-        }
-    }
 }
 
 // barycentric (src/geometry.cpp:89-103): returns (gamma, alpha, beta)
@@ -183,50 +127,172 @@ RM_DI bool transparent_test(const DevScene &S, const RaySetup &r, float t, int f
     return mat_diffuse_alpha0(S, S.materials[F.material], uv.x, uv.y) < kEps;
 }
 
-// Model::rayHit (src/model.cpp:332-341): face = -1 and t = INF on a miss
-template <bool COUNT>
-RM_DI void ray_hit(const DevScene &S, const RaySetup &r, float &t, int &face, int2 *stack, int stride, TraceCounters &cnt) {
-    float t_min = kEps;
-    t = CUDART_INF_F;
-    face = -1;
-    for (int T = 0; T < 8; T++) {
-        bvh_ray_hit<COUNT, false>(S, r, t_min, t, face, stack, stride, cnt);
-        if (t == CUDART_INF_F) return;
-        if (!S.any_cutout || !transparent_test(S, r, t, face)) return;
-        t_min = fadd(t, kEps);
-        t = CUDART_INF_F;
-        face = -1;
-    }
-}
+// ------------------------------------------------------------------------------------------
+// Persistent-warp trace engine.
+//
+// Every lane of a warp owns one ray at a time and keeps its whole traversal state in registers
+// (+ its column of the shared-memory stack).  The warp advances in lock-step iterations; in each one
+// either the lanes sitting on an inner node test their two children, or the lanes holding a leaf test
+// their next triangle - the warp votes (ballot + popc) for the step with more lanes ready.  A lane
+// whose ray is finished goes idle; when fewer than kRefillLive lanes are left the warp drops back to
+// the fetch section and the idle lanes (found with a ballot, ranked with popc) take the next rays of
+// the warp's current chunk - chunks of kTraceChunk consecutive rays are handed out from a global
+// cursor with one atomicAdd per chunk - while the busy lanes keep their state.
+//
+// The per-ray semantics are exactly the reference's:
+//   BVH::dfs_rayHit          src/bvh.cpp:56-92    near child first by tL, RIGHT child first on ties,
+//                            a deferred child is re-tested `tL < t_max` when it is popped
+//   Model::rayHit            src/model.cpp:332-341  (<= 8 re-traces through alpha cut-outs)
+//   Model::rayHit_test       src/model.cpp:343-354
+// A Job supplies the rays and consumes the results:
+//   static constexpr bool kOcclusion;
+//   bool load(int i, V3 &o, V3 &d, float &aim);          false = no ray at this index
+//   void hit(int i, float t, int face);                  closest-hit result (kOcclusion == false)
+//   void visibility(int i, bool occluded);               rayHit_test result (kOcclusion == true)
+constexpr int kTraceChunk = 64;
+constexpr int kRefillLive = 22;
 
-// Model::rayHit_test (src/model.cpp:343-354): true = blocked before aimDepth.
-// The reference runs a full closest-hit search in (t_min, aim+eps) and then asks whether the
-// closest hit lies below aimDepth.  When no material has alpha cut-outs, "the closest accepted
-// t is < aim" is equivalent to "some accepted t is < aim", and the traversal state is identical
-// up to the first accepted triangle, so stopping there (ANYHIT) returns the same boolean.
-template <bool COUNT>
-RM_DI bool ray_occluded(const DevScene &S, const RaySetup &r, float aim, int2 *stack, int stride, TraceCounters &cnt) {
-    float t_min = kEps;
-    float t_lim = fadd(aim, kEps);
-    if (!S.any_cutout) {
-        // stop at the first accepted triangle with t < aim; triangles accepted with t in
-        // [aim, aim+eps) only shrink t_max, as in the reference, and the search goes on
-        float t = t_lim;
-        int face = -1;
-        bvh_ray_hit<COUNT, true>(S, r, t_min, t, face, stack, stride, cnt, aim);
-        return !(t >= aim);
+template <class Job, bool COUNT>
+RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int root;
+    if (S.root_is_leaf) {
+        float4 rb = __ldg(S.nodes + 3);
+        root = leaf_ref(__float_as_int(rb.z), __float_as_int(rb.w));
+    } else root = 1;
+    // a rayHit_test may stop at the first accepted triangle below aimDepth when no material has alpha
+    // cut-outs: "the closest accepted t is < aim" <=> "some accepted t is < aim", and the traversal state is
+    // identical up to that triangle, so the boolean is the reference's
+    const bool anyhit = Job::kOcclusion && !S.any_cutout;
+
+    bool active = false;
+    int chunk_next = 0, chunk_end = 0;          // warp-uniform: rays of the current chunk not handed out yet
+    bool exhausted = false;                     // warp-uniform: the global cursor ran past n
+    RaySetup r;
+    float t_min = kEps, t = CUDART_INF_F, aim = CUDART_INF_F, t_reset = CUDART_INF_F;
+    int face = -1, cur = kTraceDone, sp = 0, pass = 0, idx = 0, ti = -1, tend = 0;
+
+    for (;;) {
+        // ---- fetch: idle lanes take the next rays
+        unsigned idle = __ballot_sync(FULL, !active);
+        while (idle != 0u) {
+            if (chunk_next >= chunk_end) {
+                if (exhausted) break;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kTraceChunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                chunk_next = base;
+                chunk_end = min(base + kTraceChunk, n);
+            }
+            const int avail = chunk_end - chunk_next;
+            const int rank = __popc(idle & lt_mask);
+            if (!active && rank < avail) {
+                idx = chunk_next + rank;
+                V3 o, d;
+                if (job.load(idx, o, d, aim)) {
+                    r = setup_ray(o, d);
+                    t_min = kEps;
+                    t_reset = Job::kOcclusion ? fadd(aim, kEps) : CUDART_INF_F;
+                    t = t_reset;
+                    face = -1; cur = root; sp = 0; pass = 0; ti = -1;
+                    active = true;
+                    cnt.rays++;
+                }
+            }
+            chunk_next += min(avail, __popc(idle));
+            idle = __ballot_sync(FULL, !active);
+        }
+        unsigned live = __ballot_sync(FULL, active);
+        if (live == 0u) break;
+        const int need = (exhausted && chunk_next >= chunk_end) ? 1 : kRefillLive;
+
+        // ---- trace: one step per iteration - either every lane that sits on an inner node tests its two
+        // children, or every lane that holds a leaf tests its next triangle - whichever has more lanes
+        // ready; the others wait a turn.  Lanes therefore never idle through a whole descent or a whole
+        // leaf of their neighbours, and both step bodies run with most of their lanes busy.
+        do {
+            const bool wantI = active && cur >= 0;
+            const int nI = __popc(__ballot_sync(FULL, wantI));
+            const int nL = __popc(live) - nI;
+            if (nI >= nL) {
+                if (wantI) {
+                    const float4 *nd = S.nodes + (size_t(cur) << 2);        // children 2u, 2u+1: one 64-byte block
+                    const float4 a0 = __ldg(nd), b0 = __ldg(nd + 1), a1 = __ldg(nd + 2), b1 = __ldg(nd + 3);
+                    float tL0 = t_min, tR0 = t, tL1 = t_min, tR1 = t;
+                    ray_in_box(r, a0, b0, tL0, tR0);
+                    ray_in_box(r, a1, b1, tL1, tR1);
+                    if (COUNT) cnt.box += 2;
+                    const int fr0 = __float_as_int(b0.w), fr1 = __float_as_int(b1.w);
+                    const int ref0 = fr0 ? leaf_ref(__float_as_int(b0.z), fr0) : (cur << 1);
+                    const int ref1 = fr1 ? leaf_ref(__float_as_int(b1.z), fr1) : (cur << 1 | 1);
+                    const bool ok0 = tL0 < tR0, ok1 = tL1 < tR1;
+                    const bool zero_first = tL0 < tL1;
+                    const int first = zero_first ? ref0 : ref1, second = zero_first ? ref1 : ref0;
+                    const bool okF = zero_first ? ok0 : ok1, okS = zero_first ? ok1 : ok0;
+                    const float tLS = zero_first ? tL1 : tL0;
+                    if (okF) {
+                        if (okS) { stack[sp * stride] = make_int2(second, __float_as_int(tLS)); sp++; }
+                        cur = first;
+                    } else if (okS && tLS < t) cur = second;
+                    else {
+                        cur = kTraceDone;
+                        while (sp > 0) {
+                            sp--;
+                            const int2 e = stack[sp * stride];
+                            if (__int_as_float(e.y) < t) { cur = e.x; break; }
+                        }
+                    }
+                    ti = -1;
+                }
+            } else if (active && !wantI) {
+                if (ti < 0) { const int x = ~cur; ti = x >> 4; tend = ti + (x & 15); }        // first visit of this leaf
+                const float4 *q = S.tri + size_t(ti) * 3;
+                const float tt = ray_triangle(r, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+                if (COUNT) cnt.tri++;
+                bool stop = false;
+                if (t_min < tt && tt < t) {
+                    t = tt;
+                    face = ti;
+                    stop = anyhit && tt < aim;
+                }
+                ti++;
+                if (stop || ti == tend) {
+                    cur = kTraceDone;
+                    if (!stop)
+                        while (sp > 0) {
+                            sp--;
+                            const int2 e = stack[sp * stride];
+                            if (__int_as_float(e.y) < t) { cur = e.x; break; }
+                        }
+                    ti = -1;
+                }
+            }
+            if (active && cur == kTraceDone) {
+                // one BVH::rayHit finished: resolve cut-outs, then report
+                bool again = false;
+                if (!Job::kOcclusion) {
+                    if (t != CUDART_INF_F && S.any_cutout && transparent_test(S, r, t, face)) {
+                        t_min = fadd(t, kEps); t = CUDART_INF_F; face = -1; pass++;
+                        again = pass < 8;
+                    }
+                    if (!again) job.hit(idx, t, face);
+                } else {
+                    bool occluded = !(t >= aim);
+                    if (occluded && S.any_cutout && transparent_test(S, r, t, face)) {
+                        t_min = fadd(t, kEps); t = t_reset; face = -1; pass++;
+                        again = pass < 8;                 // 8 cut-outs in a row: the reference reports "blocked"
+                    }
+                    if (!again) job.visibility(idx, occluded);
+                }
+                if (again) { cur = root; sp = 0; ti = -1; cnt.rays++; }
+                else active = false;
+            }
+            live = __ballot_sync(FULL, active);
+        } while (__popc(live) >= need);
     }
-    float t = t_lim;
-    int face = -1;
-    for (int T = 0; T < 8; T++) {
-        bvh_ray_hit<COUNT, false>(S, r, t_min, t, face, stack, stride, cnt);
-        if (t >= aim) return false;
-        if (!transparent_test(S, r, t, face)) return true;
-        t_min = fadd(t, kEps);
-        t = t_lim;
-        face = -1;
-    }
-    return true;
 }
 
 } // namespace rm

@@ -44,7 +44,7 @@ struct __align__(16) ShadowItem {
     float d[3];
     int pixel;               // bit 31: direct-light sample (goes to Dd/Ds, no firefly hold-back)
     float b[3], weight;      // LightSample::bsdfPdf, weight (final)
-    float l[3], _pad;        // LightSample::light (final)
+    float l[3], vis;         // LightSample::light (final); vis = 1 when rayHit_test found the light unoccluded
 };
 
 // per-pixel accumulators
@@ -268,7 +268,7 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
     it.o[0] = org.x; it.o[1] = org.y; it.o[2] = org.z; it.aim = n.aim;
     it.d[0] = n.dir.x; it.d[1] = n.dir.y; it.d[2] = n.dir.z; it.pixel = pixel_tag;
     it.b[0] = b.x; it.b[1] = b.y; it.b[2] = b.z; it.weight = w;
-    it.l[0] = l.x; it.l[1] = l.y; it.l[2] = l.z; it._pad = 0.0f;
+    it.l[0] = l.x; it.l[1] = l.y; it.l[2] = l.z; it.vis = 0.0f;
     float4 *dst = reinterpret_cast<float4 *>(q + slot);
     const float4 *src = reinterpret_cast<const float4 *>(&it);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -400,22 +400,19 @@ __global__ void __launch_bounds__(128) k_indirect_gen(DevScene S, DevArgs A, Fra
 }
 
 // ------------------------------------------------------------------ closest hit over the path queue
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_paths(DevScene S, PathQueue Q, const int *__restrict__ q_count, unsigned long long *counters) {
-    __shared__ int2 stack[kStackDepth * kTraceBlock];
-    const int n = min(*q_count, Q.cap);
-    TraceCounters cnt = {0, 0, 0};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+struct PathJob {
+    static constexpr bool kOcclusion = false;
+    PathQueue Q;
+    RM_DI bool load(int i, V3 &o, V3 &d, float &aim) const {
         const int c = Q.cap;
-        RaySetup r = setup_ray(mk3(Q.o[i], Q.o[c + i], Q.o[2 * c + i]), mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]));
-        float t;
-        int face;
-        ray_hit<COUNT>(S, r, t, face, stack + threadIdx.x, kTraceBlock, cnt);
-        Q.hit_t[i] = t;
-        Q.hit_face[i] = face;
+        o = mk3(Q.o[i], Q.o[c + i], Q.o[2 * c + i]);
+        d = mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
+        aim = CUDART_INF_F;
+        return true;
     }
-    flush_counters(cnt, counters, COUNT);
-}
+    RM_DI void hit(int i, float t, int face) const { Q.hit_t[i] = t; Q.hit_face[i] = face; }
+    RM_DI void visibility(int, bool) const {}
+};
 
 // ------------------------------------------------------------------ one sampleRay level
 __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6};
@@ -584,23 +581,34 @@ __global__ void __launch_bounds__(128) k_shade(DevScene S, FrameBuffers Fb, Accu
 }
 
 // ------------------------------------------------------------------ visibility + accumulation
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(DevScene S, FrameBuffers Fb, Accum Ac, const ShadowItem *__restrict__ sq,
-                                                              const int *__restrict__ s_count, int s_cap, unsigned long long *counters) {
-    __shared__ int2 stack[kStackDepth * kTraceBlock];
+// rayHit_test over the shadow queue marks each item (its `vis` word); a second, fully coalesced pass
+// accumulates the visible ones, so the divergent traversal never carries the accumulation code.
+struct ShadowJob {
+    static constexpr bool kOcclusion = true;
+    ShadowItem *sq;
+    RM_DI bool load(int i, V3 &o, V3 &d, float &aim) const {
+        const float4 *src = reinterpret_cast<const float4 *>(sq + i);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        o = mk3(a.x, a.y, a.z); aim = a.w;
+        d = mk3(b.x, b.y, b.z);
+        return true;
+    }
+    RM_DI void hit(int, float, int) const {}
+    RM_DI void visibility(int i, bool occluded) const { sq[i].vis = occluded ? 0.0f : 1.0f; }
+};
+
+__global__ void __launch_bounds__(256) k_accum_shadow(FrameBuffers Fb, Accum Ac, const ShadowItem *__restrict__ sq, const int *__restrict__ s_count, int s_cap) {
     const int n = min(*s_count, s_cap);
-    TraceCounters cnt = {0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 *src = reinterpret_cast<const float4 *>(sq + i);
-        float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
-        RaySetup r = setup_ray(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z));
-        if (ray_occluded<COUNT>(S, r, a.w, stack + threadIdx.x, kTraceBlock, cnt)) continue;
-        int tag = __float_as_int(b.w);
-        V3 bs = mk3(c.x, c.y, c.z), li = mk3(d.x, d.y, d.z);
+        const float4 d = src[3];
+        if (d.w == 0.0f) continue;
+        const float4 b = src[1], c = src[2];
+        const int tag = __float_as_int(b.w);
+        const V3 bs = mk3(c.x, c.y, c.z), li = mk3(d.x, d.y, d.z);
         if (tag < 0) add_direct(Ac, Fb, tag & 0x7fffffff, bs, li, c.w);
         else add_indirect(Ac, Fb, tag, bs, li, c.w);
     }
-    flush_counters(cnt, counters, COUNT);
 }
 
 // ------------------------------------------------------------------ resolve

@@ -1,10 +1,14 @@
 // kernels_trace.cuh — ray-casting kernels: primary rays (K1) and the batched per-ray seam.
+//
+// All of them are persistent kernels around trace_engine (dev_trace.cuh): a fixed grid of
+// kTraceCtasPerSm CTAs per SM, each warp pulling chunks of rays from a device-side cursor.
 #pragma once
 #include "dev_trace.cuh"
 
 namespace rm {
 
 constexpr int kTraceBlock = 128;
+constexpr int kTraceCtasPerSm = 8;
 
 // Work counters in device memory: [0] rays, [1] box tests, [2] triangle tests.
 RM_DI void flush_counters(const TraceCounters &c, unsigned long long *g, bool count_tests) {
@@ -15,7 +19,7 @@ RM_DI void flush_counters(const TraceCounters &c, unsigned long long *g, bool co
         if (count_tests) { b += __shfl_xor_sync(0xffffffffu, b, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(g, r);
+        if (r) atomicAdd(g, r);
         if (count_tests) { atomicAdd(g + 1, b); atomicAdd(g + 2, t); }
     }
 }
@@ -28,57 +32,69 @@ RM_DI V3 primary_d(const DevArgs &A, int x, int y) {
     return A.direction + A.accuracy * (rayX * A.right + rayY * A.up);
 }
 
-// K1: one thread per pixel; a warp covers an 8x4 pixel tile so its rays stay coherent.
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_primary(DevScene S, DevArgs A, int *__restrict__ tri_idx,
-                                                               float *__restrict__ t_out, unsigned long long *counters) {
-    __shared__ int2 stack[kStackDepth * kTraceBlock];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    TraceCounters cnt = {0, 0, 0};
-    if (x < A.width && y < A.height) {
-        RaySetup r = setup_ray(A.position, normalize(primary_d(A, x, y)));
-        float t;
-        int face;
-        ray_hit<COUNT>(S, r, t, face, stack + threadIdx.x, kTraceBlock, cnt);
+// K1: ray index -> pixel through 8x4 tiles, so the 32 rays a warp fetches together are one tile
+// and consecutive chunks are neighbouring tiles (coherent node fetches).
+struct PrimaryJob {
+    static constexpr bool kOcclusion = false;
+    DevArgs A;
+    int tiles_x;
+    int *tri_idx;
+    float *t_out;
+    RM_DI bool pixel_of(int i, int &x, int &y) const {
+        int tile = i >> 5, l = i & 31;
+        x = (tile % tiles_x) * 8 + (l & 7);
+        y = (tile / tiles_x) * 4 + (l >> 3);
+        return x < A.width && y < A.height;
+    }
+    RM_DI bool load(int i, V3 &o, V3 &d, float &aim) const {
+        int x, y;
+        if (!pixel_of(i, x, y)) return false;
+        o = A.position;
+        d = normalize(primary_d(A, x, y));
+        aim = CUDART_INF_F;
+        return true;
+    }
+    RM_DI void hit(int i, float t, int face) const {
+        int x, y;
+        pixel_of(i, x, y);
         tri_idx[y * A.width + x] = face;
         t_out[y * A.width + x] = t;
     }
-    flush_counters(cnt, counters, COUNT);
-}
+    RM_DI void visibility(int, bool) const {}
+};
 
-// Batched Model::rayHit over caller-supplied rays (org/dir [n][3]).
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(DevScene S, long long n, const float *__restrict__ org,
-                                                               const float *__restrict__ dir, int *__restrict__ tri_idx,
-                                                               float *__restrict__ t_out, unsigned long long *counters) {
-    __shared__ int2 stack[kStackDepth * kTraceBlock];
-    long long i = (long long)blockIdx.x * kTraceBlock + threadIdx.x;
-    TraceCounters cnt = {0, 0, 0};
-    if (i < n) {
-        RaySetup r = setup_ray(mk3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]), mk3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]));
-        float t;
-        int face;
-        ray_hit<COUNT>(S, r, t, face, stack + threadIdx.x, kTraceBlock, cnt);
-        tri_idx[i] = face;
-        t_out[i] = t;
+// Batched Model::rayHit / rayHit_test over caller-supplied rays (org/dir [n][3]).
+struct RayListJob {
+    const float *org, *dir, *aim_in;
+    RM_DI bool load(int i, V3 &o, V3 &d, float &aim) const {
+        const size_t k = size_t(i) * 3;
+        o = mk3(org[k], org[k + 1], org[k + 2]);
+        d = mk3(dir[k], dir[k + 1], dir[k + 2]);
+        aim = aim_in ? aim_in[i] : CUDART_INF_F;
+        return true;
     }
-    flush_counters(cnt, counters, COUNT);
-}
+};
+struct ClosestJob : RayListJob {
+    static constexpr bool kOcclusion = false;
+    int *tri_idx;
+    float *t_out;
+    RM_DI void hit(int i, float t, int face) const { tri_idx[i] = face; t_out[i] = t; }
+    RM_DI void visibility(int, bool) const {}
+};
+struct OccludedJob : RayListJob {
+    static constexpr bool kOcclusion = true;
+    unsigned char *out;
+    RM_DI void hit(int, float, int) const {}
+    RM_DI void visibility(int i, bool occluded) const { out[i] = occluded ? 1 : 0; }
+};
 
-// Batched Model::rayHit_test.
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_occluded(DevScene S, long long n, const float *__restrict__ org,
-                                                                const float *__restrict__ dir, const float *__restrict__ aim,
-                                                                unsigned char *__restrict__ out, unsigned long long *counters) {
+template <class Job, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene S, Job job, int n_host, const int *__restrict__ n_dev,
+                                                                                int *cursor, unsigned long long *counters) {
     __shared__ int2 stack[kStackDepth * kTraceBlock];
-    long long i = (long long)blockIdx.x * kTraceBlock + threadIdx.x;
     TraceCounters cnt = {0, 0, 0};
-    if (i < n) {
-        RaySetup r = setup_ray(mk3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]), mk3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]));
-        out[i] = ray_occluded<COUNT>(S, r, aim[i], stack + threadIdx.x, kTraceBlock, cnt) ? 1 : 0;
-    }
+    const int n = n_dev ? min(*n_dev, n_host) : n_host;          // queue kernels read their length on the device
+    trace_engine<Job, COUNT>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt);
     flush_counters(cnt, counters, COUNT);
 }
 

@@ -61,7 +61,9 @@ int rm_context_create(int device, void *stream, RmContext **out) {
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(stream);
     int rc = ctx->b_counters.alloc(16 * sizeof(unsigned long long));   // 3 kernel kinds x {rays, box, tri}
+    if (!rc) rc = ctx->b_cursor.alloc(4 * sizeof(int));
     if (rc) { delete ctx; return rc; }
+    ctx->sm_count = prop.multiProcessorCount;
     cudaMemsetAsync(ctx->b_counters.p, 0, ctx->b_counters.bytes, ctx->stream);
     *out = ctx;
     return RM_OK;
@@ -220,7 +222,7 @@ int64_t rm_scene_device_bytes(const RmContext *ctx) { return ctx ? ctx->scene_by
 // ------------------------------------------------------------------------ per-ray seam
 int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *dir, int32_t *tri_idx, float *t) {
     if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_trace_closest: no scene uploaded");
-    if (n < 0 || (n > 0 && (!org || !dir || !tri_idx || !t))) return rm_fail(RM_ERR_INVALID, "rm_trace_closest: bad arguments");
+    if (n < 0 || n > 0x7fffff00LL || (n > 0 && (!org || !dir || !tri_idx || !t))) return rm_fail(RM_ERR_INVALID, "rm_trace_closest: bad arguments");
     if (n == 0) return RM_OK;
     RM_CUDA(cudaSetDevice(ctx->device));
     int rc;
@@ -228,12 +230,14 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
     cudaStream_t st = ctx->stream;
     RM_CUDA(cudaMemcpyAsync(ctx->b_io[0].p, org, n * 12, cudaMemcpyHostToDevice, st));
     RM_CUDA(cudaMemcpyAsync(ctx->b_io[1].p, dir, n * 12, cudaMemcpyHostToDevice, st));
-    unsigned blocks = unsigned((n + kTraceBlock - 1) / kTraceBlock);
     auto *cnt = ctx->b_counters.as<unsigned long long>();
-    if (ctx->count_tests)
-        k_trace_closest<true><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<int>(), ctx->b_io[3].as<float>(), cnt);
-    else
-        k_trace_closest<false><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<int>(), ctx->b_io[3].as<float>(), cnt);
+    ClosestJob job;
+    job.org = ctx->b_io[0].as<float>(); job.dir = ctx->b_io[1].as<float>(); job.aim_in = nullptr;
+    job.tri_idx = ctx->b_io[2].as<int>(); job.t_out = ctx->b_io[3].as<float>();
+    RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
+    const int grid = ctx->sm_count * kTraceCtasPerSm;
+    if (ctx->count_tests) k_trace<ClosestJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
+    else k_trace<ClosestJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -244,7 +248,7 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
 
 int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *dir, const float *aim, uint8_t *out) {
     if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_trace_occluded: no scene uploaded");
-    if (n < 0 || (n > 0 && (!org || !dir || !aim || !out))) return rm_fail(RM_ERR_INVALID, "rm_trace_occluded: bad arguments");
+    if (n < 0 || n > 0x7fffff00LL || (n > 0 && (!org || !dir || !aim || !out))) return rm_fail(RM_ERR_INVALID, "rm_trace_occluded: bad arguments");
     if (n == 0) return RM_OK;
     RM_CUDA(cudaSetDevice(ctx->device));
     int rc;
@@ -253,12 +257,14 @@ int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *
     RM_CUDA(cudaMemcpyAsync(ctx->b_io[0].p, org, n * 12, cudaMemcpyHostToDevice, st));
     RM_CUDA(cudaMemcpyAsync(ctx->b_io[1].p, dir, n * 12, cudaMemcpyHostToDevice, st));
     RM_CUDA(cudaMemcpyAsync(ctx->b_io[2].p, aim, n * 4, cudaMemcpyHostToDevice, st));
-    unsigned blocks = unsigned((n + kTraceBlock - 1) / kTraceBlock);
     auto *cnt = ctx->b_counters.as<unsigned long long>();
-    if (ctx->count_tests)
-        k_trace_occluded<true><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<float>(), ctx->b_io[3].as<unsigned char>(), cnt);
-    else
-        k_trace_occluded<false><<<blocks, kTraceBlock, 0, st>>>(ctx->scene, n, ctx->b_io[0].as<float>(), ctx->b_io[1].as<float>(), ctx->b_io[2].as<float>(), ctx->b_io[3].as<unsigned char>(), cnt);
+    OccludedJob job;
+    job.org = ctx->b_io[0].as<float>(); job.dir = ctx->b_io[1].as<float>(); job.aim_in = ctx->b_io[2].as<float>();
+    job.out = ctx->b_io[3].as<unsigned char>();
+    RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
+    const int grid = ctx->sm_count * kTraceCtasPerSm;
+    if (ctx->count_tests) k_trace<OccludedJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
+    else k_trace<OccludedJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
@@ -275,14 +281,18 @@ int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx,
     const size_t npix = size_t(args->width) * args->height;
     if ((rc = ctx->b_tri_idx.alloc(npix * 4)) || (rc = ctx->b_t.alloc(npix * 4))) return rc;
     cudaStream_t st = ctx->stream;
-    dim3 grid((args->width + 15) / 16, (args->height + 7) / 8);
     auto *cnt = ctx->b_counters.as<unsigned long long>();
-    DevArgs A = to_dev_args(args);
+    PrimaryJob job;
+    job.A = to_dev_args(args);
+    job.tiles_x = (args->width + 7) / 8;
+    job.tri_idx = ctx->b_tri_idx.as<int>();
+    job.t_out = ctx->b_t.as<float>();
+    const int n_rays = job.tiles_x * ((args->height + 3) / 4) * 32;
+    RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
+    const int grid = ctx->sm_count * kTraceCtasPerSm;
     ctx->timed_begin(RM_KIND_PRIMARY);
-    if (ctx->count_tests)
-        k_trace_primary<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
-    else
-        k_trace_primary<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, A, ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), cnt);
+    if (ctx->count_tests) k_trace<PrimaryJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt);
+    else k_trace<PrimaryJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt);
     ctx->timed_end();
     ctx->launches++;
     RM_CUDA(cudaGetLastError());

@@ -65,6 +65,8 @@ struct RmContext {
 
     // counters: rays, box, tri (device)
     DevBuf b_counters;
+    DevBuf b_cursor;                       // int[4]: work cursors of the persistent trace kernels
+    int sm_count = 148;
 
     // per-frame state
     int width = 0, height = 0;
@@ -79,7 +81,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_counters, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };

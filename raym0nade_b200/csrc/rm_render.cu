@@ -220,12 +220,18 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const int grid = R->sm_count * 8;
     const bool ct = ctx->count_tests;
 
+    // counts: [0,1] path queue lengths, [2] shadow queue length, [3] overflow, [6] path-trace cursor, [7] shadow-trace cursor
+    const int tgrid = R->sm_count * kTraceCtasPerSm;
     auto trace_shadow = [&]() {
+        ShadowJob job;
+        job.sq = sq;
+        cudaMemsetAsync(counts + 7, 0, 4, st);
         ctx->timed_begin(RM_KIND_SHADOW);
-        if (ct) k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt + 6);
-        else k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Fb, Ac, sq, counts + 2, R->s_cap, cnt + 6);
+        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, counts + 2, counts + 7, cnt + 6);
+        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, counts + 2, counts + 7, cnt + 6);
         ctx->timed_end();
-        ctx->launches++;
+        k_accum_shadow<<<R->sm_count * 8, 256, 0, st>>>(Fb, Ac, sq, counts + 2, R->s_cap);
+        ctx->launches += 2;
     };
 
     // ---- direct light at the primary hit
@@ -247,9 +253,12 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         int cur = 0;
         for (int depth = 1; depth <= kMaxRayDepth; depth++) {
             PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
+            PathJob pj;
+            pj.Q = Qin;
+            cudaMemsetAsync(counts + 6, 0, 4, st);
             ctx->timed_begin(RM_KIND_PATHS);
-            if (ct) k_trace_paths<true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt + 3);
-            else k_trace_paths<false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, Qin, counts + cur, cnt + 3);
+            if (ct) k_trace<PathJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, counts + cur, counts + 6, cnt + 3);
+            else k_trace<PathJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, counts + cur, counts + 6, cnt + 3);
             ctx->timed_end();
             cudaMemsetAsync(counts + (cur ^ 1), 0, 4, st);
             cudaMemsetAsync(counts + 2, 0, 4, st);

@@ -182,15 +182,19 @@ def test_render_matches_reference_statistically(ref, which, spp):
         scene, args = scenes.glossy_dielectric(60_000, 128, 72, spp)
     R, ctx = _setup(ref, scene)
     gpu = _planes(ctx.render(args, seed=5))
+    gpu_b = _planes(ctx.render(args, seed=6))
     ca = _planes(R.render(args, threads=8, seed_base=100))
     cb = _planes(R.render(args, threads=8, seed_base=200))
     for k in ("Dd", "Ds", "Id", "Is"):
         floor = _rel_mse(ca[k], cb[k])
         got = _rel_mse(gpu[k], ca[k])
         assert got <= 1.5 * floor + 1e-6, (k, got, floor)
+    # total energy: the specular planes are heavy-tailed, so the run-to-run spread of either
+    # implementation (two seeds each) is the yardstick, with 1.5 % as the floor
     tot = lambda P: sum(P[k].sum() for k in P)
-    e_gpu, e_a, e_b = tot(gpu), tot(ca), tot(cb)
-    assert abs(e_gpu - e_a) <= max(0.015 * e_a, 3 * abs(e_a - e_b)), (e_gpu, e_a, e_b)
+    e_ga, e_gb, e_a, e_b = tot(gpu), tot(gpu_b), tot(ca), tot(cb)
+    tol = max(0.015 * e_a, 2.0 * abs(e_a - e_b), 2.0 * abs(e_ga - e_gb))
+    assert abs(0.5 * (e_ga + e_gb) - 0.5 * (e_a + e_b)) <= tol, (e_ga, e_gb, e_a, e_b)
     ctx.close()
 
 
