@@ -141,43 +141,33 @@ RM_DI V3 sample_gtr2_H(const Bsdf &B, Rng &gen, V3 tangent, V3 bitangent, float 
     return (fmul(sinTheta, cp) * tangent + fmul(sinTheta, sp) * bitangent) + cosTheta * B.s.surfaceNormal;
 }
 
-RM_DI void sample_brdf(const Bsdf &B, Rng &gen, V3 &outDir, V3 &brdfPdf, float &pdf, int &fails) {
-    V3 tangent, bitangent;
-    tangent_space_in(B.s.surfaceNormal, B.inDir, tangent, bitangent);
+// sampleCos (src/sampling.cpp:245-269) and sampleBRDF (203-236) share one rejection loop here: `ggx`
+// selects the proposal (cosine-weighted direction or GTR2 half-vector), so the BRDF evaluation exists
+// once in the instruction stream.  Draw order and arithmetic per try are the reference's.
+RM_DI void sample_lobe(const Bsdf &B, Rng &gen, bool ggx, V3 tangent, V3 bitangent, V3 &outDir, V3 &brdfPdf, float &pdf, int &fails) {
+#pragma unroll 1
     for (int T = 1; T <= kMaxTrys; T++) {
-        float cosTheta;
-        V3 H = sample_gtr2_H(B, gen, tangent, bitangent, cosTheta);
-        outDir = fmul(2.0f, dot(B.inDir, H)) * H - B.inDir;
-        float LdotH = dot(outDir, H), LdotN = dot(outDir, B.s.surfaceNormal);
-        if (LdotH <= 0.0f || LdotN <= 0.0f) pdf = 0.0f;
-        else pdf = fdiv(GTR2(cosTheta, B.s.roughness), fmul(4.0f, LdotH));
-        if (dot(outDir, B.s.shapeNormal) > 0.0f && pdf > 0.0f) {
-            brdfPdf = div_recip(get_brdf(B, outDir), pdf);
-            return;
+        if (ggx) {
+            float cosTheta;
+            V3 H = sample_gtr2_H(B, gen, tangent, bitangent, cosTheta);
+            outDir = fmul(2.0f, dot(B.inDir, H)) * H - B.inDir;
+            float LdotH = dot(outDir, H), LdotN = dot(outDir, B.s.surfaceNormal);
+            if (LdotH <= 0.0f || LdotN <= 0.0f) pdf = 0.0f;
+            else pdf = fdiv(GTR2(cosTheta, B.s.roughness), fmul(4.0f, LdotH));
+        } else {
+            float u = gen();
+            float phi = fmul(fmul(gen(), 2.0f), kPi);
+            float d = fsqrt(u);
+            float z = fsqrt(fsub(1.0f, fmul(d, d)));
+            float sp, cp;
+            sincosf(phi, &sp, &cp);
+            float x = fmul(d, cp), y = fmul(d, sp);
+            outDir = (x * tangent + y * bitangent) + z * B.s.surfaceNormal;
+            pdf = fdiv(dot(outDir, B.s.surfaceNormal), kPi);
         }
-        fails++;
-    }
-    pdf = 0.0f;
-    brdfPdf = splat3(0.0f);
-    outDir = splat3(CUDART_NAN_F);
-}
-
-RM_DI void sample_cos(const Bsdf &B, Rng &gen, V3 &outDir, V3 &brdfPdf, float &pdf, int &fails) {
-    V3 tangent, bitangent;
-    tangent_space_in(B.s.surfaceNormal, B.inDir, tangent, bitangent);
-    for (int T = 1; T <= kMaxTrys; T++) {
-        float u = gen();
-        float phi = fmul(fmul(gen(), 2.0f), kPi);
-        float d = fsqrt(u);
-        float z = fsqrt(fsub(1.0f, fmul(d, d)));
-        float sp, cp;
-        sincosf(phi, &sp, &cp);
-        float x = fmul(d, cp), y = fmul(d, sp);
-        outDir = (x * tangent + y * bitangent) + z * B.s.surfaceNormal;
-        pdf = fdiv(dot(outDir, B.s.surfaceNormal), kPi);
         if (dot(outDir, B.s.shapeNormal) > 0.0f && pdf > 0.0f) {
             brdfPdf = div_recip(get_brdf(B, outDir), pdf);
-            clamp_lum(brdfPdf);
+            if (!ggx) clamp_lum(brdfPdf);
             return;
         }
         fails++;
@@ -202,16 +192,19 @@ RM_DI void precise_refraction(const Bsdf &B, V3 &outDir, float &F) {
     F = fadd(R0, fmul(fsub(1.0f, R0), schlick(LdotN)));
 }
 
-// one-sample lobe pick (src/sampling.cpp:310-340)
+// one-sample lobe pick (src/sampling.cpp:310-340): both proposals are always drawn (cosine first, then
+// GGX - the order of the random stream), the pick uses a further draw
 RM_DI void sample_reflection(const Bsdf &B, Rng &gen, V3 &Dir, V3 &brdfPdf, int &fails) {
-    V3 Dir1, Dir2, b1, b2;
-    int fail1 = 0, fail2 = 0;
-    float pdf1, pdf2;
-    sample_cos(B, gen, Dir1, b1, pdf1, fail1);
-    sample_brdf(B, gen, Dir2, b2, pdf2, fail2);
-    float p1 = fdiv(pdf1, fadd(pdf1, pdf2));
-    if (gen() < p1) { Dir = Dir1; brdfPdf = b1; fails += fail1; }
-    else { Dir = Dir2; brdfPdf = b2; fails += fail2; }
+    V3 tangent, bitangent;
+    tangent_space_in(B.s.surfaceNormal, B.inDir, tangent, bitangent);
+    V3 dirs[2], bs[2];
+    float pdfs[2];
+    int fl[2] = {0, 0};
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) sample_lobe(B, gen, k == 1, tangent, bitangent, dirs[k], bs[k], pdfs[k], fl[k]);
+    float p1 = fdiv(pdfs[0], fadd(pdfs[0], pdfs[1]));
+    const int pick = gen() < p1 ? 0 : 1;
+    Dir = dirs[pick]; brdfPdf = bs[pick]; fails += fl[pick];
 }
 
 RM_DI V3 refract_dir(V3 V, V3 N, float eta) {

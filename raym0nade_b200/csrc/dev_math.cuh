@@ -20,13 +20,16 @@ struct V2 { float x, y; };
 struct V3 { float x, y, z; };
 
 #define RM_DI __device__ __forceinline__
+// out-of-line device function: one copy per kernel instead of one per call site (the shading kernels are
+// instruction-cache bound); arguments are scalars so they travel in registers
+#define RM_NI static __device__ __noinline__
 
 RM_DI float fmul(float a, float b) { return __fmul_rn(a, b); }
 RM_DI float fadd(float a, float b) { return __fadd_rn(a, b); }
 RM_DI float fsub(float a, float b) { return __fsub_rn(a, b); }
 RM_DI float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 RM_DI float fsqrt(float a) { return __fsqrt_rn(a); }
-RM_DI float frcp(float a) { return __fdiv_rn(1.0f, a); }
+RM_DI float frcp(float a) { return __frcp_rn(a); }          // correctly rounded, i.e. the same bits as 1.0f / a
 
 RM_DI V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 RM_DI V3 splat3(float s) { return mk3(s, s, s); }

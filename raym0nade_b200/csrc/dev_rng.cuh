@@ -46,6 +46,13 @@ __host__ __device__ inline float uniform_from_u32(uint32_t x) {
 
 enum : uint32_t { kStreamIndirect = 0u, kStreamDirect = 1u };
 
+#ifdef __CUDACC__
+// one out-of-line copy per kernel: every gen() call site would otherwise inline the ten rounds
+static __device__ __noinline__ Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+    return philox4x32_10(c0, c1, c2, 0u, k0, k1);
+}
+#endif
+
 struct Rng {
     uint32_t pixel, sample_stream;      // counter words 0,1: pixel id; sample index | stream << 31
     uint32_t k0, k1;                    // key = render seed
@@ -61,7 +68,7 @@ struct Rng {
     }
     RM_DI uint32_t next_u32() {
         uint32_t b = drawn >> 2;
-        if (b != block_id) { block = philox4x32_10(pixel, sample_stream, b, 0u, k0, k1); block_id = b; }
+        if (b != block_id) { block = philox_block(pixel, sample_stream, b, k0, k1); block_id = b; }
         uint32_t i = drawn & 3u;
         drawn++;
         return i == 0 ? block.x : (i == 1 ? block.y : (i == 2 ? block.z : block.w));

@@ -49,6 +49,7 @@ struct DevScene {
     const float *light_cdf;         // [total light faces]
     const float *sky_data;          // [h*w][3], premultiplied by texel solid angle
     const float *sky_cdf;           // [h*w]
+    const float *div255;            // [256] k / 255.0f, correctly rounded (RGBA8 decode without a division per channel)
     int32_t n_faces, n_nodes, n_materials, n_lights;
     int32_t sky_width, sky_height;
     int32_t any_cutout;             // some material has hasFullyTransparentPart

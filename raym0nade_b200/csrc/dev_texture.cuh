@@ -21,8 +21,9 @@ RM_DI int wrap_index(int x, int m) {           // the `_mod` lambda, src/materia
 
 RM_DI float lerp2(float a, float b, float t) { return fadd(fmul(a, fsub(1.0f, t)), fmul(b, t)); }
 
-// bilinear RGBA8: all four channels
-RM_DI V4 bilinear_rgba(const uint8_t *data, int w, int h, float u, float v) {
+// bilinear RGBA8: all four channels.  `lut` holds k / 255.0f (glm vec4 / scalar is a true division; the
+// table entries are that quotient, correctly rounded, so the decode is bit-identical without dividing)
+RM_DI V4 bilinear_rgba(const uint8_t *data, const float *__restrict__ lut, int w, int h, float u, float v) {
     float x = fmul(u, float(w)), y = fmul(v, float(h));
     int x0 = int(floorf(x)), y0 = int(floorf(y));
     float dx = fsub(x, float(x0)), dy = fsub(y, float(y0));
@@ -32,8 +33,7 @@ RM_DI V4 bilinear_rgba(const uint8_t *data, int w, int h, float u, float v) {
     const uchar4 *p = reinterpret_cast<const uchar4 *>(data);
     uchar4 t00 = __ldg(p + (y0 * w + x0)), t01 = __ldg(p + (y0 * w + x1));
     uchar4 t10 = __ldg(p + (y1 * w + x0)), t11 = __ldg(p + (y1 * w + x1));
-#define RM_CH(c) lerp2(lerp2(fdiv(float(t00.c), 255.0f), fdiv(float(t01.c), 255.0f), dx), \
-                       lerp2(fdiv(float(t10.c), 255.0f), fdiv(float(t11.c), 255.0f), dx), dy)
+#define RM_CH(c) lerp2(lerp2(__ldg(lut + t00.c), __ldg(lut + t01.c), dx), lerp2(__ldg(lut + t10.c), __ldg(lut + t11.c), dx), dy)
     V4 r;
     r.x = RM_CH(x); r.y = RM_CH(y); r.z = RM_CH(z); r.w = RM_CH(w);
 #undef RM_CH
@@ -69,21 +69,30 @@ RM_DI void mip_select(const DevTexture &t, float depth, int &level, int &next, f
     blend = fsub(depth, float(level));
 }
 
-RM_DI V4 texture_rgba(const DevScene &S, int tex, float u, float v, float depth) {
-    const DevTexture t = S.textures[tex];
+// ImageData::get<vec4> (src/material.cpp:81-94): trilinear = two bilinear fetches blended by the LOD fraction
+RM_NI V4 texture_rgba_impl(const DevTexture *__restrict__ textures, const uint8_t *__restrict__ texels, const float *__restrict__ lut,
+                           int tex, float u, float v, float depth) {
+    const DevTexture t = textures[tex];
     v = fsub(1.0f, v);
     int level, next;
     float blend;
     mip_select(t, depth, level, next, blend);
-    V4 a = bilinear_rgba(S.texels + t.offset[level], t.width >> level, t.height >> level, u, v);
-    V4 b = bilinear_rgba(S.texels + t.offset[next], t.width >> next, t.height >> next, u, v);
+    V4 lv[2];
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        const int l = k ? next : level;
+        lv[k] = bilinear_rgba(texels + t.offset[l], lut, t.width >> l, t.height >> l, u, v);
+    }
     V4 r;
-    r.x = lerp2(a.x, b.x, blend); r.y = lerp2(a.y, b.y, blend);
-    r.z = lerp2(a.z, b.z, blend); r.w = lerp2(a.w, b.w, blend);
+    r.x = lerp2(lv[0].x, lv[1].x, blend); r.y = lerp2(lv[0].y, lv[1].y, blend);
+    r.z = lerp2(lv[0].z, lv[1].z, blend); r.w = lerp2(lv[0].w, lv[1].w, blend);
     return r;
 }
+RM_DI V4 texture_rgba(const DevScene &S, int tex, float u, float v, float depth) {
+    return texture_rgba_impl(S.textures, S.texels, S.div255, tex, u, v, depth);
+}
 
-RM_DI V3 texture_rgb(const DevScene &S, int tex, float u, float v, float depth) {
+RM_DI V3 texture_rgb(const DevScene &S, int tex, float u, float v, float depth) {   // one call site (normal maps)
     const DevTexture t = S.textures[tex];
     v = fsub(1.0f, v);
     int level, next;
@@ -99,11 +108,14 @@ RM_DI float lod_of(const DevScene &S, int tex, float duv) {
     return isnan(duv) ? 0.0f : log2f(fmul(duv, float(S.textures[tex].width)));
 }
 
+// gammaPow (src/material.cpp:337-346)
+RM_NI float gamma_pow(float c) { return powf(c, 2.2f); }
+
 RM_DI V4 mat_diffuse(const DevScene &S, const DevMaterial &m, float u, float v, float duv) {
     V4 c;
     if (m.tex[0] < 0) { c.x = c.y = c.z = c.w = 1.0f; return c; }
     c = texture_rgba(S, m.tex[0], u, v, lod_of(S, m.tex[0], duv));
-    c.x = powf(c.x, 2.2f); c.y = powf(c.y, 2.2f); c.z = powf(c.z, 2.2f);   // gammaPow
+    c.x = gamma_pow(c.x); c.y = gamma_pow(c.y); c.z = gamma_pow(c.z);
     return c;
 }
 
@@ -116,7 +128,7 @@ RM_DI float mat_diffuse_alpha0(const DevScene &S, const DevMaterial &m, float u,
 RM_DI V3 mat_emissive(const DevScene &S, const DevMaterial &m, float u, float v, float duv) {
     if (m.tex[2] < 0) return splat3(0.0f);
     V4 c = texture_rgba(S, m.tex[2], u, v, lod_of(S, m.tex[2], duv));
-    return mk3(powf(c.x, 2.2f), powf(c.y, 2.2f), powf(c.z, 2.2f));
+    return mk3(gamma_pow(c.x), gamma_pow(c.y), gamma_pow(c.z));
 }
 
 RM_DI V3 mat_normal(const DevScene &S, const DevMaterial &m, float u, float v, float duv) {

@@ -150,10 +150,15 @@ RM_DI bool transparent_test(const DevScene &S, const RaySetup &r, float t, int f
 //   void hit(int i, float t, int face);                  closest-hit result (kOcclusion == false)
 //   void visibility(int i, bool occluded);               rayHit_test result (kOcclusion == true)
 constexpr int kTraceChunk = 64;
-constexpr int kRefillLive = 22;
+
+struct TraceTune {
+    int refill_live;     // refill idle lanes once fewer than this many lanes are busy
+    int w_inner, w_leaf; // vote weights: the inner step runs when n_inner * w_inner >= n_leaf * w_leaf
+};
 
 template <class Job, bool COUNT>
-RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt) {
+RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt,
+                        const TraceTune tune) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -207,7 +212,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
         }
         unsigned live = __ballot_sync(FULL, active);
         if (live == 0u) break;
-        const int need = (exhausted && chunk_next >= chunk_end) ? 1 : kRefillLive;
+        const int need = (exhausted && chunk_next >= chunk_end) ? 1 : tune.refill_live;
 
         // ---- trace: one step per iteration - either every lane that sits on an inner node tests its two
         // children, or every lane that holds a leaf tests its next triangle - whichever has more lanes
@@ -217,7 +222,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
             const bool wantI = active && cur >= 0;
             const int nI = __popc(__ballot_sync(FULL, wantI));
             const int nL = __popc(live) - nI;
-            if (nI >= nL) {
+            if (nI * tune.w_inner >= nL * tune.w_leaf) {
                 if (wantI) {
                     const float4 *nd = S.nodes + (size_t(cur) << 2);        // children 2u, 2u+1: one 64-byte block
                     const float4 a0 = __ldg(nd), b0 = __ldg(nd + 1), a1 = __ldg(nd + 2), b1 = __ldg(nd + 3);

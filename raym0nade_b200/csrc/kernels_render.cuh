@@ -4,11 +4,16 @@
 // reference's procedure (including its idiosyncrasies) per sample:
 //   k_gbuffer        466-495   primary hit -> HitInfo, sky emission on a miss, red nudge
 //   k_direct_gen     425-437 + sampleDirectLight (src/sampling.cpp:467-527): one NEE sample -> shadow queue
-//   k_indirect_gen   314-423   first vertex of an indirect path from the cached primary hit
-//   k_trace_paths    Model::rayHit over the path queue (closest hit)
-//   k_shade          121-312   one sampleRay level: miss/emission/NEE-termination/continue
-//   k_trace_shadow   Model::rayHit_test over the shadow queue + accumulateInwardRadiance
-//   k_resolve        510-549   firefly clamp (top-1 hold-back), exposure, variance finalise
+//   k_regen          314-423   first vertex of an indirect path from the cached primary hit; tops the
+//                              path queue up with fresh (pixel, sample) items whenever paths have ended
+//   k_trace<PathJob> Model::rayHit over the path queue (closest hit)
+//   k_surface        128-166   miss -> sky, getHitInfo, emissive hit -> the surface record of the vertex
+//   k_bounce         143-312   one sampleRay level: Fresnel / Russian roulette / reflect or refract
+//   k_nee            207-221   sampleDirectLight at a terminating vertex: 1..6 shadow items
+//   k_trace<ShadowJob> + k_accum_shadow   Model::rayHit_test + accumulateInwardRadiance
+//   k_commit_hold / k_finalise 510-549   firefly clamp (top-1 hold-back), exposure, variance finalise
+// One stage = one small kernel: the shading code is branchy and, fused into one kernel, it was bound by
+// instruction-cache misses (234 KB of SASS, 90 % of stall samples "no instruction", profiles/).
 // Recursion is unrolled into a linear chain: a path carries the product of the per-level
 // bsdfPdf*absorb (T), the first-vertex bsdfPdf (B0, kept apart because
 // accumulateInwardRadiance splits on it, src/image.cpp:630-659) and the product of the
@@ -34,8 +39,20 @@ struct PathQueue {
     int *flags;              // depth | exclude << 8 | n_medium << 16
     int *med_id;             // [kMediumSlots][cap]
     float *med;              // [4][kMediumSlots][cap]  ior, absorb rgb
-    float *hit_t;
+    float *hit_t;            // INF = this entry is finished (miss, emissive hit) - k_bounce skips it
     int *hit_face;
+    float *surf;             // [22][cap]  the vertex's HitInfo (written by k_surface), field order of RmHitInfo
+    float *hdP;              // [6][cap]   dPdx, dPdy at the hit (calc_dPdxy)
+};
+
+// a path that ended in next-event estimation (src/render.cpp:207-221, 249-263): k_nee draws its light samples
+struct __align__(16) NeeRequest {
+    int src;                 // index into the path queue the vertex lives in
+    int count;               // sampleCount[depth] | pass_absorb << 8
+    float factor;            // the `scaling` of the terminating branch: 1/P_reflect [/(1-P_RR)] or 1/(1-P_reflect) [...]
+    unsigned drawn;          // position of the sample's random stream
+    float absorb[3];
+    int _pad;
 };
 
 // one NEE / terminal sample waiting for its visibility test
@@ -102,6 +119,10 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
     return mk3((float)pow((double)a.x, (double)k), (float)pow((double)a.y, (double)k), (float)pow((double)a.z, (double)k));
 }
 
+// device-side pipeline state (ints): queue lengths, cursors
+enum { C_Q0 = 0, C_Q1 = 1, C_SQ = 2, C_OVERFLOW = 3, C_GLASS = 4, C_GLASS_LIST = 5, C_CUR_PATH = 6, C_CUR_SHADOW = 7,
+       C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_COUNT = 16 };
+
 // warp-aggregated slot allocation
 RM_DI int alloc_slot(int *counter, bool want) {
     unsigned mask = __ballot_sync(0xffffffffu, want);   // every lane of the warp calls this (loops are padded to whole warps)
@@ -125,7 +146,7 @@ RM_DI void accum_basic(float *r4, V3 inrad, float weight) {          // accumula
 }
 
 // accumulateInwardRadiance (src/image.cpp:630-659): split into demodulated diffuse + specular
-RM_DI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) {
+RM_NI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) {
     if (length(l) < kEps) return;
     V3 base0 = normalize(baseColor);
     if (length(baseColor) < kEps) { accum_basic(rs, l * b, w); return; }
@@ -260,18 +281,22 @@ RM_DI NeeOut nee_sample(const DevScene &S, const Bsdf &B, Rng &gen, const float 
     return o;
 }
 
-RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool want, int pixel_tag, V3 org, const NeeOut &n, V3 b, V3 l, float w) {
-    int slot = alloc_slot(count, want);
-    if (!want) return;
-    if (slot >= cap) { atomicExch(overflow, 1); return; }
+RM_DI void write_shadow(ShadowItem *dst_item, int pixel_tag, V3 org, const NeeOut &n, V3 b, V3 l, float w) {
     ShadowItem it;
     it.o[0] = org.x; it.o[1] = org.y; it.o[2] = org.z; it.aim = n.aim;
     it.d[0] = n.dir.x; it.d[1] = n.dir.y; it.d[2] = n.dir.z; it.pixel = pixel_tag;
     it.b[0] = b.x; it.b[1] = b.y; it.b[2] = b.z; it.weight = w;
     it.l[0] = l.x; it.l[1] = l.y; it.l[2] = l.z; it.vis = 0.0f;
-    float4 *dst = reinterpret_cast<float4 *>(q + slot);
+    float4 *dst = reinterpret_cast<float4 *>(dst_item);
     const float4 *src = reinterpret_cast<const float4 *>(&it);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
+RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool want, int pixel_tag, V3 org, const NeeOut &n, V3 b, V3 l, float w) {
+    int slot = alloc_slot(count, want);
+    if (!want) return;
+    if (slot >= cap) { atomicExch(overflow, 1); return; }
+    write_shadow(q + slot, pixel_tag, org, n, b, l, w);
 }
 
 // ------------------------------------------------------------------ direct light at the primary hit
@@ -331,12 +356,42 @@ RM_DI void store_path(const PathQueue &Q, int i, int pixel, unsigned sample, uns
     }
 }
 
+// ------------------------------------------------------------------ work items of the indirect sample loop
+// item j in [0, items_a): sample k = j / npix of pixel j % npix                      (every pixel, k < n_a)
+// item j in [items_a, total): j' = j - items_a, sample n_a + j' / n_glass of glass pixel list[j' % n_glass]
+// (glass pixels take 16x the indirect samples, src/render.cpp:498-501); local sample k is the global
+// sample index s_begin + k * s_stride (interleaved over GPUs).
+struct ItemSpace {
+    long long items_a, total;
+    int npix, n_glass, n_a;
+    const int *glass_list;
+    int s_begin, s_stride;
+};
+
+// One thread: how many fresh items fit into the path queue this round (the queue is topped up after
+// k_bounce compacted the surviving paths into it), and where they start.
+__global__ void k_plan(int *C, int q_slot, int cap, long long total) {
+    long long cur = (long long)(unsigned)C[C_ITEM_LO] | ((long long)C[C_ITEM_HI] << 32);
+    int free_slots = cap - min(C[q_slot], cap);
+    long long left = total - cur;
+    int take = (int)(left < (long long)free_slots ? left : (long long)free_slots);
+    if (take < 0) take = 0;
+    C[C_PLAN_TAKE] = take;
+    C[C_PLAN_LO] = (int)(unsigned)(cur & 0xffffffffLL);
+    C[C_PLAN_HI] = (int)(cur >> 32);
+    cur += take;
+    C[C_ITEM_LO] = (int)(unsigned)(cur & 0xffffffffLL);
+    C[C_ITEM_HI] = (int)(cur >> 32);
+    C[C_CUR_PATH] = 0;
+}
+
 // ------------------------------------------------------------------ first vertex of an indirect path
 // sampleIndirectLightFromFirstIntersection (src/render.cpp:314-423) up to the new ray.
-__global__ void __launch_bounds__(128) k_indirect_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, const int *__restrict__ pix_list,
-                                                      int npix_list, int s_begin, int s_stride, unsigned long long seed,
-                                                      PathQueue Q, int *q_count) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
+                                               PathQueue Q, int *q_count) {
+    const int n_items = C[C_PLAN_TAKE];
+    const long long first = (long long)(unsigned)C[C_PLAN_LO] | ((long long)C[C_PLAN_HI] << 32);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31); i += gridDim.x * blockDim.x) {
         bool want = false;
         int p = 0;
         unsigned s = 0;
@@ -347,9 +402,11 @@ __global__ void __launch_bounds__(128) k_indirect_gen(DevScene S, DevArgs A, Fra
         Medium med;
         med.n = 0;
         if (i < n_items) {
-            int li = int(i % npix_list);
-            p = pix_list ? pix_list[li] : li;
-            s = unsigned(s_begin + int(i / npix_list) * s_stride);
+            const long long j = first + i;
+            int k;
+            if (j < I.items_a) { k = int(j / I.npix); p = int(j % I.npix); }
+            else { const long long jj = j - I.items_a; k = I.n_a + int(jj / I.n_glass); p = I.glass_list[int(jj % I.n_glass)]; }
+            s = unsigned(I.s_begin + k * I.s_stride);
             int n_ind = Fb.n_ind[p];
             Surface g = load_hitinfo(Fb.gbuffer + p);
             if ((int)s < n_ind && !(length(g.emission) > 0.0f)) {
@@ -414,169 +471,293 @@ struct PathJob {
     RM_DI void visibility(int, bool) const {}
 };
 
+// ------------------------------------------------------------------ the surface record of a path vertex
+RM_DI void store_surface(const PathQueue &Q, int i, const Surface &s, V3 dPdx, V3 dPdy) {
+    const int c = Q.cap;
+    float *f = Q.surf + i;
+    f[0 * c] = s.shapeNormal.x; f[1 * c] = s.shapeNormal.y; f[2 * c] = s.shapeNormal.z;
+    f[3 * c] = s.surfaceNormal.x; f[4 * c] = s.surfaceNormal.y; f[5 * c] = s.surfaceNormal.z;
+    f[6 * c] = s.emission.x; f[7 * c] = s.emission.y; f[8 * c] = s.emission.z;
+    f[9 * c] = s.baseColor.x; f[10 * c] = s.baseColor.y; f[11 * c] = s.baseColor.z;
+    f[12 * c] = s.position.x; f[13 * c] = s.position.y; f[14 * c] = s.position.z;
+    f[15 * c] = s.specular; f[16 * c] = s.roughness; f[17 * c] = s.metallic; f[18 * c] = s.opacity; f[19 * c] = s.eta;
+    f[20 * c] = __int_as_float(s.id); f[21 * c] = __int_as_float(s.entering ? 1 : 0);
+    float *h = Q.hdP + i;
+    h[0 * c] = dPdx.x; h[1 * c] = dPdx.y; h[2 * c] = dPdx.z; h[3 * c] = dPdy.x; h[4 * c] = dPdy.y; h[5 * c] = dPdy.z;
+}
+
+RM_DI Surface load_surface(const PathQueue &Q, int i) {
+    const int c = Q.cap;
+    const float *f = Q.surf + i;
+    Surface s;
+    s.shapeNormal = mk3(f[0 * c], f[1 * c], f[2 * c]);
+    s.surfaceNormal = mk3(f[3 * c], f[4 * c], f[5 * c]);
+    s.emission = mk3(f[6 * c], f[7 * c], f[8 * c]);
+    s.baseColor = mk3(f[9 * c], f[10 * c], f[11 * c]);
+    s.position = mk3(f[12 * c], f[13 * c], f[14 * c]);
+    s.specular = f[15 * c]; s.roughness = f[16 * c]; s.metallic = f[17 * c]; s.opacity = f[18 * c]; s.eta = f[19 * c];
+    s.id = __float_as_int(f[20 * c]);
+    s.entering = __float_as_int(f[21 * c]) != 0;
+    return s;
+}
+
+RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
+    const int c = Q.cap;
+    med.n = n;
+    for (int k = 0; k < n; k++) {
+        med.id[k] = Q.med_id[k * c + i];
+        med.ior[k] = Q.med[(4 * k) * c + i];
+        med.ab[k] = mk3(Q.med[(4 * k + 1) * c + i], Q.med[(4 * k + 2) * c + i], Q.med[(4 * k + 3) * c + i]);
+    }
+}
+
+// sampleRay up to the surface (src/render.cpp:128-166): a miss returns the sky (unless direct light is
+// excluded), a hit builds the HitInfo, an emissive hit returns its emission.  Finished entries get
+// hit_t = INF.  Thread 0 also resets the counters the later stages of this round append to.
+__global__ void __launch_bounds__(128) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
+    const int n = min(C[q_slot], Q.cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; C[C_SQ] = 0; C[C_CUR_SHADOW] = 0; }
+    const int c = Q.cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = Q.pixel[i];
+        const int fl = Q.flags[i];
+        const bool exclude = (fl & 256) != 0;
+        const V3 dir = mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
+        const float t = Q.hit_t[i];
+        bool add = false;                       // this vertex ends the path with a light sample (1, light, 1)
+        V3 light = splat3(0.0f);
+        if (t == CUDART_INF_F) {
+            // miss (src/render.cpp:129-133)
+            if (!(exclude || S.sky_width == 0)) { light = sky_get(S, dir) * splat3(1.0f); add = true; }
+        } else {
+            const V3 org = mk3(Q.o[i], Q.o[c + i], Q.o[2 * c + i]);
+            RayDiff bd;
+            bd.dPdx = mk3(Q.diff[0 * c + i], Q.diff[1 * c + i], Q.diff[2 * c + i]);
+            bd.dPdy = mk3(Q.diff[3 * c + i], Q.diff[4 * c + i], Q.diff[5 * c + i]);
+            bd.dDdx = mk3(Q.diff[6 * c + i], Q.diff[7 * c + i], Q.diff[8 * c + i]);
+            bd.dDdy = mk3(Q.diff[9 * c + i], Q.diff[10 * c + i], Q.diff[11 * c + i]);
+            Surface sf = default_surface();
+            sf.position = org + dir * t;
+            V3 dPdx, dPdy;
+            get_hit_info(S, Q.hit_face[i], t, dir, bd, dPdx, dPdy, sf);
+            if (length(sf.emission) > kEps) {
+                // emissive surface (src/render.cpp:162-166)
+                if (!exclude) {
+                    Medium med;
+                    load_medium(Q, i, fl >> 16, med);
+                    light = sf.emission * get_absorb(medium_absorb(med), t);
+                    add = true;
+                }
+                Q.hit_t[i] = CUDART_INF_F;
+            } else store_surface(Q, i, sf, dPdx, dPdy);
+        }
+        if (add) {
+            const V3 T = mk3(Q.T[i], Q.T[c + i], Q.T[2 * c + i]), B0 = mk3(Q.B0[i], Q.B0[c + i], Q.B0[2 * c + i]);
+            const float inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));
+            add_indirect(Ac, Fb, p, B0, light * T, fmul(fmul(1.0f, Q.W[i]), inv_spp));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ one sampleRay level
 __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6};
 
-__global__ void __launch_bounds__(128) k_shade(DevScene S, FrameBuffers Fb, Accum Ac, unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
-                                               PathQueue Qout, int *out_count, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+// sampleRay from the surface on (src/render.cpp:143-312): roughness regularisation, Russian roulette,
+// Fresnel split, then either a NEE termination (-> NeeRequest) or a sampled continuation (-> Qout).
+__global__ void __launch_bounds__(128) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
+                                                PathQueue Qout, int *out_count, NeeRequest *nq, int *nee_count) {
     const int n = min(*in_count, Qin.cap);
     const int n_pad = (n + 31) & ~31;
+    const int c = Qin.cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-        bool cont = false;            // continue the path
-        int n_nee = 0;                // NEE samples to emit (terminating vertex)
-        bool alive = i < n;
-        const int c = Qin.cap;
+        bool cont = false, terminate = false;
         int p = 0, depth = 0;
         unsigned sample = 0;
-        bool exclude = false;
         Rng gen;
-        V3 dir = splat3(0.0f), T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), bsdfPdf = splat3(CUDART_NAN_F), absorb = splat3(1.0f);
-        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f, inv_spp = 0.0f;
+        V3 T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), absorb = splat3(1.0f), pos = splat3(0.0f);
+        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f;
         bool nee_pass_absorb = false, doDirect = false;
-        RayDiff bd, next;
+        RayDiff next;
         Medium med;
         med.n = 0;
-        Bsdf B;
-        B.s = default_surface();
-        B.inDir = splat3(0.0f);
-        float lw[kMaxLights];
-        float lw_total = 0.0f;
-        if (alive) {
+        const float t = i < n ? Qin.hit_t[i] : CUDART_INF_F;
+        if (t != CUDART_INF_F) {
             p = Qin.pixel[i];
             sample = Qin.sample[i];
-            int fl = Qin.flags[i];
+            const int fl = Qin.flags[i];
             depth = fl & 255;
-            exclude = (fl & 256) != 0;
-            med.n = fl >> 16;
-            for (int k = 0; k < med.n; k++) {
-                med.id[k] = Qin.med_id[k * c + i];
-                med.ior[k] = Qin.med[(4 * k) * c + i];
-                med.ab[k] = mk3(Qin.med[(4 * k + 1) * c + i], Qin.med[(4 * k + 2) * c + i], Qin.med[(4 * k + 3) * c + i]);
-            }
-            V3 org = mk3(Qin.o[i], Qin.o[c + i], Qin.o[2 * c + i]);
-            dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
+            load_medium(Qin, i, fl >> 16, med);
+            const V3 dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
             T = mk3(Qin.T[i], Qin.T[c + i], Qin.T[2 * c + i]);
             B0 = mk3(Qin.B0[i], Qin.B0[c + i], Qin.B0[2 * c + i]);
             W = Qin.W[i];
             rough = Qin.rough[i];
-            inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));
             gen.init(seed, (unsigned)p, sample, kStreamIndirect, Qin.drawn[i]);
-            V3 *dv = &bd.dPdx;
-#pragma unroll
-            for (int k = 0; k < 4; k++) dv[k] = mk3(Qin.diff[(3 * k) * c + i], Qin.diff[(3 * k + 1) * c + i], Qin.diff[(3 * k + 2) * c + i]);
-            const float t = Qin.hit_t[i];
-            const int face = Qin.hit_face[i];
-            if (t == CUDART_INF_F) {
-                // miss (src/render.cpp:129-133)
-                if (!(exclude || S.sky_width == 0)) {
-                    V3 l = (sky_get(S, dir) * splat3(1.0f)) * T;
-                    add_indirect(Ac, Fb, p, B0, l, fmul(fmul(1.0f, W), inv_spp));
+            RayDiff bd;                                   // only the direction differentials are used below
+            bd.dPdx = bd.dPdy = splat3(0.0f);
+            bd.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
+            bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
+            Bsdf B;
+            B.inDir = -dir;
+            B.s = load_surface(Qin, i);
+            pos = B.s.position;
+            const float ior = B.s.eta;
+            rough = fmaxf(rough, fmul(1.0f, B.s.roughness));
+            B.s.roughness = fmaxf(B.s.roughness, rough);
+            const float P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
+            doDirect = P_RR < 0.9f;
+            absorb = get_absorb(medium_absorb(med), t);
+            float P_reflect = 1.0f, F = 0.0f;
+            V3 refr;
+            if (B.s.opacity < kEps) {
+                // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
+                float eta1 = medium_ior(med), eta2;
+                if (B.s.entering) eta2 = fmaxf(eta1, B.s.eta);
+                else {
+                    medium_erase(med, B.s.id);
+                    eta2 = medium_ior(med);
+                    medium_insert(med, B.s.id, B.s.eta, B.s.baseColor);
+                }
+                B.s.eta = fdiv(eta1, eta2);
+                precise_refraction(B, refr, F);
+                if (med.n == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
+                else P_reflect = F;
+                P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
+            }
+            int fails = 0;
+            V3 bsdfPdf = splat3(CUDART_NAN_F);
+            if (gen() <= P_reflect) {
+                doDirect = doDirect && B.s.entering && med.n == 0;
+                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                    terminate = true;
+                    nee_factor = fdiv(1.0f, P_reflect);
+                    if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
+                } else {
+                    sample_reflection(B, gen, newDir, bsdfPdf, fails);
+                    bsdfPdf = div_true(bsdfPdf, P_reflect);
+                    if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+                    V3 dDdx, dDdy;
+                    calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
+                    next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
+                    next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
+                    next.dDdx = dDdx; next.dDdy = dDdy;
                 }
             } else {
-                B.inDir = -dir;
-                B.s.position = org + dir * t;
-                V3 dPdx, dPdy;
-                get_hit_info(S, face, t, dir, bd, dPdx, dPdy, B.s);
-                const float ior = B.s.eta;
-                rough = fmaxf(rough, fmul(1.0f, B.s.roughness));
-                B.s.roughness = fmaxf(B.s.roughness, rough);
-                const float P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
-                doDirect = P_RR < 0.9f;
-                absorb = get_absorb(medium_absorb(med), t);
-                if (length(B.s.emission) > kEps) {
-                    if (!exclude) {
-                        V3 l = (B.s.emission * absorb) * T;
-                        add_indirect(Ac, Fb, p, B0, l, fmul(fmul(1.0f, W), inv_spp));
-                    }
+                doDirect = doDirect && !B.s.entering && med.n == 1;
+                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                    terminate = true;
+                    nee_pass_absorb = true;
+                    nee_factor = fdiv(1.0f, fsub(1.0f, P_reflect));
+                    if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
                 } else {
-                    float P_reflect = 1.0f, F = 0.0f;
-                    V3 refr;
-                    if (B.s.opacity < kEps) {
-                        // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
-                        float eta1 = medium_ior(med), eta2;
-                        if (B.s.entering) eta2 = fmaxf(eta1, B.s.eta);
-                        else {
-                            medium_erase(med, B.s.id);
-                            eta2 = medium_ior(med);
-                            medium_insert(med, B.s.id, B.s.eta, B.s.baseColor);
-                        }
-                        B.s.eta = fdiv(eta1, eta2);
-                        precise_refraction(B, refr, F);
-                        if (med.n == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
-                        else P_reflect = F;
-                        P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
+                    if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
+                    else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
+                    // refraction passes the incoming differentials through unchanged (src/render.cpp:268,273)
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        (&next.dPdx)[k] = mk3(Qin.diff[(3 * k) * c + i], Qin.diff[(3 * k + 1) * c + i], Qin.diff[(3 * k + 2) * c + i]);
                     }
-                    int fails = 0;
-                    bool terminate = false;
-                    if (gen() <= P_reflect) {
-                        doDirect = doDirect && B.s.entering && med.n == 0;
-                        if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                            terminate = true;
-                            nee_factor = fdiv(1.0f, P_reflect);
-                            if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                        } else {
-                            sample_reflection(B, gen, newDir, bsdfPdf, fails);
-                            bsdfPdf = div_true(bsdfPdf, P_reflect);
-                            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-                            V3 dDdx, dDdy;
-                            calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
-                            next.dPdx = dPdx; next.dPdy = dPdy; next.dDdx = dDdx; next.dDdy = dDdy;
-                        }
-                    } else {
-                        doDirect = doDirect && !B.s.entering && med.n == 1;
-                        if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                            terminate = true;
-                            nee_pass_absorb = true;
-                            nee_factor = fdiv(1.0f, fsub(1.0f, P_reflect));
-                            if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                        } else {
-                            if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
-                            else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
-                            next = bd;
-                            bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
-                            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-                            if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
-                            else medium_erase(med, B.s.id);
-                        }
-                    }
-                    if (terminate) {
-                        n_nee = c_sampleCount[depth];
-                        if (S.sky_width == 0) { lw_total = light_weights(S, B, lw); if (lw_total == 0.0f) n_nee = 0; }
-                    } else if (isfinite_any(newDir) && depth != kMaxRayDepth) {
-                        cont = true;
-                        bsdfPdf = bsdfPdf * absorb;
-                        T = T * bsdfPdf;
-                        if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
-                    }
+                    next.dDdx = bd.dDdx; next.dDdy = bd.dDdy;
+                    bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
+                    if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+                    if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
+                    else medium_erase(med, B.s.id);
                 }
             }
+            if (terminate) {
+                // the light samples see the regularised roughness and the relative eta of this vertex
+                Qin.surf[16 * c + i] = B.s.roughness;
+                Qin.surf[19 * c + i] = B.s.eta;
+            } else if (isfinite_any(newDir) && depth != kMaxRayDepth) {
+                cont = true;
+                bsdfPdf = bsdfPdf * absorb;
+                T = T * bsdfPdf;
+                if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
+            }
         }
-        // NEE samples of a terminating vertex: sampleDirectLight(bsdf, model, gen, sampleCount[depth])
-        const int cnt = n_nee;
-        int max_nee = cnt;
+        const int ns = alloc_slot(nee_count, terminate);
+        if (terminate) {
+            NeeRequest rq;
+            rq.src = i;
+            rq.count = c_sampleCount[depth] | (nee_pass_absorb ? 256 : 0);
+            rq.factor = nee_factor;
+            rq.drawn = gen.drawn;
+            rq.absorb[0] = absorb.x; rq.absorb[1] = absorb.y; rq.absorb[2] = absorb.z;
+            rq._pad = 0;
+            float4 *dst = reinterpret_cast<float4 *>(nq + ns);
+            const float4 *src = reinterpret_cast<const float4 *>(&rq);
+            dst[0] = src[0]; dst[1] = src[1];
+        }
+        const int slot = alloc_slot(out_count, cont);
+        if (cont && slot < Qout.cap)
+            store_path(Qout, slot, p, sample, gen.drawn, pos, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
+    }
+}
+
+// ------------------------------------------------------------------ NEE at a terminating vertex
+// sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every NeeRequest.
+// The request reserves its 1..6 shadow-queue slots up front; a sample that comes out invalid leaves a
+// null item (aim = NaN) that the visibility pass skips.
+__global__ void __launch_bounds__(128) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
+                                             const int *__restrict__ nee_count, int nq_cap, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+    const int n = min(*nee_count, nq_cap);
+    const int n_pad = (n + 31) & ~31;
+    const int c = Q.cap;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += gridDim.x * blockDim.x) {
+        int cnt = 0, i = 0;
+        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0;
+        if (r < n) {
+            const float4 *src = reinterpret_cast<const float4 *>(nq + r);
+            q0 = __ldg(src); q1 = __ldg(src + 1);
+            i = __float_as_int(q0.x);
+            cnt = __float_as_int(q0.y) & 255;
+        }
+        // reserve cnt consecutive shadow slots per request: warp scan + one atomic per warp
+        int incl = cnt;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) max_nee = max(max_nee, __shfl_xor_sync(0xffffffffu, max_nee, o));
-        for (int k = 0; k < max_nee; k++) {
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(s_count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        if (cnt == 0) continue;
+        const bool pass_absorb = (__float_as_int(q0.y) & 256) != 0;
+        const float nee_factor = q0.z;
+        const V3 absorb = mk3(q1.x, q1.y, q1.z);
+        const int p = Q.pixel[i];
+        Rng gen;
+        gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, __float_as_uint(q0.w));
+        Bsdf B;
+        B.inDir = -mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
+        B.s = load_surface(Q, i);
+        const V3 T = mk3(Q.T[i], Q.T[c + i], Q.T[2 * c + i]), B0 = mk3(Q.B0[i], Q.B0[c + i], Q.B0[2 * c + i]);
+        const float W = Q.W[i];
+        const float inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));
+        float lw[kMaxLights];
+        float lw_total = 0.0f;
+        bool any = true;
+        if (S.sky_width == 0) { lw_total = light_weights(S, B, lw); any = lw_total != 0.0f; }
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
             NeeOut ne;
             ne.valid = false;
-            V3 b = splat3(0.0f), l = splat3(0.0f);
+            if (any) ne = nee_sample(S, B, gen, lw, lw_total, cnt);
+            V3 b = B0, l = splat3(0.0f);
             float w = 0.0f;
-            if (k < cnt) {
-                ne = nee_sample(S, B, gen, lw, lw_total, cnt);
-                if (ne.valid) {
-                    V3 sb = ne.bsdf * nee_factor;                 // scaling()
-                    V3 lt = ne.light * sb;                        // passBsdf: light *= bsdfPdf
-                    if (nee_pass_absorb) lt = lt * absorb;        // refract branch: passBsdf(samples, absorb) then one more level
-                    l = lt * T;
-                    b = B0;
-                    w = fmul(fmul(ne.weight, W), inv_spp);
-                }
+            if (ne.valid) {
+                V3 sb = ne.bsdf * nee_factor;                 // scaling()
+                V3 lt = ne.light * sb;                        // passBsdf: light *= bsdfPdf
+                if (pass_absorb) lt = lt * absorb;            // refract branch: passBsdf(samples, absorb) then one more level
+                l = lt * T;
+                w = fmul(fmul(ne.weight, W), inv_spp);
+            } else {
+                ne.dir = splat3(0.0f);
+                ne.aim = CUDART_NAN_F;                        // null item
             }
-            push_shadow(sq, s_count, s_cap, overflow, ne.valid, p, B.s.position, ne, b, l, w);
+            const int slot = base + k;
+            if (slot >= s_cap) { atomicExch(overflow, 1); break; }
+            write_shadow(sq + slot, p, B.s.position, ne, b, l, w);
         }
-        int slot = alloc_slot(out_count, cont);
-        if (cont && slot < Qout.cap)
-            store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
     }
 }
 
@@ -591,7 +772,7 @@ struct ShadowJob {
         const float4 a = __ldg(src), b = __ldg(src + 1);
         o = mk3(a.x, a.y, a.z); aim = a.w;
         d = mk3(b.x, b.y, b.z);
-        return true;
+        return !isnan(aim);                    // null item (k_nee): vis stays 0
     }
     RM_DI void hit(int, float, int) const {}
     RM_DI void visibility(int i, bool occluded) const { sq[i].vis = occluded ? 0.0f : 1.0f; }

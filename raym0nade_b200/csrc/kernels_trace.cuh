@@ -90,11 +90,11 @@ struct OccludedJob : RayListJob {
 
 template <class Job, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene S, Job job, int n_host, const int *__restrict__ n_dev,
-                                                                                int *cursor, unsigned long long *counters) {
+                                                                                int *cursor, unsigned long long *counters, TraceTune tune) {
     __shared__ int2 stack[kStackDepth * kTraceBlock];
     TraceCounters cnt = {0, 0, 0};
     const int n = n_dev ? min(*n_dev, n_host) : n_host;          // queue kernels read their length on the device
-    trace_engine<Job, COUNT>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt);
+    trace_engine<Job, COUNT>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt, tune);
     flush_counters(cnt, counters, COUNT);
 }
 

@@ -188,6 +188,10 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if (nsky && (!sc->sky_data || !sc->sky_cdf)) return rm_fail(RM_ERR_INVALID, "sky size set but sky_data/sky_cdf missing");
     if ((rc = upload(ctx->b_sky, sc->sky_data, nsky * 12, st, total))) return rc;
     if ((rc = upload(ctx->b_skycdf, sc->sky_cdf, nsky * 4, st, total))) return rc;
+    // k / 255.0f, correctly rounded: the RGBA8 decode table (dev_texture.cuh)
+    float lut[256];
+    for (int k = 0; k < 256; k++) lut[k] = float(k) / 255.0f;
+    if ((rc = upload(ctx->b_lut, lut, sizeof(lut), st, total))) return rc;
     RM_CUDA(cudaStreamSynchronize(st));    // host staging vectors die at scope exit
 
     DevScene &S = ctx->scene;
@@ -203,6 +207,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     S.light_cdf = ctx->b_lcdf.as<float>();
     S.sky_data = ctx->b_sky.as<float>();
     S.sky_cdf = ctx->b_skycdf.as<float>();
+    S.div255 = ctx->b_lut.as<float>();
     S.n_faces = n;
     S.n_nodes = sc->n_nodes;
     S.n_materials = sc->n_materials;
@@ -236,8 +241,8 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
     job.tri_idx = ctx->b_io[2].as<int>(); job.t_out = ctx->b_io[3].as<float>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    if (ctx->count_tests) k_trace<ClosestJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
-    else k_trace<ClosestJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
+    if (ctx->count_tests) k_trace<ClosestJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    else k_trace<ClosestJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -263,8 +268,8 @@ int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *
     job.out = ctx->b_io[3].as<unsigned char>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    if (ctx->count_tests) k_trace<OccludedJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
-    else k_trace<OccludedJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt);
+    if (ctx->count_tests) k_trace<OccludedJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    else k_trace<OccludedJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
@@ -291,8 +296,8 @@ int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx,
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
     ctx->timed_begin(RM_KIND_PRIMARY);
-    if (ctx->count_tests) k_trace<PrimaryJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt);
-    else k_trace<PrimaryJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt);
+    if (ctx->count_tests) k_trace<PrimaryJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    else k_trace<PrimaryJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->timed_end();
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
@@ -351,6 +356,10 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
+    if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
 }

@@ -8,6 +8,7 @@
 #include "raym0nade_b200.h"
 #include "rm_internal.h"
 #include "dev_scene.cuh"
+#include "dev_trace.cuh"
 
 #define RM_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -60,13 +61,15 @@ struct RmContext {
 
     // scene
     rm::DevScene scene{};
-    DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf;
+    DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf, b_lut;
     int64_t scene_bytes = 0;
 
     // counters: rays, box, tri (device)
     DevBuf b_counters;
     DevBuf b_cursor;                       // int[4]: work cursors of the persistent trace kernels
     int sm_count = 148;
+    rm::TraceTune tune{24, 1, 2};          // see dev_trace.cuh; adjustable through rm_set_option for perf experiments
+    int max_depth = 16;                    // perf experiments only: bounce limit of the wavefront loop (16 = the reference's maxRayDepth)
 
     // per-frame state
     int width = 0, height = 0;
@@ -81,7 +84,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_lut, &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };

@@ -24,9 +24,10 @@ struct RenderState {
     bool accum_valid = false, hold_committed = false;
     // queues
     int q_cap = 0, s_cap = 0;
-    DevBuf q[2][16];
-    DevBuf shadow;
-    DevBuf counts;            // int[8]: 0,1 path queue lengths; 2 shadow length; 3 overflow; 4 glass count; 5 glass list length
+    DevBuf q[2][20];
+    DevBuf shadow, nee;
+    DevBuf counts;            // int[C_COUNT]: device-side pipeline state, see the C_* indices in kernels_render.cuh
+    int *h_counts = nullptr;  // pinned mirror of `counts`
     // resolved planes + output images
     DevBuf planes[4], g_out, rgb[2];
     int n_glass = 0;
@@ -55,6 +56,7 @@ PathQueue make_queue(RenderState *R, int which) {
     Q.T = b[6].as<float>(); Q.B0 = b[7].as<float>(); Q.W = b[8].as<float>(); Q.rough = b[9].as<float>();
     Q.flags = b[10].as<int>(); Q.med_id = b[11].as<int>(); Q.med = b[12].as<float>();
     Q.hit_t = b[13].as<float>(); Q.hit_face = b[14].as<int>();
+    Q.surf = b[15].as<float>(); Q.hdP = b[16].as<float>();
     return Q;
 }
 
@@ -62,10 +64,11 @@ int alloc_queues(RenderState *R, int q_cap, int s_cap) {
     int rc;
     if (q_cap > R->q_cap) {
         const size_t c = size_t(q_cap);
-        const size_t words[15] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1};
+        const size_t words[17] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6};
         for (int w = 0; w < 2; w++)
-            for (int k = 0; k < 15; k++)
+            for (int k = 0; k < 17; k++)
                 if ((rc = R->q[w][k].alloc(c * words[k] * 4))) return rc;
+        if ((rc = R->nee.alloc(c * sizeof(NeeRequest)))) return rc;
         R->q_cap = q_cap;
     }
     if (s_cap > R->s_cap) {
@@ -118,7 +121,9 @@ void rm_render_state_free(RmContext *ctx) {
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1]})
         b->release();
     for (int w = 0; w < 2; w++)
-        for (int k = 0; k < 16; k++) R->q[w][k].release();
+        for (int k = 0; k < 20; k++) R->q[w][k].release();
+    R->nee.release();
+    if (R->h_counts) cudaFreeHost(R->h_counts);
     delete R;
     ctx->render_state = nullptr;
 }
@@ -137,11 +142,11 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
     const int npix = args->width * args->height;
     if ((rc = R->gbuffer.alloc(size_t(npix) * sizeof(RmHitInfo))) || (rc = R->sav_base.alloc(size_t(npix) * 12)) ||
-        (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(64)))
+        (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(C_COUNT * 4)))
         return rc;
     R->npix = npix;
     cudaStream_t st = ctx->stream;
-    RM_CUDA(cudaMemsetAsync(R->counts.p, 0, 64, st));
+    RM_CUDA(cudaMemsetAsync(R->counts.p, 0, C_COUNT * 4, st));
     const int spp_d = spp_direct_of(args), base = args->spp - spp_d;
     int *counts = R->counts.as<int>();
     k_gbuffer<<<(npix + 127) / 128, 128, 0, st>>>(ctx->scene, to_dev_args(args), ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), frame(R), spp_d, base, counts + 4);
@@ -199,79 +204,96 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const int n_d = local_count(spp_d), n_a = local_count(base);
     const int n_b_total = (R->n_glass > 0) ? local_count(16 * base) : 0;     // local samples below 16*base; the first n_a are phase A's
 
-    // wave sizes
+    // queue sizes: the path queue holds `wave_paths` vertices and is kept full by k_regen; a vertex that
+    // terminates emits at most 6 shadow rays; a direct wave is one shadow item per (pixel, sample)
     const long long target = R->wave_paths;
     const int S_all = int(std::max(1LL, target / npix));
-    const int S_glass = R->n_glass > 0 ? int(std::max(1LL, target / R->n_glass)) : 1;
-    long long max_paths = 0, max_direct = 0;
-    if (n_a > 0) max_paths = (long long)npix * std::min(S_all, n_a);
-    if (n_b_total > n_a) max_paths = std::max(max_paths, (long long)R->n_glass * std::min(S_glass, n_b_total - n_a));
-    if (n_d > 0) max_direct = (long long)npix * std::min(S_all, n_d);
-    if (max_paths > 0x7fffffffLL / 8 || max_direct > 0x7fffffffLL / 2) return rm_fail(RM_ERR_INVALID, "rm_render_samples: wave too large");
-    if ((rc = alloc_queues(R, int(std::max(max_paths, 1LL)), int(std::max({max_direct, 6 * max_paths, 1LL}))))) return rc;
+    const long long items_a = (long long)npix * n_a;
+    const long long items_b = n_b_total > n_a ? (long long)R->n_glass * (n_b_total - n_a) : 0;
+    const long long total_items = items_a + items_b;
+    const long long max_direct = n_d > 0 ? (long long)npix * std::min(S_all, n_d) : 0;
+    const long long q_cap = std::max(1024LL, std::min(target, total_items));
+    if (q_cap > 0x7fffffffLL / 8 || max_direct > 0x7fffffffLL / 2) return rm_fail(RM_ERR_INVALID, "rm_render_samples: wave too large");
+    if ((rc = alloc_queues(R, int(q_cap), int(std::max({max_direct, 6 * q_cap, 1LL}))))) return rc;
+    if (!R->h_counts) RM_CUDA(cudaMallocHost(&R->h_counts, C_COUNT * sizeof(int)));
 
     cudaStream_t st = ctx->stream;
-    int *counts = R->counts.as<int>();
+    int *C = R->counts.as<int>();
     auto *cnt = ctx->b_counters.as<unsigned long long>();
     const DevArgs A = to_dev_args(args);
     const FrameBuffers Fb = frame(R);
     const Accum Ac = accum(R);
     ShadowItem *sq = R->shadow.as<ShadowItem>();
+    NeeRequest *nq = R->nee.as<NeeRequest>();
     const int grid = R->sm_count * 8;
+    const int tgrid = R->sm_count * kTraceCtasPerSm;
     const bool ct = ctx->count_tests;
 
-    // counts: [0,1] path queue lengths, [2] shadow queue length, [3] overflow, [6] path-trace cursor, [7] shadow-trace cursor
-    const int tgrid = R->sm_count * kTraceCtasPerSm;
+    // rayHit_test over the shadow queue, then the coalesced accumulation pass (C_CUR_SHADOW must be 0)
     auto trace_shadow = [&]() {
         ShadowJob job;
         job.sq = sq;
-        cudaMemsetAsync(counts + 7, 0, 4, st);
         ctx->timed_begin(RM_KIND_SHADOW);
-        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, counts + 2, counts + 7, cnt + 6);
-        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, counts + 2, counts + 7, cnt + 6);
+        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, C + C_SQ, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
+        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, C + C_SQ, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
         ctx->timed_end();
-        k_accum_shadow<<<R->sm_count * 8, 256, 0, st>>>(Fb, Ac, sq, counts + 2, R->s_cap);
+        k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, C + C_SQ, R->s_cap);
         ctx->launches += 2;
     };
 
-    // ---- direct light at the primary hit
+    // ---- direct light at the primary hit: waves of S_all samples per pixel, one shadow item each
     for (int k0 = 0; k0 < n_d; k0 += S_all) {
         const int S = std::min(S_all, n_d - k0);
-        RM_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
+        RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, 4, st));
+        RM_CUDA(cudaMemsetAsync(C + C_CUR_SHADOW, 0, 4, st));
         k_direct_gen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, (long long)npix * S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
-                                           seed, sq, counts + 2, R->s_cap, counts + 3);
+                                           seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
         trace_shadow();
     }
 
-    // ---- indirect paths: phase A = every pixel, samples below `base`; phase B = glass pixels, samples in [base, 16*base)
-    auto run_wave = [&](const int *pix_list, int n_list, int k0, int S) {
-        cudaMemsetAsync(counts, 0, 12, st);
-        k_indirect_gen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, (long long)n_list * S, pix_list, n_list, sample_begin + k0 * sample_stride,
-                                             sample_stride, seed, make_queue(R, 0), counts);
-        ctx->launches++;
+    // ---- indirect paths.  One round = every vertex in the path queue advances by one bounce:
+    //   plan + regen (top the queue up with fresh first vertices) -> closest hit -> surface -> bounce
+    //   (-> next queue, NEE requests) -> NEE -> visibility -> accumulate.
+    // The host issues rounds in batches and looks at the device counters between batches: the loop ends when
+    // every item has been handed out and the queue has drained.
+    if (total_items > 0) {
+        ItemSpace I;
+        I.items_a = items_a; I.total = total_items; I.npix = npix; I.n_glass = std::max(R->n_glass, 1); I.n_a = n_a;
+        I.glass_list = R->glass_list.as<int>(); I.s_begin = sample_begin; I.s_stride = sample_stride;
+        RM_CUDA(cudaMemsetAsync(C, 0, 2 * sizeof(int), st));                       // both path queues empty
+        RM_CUDA(cudaMemsetAsync(C + C_NEE, 0, (C_COUNT - C_NEE) * sizeof(int), st)); // item cursor = 0
         int cur = 0;
-        for (int depth = 1; depth <= kMaxRayDepth; depth++) {
-            PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
-            PathJob pj;
-            pj.Q = Qin;
-            cudaMemsetAsync(counts + 6, 0, 4, st);
-            ctx->timed_begin(RM_KIND_PATHS);
-            if (ct) k_trace<PathJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, counts + cur, counts + 6, cnt + 3);
-            else k_trace<PathJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, counts + cur, counts + 6, cnt + 3);
-            ctx->timed_end();
-            cudaMemsetAsync(counts + (cur ^ 1), 0, 4, st);
-            cudaMemsetAsync(counts + 2, 0, 4, st);
-            ctx->timed_begin(RM_KIND_SHADE);
-            k_shade<<<grid, 128, 0, st>>>(ctx->scene, Fb, Ac, seed, Qin, counts + cur, Qout, counts + (cur ^ 1), sq, counts + 2, R->s_cap, counts + 3);
-            ctx->timed_end();
-            ctx->launches += 2;
-            trace_shadow();
-            cur ^= 1;
+        const int batch = 4;
+        const int max_rounds = ctx->max_depth < kMaxRayDepth ? ctx->max_depth : 0x7fffffff;   // perf experiments only
+        int rounds = 0;
+        bool done = false;
+        while (!done) {
+            for (int b = 0; b < batch && rounds < max_rounds; b++, rounds++) {
+                PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
+                k_plan<<<1, 1, 0, st>>>(C, cur, Qin.cap, total_items);
+                k_regen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
+                PathJob pj;
+                pj.Q = Qin;
+                ctx->timed_begin(RM_KIND_PATHS);
+                if (ct) k_trace<PathJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
+                else k_trace<PathJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
+                ctx->timed_end();
+                ctx->timed_begin(RM_KIND_SHADE);
+                k_surface<<<grid, 128, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
+                k_bounce<<<grid, 128, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
+                k_nee<<<grid, 128, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+                ctx->timed_end();
+                ctx->launches += 6;
+                trace_shadow();
+                cur ^= 1;
+            }
+            RM_CUDA(cudaMemcpyAsync(R->h_counts, C, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+            RM_CUDA(cudaStreamSynchronize(st));
+            const long long handed = (long long)(unsigned)R->h_counts[C_ITEM_LO] | ((long long)R->h_counts[C_ITEM_HI] << 32);
+            done = (handed >= total_items && R->h_counts[cur] == 0) || rounds >= max_rounds;
         }
-    };
-    for (int k0 = 0; k0 < n_a; k0 += S_all) run_wave(nullptr, npix, k0, std::min(S_all, n_a - k0));
-    for (int k0 = n_a; k0 < n_b_total; k0 += S_glass) run_wave(R->glass_list.as<int>(), R->n_glass, k0, std::min(S_glass, n_b_total - k0));
+    }
     RM_CUDA(cudaGetLastError());
     ctx->have_resolved = false;
     return RM_OK;
