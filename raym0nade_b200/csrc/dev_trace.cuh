@@ -60,6 +60,23 @@ RM_DI void ray_in_box(const RaySetup &r, float4 a, float4 b, float &tL, float &t
     slab_axis(r.flags & 4u, r.flags & 64u, r.o.z, r.inv[2], a.z, b.y, tL, tR, live);
 }
 
+// The same test for a ray without a "parallel" axis (all |d[i]| >= eps_zero - almost every ray): the
+// near / far plane of each axis is picked once per ray (lo/hi hold the selectors), and the early
+// return becomes a predicate on the remaining updates.
+RM_DI void slab_fast(float o, float inv, float bn, float bf, float &tL, float &tR, bool &live) {
+    const float nL = fmaxf(tL, fmul(fsub(bn, o), inv));
+    const float nR = fadd(fminf(tR, fmul(fsub(bf, o), inv)), kEps);
+    if (live) { tL = nL; tR = nR; }
+    live = live && !(nL > nR);
+}
+RM_DI void ray_in_box_fast(const RaySetup &r, float4 a, float4 b, float &tL, float &tR) {
+    const bool nx = r.flags & 16u, ny = r.flags & 32u, nz = r.flags & 64u;
+    bool live = true;
+    slab_fast(r.o.x, r.inv[0], nx ? a.w : a.x, nx ? a.x : a.w, tL, tR, live);
+    slab_fast(r.o.y, r.inv[1], ny ? b.x : a.y, ny ? a.y : b.x, tL, tR, live);
+    slab_fast(r.o.z, r.inv[2], nz ? b.y : a.z, nz ? a.z : b.y, tL, tR, live);
+}
+
 // returns t or +INF
 RM_DI float ray_triangle(const RaySetup &r, float4 q0, float4 q1, float4 q2) {
     V3 v0 = mk3(q0.x, q0.y, q0.z);
@@ -227,8 +244,8 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     const float4 *nd = S.nodes + (size_t(cur) << 2);        // children 2u, 2u+1: one 64-byte block
                     const float4 a0 = __ldg(nd), b0 = __ldg(nd + 1), a1 = __ldg(nd + 2), b1 = __ldg(nd + 3);
                     float tL0 = t_min, tR0 = t, tL1 = t_min, tR1 = t;
-                    ray_in_box(r, a0, b0, tL0, tR0);
-                    ray_in_box(r, a1, b1, tL1, tR1);
+                    if (r.flags & 7u) { ray_in_box(r, a0, b0, tL0, tR0); ray_in_box(r, a1, b1, tL1, tR1); }
+                    else { ray_in_box_fast(r, a0, b0, tL0, tR0); ray_in_box_fast(r, a1, b1, tL1, tR1); }
                     if (COUNT) cnt.box += 2;
                     const int fr0 = __float_as_int(b0.w), fr1 = __float_as_int(b1.w);
                     const int ref0 = fr0 ? leaf_ref(__float_as_int(b0.z), fr0) : (cur << 1);
@@ -254,14 +271,29 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                 }
             } else if (active && !wantI) {
                 if (ti < 0) { const int x = ~cur; ti = x >> 4; tend = ti + (x & 15); }        // first visit of this leaf
+                // up to two triangles of the leaf per step, their six loads issued together
                 const float4 *q = S.tri + size_t(ti) * 3;
-                const float tt = ray_triangle(r, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+                const bool two = ti + 1 < tend;
+                const float4 qa = __ldg(q), qb = __ldg(q + 1), qc = __ldg(q + 2);
+                float4 qd = qa, qe = qb, qf = qc;
+                if (two) { qd = __ldg(q + 3); qe = __ldg(q + 4); qf = __ldg(q + 5); }
+                const float tt = ray_triangle(r, qa, qb, qc);
                 if (COUNT) cnt.tri++;
                 bool stop = false;
                 if (t_min < tt && tt < t) {
                     t = tt;
                     face = ti;
                     stop = anyhit && tt < aim;
+                }
+                if (two && !stop) {
+                    ti++;
+                    const float t2 = ray_triangle(r, qd, qe, qf);
+                    if (COUNT) cnt.tri++;
+                    if (t_min < t2 && t2 < t) {
+                        t = t2;
+                        face = ti;
+                        stop = anyhit && t2 < aim;
+                    }
                 }
                 ti++;
                 if (stop || ti == tend) {

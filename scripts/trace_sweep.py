@@ -27,8 +27,8 @@ variants = [("refill22 1:1", dict(trace_refill=22, trace_w_inner=1, trace_w_leaf
 if len(sys.argv) > 2:
     variants = []
     for spec in sys.argv[2:]:
-        r, wi, wl = (int(x) for x in spec.split(":"))
-        variants.append(("refill%d %d:%d" % (r, wi, wl), dict(trace_refill=r, trace_w_inner=wi, trace_w_leaf=wl)))
+        f = [int(x) for x in spec.split(":")] + [0, 0]
+        r, wi, wl, pf, t2 = f[:5]
+        variants.append(("refill%d %d:%d pf%d tri2=%d" % (r, wi, wl, pf, t2), dict(trace_refill=r, trace_w_inner=wi, trace_w_leaf=wl)))
 for label, o in variants:
-    run(label + " depth1", 1, **o)
-    run(label + " full", 16, **o)
+    run(label, 16, **o)
