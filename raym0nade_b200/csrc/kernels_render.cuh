@@ -121,7 +121,7 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
 
 // device-side pipeline state (ints): queue lengths, cursors
 enum { C_Q0 = 0, C_Q1 = 1, C_SQ = 2, C_OVERFLOW = 3, C_GLASS = 4, C_GLASS_LIST = 5, C_CUR_PATH = 6, C_CUR_SHADOW = 7,
-       C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_COUNT = 16 };
+       C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_SQ_RUN = 14, C_COUNT = 16 };
 
 // warp-aggregated slot allocation
 RM_DI int alloc_slot(int *counter, bool want) {
@@ -301,10 +301,12 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
 
 // ------------------------------------------------------------------ direct light at the primary hit
 // item = (pixel, k-th direct sample of this wave); sample index s = s_begin + k*s_stride
-__global__ void __launch_bounds__(128) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, int npix, int s_begin,
+__global__ void __launch_bounds__(256) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, int npix, int s_begin,
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_items; base += (long long)gridDim.x * blockDim.x) {
+        __syncthreads();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
+        const long long i = base + threadIdx.x;
         bool want = false;
         NeeOut n;
         int p = 0;
@@ -383,15 +385,26 @@ __global__ void k_plan(int *C, int q_slot, int cap, long long total) {
     C[C_ITEM_LO] = (int)(unsigned)(cur & 0xffffffffLL);
     C[C_ITEM_HI] = (int)(cur >> 32);
     C[C_CUR_PATH] = 0;
+    if (C[C_SQ_RUN]) { C[C_SQ] = 0; C[C_SQ_RUN] = 0; }       // the shadow queue was traced last round: start it afresh
+}
+
+// Shadow items pile up over rounds (their results only feed the accumulators) and are traced once enough of them
+// wait for a full-width launch - or when the render ends (flush).
+__global__ void k_shadow_gate(int *C, int threshold, int cap, int flush) {
+    const int n = min(C[C_SQ], cap);
+    C[C_SQ_RUN] = (n >= threshold || (flush && n > 0)) ? n : 0;
+    C[C_CUR_SHADOW] = 0;
 }
 
 // ------------------------------------------------------------------ first vertex of an indirect path
 // sampleIndirectLightFromFirstIntersection (src/render.cpp:314-423) up to the new ray.
-__global__ void __launch_bounds__(128) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
+__global__ void __launch_bounds__(256) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
                                                PathQueue Q, int *q_count) {
     const int n_items = C[C_PLAN_TAKE];
     const long long first = (long long)(unsigned)C[C_PLAN_LO] | ((long long)C[C_PLAN_HI] << 32);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n_items + 31) & ~31); i += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * blockDim.x; base < n_items; base += gridDim.x * blockDim.x) {
+        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        const int i = base + threadIdx.x;
         bool want = false;
         int p = 0;
         unsigned s = 0;
@@ -514,11 +527,14 @@ RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
 // sampleRay up to the surface (src/render.cpp:128-166): a miss returns the sky (unless direct light is
 // excluded), a hit builds the HitInfo, an emissive hit returns its emission.  Finished entries get
 // hit_t = INF.  Thread 0 also resets the counters the later stages of this round append to.
-__global__ void __launch_bounds__(128) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
+__global__ void __launch_bounds__(256) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
     const int n = min(C[q_slot], Q.cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; C[C_SQ] = 0; C[C_CUR_SHADOW] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; }
     const int c = Q.cap;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        const int i = base + threadIdx.x;
+        if (i >= n) continue;
         const int p = Q.pixel[i];
         const int fl = Q.flags[i];
         const bool exclude = (fl & 256) != 0;
@@ -564,51 +580,55 @@ __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4
 
 // sampleRay from the surface on (src/render.cpp:143-312): roughness regularisation, Russian roulette,
 // Fresnel split, then either a NEE termination (-> NeeRequest) or a sampled continuation (-> Qout).
-__global__ void __launch_bounds__(128) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
+// The body is cut into phases (decide / reflect / refract / store) with a CTA barrier between them: the
+// warps of a CTA then run the same stretch of this large, branchy kernel at the same time and share its
+// instruction-cache lines instead of evicting each other's (the kernel was bound by instruction fetch).
+enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 };
+
+__global__ void __launch_bounds__(384) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
                                                 PathQueue Qout, int *out_count, NeeRequest *nq, int *nee_count) {
     const int n = min(*in_count, Qin.cap);
-    const int n_pad = (n + 31) & ~31;
     const int c = Qin.cap;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-        bool cont = false, terminate = false;
-        int p = 0, depth = 0;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        __syncthreads();
+        const int i = base + threadIdx.x;
+        int mode = kBounceDead;
+        int p = 0, depth = 0, fails = 0;
         unsigned sample = 0;
         Rng gen;
-        V3 T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), absorb = splat3(1.0f), pos = splat3(0.0f);
-        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f;
+        V3 T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), absorb = splat3(1.0f), dir = splat3(0.0f);
+        V3 bsdfPdf = splat3(CUDART_NAN_F);
+        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f, ior = 1.0f, P_reflect = 1.0f, P_RR = 1.0f, F = 0.0f;
         bool nee_pass_absorb = false, doDirect = false;
         RayDiff next;
         Medium med;
         med.n = 0;
+        Bsdf B;
+        B.s = default_surface();
+        B.inDir = splat3(0.0f);
         const float t = i < n ? Qin.hit_t[i] : CUDART_INF_F;
+
+        // ---- phase 1: load the vertex, Fresnel and roulette decisions
         if (t != CUDART_INF_F) {
             p = Qin.pixel[i];
             sample = Qin.sample[i];
             const int fl = Qin.flags[i];
             depth = fl & 255;
             load_medium(Qin, i, fl >> 16, med);
-            const V3 dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
+            dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
             T = mk3(Qin.T[i], Qin.T[c + i], Qin.T[2 * c + i]);
             B0 = mk3(Qin.B0[i], Qin.B0[c + i], Qin.B0[2 * c + i]);
             W = Qin.W[i];
             rough = Qin.rough[i];
             gen.init(seed, (unsigned)p, sample, kStreamIndirect, Qin.drawn[i]);
-            RayDiff bd;                                   // only the direction differentials are used below
-            bd.dPdx = bd.dPdy = splat3(0.0f);
-            bd.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
-            bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
-            Bsdf B;
             B.inDir = -dir;
             B.s = load_surface(Qin, i);
-            pos = B.s.position;
-            const float ior = B.s.eta;
+            ior = B.s.eta;
             rough = fmaxf(rough, fmul(1.0f, B.s.roughness));
             B.s.roughness = fmaxf(B.s.roughness, rough);
-            const float P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
+            P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
             doDirect = P_RR < 0.9f;
             absorb = get_absorb(medium_absorb(med), t);
-            float P_reflect = 1.0f, F = 0.0f;
-            V3 refr;
             if (B.s.opacity < kEps) {
                 // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
                 float eta1 = medium_ior(med), eta2;
@@ -619,61 +639,75 @@ __global__ void __launch_bounds__(128) k_bounce(unsigned long long seed, PathQue
                     medium_insert(med, B.s.id, B.s.eta, B.s.baseColor);
                 }
                 B.s.eta = fdiv(eta1, eta2);
+                V3 refr;
                 precise_refraction(B, refr, F);
                 if (med.n == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
                 else P_reflect = F;
                 P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
             }
-            int fails = 0;
-            V3 bsdfPdf = splat3(CUDART_NAN_F);
             if (gen() <= P_reflect) {
                 doDirect = doDirect && B.s.entering && med.n == 0;
                 if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                    terminate = true;
+                    mode = kBounceNee;
                     nee_factor = fdiv(1.0f, P_reflect);
                     if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                } else {
-                    sample_reflection(B, gen, newDir, bsdfPdf, fails);
-                    bsdfPdf = div_true(bsdfPdf, P_reflect);
-                    if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-                    V3 dDdx, dDdy;
-                    calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
-                    next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
-                    next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
-                    next.dDdx = dDdx; next.dDdy = dDdy;
-                }
+                } else mode = kBounceReflect;
             } else {
                 doDirect = doDirect && !B.s.entering && med.n == 1;
                 if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                    terminate = true;
+                    mode = kBounceNee;
                     nee_pass_absorb = true;
                     nee_factor = fdiv(1.0f, fsub(1.0f, P_reflect));
                     if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                } else {
-                    if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
-                    else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
-                    // refraction passes the incoming differentials through unchanged (src/render.cpp:268,273)
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        (&next.dPdx)[k] = mk3(Qin.diff[(3 * k) * c + i], Qin.diff[(3 * k + 1) * c + i], Qin.diff[(3 * k + 2) * c + i]);
-                    }
-                    next.dDdx = bd.dDdx; next.dDdy = bd.dDdy;
-                    bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
-                    if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-                    if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
-                    else medium_erase(med, B.s.id);
-                }
+                } else mode = kBounceRefract;
             }
-            if (terminate) {
-                // the light samples see the regularised roughness and the relative eta of this vertex
-                Qin.surf[16 * c + i] = B.s.roughness;
-                Qin.surf[19 * c + i] = B.s.eta;
-            } else if (isfinite_any(newDir) && depth != kMaxRayDepth) {
-                cont = true;
-                bsdfPdf = bsdfPdf * absorb;
-                T = T * bsdfPdf;
-                if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
-            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: reflection (src/render.cpp:222-236)
+        if (mode == kBounceReflect) {
+            sample_reflection(B, gen, newDir, bsdfPdf, fails);
+            bsdfPdf = div_true(bsdfPdf, P_reflect);
+            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+            RayDiff bd;                                   // only the direction differentials enter calc_dDdxy
+            bd.dPdx = bd.dPdy = splat3(0.0f);
+            bd.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
+            bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
+            V3 dDdx, dDdy;
+            calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
+            next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
+            next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
+            next.dDdx = dDdx; next.dDdy = dDdy;
+        }
+        __syncthreads();
+
+        // ---- phase 3: refraction (src/render.cpp:264-283); the incoming differentials pass through unchanged (268,273)
+        if (mode == kBounceRefract) {
+            if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
+            else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
+            next.dPdx = mk3(Qin.diff[0 * c + i], Qin.diff[1 * c + i], Qin.diff[2 * c + i]);
+            next.dPdy = mk3(Qin.diff[3 * c + i], Qin.diff[4 * c + i], Qin.diff[5 * c + i]);
+            next.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
+            next.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
+            bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
+            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+            if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
+            else medium_erase(med, B.s.id);
+        }
+        __syncthreads();
+
+        // ---- phase 4: hand the vertex on
+        const bool terminate = mode == kBounceNee;
+        bool cont = false;
+        if (terminate) {
+            // the light samples see the regularised roughness and the relative eta of this vertex
+            Qin.surf[16 * c + i] = B.s.roughness;
+            Qin.surf[19 * c + i] = B.s.eta;
+        } else if (mode != kBounceDead && isfinite_any(newDir) && depth != kMaxRayDepth) {
+            cont = true;
+            bsdfPdf = bsdfPdf * absorb;
+            T = T * bsdfPdf;
+            if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
         }
         const int ns = alloc_slot(nee_count, terminate);
         if (terminate) {
@@ -690,7 +724,7 @@ __global__ void __launch_bounds__(128) k_bounce(unsigned long long seed, PathQue
         }
         const int slot = alloc_slot(out_count, cont);
         if (cont && slot < Qout.cap)
-            store_path(Qout, slot, p, sample, gen.drawn, pos, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
+            store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
     }
 }
 
@@ -698,13 +732,14 @@ __global__ void __launch_bounds__(128) k_bounce(unsigned long long seed, PathQue
 // sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every NeeRequest.
 // The request reserves its 1..6 shadow-queue slots up front; a sample that comes out invalid leaves a
 // null item (aim = NaN) that the visibility pass skips.
-__global__ void __launch_bounds__(128) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
+__global__ void __launch_bounds__(256) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
                                              const int *__restrict__ nee_count, int nq_cap, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int n = min(*nee_count, nq_cap);
-    const int n_pad = (n + 31) & ~31;
     const int c = Q.cap;
     const int lane = threadIdx.x & 31;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        const int r = base + threadIdx.x;
         int cnt = 0, i = 0;
         float4 q0 = make_float4(0, 0, 0, 0), q1 = q0;
         if (r < n) {
@@ -717,9 +752,9 @@ __global__ void __launch_bounds__(128) k_nee(DevScene S, FrameBuffers Fb, unsign
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        int base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(s_count, incl);
-        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        int first = 0;
+        if (lane == 31 && incl > 0) first = atomicAdd(s_count, incl);
+        first = __shfl_sync(0xffffffffu, first, 31) + incl - cnt;
         if (cnt == 0) continue;
         const bool pass_absorb = (__float_as_int(q0.y) & 256) != 0;
         const float nee_factor = q0.z;
@@ -754,7 +789,7 @@ __global__ void __launch_bounds__(128) k_nee(DevScene S, FrameBuffers Fb, unsign
                 ne.dir = splat3(0.0f);
                 ne.aim = CUDART_NAN_F;                        // null item
             }
-            const int slot = base + k;
+            const int slot = first + k;
             if (slot >= s_cap) { atomicExch(overflow, 1); break; }
             write_shadow(sq + slot, p, B.s.position, ne, b, l, w);
         }

@@ -227,17 +227,19 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     NeeRequest *nq = R->nee.as<NeeRequest>();
     const int grid = R->sm_count * 8;
     const int tgrid = R->sm_count * kTraceCtasPerSm;
+    const int sgrid = R->sm_count * 2;             // shading stages: 2 CTAs of 256 threads per SM, lock-stepped per batch
     const bool ct = ctx->count_tests;
 
-    // rayHit_test over the shadow queue, then the coalesced accumulation pass (C_CUR_SHADOW must be 0)
-    auto trace_shadow = [&]() {
+    // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
+    // (C_CUR_SHADOW must be 0)
+    auto trace_shadow = [&](const int *n_dev) {
         ShadowJob job;
         job.sq = sq;
         ctx->timed_begin(RM_KIND_SHADOW);
-        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, C + C_SQ, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
-        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, C + C_SQ, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
+        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
+        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
         ctx->timed_end();
-        k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, C + C_SQ, R->s_cap);
+        k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
         ctx->launches += 2;
     };
 
@@ -246,10 +248,10 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         const int S = std::min(S_all, n_d - k0);
         RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, 4, st));
         RM_CUDA(cudaMemsetAsync(C + C_CUR_SHADOW, 0, 4, st));
-        k_direct_gen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, (long long)npix * S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+        k_direct_gen<<<sgrid, 256, 0, st>>>(ctx->scene, A, Fb, (long long)npix * S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
                                            seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
-        trace_shadow();
+        trace_shadow(C + C_SQ);
     }
 
     // ---- indirect paths.  One round = every vertex in the path queue advances by one bounce:
@@ -263,6 +265,8 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         I.glass_list = R->glass_list.as<int>(); I.s_begin = sample_begin; I.s_stride = sample_stride;
         RM_CUDA(cudaMemsetAsync(C, 0, 2 * sizeof(int), st));                       // both path queues empty
         RM_CUDA(cudaMemsetAsync(C + C_NEE, 0, (C_COUNT - C_NEE) * sizeof(int), st)); // item cursor = 0
+        RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, sizeof(int), st));
+        const int shadow_threshold = std::max(1, R->q_cap / 2);
         int cur = 0;
         const int batch = 4;
         const int max_rounds = ctx->max_depth < kMaxRayDepth ? ctx->max_depth : 0x7fffffff;   // perf experiments only
@@ -272,7 +276,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
             for (int b = 0; b < batch && rounds < max_rounds; b++, rounds++) {
                 PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
                 k_plan<<<1, 1, 0, st>>>(C, cur, Qin.cap, total_items);
-                k_regen<<<grid, 128, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
+                k_regen<<<sgrid, 256, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
                 PathJob pj;
                 pj.Q = Qin;
                 ctx->timed_begin(RM_KIND_PATHS);
@@ -280,12 +284,13 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
                 else k_trace<PathJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
                 ctx->timed_end();
                 ctx->timed_begin(RM_KIND_SHADE);
-                k_surface<<<grid, 128, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
-                k_bounce<<<grid, 128, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
-                k_nee<<<grid, 128, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+                k_surface<<<sgrid, 256, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
+                k_bounce<<<sgrid, 256, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
+                k_nee<<<sgrid, 256, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
                 ctx->timed_end();
-                ctx->launches += 6;
-                trace_shadow();
+                k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 0);
+                ctx->launches += 7;
+                trace_shadow(C + C_SQ_RUN);
                 cur ^= 1;
             }
             RM_CUDA(cudaMemcpyAsync(R->h_counts, C, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -293,6 +298,10 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
             const long long handed = (long long)(unsigned)R->h_counts[C_ITEM_LO] | ((long long)R->h_counts[C_ITEM_HI] << 32);
             done = (handed >= total_items && R->h_counts[cur] == 0) || rounds >= max_rounds;
         }
+        k_plan<<<1, 1, 0, st>>>(C, cur, R->q_cap, total_items);          // retires a queue traced in the last round
+        k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 1);
+        trace_shadow(C + C_SQ_RUN);
+        ctx->launches += 2;
     }
     RM_CUDA(cudaGetLastError());
     ctx->have_resolved = false;

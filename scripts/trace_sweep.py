@@ -27,8 +27,11 @@ variants = [("refill22 1:1", dict(trace_refill=22, trace_w_inner=1, trace_w_leaf
 if len(sys.argv) > 2:
     variants = []
     for spec in sys.argv[2:]:
-        f = [int(x) for x in spec.split(":")] + [0, 0]
-        r, wi, wl, pf, t2 = f[:5]
-        variants.append(("refill%d %d:%d pf%d tri2=%d" % (r, wi, wl, pf, t2), dict(trace_refill=r, trace_w_inner=wi, trace_w_leaf=wl)))
+        if spec.startswith("s"):          # shade launch shape: s<block>:<ctas per sm>:<lockstep>
+            b, c, l = (int(x) for x in spec[1:].split(":"))
+            variants.append(("shade block%d ctas%d lockstep%d" % (b, c, l), dict(shade_block=b, shade_ctas=c, shade_lockstep=l)))
+            continue
+        r, wi, wl = (int(x) for x in spec.split(":"))
+        variants.append(("refill%d %d:%d" % (r, wi, wl), dict(trace_refill=r, trace_w_inner=wi, trace_w_leaf=wl)))
 for label, o in variants:
     run(label, 16, **o)
