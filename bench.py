@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 import numpy as np
 
 WORKLOAD = "configs[2]: 1M-triangle glossy/dielectric synthetic scene (990,744 tris), 1920x1080"
-CPU_SAMPLE = dict(width=480, height=270, spp=8)      # bounded sample of the same scene/camera for the CPU legs
+CPU_SAMPLE = dict(width=960, height=540, spp=16)     # bounded sample of the same scene/camera for the CPU legs (~10-20 s of host time)
 
 
 def build_workload(spp, width=1920, height=1080, n_tris=1_000_000):
@@ -136,7 +136,18 @@ def run_ours(opt, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout when the communicator is created; keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     scene, args = build_workload(opt.spp)
     npix = args.width * args.height
     model = Model(scene)
@@ -244,14 +255,16 @@ def run_ours(opt, rank, world, local_rank):
                            "mrays_per_s_kernel_only": c["rays"] * opt.steps / (t["ms"] * 1e-3) / 1e6}
         per_kind["shade"] = {"ms_per_step": kinds["shade"]["ms"] / opt.steps, "launches_per_step": kinds["shade"]["launches"] / opt.steps}
         dom = max((k for k in per_kind if k != "shade"), key=lambda k: per_kind[k]["ms_per_step"])
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": {"primary": "k_trace_primary", "paths": "k_trace_paths", "shadow": "k_trace_shadow"}[dom],
+        roofline = {"bound": "hbm", "kernel": {"primary": "k_trace<PrimaryJob>", "paths": "k_trace<PathJob>", "shadow": "k_trace<ShadowJob>"}[dom],
                     "achieved": per_kind[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kind[dom]["achieved_gbs"] / peak,
                     "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": 32.0 * counted[dom]["box"] / max(kinds[dom]["launches"] / opt.steps, 1) + 36.0 * counted[dom]["tri"] / max(kinds[dom]["launches"] / opt.steps, 1),
                     "note": "achieved = (32 B x box tests + 36 B x triangle tests) of this kernel's launches / its CUDA-event time; "
                             "the 1M-triangle scene (167 MB) is L2-resident, see DESIGN.md"}
         # reference CPU path on this box's host cores, bounded sample of the same workload
