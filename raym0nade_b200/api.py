@@ -18,7 +18,8 @@ from .ctypes_defs import (BVHNODE_DTYPE, HITINFO_DTYPE, RADIANCE_DTYPE, RmRawSce
 from .scenes import RawScene, RenderArgs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraym0nade_b200.so")
+# RM_LIB_PATH: A/B perf experiments load another build of the same CUDA library (scripts/ab_probe.py)
+LIB_PATH = os.environ.get("RM_LIB_PATH") or os.path.join(_HERE, "libraym0nade_b200.so")
 _LIB = None
 
 

@@ -15,9 +15,11 @@ namespace rm {
 struct V4 { float x, y, z, w; };
 
 RM_DI int wrap_index(int x, int m) {           // the `_mod` lambda, src/material.cpp:51-56
+    if ((m & (m - 1)) == 0) return x & (m - 1);            // power-of-two size: the two's-complement AND is the mathematical mod
     if (x < 0 || x >= m) { x %= m; if (x < 0) x += m; }
     return x;
 }
+RM_DI int wrap_next(int x, int m) { return x + 1 == m ? 0 : x + 1; }          // (x + 1) % m for 0 <= x < m
 
 RM_DI float lerp2(float a, float b, float t) { return fadd(fmul(a, fsub(1.0f, t)), fmul(b, t)); }
 
@@ -29,7 +31,7 @@ RM_DI V4 bilinear_rgba(const uint8_t *data, const float *__restrict__ lut, int w
     float dx = fsub(x, float(x0)), dy = fsub(y, float(y0));
     x0 = wrap_index(x0, w);
     y0 = wrap_index(y0, h);
-    int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    int x1 = wrap_next(x0, w), y1 = wrap_next(y0, h);
     const uchar4 *p = reinterpret_cast<const uchar4 *>(data);
     uchar4 t00 = __ldg(p + (y0 * w + x0)), t01 = __ldg(p + (y0 * w + x1));
     uchar4 t10 = __ldg(p + (y1 * w + x0)), t11 = __ldg(p + (y1 * w + x1));
@@ -47,7 +49,7 @@ RM_DI V3 bilinear_rgb(const uint8_t *data, int w, int h, float u, float v) {
     float dx = fsub(x, float(x0)), dy = fsub(y, float(y0));
     x0 = wrap_index(x0, w);
     y0 = wrap_index(y0, h);
-    int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    int x1 = wrap_next(x0, w), y1 = wrap_next(y0, h);
     const uint8_t *p00 = data + (y0 * w + x0) * 3, *p01 = data + (y0 * w + x1) * 3;
     const uint8_t *p10 = data + (y1 * w + x0) * 3, *p11 = data + (y1 * w + x1) * 3;
     const float r255 = frcp(255.0f);
@@ -77,12 +79,16 @@ RM_NI V4 texture_rgba_impl(const DevTexture *__restrict__ textures, const uint8_
     int level, next;
     float blend;
     mip_select(t, depth, level, next, blend);
+    // a zero LOD fraction (magnified or past the last level: most fetches) makes the blend a * 1 + b * 0 = a exactly
+    // (texels are finite), so the second level is not fetched
     V4 lv[2];
 #pragma unroll 1
     for (int k = 0; k < 2; k++) {
+        if (k == 1 && blend == 0.0f) { lv[1] = lv[0]; break; }
         const int l = k ? next : level;
         lv[k] = bilinear_rgba(texels + t.offset[l], lut, t.width >> l, t.height >> l, u, v);
     }
+    if (blend == 0.0f) return lv[0];
     V4 r;
     r.x = lerp2(lv[0].x, lv[1].x, blend); r.y = lerp2(lv[0].y, lv[1].y, blend);
     r.z = lerp2(lv[0].z, lv[1].z, blend); r.w = lerp2(lv[0].w, lv[1].w, blend);
@@ -99,6 +105,7 @@ RM_DI V3 texture_rgb(const DevScene &S, int tex, float u, float v, float depth) 
     float blend;
     mip_select(t, depth, level, next, blend);
     V3 a = bilinear_rgb(S.texels + t.offset[level], t.width >> level, t.height >> level, u, v);
+    if (blend == 0.0f) return a;               // a * 1 + b * 0 = a exactly
     V3 b = bilinear_rgb(S.texels + t.offset[next], t.width >> next, t.height >> next, u, v);
     return mk3(lerp2(a.x, b.x, blend), lerp2(a.y, b.y, blend), lerp2(a.z, b.z, blend));
 }

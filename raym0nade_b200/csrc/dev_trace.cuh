@@ -16,8 +16,6 @@
 
 namespace rm {
 
-constexpr int kStackDepth = 24;   // one deferred child per tree level; depth is <= 20 for 5 M triangles
-
 struct TraceCounters { unsigned long long rays, box, tri; };
 
 // One 256-bit read-only load (sm_100 LDG.E.256): half the L1 lookups of two 128-bit loads.  p is 32-byte aligned.
@@ -25,6 +23,19 @@ RM_DI void ldg256(const float4 *p, float4 &a, float4 &b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
+}
+
+// Experiment (RM_PREFETCH): pull the line a lane will need in its next step into L1 while it waits for its turn.
+RM_DI void prefetch_l1(const void *p) {
+#ifdef RM_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+RM_DI void prefetch_ref(const DevScene &S, int ref) {
+#ifdef RM_PREFETCH
+    if (ref >= 0) prefetch_l1(S.nodes + (size_t(ref) << 2));
+    else if (ref != int(0x80000000u)) prefetch_l1(S.tri + size_t((~ref) >> 4) * 3);
+#endif
 }
 
 // A reference to a BVH child: inner node index u >= 1, or a leaf encoded as ~(faceL<<4 | count).
@@ -84,7 +95,9 @@ RM_DI void ray_in_box_fast(const RaySetup &r, float4 a, float4 b, float &tL, flo
     slab_fast(r.o.z, r.inv[2], nz ? b.y : a.z, nz ? a.z : b.y, tL, tR, live);
 }
 
-// returns t or +INF
+// returns t or +INF.  Straight-line: the early returns of the reference become one select at the end.  Under SIMT
+// an early return only saves work when every lane of the warp takes it, and the divergent returns cost more than
+// the arithmetic they skip; the value is a pure function of the inputs, so the result is the reference's.
 RM_DI float ray_triangle(const RaySetup &r, float4 q0, float4 q1, float4 q2) {
     V3 v0 = mk3(q0.x, q0.y, q0.z);
     V3 e1 = mk3(q0.w, q1.x, q1.y);
@@ -95,15 +108,16 @@ RM_DI float ray_triangle(const RaySetup &r, float4 q0, float4 q1, float4 q2) {
     // eps_zero when |a| < 1.0001e-4 * |e1| (rounding moves either side by < 1e-7 relative), so the
     // division is evaluated only in that sliver; NaN / zero |e1| take the same side as the reference.
     float aa = fabsf(a);
-    if (aa < fmul(1.0001e-4f, q2.y) && fdiv(aa, q2.y) < kEps) return CUDART_INF_F;
+    bool miss = false;
+    if (aa < fmul(1.0001e-4f, q2.y)) miss = fdiv(aa, q2.y) < kEps;
     float f = __frcp_rn(a);
     V3 s = r.o - v0;
     float u = fmul(f, dot(s, h));
-    if (u < 0.0f || u > 1.0f) return CUDART_INF_F;
     V3 q = cross(s, e1);
     float v = fmul(f, dot(r.d, q));
-    if (v < 0.0f || fadd(u, v) > 1.0f) return CUDART_INF_F;
-    return fmul(f, dot(e2, q));
+    float t = fmul(f, dot(e2, q));
+    miss = miss || u < 0.0f || u > 1.0f || v < 0.0f || fadd(u, v) > 1.0f;
+    return miss ? CUDART_INF_F : t;
 }
 
 // barycentric (src/geometry.cpp:89-103): returns (gamma, alpha, beta)
@@ -277,6 +291,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                         }
                     }
                     ti = -1;
+                    prefetch_ref(S, cur);
                 }
             } else if (active && !wantI) {
                 if (ti < 0) { const int x = ~cur; ti = x >> 4; tend = ti + (x & 15); }        // first visit of this leaf
@@ -286,7 +301,9 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                 const float4 qa = __ldg(q), qb = __ldg(q + 1), qc = __ldg(q + 2);
                 float4 qd = qa, qe = qb, qf = qc;
                 if (two) { qd = __ldg(q + 3); qe = __ldg(q + 4); qf = __ldg(q + 5); }
+                // both tests are evaluated straight-line and interleaved (a lane without a second triangle repeats the first)
                 const float tt = ray_triangle(r, qa, qb, qc);
+                const float t2 = ray_triangle(r, qd, qe, qf);
                 if (COUNT) cnt.tri++;
                 bool stop = false;
                 if (t_min < tt && tt < t) {
@@ -296,7 +313,6 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                 }
                 if (two && !stop) {
                     ti++;
-                    const float t2 = ray_triangle(r, qd, qe, qf);
                     if (COUNT) cnt.tri++;
                     if (t_min < t2 && t2 < t) {
                         t = t2;
@@ -314,7 +330,8 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                             if (__int_as_float(e.y) < t) { cur = e.x; break; }
                         }
                     ti = -1;
-                }
+                    prefetch_ref(S, cur);
+                } else prefetch_l1(S.tri + size_t(ti) * 3);
             }
             if (active && cur == kTraceDone) {
                 // one BVH::rayHit finished: resolve cut-outs, then report

@@ -24,6 +24,16 @@
 
 namespace rm {
 
+// shading-stage launch shape: kShadeCtasPerSm CTAs of kShadeBlock threads per SM (register budget = 64K / their product)
+#ifndef RM_SHADE_BLOCK
+#define RM_SHADE_BLOCK 256
+#endif
+#ifndef RM_SHADE_CTAS
+#define RM_SHADE_CTAS 2
+#endif
+constexpr int kShadeBlock = RM_SHADE_BLOCK;
+constexpr int kShadeCtasPerSm = RM_SHADE_CTAS;
+
 constexpr int kMediumSlots = 6;     // nested-dielectric entries kept per path besides the air base entry
 constexpr int kMaxRayDepth = 16;    // maxRayDepth, src/render.cpp:125
 
@@ -133,6 +143,32 @@ RM_DI int alloc_slot(int *counter, bool want) {
     if (lane == leader) base = atomicAdd(counter, __popc(mask));
     base = __shfl_sync(mask, base, leader);
     return base + __popc(mask & ((1u << lane) - 1));
+}
+
+// CTA-local compaction.  A path queue mixes live entries with finished ones (a miss, an emissive hit); run one
+// thread per queue slot and most lanes idle through the shading code.  Instead a CTA scans a window of
+// kWindow consecutive slots, packs the indices of the live ones into shared memory (ballot + popc per warp, one
+// shared atomic per warp) and then works through that dense list 256 at a time, so its warps run full.  The
+// gathers stay inside the window's few KB per SoA array.  Returns the number of live entries; s_idx / s_n are
+// shared.  Every thread of the CTA calls this.
+constexpr int kWindow = 1024;
+template <class Pred>
+RM_DI int cta_compact(int base, int n, int *s_idx, int *s_n, Pred live_at) {
+    const int lane = threadIdx.x & 31;
+    __syncthreads();                           // the previous window's list is no longer read
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < kWindow; k += blockDim.x) {
+        const int i = base + k;
+        const bool live = i < n && live_at(i);
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        int wbase = 0;
+        if (lane == 0 && m) wbase = atomicAdd(s_n, __popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (live) s_idx[wbase + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+    __syncthreads();
+    return *s_n;
 }
 
 // ------------------------------------------------------------------ accumulation
@@ -300,40 +336,43 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
 }
 
 // ------------------------------------------------------------------ direct light at the primary hit
-// item = (pixel, k-th direct sample of this wave); sample index s = s_begin + k*s_stride
-__global__ void __launch_bounds__(256) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, long long n_items, int npix, int s_begin,
+// One thread per pixel draws the wave's S direct samples (sample index s = s_begin + k*s_stride, k < S): the
+// G-buffer record and the per-light-object weights (getLightObjectWeight, one BSDF evaluation per light object,
+// src/sampling.cpp:406-417) depend on the pixel only and are formed once instead of once per sample.  Every
+// sample keeps its own random stream, so the samples are the ones a per-sample loop draws.
+__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, int n_samples, int npix, int s_begin,
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_items; base += (long long)gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * blockDim.x; base < npix; base += gridDim.x * blockDim.x) {
         __syncthreads();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
-        const long long i = base + threadIdx.x;
-        bool want = false;
-        NeeOut n;
-        int p = 0;
-        V3 org = splat3(0.0f);
-        if (i < n_items) {
-            p = int(i % npix);
-            int s = s_begin + int(i / npix) * s_stride;
-            Surface g = load_hitinfo(Fb.gbuffer + p);
-            if (s < spp_direct && isfinite_any(g.position) && !(length(g.emission) > 0.0f)) {
-                V3 inDir = normalize(g.position - A.position);
-                Bsdf B;
-                B.inDir = -inDir;
-                B.s = g;
-                float lw[kMaxLights];
-                float total = 0.0f;
-                bool go = true;
+        const int p = base + threadIdx.x;
+        bool go = false;
+        Bsdf B;
+        B.s = default_surface();
+        B.inDir = splat3(0.0f);
+        float lw[kMaxLights];
+        float total = 0.0f;
+        if (p < npix) {
+            B.s = load_hitinfo(Fb.gbuffer + p);
+            if (isfinite_any(B.s.position) && !(length(B.s.emission) > 0.0f)) {
+                B.inDir = -normalize(B.s.position - A.position);
+                go = true;
                 if (S.sky_width == 0) { total = light_weights(S, B, lw); if (total == 0.0f) go = false; }
-                if (go) {
-                    Rng gen;
-                    gen.init(seed, (unsigned)p, (unsigned)s, kStreamDirect);
-                    n = nee_sample(S, B, gen, lw, total, spp_direct);
-                    want = n.valid;
-                    org = g.position;
-                }
             }
         }
-        push_shadow(sq, s_count, s_cap, overflow, want, p | 0x80000000, org, n, n.bsdf, n.light, n.weight);
+#pragma unroll 1
+        for (int k = 0; k < n_samples; k++) {
+            const int s = s_begin + k * s_stride;
+            bool want = false;
+            NeeOut n;
+            if (go && s < spp_direct) {
+                Rng gen;
+                gen.init(seed, (unsigned)p, (unsigned)s, kStreamDirect);
+                n = nee_sample(S, B, gen, lw, total, spp_direct);
+                want = n.valid;
+            }
+            push_shadow(sq, s_count, s_cap, overflow, want, p | 0x80000000, B.s.position, n, n.bsdf, n.light, n.weight);
+        }
     }
 }
 
@@ -398,7 +437,7 @@ __global__ void k_shadow_gate(int *C, int threshold, int cap, int flush) {
 
 // ------------------------------------------------------------------ first vertex of an indirect path
 // sampleIndirectLightFromFirstIntersection (src/render.cpp:314-423) up to the new ray.
-__global__ void __launch_bounds__(256) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
+__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
                                                PathQueue Q, int *q_count) {
     const int n_items = C[C_PLAN_TAKE];
     const long long first = (long long)(unsigned)C[C_PLAN_LO] | ((long long)C[C_PLAN_HI] << 32);
@@ -527,14 +566,21 @@ RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
 // sampleRay up to the surface (src/render.cpp:128-166): a miss returns the sky (unless direct light is
 // excluded), a hit builds the HitInfo, an emissive hit returns its emission.  Finished entries get
 // hit_t = INF.  Thread 0 also resets the counters the later stages of this round append to.
-__global__ void __launch_bounds__(256) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
+__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
     const int n = min(C[q_slot], Q.cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; }
     const int c = Q.cap;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    __shared__ int s_idx[kWindow];
+    __shared__ int s_n;
+    const bool sky = S.sky_width != 0;
+    for (int base = blockIdx.x * kWindow; base < n; base += gridDim.x * kWindow) {
+      // live here: a hit, or a miss that returns the sky (src/render.cpp:129-133)
+      const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Q.hit_t[i] != CUDART_INF_F || (sky && !(Q.flags[i] & 256)); });
+      for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
         __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
-        const int i = base + threadIdx.x;
-        if (i >= n) continue;
+        const int j = j0 + threadIdx.x;
+        if (j >= n_live) continue;
+        const int i = s_idx[j];
         const int p = Q.pixel[i];
         const int fl = Q.flags[i];
         const bool exclude = (fl & 256) != 0;
@@ -572,6 +618,7 @@ __global__ void __launch_bounds__(256) k_surface(DevScene S, FrameBuffers Fb, Ac
             const float inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));
             add_indirect(Ac, Fb, p, B0, light * T, fmul(fmul(1.0f, Q.W[i]), inv_spp));
         }
+      }
     }
 }
 
@@ -585,13 +632,19 @@ __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4
 // instruction-cache lines instead of evicting each other's (the kernel was bound by instruction fetch).
 enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 };
 
-__global__ void __launch_bounds__(384) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
+__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
                                                 PathQueue Qout, int *out_count, NeeRequest *nq, int *nee_count) {
     const int n = min(*in_count, Qin.cap);
     const int c = Qin.cap;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    __shared__ int s_idx[kWindow];
+    __shared__ int s_n;
+    for (int base = blockIdx.x * kWindow; base < n; base += gridDim.x * kWindow) {
+      // live here: a hit on a non-emissive surface (k_surface marked the others finished)
+      const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Qin.hit_t[i] != CUDART_INF_F; });
+      for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
         __syncthreads();
-        const int i = base + threadIdx.x;
+        const int j = j0 + threadIdx.x;
+        const int i = j < n_live ? s_idx[j] : -1;
         int mode = kBounceDead;
         int p = 0, depth = 0, fails = 0;
         unsigned sample = 0;
@@ -606,7 +659,7 @@ __global__ void __launch_bounds__(384) k_bounce(unsigned long long seed, PathQue
         Bsdf B;
         B.s = default_surface();
         B.inDir = splat3(0.0f);
-        const float t = i < n ? Qin.hit_t[i] : CUDART_INF_F;
+        const float t = i >= 0 ? Qin.hit_t[i] : CUDART_INF_F;
 
         // ---- phase 1: load the vertex, Fresnel and roulette decisions
         if (t != CUDART_INF_F) {
@@ -725,6 +778,7 @@ __global__ void __launch_bounds__(384) k_bounce(unsigned long long seed, PathQue
         const int slot = alloc_slot(out_count, cont);
         if (cont && slot < Qout.cap)
             store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
+      }
     }
 }
 
@@ -732,7 +786,7 @@ __global__ void __launch_bounds__(384) k_bounce(unsigned long long seed, PathQue
 // sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every NeeRequest.
 // The request reserves its 1..6 shadow-queue slots up front; a sample that comes out invalid leaves a
 // null item (aim = NaN) that the visibility pass skips.
-__global__ void __launch_bounds__(256) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
+__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
                                              const int *__restrict__ nee_count, int nq_cap, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int n = min(*nee_count, nq_cap);
     const int c = Q.cap;

@@ -91,11 +91,22 @@ struct OccludedJob : RayListJob {
 template <class Job, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene S, Job job, int n_host, const int *__restrict__ n_dev,
                                                                                 int *cursor, unsigned long long *counters, TraceTune tune) {
-    __shared__ int2 stack[kStackDepth * kTraceBlock];
+    // one deferred child per tree level and thread: [levels][kTraceBlock] int2, sized by the launcher from the scene's
+    // tree depth - the shallower the stack, the more of the SM's 256 KB stays L1 for node and triangle lines
+    extern __shared__ int2 stack[];
     TraceCounters cnt = {0, 0, 0};
     const int n = n_dev ? min(*n_dev, n_host) : n_host;          // queue kernels read their length on the device
     trace_engine<Job, COUNT>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt, tune);
     flush_counters(cnt, counters, COUNT);
+}
+
+// Launch geometry of every trace kernel: kTraceCtasPerSm CTAs per SM, stack sized by the tree depth.
+template <class Job>
+inline void launch_trace(const DevScene &S, int stack_levels, bool count, int grid, cudaStream_t st, const Job &job, int n_host, const int *n_dev,
+                         int *cursor, unsigned long long *counters, const TraceTune &tune) {
+    const size_t smem = size_t(stack_levels) * kTraceBlock * sizeof(int2);
+    if (count) k_trace<Job, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, tune);
+    else k_trace<Job, false><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, tune);
 }
 
 } // namespace rm

@@ -216,6 +216,10 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     S.sky_height = sc->sky_height;
     S.any_cutout = any_cutout ? 1 : 0;
     S.root_is_leaf = sc->nodes[1].faceR != 0;
+    // deferred children per ray <= inner levels of the heap-indexed tree (node indices < n_nodes)
+    int levels = 1;
+    while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
+    ctx->stack_levels = std::min(std::max(levels, 2), 40);
     ctx->scene_bytes = total;
     ctx->has_scene = true;
     ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
@@ -241,8 +245,7 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
     job.tri_idx = ctx->b_io[2].as<int>(); job.t_out = ctx->b_io[3].as<float>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    if (ctx->count_tests) k_trace<ClosestJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
-    else k_trace<ClosestJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(ctx->scene, ctx->stack_levels, ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -268,8 +271,7 @@ int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *
     job.out = ctx->b_io[3].as<unsigned char>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    if (ctx->count_tests) k_trace<OccludedJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
-    else k_trace<OccludedJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(ctx->scene, ctx->stack_levels, ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
@@ -296,8 +298,7 @@ int rm_trace_primary(RmContext *ctx, const RmRenderArgs *args, int32_t *tri_idx,
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
     ctx->timed_begin(RM_KIND_PRIMARY);
-    if (ctx->count_tests) k_trace<PrimaryJob, true><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
-    else k_trace<PrimaryJob, false><<<grid, kTraceBlock, 0, st>>>(ctx->scene, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(ctx->scene, ctx->stack_levels, ctx->count_tests, grid, st, job, n_rays, nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->timed_end();
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
@@ -359,6 +360,10 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
     if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
     if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "stack_levels")) {       // perf experiments only: never below the tree depth rm_scene_upload derived
+        ctx->stack_levels = int(std::min<int64_t>(std::max<int64_t>(value, ctx->stack_levels), 40));
+        return RM_OK;
+    }
     if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);

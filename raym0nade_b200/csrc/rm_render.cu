@@ -211,8 +211,9 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const long long items_a = (long long)npix * n_a;
     const long long items_b = n_b_total > n_a ? (long long)R->n_glass * (n_b_total - n_a) : 0;
     const long long total_items = items_a + items_b;
-    const long long max_direct = n_d > 0 ? (long long)npix * std::min(S_all, n_d) : 0;
     const long long q_cap = std::max(1024LL, std::min(target, total_items));
+    const int S_dir = int(std::max<long long>(S_all, std::min<long long>(6 * q_cap / npix, 64)));
+    const long long max_direct = n_d > 0 ? (long long)npix * std::min(S_dir, n_d) : 0;
     if (q_cap > 0x7fffffffLL / 8 || max_direct > 0x7fffffffLL / 2) return rm_fail(RM_ERR_INVALID, "rm_render_samples: wave too large");
     if ((rc = alloc_queues(R, int(q_cap), int(std::max({max_direct, 6 * q_cap, 1LL}))))) return rc;
     if (!R->h_counts) RM_CUDA(cudaMallocHost(&R->h_counts, C_COUNT * sizeof(int)));
@@ -227,7 +228,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     NeeRequest *nq = R->nee.as<NeeRequest>();
     const int grid = R->sm_count * 8;
     const int tgrid = R->sm_count * kTraceCtasPerSm;
-    const int sgrid = R->sm_count * 2;             // shading stages: 2 CTAs of 256 threads per SM, lock-stepped per batch
+    const int sgrid = R->sm_count * kShadeCtasPerSm;             // shading stages: resident CTAs only, lock-stepped per batch
     const bool ct = ctx->count_tests;
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
@@ -236,19 +237,19 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         ShadowJob job;
         job.sq = sq;
         ctx->timed_begin(RM_KIND_SHADOW);
-        if (ct) k_trace<ShadowJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
-        else k_trace<ShadowJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
+        launch_trace(ctx->scene, ctx->stack_levels, ct, tgrid, st, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
         ctx->timed_end();
         k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
         ctx->launches += 2;
     };
 
-    // ---- direct light at the primary hit: waves of S_all samples per pixel, one shadow item each
-    for (int k0 = 0; k0 < n_d; k0 += S_all) {
-        const int S = std::min(S_all, n_d - k0);
+    // ---- direct light at the primary hit: waves of S_dir samples per pixel, one shadow item each (as many as the
+    // shadow queue holds anyway for the indirect rounds: fewer, fuller launches)
+    for (int k0 = 0; k0 < n_d; k0 += S_dir) {
+        const int S = std::min(S_dir, n_d - k0);
         RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, 4, st));
         RM_CUDA(cudaMemsetAsync(C + C_CUR_SHADOW, 0, 4, st));
-        k_direct_gen<<<sgrid, 256, 0, st>>>(ctx->scene, A, Fb, (long long)npix * S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+        k_direct_gen<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
                                            seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
         trace_shadow(C + C_SQ);
@@ -276,17 +277,16 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
             for (int b = 0; b < batch && rounds < max_rounds; b++, rounds++) {
                 PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
                 k_plan<<<1, 1, 0, st>>>(C, cur, Qin.cap, total_items);
-                k_regen<<<sgrid, 256, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
+                k_regen<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
                 PathJob pj;
                 pj.Q = Qin;
                 ctx->timed_begin(RM_KIND_PATHS);
-                if (ct) k_trace<PathJob, true><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
-                else k_trace<PathJob, false><<<tgrid, kTraceBlock, 0, st>>>(ctx->scene, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
+                launch_trace(ctx->scene, ctx->stack_levels, ct, tgrid, st, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
                 ctx->timed_end();
                 ctx->timed_begin(RM_KIND_SHADE);
-                k_surface<<<sgrid, 256, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
-                k_bounce<<<sgrid, 256, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
-                k_nee<<<sgrid, 256, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+                k_surface<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
+                k_bounce<<<sgrid, kShadeBlock, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
+                k_nee<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
                 ctx->timed_end();
                 k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 0);
                 ctx->launches += 7;

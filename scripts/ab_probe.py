@@ -1,0 +1,36 @@
+"""A/B perf probe: per-kernel-kind device times of one render (CUDA events inside the library).
+usage: [RM_LIB_PATH=variant.so] python scripts/ab_probe.py label spp [opt=value ...]
+Scene: the bench workload (glossy/dielectric 1M tris, 1080p)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from raym0nade_b200 import scenes
+from raym0nade_b200.api import Context, Model
+
+label, spp = sys.argv[1], int(sys.argv[2])
+opts = dict(a.split("=") for a in sys.argv[3:])
+which = opts.pop("scene", "glossy")
+import pickle
+cache = "/tmp/ab_scene_%s_%d.pkl" % (which, spp)
+if os.path.exists(cache):
+    scene, args = pickle.load(open(cache, "rb"))
+else:
+    if which == "glossy": scene, args = scenes.glossy_dielectric(1000000, 1920, 1080, spp)
+    elif which == "sponza": scene, args = scenes.sponza_scale(260000, 1920, 1080, spp, tex_size=1024)
+    try: pickle.dump((scene, args), open(cache, "wb"), protocol=4)
+    except Exception as e: print("scene cache not written:", e)
+model = Model(scene)
+ctx = Context(0).upload(model)
+for k, v in opts.items(): ctx.set_option(k, int(v))
+ctx.trace_primary(args, download=False); ctx.gbuffer(args, download=False)
+ctx.render_samples(args, seed=1); ctx.synchronize()          # warm-up
+best = None
+for rep in range(2):
+    ctx.set_option("time_kernels", 1); ctx.stats_reset(); ctx.synchronize()
+    t0 = time.time(); ctx.render_samples(args, seed=2 + rep); ctx.synchronize(); wall = (time.time() - t0) * 1e3
+    k = ctx.stats_kernels(); s = ctx.stats(); ctx.set_option("time_kernels", 0)
+    if best is None or wall < best[0]: best = (wall, k, s)
+wall, k, s = best
+print("%-22s wall %8.1f ms  %7.1f Mrays/s | paths %7.1f ms (%6.0f Mr/s)  shadow %7.1f ms (%6.0f Mr/s)  shade %7.1f ms | other %6.1f ms  launches %d" % (
+    label, wall, s["rays"] / wall / 1e3, k["paths"]["ms"], k["paths"]["rays"] / max(k["paths"]["ms"], 1e-9) / 1e3,
+    k["shadow"]["ms"], k["shadow"]["rays"] / max(k["shadow"]["ms"], 1e-9) / 1e3, k["shade"]["ms"],
+    wall - k["paths"]["ms"] - k["shadow"]["ms"] - k["shade"]["ms"], s["launches"]), flush=True)
