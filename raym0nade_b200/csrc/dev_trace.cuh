@@ -25,19 +25,6 @@ RM_DI void ldg256(const float4 *p, float4 &a, float4 &b) {
                  : "l"(p));
 }
 
-// Experiment (RM_PREFETCH): pull the line a lane will need in its next step into L1 while it waits for its turn.
-RM_DI void prefetch_l1(const void *p) {
-#ifdef RM_PREFETCH
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-RM_DI void prefetch_ref(const DevScene &S, int ref) {
-#ifdef RM_PREFETCH
-    if (ref >= 0) prefetch_l1(S.nodes + (size_t(ref) << 2));
-    else if (ref != int(0x80000000u)) prefetch_l1(S.tri + size_t((~ref) >> 4) * 3);
-#endif
-}
-
 // A reference to a BVH child: inner node index u >= 1, or a leaf encoded as ~(faceL<<4 | count).
 RM_DI int leaf_ref(int faceL, int faceR) { return ~((faceL << 4) | (faceR - faceL)); }
 constexpr int kTraceDone = int(0x80000000u);     // "stack empty": never a valid leaf ref (faceL < 2^27)
@@ -188,6 +175,9 @@ RM_DI bool transparent_test(const DevScene &S, const RaySetup &r, float t, int f
 //   void hit(int i, float t, int face);                  closest-hit result (kOcclusion == false)
 //   void visibility(int i, bool occluded);               rayHit_test result (kOcclusion == true)
 constexpr int kTraceChunk = 64;
+#ifndef RM_LEAF_REPS
+#define RM_LEAF_REPS 1              // leaf sub-steps (of two triangles each) a warp runs before it votes again
+#endif
 
 struct TraceTune {
     int refill_live;     // refill idle lanes once fewer than this many lanes are busy
@@ -291,10 +281,13 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                         }
                     }
                     ti = -1;
-                    prefetch_ref(S, cur);
                 }
             } else if (active && !wantI) {
                 if (ti < 0) { const int x = ~cur; ti = x >> 4; tend = ti + (x & 15); }        // first visit of this leaf
+#if RM_LEAF_REPS > 1
+#pragma unroll 1
+              for (int rep = 0; rep < RM_LEAF_REPS && ti >= 0; rep++) {
+#endif
                 // up to two triangles of the leaf per step, their six loads issued together
                 const float4 *q = S.tri + size_t(ti) * 3;
                 const bool two = ti + 1 < tend;
@@ -330,8 +323,10 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                             if (__int_as_float(e.y) < t) { cur = e.x; break; }
                         }
                     ti = -1;
-                    prefetch_ref(S, cur);
-                } else prefetch_l1(S.tri + size_t(ti) * 3);
+                }
+#if RM_LEAF_REPS > 1
+              }
+#endif
             }
             if (active && cur == kTraceDone) {
                 // one BVH::rayHit finished: resolve cut-outs, then report

@@ -29,7 +29,7 @@ namespace rm {
 #define RM_SHADE_BLOCK 256
 #endif
 #ifndef RM_SHADE_CTAS
-#define RM_SHADE_CTAS 2
+#define RM_SHADE_CTAS 3
 #endif
 constexpr int kShadeBlock = RM_SHADE_BLOCK;
 constexpr int kShadeCtasPerSm = RM_SHADE_CTAS;

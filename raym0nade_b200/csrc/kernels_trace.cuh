@@ -7,8 +7,11 @@
 
 namespace rm {
 
-constexpr int kTraceBlock = 128;
-constexpr int kTraceCtasPerSm = 8;
+#ifndef RM_TRACE_BLOCK
+#define RM_TRACE_BLOCK 128
+#endif
+constexpr int kTraceBlock = RM_TRACE_BLOCK;
+constexpr int kTraceCtasPerSm = 1024 / RM_TRACE_BLOCK;      // 1024 threads x 64 registers = the SM's register file
 
 // Work counters in device memory: [0] rays, [1] box tests, [2] triangle tests.
 RM_DI void flush_counters(const TraceCounters &c, unsigned long long *g, bool count_tests) {

@@ -69,7 +69,7 @@ struct RmContext {
     DevBuf b_cursor;                       // int[4]: work cursors of the persistent trace kernels
     int sm_count = 148;
     int stack_levels = 24;                 // traversal stack entries per ray = tree depth of the uploaded scene (rm_scene_upload)
-    rm::TraceTune tune{24, 1, 1};          // see dev_trace.cuh; adjustable through rm_set_option for perf experiments
+    rm::TraceTune tune{28, 1, 1};          // see dev_trace.cuh; adjustable through rm_set_option for perf experiments
     int max_depth = 16;                    // perf experiments only: bounce limit of the wavefront loop (16 = the reference's maxRayDepth)
 
     // per-frame state

@@ -14,12 +14,12 @@ pytestmark = pytest.mark.gpu
 T_REL_TOL = 1e-5   # the north star's stated tolerance; asserted in addition to bit equality
 
 
-def _compare_primary(ref, scene, args):
+def _compare_primary(ref, scene, args, threads=8):
     model = Model(scene)
     R = ref.RefScene(scene)
     ctx = Context(0).upload(model)
     tri, t = ctx.trace_primary(args)
-    rtri, rt = R.trace_primary(args)
+    rtri, rt = R.trace_primary(args, threads=threads)
     assert np.array_equal(tri, rtri), "tri_idx mismatches: %d of %d" % ((tri != rtri).sum(), tri.size)
     hit = rtri >= 0
     assert np.all(np.isinf(t[~hit])) and np.all(np.isinf(rt[~hit]))
@@ -49,6 +49,40 @@ def test_primary_cutout_materials(ref):
     """alpha cut-outs exercise the <=8 re-trace loop of Model::rayHit (src/model.cpp:332-341)"""
     scene, args = scenes.texture_heavy(40_000, 320, 180, tex_size=64, n_materials=8)
     assert _compare_primary(ref, scene, args) > 0.3
+
+
+def test_primary_glossy_1m_1080p_full_size(ref):
+    """BASELINE config 3's scene and frame at full size: every one of the 2 073 600 primary hits against the reference"""
+    import os
+    scene, args = scenes.glossy_dielectric(1_000_000, 1920, 1080, 0)
+    assert _compare_primary(ref, scene, args, threads=os.cpu_count() or 8) > 0.3
+
+
+def test_primary_five_million_4k_full_size(ref):
+    """BASELINE config 5 at full size: 5 M triangles, 3840x2160 - tri_idx identical and t bit-equal for all
+    8 294 400 pixels, then the FXAA pass over the shaded 4K frame bit-equal to Photo::FXAA"""
+    import os
+    scene, args = scenes.five_million(5_000_000, 3840, 2160)
+    model = Model(scene)
+    R = ref.RefScene(scene)
+    ctx = Context(0).upload(model)
+    tri, t = ctx.trace_primary(args)
+    rtri, rt = R.trace_primary(args, threads=os.cpu_count() or 8)
+    assert np.array_equal(tri, rtri), "tri_idx mismatches: %d of %d" % ((tri != rtri).sum(), tri.size)
+    assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)), "t not bit-equal"
+    assert 0.3 < (rtri >= 0).mean() < 1.0
+    # FXAA on the 4K frame shaded from the G-buffer (base colour x facing ratio stands in for the lit image: the
+    # pass only sees an rgb frame); compared with the reference's own Photo::FXAA on the same input
+    g = ctx.gbuffer(args.replace(spp=0))
+    hit = ~np.isnan(g["position"][:, 0])
+    view = np.asarray(args.direction, np.float32)
+    facing = np.abs(g["shapeNormal"] @ view).astype(np.float32)
+    img = np.where(hit[:, None], g["baseColor"] * facing[:, None], np.float32(0.1)).astype(np.float32).reshape(args.height, args.width, 3)
+    got = ctx.fxaa(img)
+    want = ref.fxaa(img)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert not np.array_equal(got, img)            # the pass did smooth edges
+    ctx.close()
 
 
 def _random_rays(scene, n, seed):
