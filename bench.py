@@ -88,13 +88,30 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+class StdoutToStderr:
+    """The reference's C++ code prints progress on stdout (std::cout in Model / BVH); stdout carries the JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def cpu_reference_run(scene, args, threads):
     """The reference's own renderPixel loop (oracle/_ref) on a bounded sample of the workload."""
     from oracle import refbind
     a = args.replace(**CPU_SAMPLE)
-    R = refbind.RefScene(scene)
-    out = R.render(a, threads=threads, seed_base=0)
-    R.close()
+    with StdoutToStderr():
+        R = refbind.RefScene(scene)
+        out = R.render(a, threads=threads, seed_base=0)
+        R.close()
     return out, a
 
 
@@ -110,14 +127,15 @@ def run_reference(opt, rank, world):
     threads = os.cpu_count() or 1
     scene, args = build_workload(opt.spp)
     a = args.replace(**CPU_SAMPLE)
-    R = refbind.RefScene(scene)
-    for _ in range(opt.warmup):
-        R.render(a, threads=threads, seed_base=0)
     rays, secs = 0, 0.0
-    for i in range(opt.steps):
-        o = R.render(a, threads=threads, seed_base=1000 * (i + 1))
-        rays += o["rays"]
-        secs += o["seconds"]
+    with StdoutToStderr():
+        R = refbind.RefScene(scene)
+        for _ in range(opt.warmup):
+            R.render(a, threads=threads, seed_base=0)
+        for i in range(opt.steps):
+            o = R.render(a, threads=threads, seed_base=1000 * (i + 1))
+            rays += o["rays"]
+            secs += o["seconds"]
     value = rays / secs / 1e6
     sample = "same scene and camera at %dx%d, %d spp per step (cost is linear in pixels x spp)" % (a.width, a.height, a.spp)
     print(json.dumps(dict(base, value=value, ms_per_step=1e3 * secs / opt.steps,

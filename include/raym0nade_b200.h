@@ -173,8 +173,21 @@ int rm_render(RmContext *ctx, const RmRenderArgs *args, uint64_t seed,
 int rm_fxaa(RmContext *ctx, const float *rgb_in, float *rgb_out, int32_t width, int32_t height);
 /* Same on device buffers (no copies): d_rgb_in/d_rgb_out [h][w][3]. */
 int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int32_t width, int32_t height);
-/* Photo::shade (src/image.cpp:215-246) + gammaCorrection (454-468) [+ FXAA when
- * shade_options has DoFXAA = 512] on the context's resolved planes -> host RGB. */
+/* Stage host Photo buffers (Gbuffer + radiance_Dd/Ds/Id/Is, include/image.h:38-47) as the context's resolved
+ * frame, so the image-space passes below can run on planes produced elsewhere (e.g. the reference's CPU render). */
+int rm_upload_resolved(RmContext *ctx, const RmRenderArgs *args, const RmHitInfo *gbuffer, const RmRadiance *Dd,
+                       const RmRadiance *Ds, const RmRadiance *Id, const RmRadiance *Is);
+/* Photo::spatialClamp (include/image.h, src/image.cpp:30-82): 7x7 separable luminance blur per plane and a
+ * rescale of pixels brighter than 36x their neighbourhood; in place on the context's resolved planes
+ * (device).  render_multiThread applies it before the "Raw" exports (src/render.cpp:645). */
+int rm_spatial_clamp(RmContext *ctx, const RmRenderArgs *args);
+/* Photo::filter (src/image.cpp:84-213): filterVar, then five edge-stopping a-trous passes (steps 1,2,4,8,16)
+ * over each of the four planes, guided by the resolved G-buffer; in place on the context's planes (device).
+ * Fetch the result with rm_download_resolved or shade it with rm_postprocess. */
+int rm_filter(RmContext *ctx, const RmRenderArgs *args);
+/* Photo::postProcessing (src/image.cpp:470-479) without depth-of-field: shade (215-246) [+ bloom (248-283) when
+ * shade_options has DoBloom = 256] + gammaCorrection (454-468) [+ FXAA when it has DoFXAA = 512] on the
+ * context's resolved planes -> host RGB. */
 int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_options, float *rgb_out);
 
 /* ---------------------------------------------------------------------------------

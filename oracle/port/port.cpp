@@ -544,8 +544,9 @@ void fxaa(const vec3 *data, vec3 *output, int width, int height) {
         }
 }
 
-// Photo::shade + gammaCorrection (src/image.cpp:215-246, 454-468)
-vec3 shadeGamma(const RmHitInfo &G, const RmRadiance *pl[4], size_t i, float exposure, int options) {
+// Photo::shade (src/image.cpp:215-246)
+vec3 gammaPixel(vec3 pix);
+vec3 shadePixel(const RmHitInfo &G, const RmRadiance *pl[4], size_t i, float exposure, int options) {
     vec3 pix;
     if (options & 64) pix = div_scalar(v3(G.shapeNormal) + v3(1.0f), 2.0f);
     else if (options & 128) pix = div_scalar(v3(G.surfaceNormal) + v3(1.0f), 2.0f);
@@ -558,6 +559,11 @@ vec3 shadeGamma(const RmHitInfo &G, const RmRadiance *pl[4], size_t i, float exp
         pix = dc * rd + rs;
         if (options & 2) pix = pix + v3(G.emission) * exposure;
     }
+    return pix;
+}
+
+// Photo::gammaCorrection (src/image.cpp:454-468)
+vec3 gammaPixel(vec3 pix) {
     auto mx = [](float x, float y) { return (x < y) ? y : x; };
     auto mn = [](float x, float y) { return (y < x) ? y : x; };
     pix = {mx(pix.x, 0.0f), mx(pix.y, 0.0f), mx(pix.z, 0.0f)};
@@ -597,6 +603,8 @@ void toRm(const HitInfo &h, RmHitInfo &g) {
 } // namespace port
 
 using namespace port;
+
+extern "C" void port_bloom(float *rgb, int width, int height);
 
 extern "C" {
 
@@ -735,7 +743,9 @@ void port_postprocess(const RmHitInfo *g, const RmRadiance *Dd, const RmRadiance
     const RmRadiance *pl[4] = {Dd, Ds, Id, Is};
     size_t n = size_t(width) * height;
     std::vector<vec3> img(n), tmp;
-    for (size_t i = 0; i < n; i++) img[i] = shadeGamma(g[i], pl, i, exposure, options);
+    for (size_t i = 0; i < n; i++) img[i] = shadePixel(g[i], pl, i, exposure, options);
+    if (options & 256) port_bloom(reinterpret_cast<float *>(img.data()), width, height);      // DoBloom (port_post.cpp)
+    for (size_t i = 0; i < n; i++) img[i] = gammaPixel(img[i]);
     if (options & 512) { tmp.resize(n); fxaa(img.data(), tmp.data(), width, height); img.swap(tmp); }
     std::memcpy(rgb_out, img.data(), n * sizeof(vec3));
 }

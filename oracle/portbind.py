@@ -37,6 +37,8 @@ def load():
     L.port_gbuffer.argtypes = [vp, C.POINTER(RmRenderArgs), i32, vp]
     L.port_fxaa.argtypes = [vp, vp, i32, i32]
     L.port_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
+    L.port_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
+    L.port_bloom.argtypes = [vp, i32, i32]
     L.port_kat_ray_in_box.argtypes = [i64, vp, vp, vp]
     L.port_kat_ray_triangle.argtypes = [i64, vp, vp, vp]
     L.port_kat_barycentric.argtypes = [i64, vp, vp, vp]
@@ -168,6 +170,13 @@ def fxaa(rgb):
     out = np.zeros_like(rgb)
     load().port_fxaa(_p(rgb), _p(out), w, h)
     return out
+
+
+def denoise(gbuffer, Dd, Ds, Id, Is, width, height, stages):
+    """Photo::spatialClamp (stages & 1) then Photo::filter (stages & 2) on copies of the four planes"""
+    planes = [np.ascontiguousarray(p).copy() for p in (Dd, Ds, Id, Is)]
+    load().port_denoise(_p(gbuffer), *[_p(p) for p in planes], width, height, stages)
+    return dict(Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
 
 
 def postprocess(gbuffer, Dd, Ds, Id, Is, width, height, exposure, shade_options):

@@ -448,8 +448,8 @@ void ref_fxaa(const float *rgb_in, float *rgb_out, int width, int height) {
     photo.pixelarray = nullptr;
 }
 
-// Photo::shade + gammaCorrection [+ FXAA] = Photo::postProcessing (src/image.cpp:470-479)
-// without bloom / depth-of-field, on caller-supplied planes.
+// Photo::shade [+ bloom] + gammaCorrection [+ FXAA] = Photo::postProcessing (src/image.cpp:470-479)
+// without depth-of-field, on caller-supplied planes.
 void ref_postprocess(const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRadiance *Ds, const RmRadiance *Id,
                      const RmRadiance *Is, int width, int height, float exposure, int shade_options, float *rgb_out) {
     Photo photo(width, height);
@@ -460,8 +460,25 @@ void ref_postprocess(const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRad
     std::memcpy(static_cast<void *>(photo.radiance_Ds), Ds, n * sizeof(RmRadiance));
     std::memcpy(static_cast<void *>(photo.radiance_Id), Id, n * sizeof(RmRadiance));
     std::memcpy(static_cast<void *>(photo.radiance_Is), Is, n * sizeof(RmRadiance));
-    photo.postProcessing(shade_options & ~(Photo::DoBloom | Photo::DoDepthFieldBlur));
+    photo.postProcessing(shade_options & ~Photo::DoDepthFieldBlur);
     std::memcpy(rgb_out, photo.pixelarray, n * sizeof(vec3));
+    delete[] photo.pixelarray;
+    photo.pixelarray = nullptr;
+}
+
+// Photo::spatialClamp (src/image.cpp:78-83) and Photo::filter (203-213) on caller-supplied planes, in place,
+// in the order render_multiThread applies them (src/render.cpp:645, 654).  stages: bit 0 clamp, bit 1 filter.
+void ref_denoise(const RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is,
+                 int width, int height, int stages) {
+    Photo photo(width, height);
+    size_t n = size_t(width) * height;
+    RmRadiance *host[4] = {Dd, Ds, Id, Is};
+    RadianceData *mine[4] = {photo.radiance_Dd, photo.radiance_Ds, photo.radiance_Id, photo.radiance_Is};
+    std::memcpy(static_cast<void *>(photo.Gbuffer), gbuffer, n * sizeof(RmHitInfo));
+    for (int k = 0; k < 4; k++) std::memcpy(static_cast<void *>(mine[k]), host[k], n * sizeof(RmRadiance));
+    if (stages & 1) photo.spatialClamp();
+    if (stages & 2) photo.filter();
+    for (int k = 0; k < 4; k++) std::memcpy(host[k], mine[k], n * sizeof(RmRadiance));
     delete[] photo.pixelarray;
     photo.pixelarray = nullptr;
 }

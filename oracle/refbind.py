@@ -58,6 +58,7 @@ def load(flavour="plain"):
     L.ref_gbuffer.argtypes = [vp, C.POINTER(RmRenderArgs), i32, vp]
     L.ref_fxaa.argtypes = [vp, vp, i32, i32]
     L.ref_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
+    L.ref_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
     L.ref_kat_ray_in_box.argtypes = [i64, vp, vp, vp]
     L.ref_kat_ray_triangle.argtypes = [i64, vp, vp, vp]
     L.ref_kat_barycentric.argtypes = [i64, vp, vp, vp]
@@ -291,6 +292,14 @@ def fxaa(rgb):
     out = np.zeros_like(rgb)
     L.ref_fxaa(_p(rgb), _p(out), w, h)
     return out
+
+
+def denoise(gbuffer, Dd, Ds, Id, Is, width, height, stages):
+    """Photo::spatialClamp (stages & 1) then Photo::filter (stages & 2) on copies of the four planes"""
+    L = load()
+    planes = [np.ascontiguousarray(p).copy() for p in (Dd, Ds, Id, Is)]
+    L.ref_denoise(_p(gbuffer), *[_p(p) for p in planes], width, height, stages)
+    return dict(Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
 
 
 def postprocess(gbuffer, Dd, Ds, Id, Is, width, height, exposure, shade_options):

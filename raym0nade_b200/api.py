@@ -56,7 +56,7 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
-           "rm_fxaa_device", "rm_postprocess", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -97,6 +97,9 @@ def lib():
     L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
     L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
+    L.rm_upload_resolved.argtypes = [vp, ARGS, vp, vp, vp, vp, vp]
+    L.rm_spatial_clamp.argtypes = [vp, ARGS]
+    L.rm_filter.argtypes = [vp, ARGS]
     L.rm_stats_reset.argtypes = [vp]
     L.rm_stats_read.argtypes = [vp, vp]
     L.rm_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -302,6 +305,31 @@ class Context:
 
     def fxaa_device(self, d_in: int, d_out: int, width: int, height: int):
         _check(lib().rm_fxaa_device(self.h, C.c_void_p(d_in), C.c_void_p(d_out), width, height))
+
+    def upload_resolved(self, args: RenderArgs, gbuffer, planes):
+        """stage host Photo buffers (G-buffer + [Dd, Ds, Id, Is]) as the resolved frame"""
+        a = args.to_c()
+        g = np.ascontiguousarray(gbuffer)
+        pl = [np.ascontiguousarray(p) for p in planes]
+        _check(lib().rm_upload_resolved(self.h, C.byref(a), _p(g), *[_p(p) for p in pl]))
+
+    def spatial_clamp(self, args: RenderArgs):
+        """Photo::spatialClamp on the resolved planes (device, in place)"""
+        a = args.to_c()
+        _check(lib().rm_spatial_clamp(self.h, C.byref(a)))
+
+    def filter(self, args: RenderArgs):
+        """Photo::filter on the resolved planes (device, in place)"""
+        a = args.to_c()
+        _check(lib().rm_filter(self.h, C.byref(a)))
+
+    def resolved(self, args: RenderArgs):
+        """the resolved G-buffer + four planes as they currently stand on the device"""
+        n = args.width * args.height
+        g = np.zeros(n, HITINFO_DTYPE)
+        planes = [np.zeros(n, RADIANCE_DTYPE) for _ in range(4)]
+        self.download_resolved(g, planes)
+        return dict(gbuffer=g, Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
 
     def postprocess(self, args: RenderArgs, shade_options: int):
         a = args.to_c()

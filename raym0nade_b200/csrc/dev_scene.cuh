@@ -15,6 +15,13 @@
 
 namespace rm {
 
+// float4 per face in the traversal stream `tri`: 3 used; 4 = each record padded to one aligned 64-byte block so its
+// first 32 bytes come with a single 256-bit load (the L1 data pipe is bound by per-lane load count, not bytes)
+#ifndef RM_TRI_STRIDE
+#define RM_TRI_STRIDE 3
+#endif
+constexpr int kTriStride = RM_TRI_STRIDE;
+
 struct DevTexture {
     int32_t width, height, channels, map_depth;
     uint32_t offset[8];             // byte offset of each level in the texel blob

@@ -143,7 +143,7 @@ RM_DI V2 interp_uv(const FaceShade &F, V3 bary) {
 
 // TransparentTest (src/model.cpp:217-230): true when the hit texel is an alpha cut-out
 RM_DI bool transparent_test(const DevScene &S, const RaySetup &r, float t, int face) {
-    float cut = __ldg(&S.tri[size_t(face) * 3 + 2].z);
+    float cut = __ldg(&S.tri[size_t(face) * kTriStride + 2].z);
     if (cut == 0.0f) return false;                       // material without hasFullyTransparentPart
     FaceShade F = load_face(S, face);
     V3 P = r.o + r.d * t;
@@ -289,11 +289,20 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
               for (int rep = 0; rep < RM_LEAF_REPS && ti >= 0; rep++) {
 #endif
                 // up to two triangles of the leaf per step, their six loads issued together
-                const float4 *q = S.tri + size_t(ti) * 3;
+                const float4 *q = S.tri + size_t(ti) * kTriStride;
                 const bool two = ti + 1 < tend;
+#if RM_TRI_STRIDE == 4
+                float4 qa, qb, qd, qe;
+                ldg256(q, qa, qb);
+                const float4 qc = __ldg(q + 2);
+                float4 qf = qc;
+                qd = qa; qe = qb;
+                if (two) { ldg256(q + 4, qd, qe); qf = __ldg(q + 6); }
+#else
                 const float4 qa = __ldg(q), qb = __ldg(q + 1), qc = __ldg(q + 2);
                 float4 qd = qa, qe = qb, qf = qc;
                 if (two) { qd = __ldg(q + 3); qe = __ldg(q + 4); qf = __ldg(q + 5); }
+#endif
                 // both tests are evaluated straight-line and interleaved (a lane without a second triangle repeats the first)
                 const float tt = ray_triangle(r, qa, qb, qc);
                 const float t2 = ray_triangle(r, qd, qe, qf);

@@ -82,9 +82,22 @@ __global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__res
 // Photo::ShadeOption bits (include/image.h:17-36)
 enum { kBaseColor = 1, kEmission = 2, kDirect = 4, kIndirect = 8, kDiffuse = 16, kSpecular = 32, kShapeNormal = 64, kSurfaceNormal = 128 };
 
+// Photo::gammaCorrection for one pixel (src/image.cpp:454-468)
+RM_DI V3 gamma_pixel(V3 pix) {
+    pix.x = (pix.x < 0.0f) ? 0.0f : pix.x; pix.y = (pix.y < 0.0f) ? 0.0f : pix.y; pix.z = (pix.z < 0.0f) ? 0.0f : pix.z;
+    float C = lum(pix);
+    if (C > 0.75f) {
+        float bound = fadd(fdiv(tanhf(fmul(3.0f, fsub(C, 0.75f))), 3.0f), 0.75f);
+        pix = div_recip(pix, C) * bound;
+    }
+    pix.x = (1.0f < pix.x) ? 1.0f : pix.x; pix.y = (1.0f < pix.y) ? 1.0f : pix.y; pix.z = (1.0f < pix.z) ? 1.0f : pix.z;
+    const float ig = fdiv(1.0f, 2.2f);
+    return mk3(powf(pix.x, ig), powf(pix.y, ig), powf(pix.z, ig));
+}
+
 __global__ void k_shade_gamma(const RmHitInfo *__restrict__ G, const RmRadiance *__restrict__ Dd, const RmRadiance *__restrict__ Ds,
                               const RmRadiance *__restrict__ Id, const RmRadiance *__restrict__ Is, int npix, float exposure, int options,
-                              float *__restrict__ rgb) {
+                              bool do_gamma, float *__restrict__ rgb) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     const float *g = reinterpret_cast<const float *>(G + i);
@@ -106,16 +119,235 @@ __global__ void k_shade_gamma(const RmHitInfo *__restrict__ G, const RmRadiance 
         pix = dc * rd + rs;
         if (options & kEmission) pix = pix + mk3(g[6], g[7], g[8]) * exposure;
     }
-    // gammaCorrection
-    pix.x = (pix.x < 0.0f) ? 0.0f : pix.x; pix.y = (pix.y < 0.0f) ? 0.0f : pix.y; pix.z = (pix.z < 0.0f) ? 0.0f : pix.z;
-    float C = lum(pix);
-    if (C > 0.75f) {
-        float bound = fadd(fdiv(tanhf(fmul(3.0f, fsub(C, 0.75f))), 3.0f), 0.75f);
-        pix = div_recip(pix, C) * bound;
+    if (do_gamma) pix = gamma_pixel(pix);
+    rgb[3 * i] = pix.x; rgb[3 * i + 1] = pix.y; rgb[3 * i + 2] = pix.z;
+}
+
+// Photo::gammaCorrection alone, in place (used when bloom sits between shade and gamma)
+__global__ void k_gamma(float *__restrict__ rgb, int npix) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    V3 pix = gamma_pixel(mk3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
+    rgb[3 * i] = pix.x; rgb[3 * i + 1] = pix.y; rgb[3 * i + 2] = pix.z;
+}
+
+// ------------------------------------------------------------------ image-space passes over the radiance planes
+// (SURVEY.md section 8f).  The four planes Dd, Ds, Id, Is are handled by one launch each pass; every pass reads one
+// set of planes and writes another (the reference filters into temporaries and copies back).
+struct Planes4 { RmRadiance *p[4]; };
+
+RM_DI float4 ld_rad(const RmRadiance *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+RM_DI void st_rad(RmRadiance *p, V3 r, float var) { *reinterpret_cast<float4 *>(p) = make_float4(r.x, r.y, r.z, var); }
+
+// clamp / Photo::spatialClamp (src/image.cpp:30-82): luminance, 7-tap blur along x then y (taps outside the image
+// skipped - adding their +0 products instead is the same sum), and a rescale of pixels that outshine 36x the
+// blurred luminance of their neighbourhood.  One CTA = a 32x8 tile with a 3-pixel apron in shared memory;
+// blockIdx.z = plane.  Summation order is the reference's, so the result is bit-equal.
+constexpr int kClW = 32, kClH = 8, kClR = 3;
+__constant__ float c_tap7[7] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+
+__global__ void __launch_bounds__(kClW * kClH) k_spatial_clamp(Planes4 in, Planes4 out, int width, int height) {
+    __shared__ float s_lum[kClH + 2 * kClR][kClW + 2 * kClR];
+    __shared__ float s_bx[kClH + 2 * kClR][kClW];
+    const RmRadiance *src = in.p[blockIdx.z];
+    const int x0 = blockIdx.x * kClW, y0 = blockIdx.y * kClH;
+    const int tid = threadIdx.y * kClW + threadIdx.x;
+    for (int k = tid; k < (kClH + 2 * kClR) * (kClW + 2 * kClR); k += kClW * kClH) {
+        const int ty = k / (kClW + 2 * kClR), tx = k % (kClW + 2 * kClR);
+        const int gx = x0 + tx - kClR, gy = y0 + ty - kClR;
+        float l = 0.0f;
+        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
+            const float4 r = ld_rad(src + size_t(gy) * width + gx);
+            l = lum(mk3(r.x, r.y, r.z));
+        }
+        s_lum[ty][tx] = l;
     }
-    pix.x = (1.0f < pix.x) ? 1.0f : pix.x; pix.y = (1.0f < pix.y) ? 1.0f : pix.y; pix.z = (1.0f < pix.z) ? 1.0f : pix.z;
-    const float ig = fdiv(1.0f, 2.2f);
-    rgb[3 * i] = powf(pix.x, ig); rgb[3 * i + 1] = powf(pix.y, ig); rgb[3 * i + 2] = powf(pix.z, ig);
+    __syncthreads();
+    for (int k = tid; k < (kClH + 2 * kClR) * kClW; k += kClW * kClH) {
+        const int ty = k / kClW, tx = k % kClW;
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < 7; d++) acc = fadd(acc, fmul(s_lum[ty][tx + d], c_tap7[d]));
+        // rows outside the image must contribute nothing to the vertical pass
+        const int gy = y0 + ty - kClR;
+        s_bx[ty][tx] = (gy >= 0 && gy < height) ? acc : 0.0f;
+    }
+    __syncthreads();
+    const int gx = x0 + threadIdx.x, gy = y0 + threadIdx.y;
+    if (gx >= width || gy >= height) return;
+    float acc = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 7; d++) acc = fadd(acc, fmul(s_bx[threadIdx.y + d][threadIdx.x], c_tap7[d]));
+    const float centre = fmul(c_tap7[3], c_tap7[3]);
+    const float l = s_lum[threadIdx.y + kClR][threadIdx.x + kClR];
+    const float others = fsub(acc, fmul(centre, l));
+    const size_t p = size_t(gy) * width + gx;
+    float4 r = ld_rad(src + p);
+    if (l > fmul(36.0f, others)) {
+        const float sc = fdiv(fdiv(others, fadd(l, kEps)), fsub(1.0f, centre));
+        r.x = fmul(r.x, sc); r.y = fmul(r.y, sc); r.z = fmul(r.z, sc);
+    }
+    *reinterpret_cast<float4 *>(out.p[blockIdx.z] + p) = r;
+}
+
+// filterVar (src/image.cpp:84-107): 3x3 binomial estimate of the variance; radiance passes through
+__global__ void k_filter_var(Planes4 in, Planes4 out, int width, int height) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const RmRadiance *src = in.p[blockIdx.z];
+    const float tap[3] = {0.25f, 0.5f, 0.25f};
+    V3 E = splat3(0.0f);
+    float E2 = 0.0f, Vs = 0.0f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            const int nx = x + dx, ny = y + dy;
+            if (nx < 0 || nx >= width || ny < 0 || ny >= height) continue;
+            const float4 q = ld_rad(src + size_t(ny) * width + nx);
+            const V3 r = mk3(q.x, q.y, q.z);
+            const float w = fmul(tap[dx + 1], tap[dy + 1]);
+            E = E + r * w;
+            E2 = fadd(E2, fmul(dot(r, r), w));
+            Vs = fadd(Vs, fmul(q.w, w));
+        }
+    const size_t p = size_t(y) * width + x;
+    const float4 c = ld_rad(src + p);
+    st_rad(out.p[blockIdx.z] + p, mk3(c.x, c.y, c.z), fsub(fadd(Vs, E2), dot(E, E)));
+}
+
+// The G-buffer fields the edge-stopping weight reads at a NEIGHBOUR (src/image.cpp:109-158), packed from the 88-byte
+// HitInfo records into two float4 per pixel: {position, metallic} {surfaceNormal, specular} + opacity.
+struct FilterG { float4 *pm, *ns; float *opacity; };
+
+__global__ void k_filter_pack(const RmHitInfo *__restrict__ G, FilterG F, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float *g = reinterpret_cast<const float *>(G + i);
+    F.pm[i] = make_float4(g[12], g[13], g[14], g[17]);
+    F.ns[i] = make_float4(g[3], g[4], g[5], g[15]);
+    F.opacity[i] = g[18];
+}
+
+// One a-trous pass of filterRadiance (src/image.cpp:160-191) for all four planes: the geometric factors of getWeight
+// (normal power, grazing-angle term, material distance) are shared by the planes, the radiance-distance term and
+// exp() are per plane.  powf / expf are CUDA's (<= 2 ulp from glibc's): results agree with the reference to ~1e-6
+// relative, not bit for bit - the tolerance is stated in tests/test_gpu_post.py.
+__global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G, FilterG F, Planes4 in, Planes4 out, int width, int height, int step) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const size_t p = size_t(y) * width + x;
+    const float4 Ap = __ldg(F.pm + p);
+    const V3 posp = mk3(Ap.x, Ap.y, Ap.z);
+    if (!isfinite_any(posp)) {                  // background: the reference leaves its zero-initialised buffers
+#pragma unroll
+        for (int j = 0; j < 4; j++) st_rad(out.p[j] + p, splat3(0.0f), 0.0f);
+        return;
+    }
+    const float4 Bp = __ldg(F.ns + p);
+    const V3 snp = mk3(Bp.x, Bp.y, Bp.z);
+    const float opp = __ldg(F.opacity + p);
+    const float *gp = reinterpret_cast<const float *>(G + p);
+    const V3 shp = mk3(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2));
+    const float rough = __ldg(gp + 16);
+    const float spec_scale = (rough < 4e-2f) ? 4e-2f : rough;          // std::max(Gp.roughness, eps_r)
+    float4 Lp[4];
+    float sig[4], wsum[4], var[4];
+    V3 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        Lp[j] = ld_rad(in.p[j] + p);
+        sig[j] = fadd(fsqrt(Lp[j].w), 1e-2f);                          // sigma_l * sqrt(Lp.Var) + eps
+        wsum[j] = 0.0f; var[j] = 0.0f; acc[j] = splat3(0.0f);
+    }
+    const float tap[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+#pragma unroll 1
+    for (int dy = -2; dy <= 2; dy++)
+#pragma unroll 1
+        for (int dx = -2; dx <= 2; dx++) {
+            const int nx = x + dx * step, ny = y + dy * step;
+            if (nx < 0 || nx >= width || ny < 0 || ny >= height) continue;
+            const size_t q = size_t(ny) * width + nx;
+            const float base = fmul(tap[dx + 2], tap[dy + 2]);
+            float4 Lq[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) Lq[j] = ld_rad(in.p[j] + q);
+            float w[4] = {base, base, base, base};
+            if (dx != 0 || dy != 0) {
+                const float4 Aq = __ldg(F.pm + q);
+                const V3 posq = mk3(Aq.x, Aq.y, Aq.z);
+                float wn = 0.0f, kg = 0.0f;
+                if (isfinite_any(posq)) {
+                    const float4 Bq = __ldg(F.ns + q);
+                    const float d = dot(snp, mk3(Bq.x, Bq.y, Bq.z));
+                    wn = powf((0.0f < d) ? d : 0.0f, 1024.0f);
+                    if (wn < 1e-6f) wn = 0.0f;
+                    else {
+                        const V3 dir = normalize(posq - posp);
+                        const float sn = fabsf(dot(shp, dir));
+                        const float tanT = fdiv(sn, fadd(fsqrt(fsub(1.0f, fmul(sn, sn))), kEps));
+                        const float dm = length(mk3(fsub(Ap.w, Aq.w), fsub(Bp.w, Bq.w), fsub(opp, __ldg(F.opacity + q))));
+                        // k = ((0 - tan/sigma_z) - radianceDiff) - materialDiff/sigma_m; the middle term is per plane
+                        kg = -tanT;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float dr = fdiv(length(mk3(fsub(Lp[j].x, Lq[j].x), fsub(Lp[j].y, Lq[j].y), fsub(Lp[j].z, Lq[j].z))), sig[j]);
+                            const float k = fadd(fadd(kg, -dr), -dm);
+                            float wj = 0.0f;
+                            if (!(k < -7.5f)) {
+                                wj = fmul(wn, expf(k));
+                                if (j & 1) wj = fmul(wj, spec_scale);
+                                if (!isfinite(wj)) wj = 0.0f;
+                            }
+                            w[j] = fmul(base, wj);
+                        }
+                    }
+                }
+                if (wn == 0.0f) { w[0] = w[1] = w[2] = w[3] = fmul(base, 0.0f); }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                wsum[j] = fadd(wsum[j], w[j]);
+                acc[j] = acc[j] + mk3(Lq[j].x, Lq[j].y, Lq[j].z) * w[j];
+                var[j] = fadd(var[j], fmul(fmul(Lq[j].w, w[j]), w[j]));
+            }
+        }
+#pragma unroll
+    for (int j = 0; j < 4; j++) st_rad(out.p[j] + p, div_true(acc[j], wsum[j]), fdiv(var[j], fmul(wsum[j], wsum[j])));
+}
+
+// Photo::bloom (src/image.cpp:248-283): bright pass, then five dilated 5x5 binomial blurs, each added at 1/6
+__global__ void k_bloom_bright(const float *__restrict__ rgb, float *__restrict__ glow, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const V3 c = mk3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    const float L = lum(c);
+    V3 g = splat3(0.0f);
+    if (!(L < 1.0f)) {
+        const V3 b = div_recip(c, powf(L, 0.65f));
+        g = mk3(fmaxf(fsub(b.x, 1.0f), 0.0f), fmaxf(fsub(b.y, 1.0f), 0.0f), fmaxf(fsub(b.z, 1.0f), 0.0f));
+    }
+    glow[3 * i] = g.x; glow[3 * i + 1] = g.y; glow[3 * i + 2] = g.z;
+}
+
+__global__ void k_bloom_pass(const float *__restrict__ prev, float *__restrict__ glow, float *__restrict__ rgb, int width, int height, int step) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const float tap[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    V3 acc = splat3(0.0f);
+#pragma unroll
+    for (int ky = -2; ky <= 2; ky++)
+#pragma unroll
+        for (int kx = -2; kx <= 2; kx++) {
+            const int nx = x + kx * step, ny = y + ky * step;
+            if (nx < 0 || nx >= width || ny < 0 || ny >= height) continue;
+            const float *q = prev + (size_t(ny) * width + nx) * 3;
+            acc = acc + (mk3(__ldg(q), __ldg(q + 1), __ldg(q + 2)) * tap[ky + 2]) * tap[kx + 2];
+        }
+    const size_t i = size_t(y) * width + x;
+    glow[3 * i] = acc.x; glow[3 * i + 1] = acc.y; glow[3 * i + 2] = acc.z;
+    const V3 add = div_recip(acc, 6.0f);
+    rgb[3 * i] = fadd(rgb[3 * i], add.x); rgb[3 * i + 1] = fadd(rgb[3 * i + 1], add.y); rgb[3 * i + 2] = fadd(rgb[3 * i + 2], add.z);
 }
 
 } // namespace rm

@@ -119,7 +119,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if ((rc = upload(ctx->b_mats, mats.data(), mats.size() * sizeof(DevMaterial), st, total))) return rc;
 
     // traversal records (48 B) and shading records (112 B)
-    std::vector<float> tri(size_t(n) * 12), shade(size_t(n) * 28, 0.0f);
+    std::vector<float> tri(size_t(n) * 4 * kTriStride, 0.0f), shade(size_t(n) * 28, 0.0f);
     for (int i = 0; i < n; i++) {
         const float *p = sc->positions + size_t(i) * 9;
         int mat = sc->face_material[i];
@@ -127,7 +127,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         float e1[3], e2[3];
         for (int k = 0; k < 3; k++) { e1[k] = p[3 + k] - p[k]; e2[k] = p[6 + k] - p[k]; }
         float len = std::sqrt((e1[0] * e1[0] + e1[1] * e1[1]) + e1[2] * e1[2]);   // glm::length(edge1)
-        float *t = &tri[size_t(i) * 12];
+        float *t = &tri[size_t(i) * 4 * kTriStride];
         t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = e1[0];
         t[4] = e1[1]; t[5] = e1[2]; t[6] = e2[0]; t[7] = e2[1];
         t[8] = e2[2]; t[9] = len; t[10] = mats[mat].cutout ? 1.0f : 0.0f; t[11] = 0.0f;

@@ -30,6 +30,9 @@ struct RenderState {
     int *h_counts = nullptr;  // pinned mirror of `counts`
     // resolved planes + output images
     DevBuf planes[4], g_out, rgb[2];
+    DevBuf planes_alt[4];     // second set of planes: every image-space pass reads one set and writes the other
+    DevBuf f_pm, f_ns, f_op;  // packed neighbour fields of the G-buffer for the edge-stopping filter
+    DevBuf glow[2];           // bloom
     int n_glass = 0;
     int sm_count = 148;
     int wave_paths = 1 << 22;
@@ -118,7 +121,8 @@ void rm_render_state_free(RmContext *ctx) {
     auto *R = static_cast<RenderState *>(ctx->render_state);
     if (!R) return;
     for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
-                      &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1]})
+                      &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
+                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1]})
         b->release();
     for (int w = 0; w < 2; w++)
         for (int k = 0; k < 20; k++) R->q[w][k].release();
@@ -412,6 +416,92 @@ int rm_render(RmContext *ctx, const RmRenderArgs *args, uint64_t seed, RmHitInfo
     return RM_OK;
 }
 
+// ------------------------------------------------------------------------ image-space passes over the resolved planes
+namespace {
+Planes4 planes_of(DevBuf *b) {
+    Planes4 P;
+    for (int k = 0; k < 4; k++) P.p[k] = b[k].as<RmRadiance>();
+    return P;
+}
+void swap_planes(RenderState *R) {
+    for (int k = 0; k < 4; k++) std::swap(R->planes[k], R->planes_alt[k]);
+}
+int post_ready(RmContext *ctx, const RmRenderArgs *args, const char *who, RenderState **out) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "%s: nothing resolved yet", who);
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RenderState *R = state(ctx);
+    if (!ctx->have_resolved || R->npix != args->width * args->height) return rm_fail(RM_ERR_STATE, "%s: call rm_resolve for these args first", who);
+    RM_CUDA(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 4; k++)
+        if ((rc = R->planes_alt[k].alloc(size_t(R->npix) * sizeof(RmRadiance)))) return rc;
+    *out = R;
+    return RM_OK;
+}
+} // namespace
+
+// Stage host-side Photo buffers (G-buffer + the four planes) as the context's resolved frame, so the image-space
+// passes can run on planes produced elsewhere (e.g. by the reference's own CPU render).
+int rm_upload_resolved(RmContext *ctx, const RmRenderArgs *args, const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRadiance *Ds,
+                       const RmRadiance *Id, const RmRadiance *Is) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    if (!gbuffer || !Dd || !Ds || !Id || !Is) return rm_fail(RM_ERR_INVALID, "rm_upload_resolved: NULL buffer");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    RenderState *R = state(ctx);
+    if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    const size_t npix = size_t(args->width) * args->height;
+    const RmRadiance *host[4] = {Dd, Ds, Id, Is};
+    for (int k = 0; k < 4; k++) {
+        if ((rc = R->planes[k].alloc(npix * sizeof(RmRadiance)))) return rc;
+        RM_CUDA(cudaMemcpyAsync(R->planes[k].p, host[k], npix * sizeof(RmRadiance), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = R->g_out.alloc(npix * sizeof(RmHitInfo)))) return rc;
+    RM_CUDA(cudaMemcpyAsync(R->g_out.p, gbuffer, npix * sizeof(RmHitInfo), cudaMemcpyHostToDevice, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (R->npix != int(npix)) { R->accum_valid = false; ctx->have_gbuffer = false; ctx->have_primary = false; }
+    R->npix = int(npix);
+    ctx->have_resolved = true;
+    return RM_OK;
+}
+
+int rm_spatial_clamp(RmContext *ctx, const RmRenderArgs *args) {
+    RenderState *R = nullptr;
+    int rc = post_ready(ctx, args, "rm_spatial_clamp", &R);
+    if (rc) return rc;
+    dim3 grid((args->width + kClW - 1) / kClW, (args->height + kClH - 1) / kClH, 4), block(kClW, kClH);
+    k_spatial_clamp<<<grid, block, 0, ctx->stream>>>(planes_of(R->planes), planes_of(R->planes_alt), args->width, args->height);
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    swap_planes(R);
+    return RM_OK;
+}
+
+int rm_filter(RmContext *ctx, const RmRenderArgs *args) {
+    RenderState *R = nullptr;
+    int rc = post_ready(ctx, args, "rm_filter", &R);
+    if (rc) return rc;
+    const int npix = R->npix, w = args->width, h = args->height;
+    if ((rc = R->f_pm.alloc(size_t(npix) * 16)) || (rc = R->f_ns.alloc(size_t(npix) * 16)) || (rc = R->f_op.alloc(size_t(npix) * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    FilterG F;
+    F.pm = R->f_pm.as<float4>(); F.ns = R->f_ns.as<float4>(); F.opacity = R->f_op.as<float>();
+    k_filter_pack<<<(npix + 255) / 256, 256, 0, st>>>(R->g_out.as<RmHitInfo>(), F, npix);
+    dim3 block(32, 4), grid((w + 31) / 32, (h + 3) / 4, 4);
+    k_filter_var<<<grid, block, 0, st>>>(planes_of(R->planes), planes_of(R->planes_alt), w, h);
+    swap_planes(R);
+    ctx->launches += 2;
+    dim3 grid1((w + 31) / 32, (h + 3) / 4, 1);
+    for (int step = 1; step <= 16; step *= 2) {
+        k_atrous<<<grid1, block, 0, st>>>(R->g_out.as<RmHitInfo>(), F, planes_of(R->planes), planes_of(R->planes_alt), w, h, step);
+        swap_planes(R);
+        ctx->launches++;
+    }
+    RM_CUDA(cudaGetLastError());
+    return RM_OK;
+}
+
 // ------------------------------------------------------------------------ post pass
 int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int32_t width, int32_t height) {
     if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
@@ -453,10 +543,22 @@ int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_optio
     const size_t bytes = size_t(npix) * 12;
     if ((rc = R->rgb[0].alloc(bytes)) || (rc = R->rgb[1].alloc(bytes))) return rc;
     cudaStream_t st = ctx->stream;
+    const bool bloom = (shade_options & 256) != 0;          // DoBloom sits between shade and gammaCorrection (src/image.cpp:470-479)
     k_shade_gamma<<<(npix + 255) / 256, 256, 0, st>>>(R->g_out.as<RmHitInfo>(), R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
                                                        R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), npix, args->exposure, shade_options,
-                                                       R->rgb[0].as<float>());
+                                                       !bloom, R->rgb[0].as<float>());
     ctx->launches++;
+    if (bloom) {
+        if ((rc = R->glow[0].alloc(bytes)) || (rc = R->glow[1].alloc(bytes))) return rc;
+        float *img = R->rgb[0].as<float>();
+        k_bloom_bright<<<(npix + 255) / 256, 256, 0, st>>>(img, R->glow[0].as<float>(), npix);
+        dim3 block(32, 8), grid((args->width + 31) / 32, (args->height + 7) / 8);
+        int cur = 0;
+        for (int step = 1; step <= 16; step *= 2, cur ^= 1)
+            k_bloom_pass<<<grid, block, 0, st>>>(R->glow[cur].as<float>(), R->glow[cur ^ 1].as<float>(), img, args->width, args->height, step);
+        k_gamma<<<(npix + 255) / 256, 256, 0, st>>>(img, npix);
+        ctx->launches += 7;
+    }
     int out = 0;
     if (shade_options & 512) {          // DoFXAA
         if ((rc = rm_fxaa_device(ctx, R->rgb[0].as<float>(), R->rgb[1].as<float>(), args->width, args->height))) return rc;

@@ -113,3 +113,41 @@ def test_port_postprocess_matches_reference(ref):
         got = portbind.postprocess(o["gbuffer"], o["Dd"], o["Ds"], o["Id"], o["Is"], 48, 48, args.exposure, opts)
         assert same(got, want), opts
     R.close()
+
+
+# --------------------------------------------------------------------------- image-space passes
+GP = np.load(os.path.join(os.path.dirname(__file__), "golden", "post_vectors.npz"))
+PLANES = ("Dd", "Ds", "Id", "Is")
+
+
+def same_planes(a, b):
+    return all(same(a[k]["radiance"], b[k]["radiance"]) and same(a[k]["Var"], b[k]["Var"]) for k in PLANES)
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+@pytest.mark.parametrize("stages", [1, 2, 3])
+def test_port_clamp_and_filter_match_reference_vectors(name, stages):
+    """spatialClamp (1), filter (2) and both in the reference's order (3): the restatement is bit-equal"""
+    w, h = (int(v) for v in GP[name + "_wh"])
+    inp = [GP["%s_in_%s" % (name, k)] for k in PLANES]
+    got = portbind.denoise(GP[name + "_gbuffer"], *inp, w, h, stages)
+    want = {k: GP["%s_s%d_%s" % (name, stages, k)] for k in PLANES}
+    assert same_planes(got, want)
+    assert any(not same(got[k]["radiance"], i["radiance"]) for k, i in zip(PLANES, inp))       # the pass did something
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+def test_port_bloom_matches_reference_vectors(name):
+    w, h = (int(v) for v in GP[name + "_wh"])
+    inp = [GP["%s_in_%s" % (name, k)] for k in PLANES]
+    for opts in (63 | 256, 63 | 256 | 512):
+        got = portbind.postprocess(GP[name + "_gbuffer"], *inp, w, h, float(GP[name + "_exposure"][0]), opts)
+        assert same(got, GP["%s_post_%d" % (name, opts)]), opts
+
+
+def test_post_golden_vectors_are_current(ref):
+    for name in ("box", "hf"):
+        w, h = (int(v) for v in GP[name + "_wh"])
+        inp = [GP["%s_in_%s" % (name, k)] for k in PLANES]
+        got = ref.denoise(GP[name + "_gbuffer"], *inp, w, h, 3)
+        assert same_planes(got, {k: GP["%s_s3_%s" % (name, k)] for k in PLANES})
