@@ -154,6 +154,14 @@ int rm_accum_view(RmContext *ctx, float **d_sum, int64_t *n_sum, float **d_max, 
 int rm_accum_after_reduce(RmContext *ctx, int32_t rank, int32_t world);
 int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad);
 
+/* Progressive checkpoint / resume (the reference has none): the un-finalised accumulators
+ * of the current frame as one opaque blob of rm_checkpoint_bytes(args) bytes.  Save after any rm_render_samples call;
+ * after rm_checkpoint_load (same scene uploaded, same args) further rm_render_samples calls with reset = 0 add the
+ * remaining sample shards, and rm_resolve gives the frame a single uninterrupted render would have given. */
+int64_t rm_checkpoint_bytes(const RmRenderArgs *args);
+int rm_checkpoint_save(RmContext *ctx, void *host, int64_t bytes);
+int rm_checkpoint_load(RmContext *ctx, const RmRenderArgs *args, const void *host, int64_t bytes);
+
 /* Resolve: firefly clamp + diffuse/specular split + exposure/variance finalise
  * (render.cpp:510-549) -> the four RadianceData planes (host, reference AoS layout). */
 int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);

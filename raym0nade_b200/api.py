@@ -56,7 +56,8 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
-           "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved",
+           "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -97,6 +98,10 @@ def lib():
     L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
     L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
+    L.rm_checkpoint_bytes.restype = i64
+    L.rm_checkpoint_bytes.argtypes = [ARGS]
+    L.rm_checkpoint_save.argtypes = [vp, vp, i64]
+    L.rm_checkpoint_load.argtypes = [vp, ARGS, vp, i64]
     L.rm_upload_resolved.argtypes = [vp, ARGS, vp, vp, vp, vp, vp]
     L.rm_spatial_clamp.argtypes = [vp, ARGS]
     L.rm_filter.argtypes = [vp, ARGS]
@@ -305,6 +310,19 @@ class Context:
 
     def fxaa_device(self, d_in: int, d_out: int, width: int, height: int):
         _check(lib().rm_fxaa_device(self.h, C.c_void_p(d_in), C.c_void_p(d_out), width, height))
+
+    def checkpoint_save(self, args: RenderArgs):
+        """the un-finalised accumulators of the current frame as a byte blob"""
+        a = args.to_c()
+        n = lib().rm_checkpoint_bytes(C.byref(a))
+        blob = np.zeros(n, np.uint8)
+        _check(lib().rm_checkpoint_save(self.h, _p(blob), n))
+        return blob
+
+    def checkpoint_load(self, args: RenderArgs, blob):
+        a = args.to_c()
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _check(lib().rm_checkpoint_load(self.h, C.byref(a), _p(blob), blob.size))
 
     def upload_resolved(self, args: RenderArgs, gbuffer, planes):
         """stage host Photo buffers (G-buffer + [Dd, Ds, Id, Is]) as the resolved frame"""

@@ -35,7 +35,6 @@ struct RenderState {
     DevBuf glow[2];           // bloom
     int n_glass = 0;
     int sm_count = 148;
-    int wave_paths = 1 << 22;
 };
 
 RenderState *state(RmContext *ctx) {
@@ -210,7 +209,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
 
     // queue sizes: the path queue holds `wave_paths` vertices and is kept full by k_regen; a vertex that
     // terminates emits at most 6 shadow rays; a direct wave is one shadow item per (pixel, sample)
-    const long long target = R->wave_paths;
+    const long long target = ctx->wave_paths;
     const int S_all = int(std::max(1LL, target / npix));
     const long long items_a = (long long)npix * n_a;
     const long long items_b = n_b_total > n_a ? (long long)R->n_glass * (n_b_total - n_a) : 0;
@@ -353,6 +352,81 @@ int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad) {
     if (!R->accum_valid || !R->hold_committed) return rm_fail(RM_ERR_STATE, "rm_accum_radiance: call rm_accum_after_reduce first");
     if (d_rad) *d_rad = R->rad.as<float>();
     if (n_rad) *n_rad = int64_t(R->npix) * 16;
+    return RM_OK;
+}
+
+// ------------------------------------------------------------------------ progressive checkpoint / resume
+// The un-finalised accumulators of the current frame as one blob: a 64-byte header, then per plane-of-floats
+// rad[npix][16], clum_sum[npix][2], clum_max[npix], hold_clum[npix], hold[npix][8].  A render stopped after some sample
+// shards (rm_render_samples with reset = 0 adds more) can be resumed later, in another context or on another GPU.
+namespace {
+struct CheckpointHeader {
+    char magic[4];
+    int32_t version, width, height, spp;
+    float P_Direct;
+    int32_t hold_committed;
+    int32_t _pad[9];
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header is 64 bytes");
+constexpr int kCkFloatsPerPixel = 16 + 2 + 1 + 1 + 8;
+} // namespace
+
+int64_t rm_checkpoint_bytes(const RmRenderArgs *args) {
+    if (rm_check_args(args)) return -1;
+    return int64_t(sizeof(CheckpointHeader)) + int64_t(args->width) * args->height * kCkFloatsPerPixel * 4;
+}
+
+int rm_checkpoint_save(RmContext *ctx, void *host, int64_t bytes) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_checkpoint_save: nothing rendered yet");
+    RenderState *R = state(ctx);
+    if (!R->accum_valid) return rm_fail(RM_ERR_STATE, "rm_checkpoint_save: nothing rendered yet");
+    const RmRenderArgs &a = ctx->frame_args;
+    if (!host || bytes != rm_checkpoint_bytes(&a)) return rm_fail(RM_ERR_INVALID, "rm_checkpoint_save: buffer must hold rm_checkpoint_bytes() bytes");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    CheckpointHeader h{};
+    std::memcpy(h.magic, "RMCK", 4);
+    h.version = 1; h.width = a.width; h.height = a.height; h.spp = a.spp; h.P_Direct = a.P_Direct;
+    h.hold_committed = R->hold_committed ? 1 : 0;
+    std::memcpy(host, &h, sizeof(h));
+    const size_t n = size_t(R->npix);
+    char *dst = static_cast<char *>(host) + sizeof(h);
+    const DevBuf *src[5] = {&R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold};
+    const size_t words[5] = {16, 2, 1, 1, 8};
+    for (int k = 0; k < 5; k++) {
+        RM_CUDA(cudaMemcpyAsync(dst, src[k]->p, n * words[k] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        dst += n * words[k] * 4;
+    }
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RM_OK;
+}
+
+int rm_checkpoint_load(RmContext *ctx, const RmRenderArgs *args, const void *host, int64_t bytes) {
+    if (!ctx || !ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_checkpoint_load: no scene uploaded");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    if (!host || bytes != rm_checkpoint_bytes(args)) return rm_fail(RM_ERR_INVALID, "rm_checkpoint_load: size does not match these args");
+    CheckpointHeader h;
+    std::memcpy(&h, host, sizeof(h));
+    if (std::memcmp(h.magic, "RMCK", 4) || h.version != 1) return rm_fail(RM_ERR_INVALID, "rm_checkpoint_load: not a checkpoint");
+    if (h.width != args->width || h.height != args->height || h.spp != args->spp || h.P_Direct != args->P_Direct)
+        return rm_fail(RM_ERR_INVALID, "rm_checkpoint_load: checkpoint was made for %dx%d spp %d P_Direct %g", h.width, h.height, h.spp, h.P_Direct);
+    RM_CUDA(cudaSetDevice(ctx->device));
+    // the frame state the samplers read (primary hits, G-buffer) is a pure function of scene + args: recompute it
+    if (!ctx->have_gbuffer || !same_args(ctx->frame_args, *args))
+        if ((rc = rm_gbuffer(ctx, args, nullptr))) return rc;
+    RenderState *R = state(ctx);
+    if ((rc = reset_accum(ctx, R))) return rc;
+    const size_t n = size_t(R->npix);
+    const char *src = static_cast<const char *>(host) + sizeof(h);
+    DevBuf *dst[5] = {&R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold};
+    const size_t words[5] = {16, 2, 1, 1, 8};
+    for (int k = 0; k < 5; k++) {
+        RM_CUDA(cudaMemcpyAsync(dst[k]->p, src, n * words[k] * 4, cudaMemcpyHostToDevice, ctx->stream));
+        src += n * words[k] * 4;
+    }
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    R->hold_committed = h.hold_committed != 0;
+    ctx->have_resolved = false;
     return RM_OK;
 }
 

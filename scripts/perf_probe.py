@@ -13,6 +13,7 @@ if which == "glossy": scene, args = scenes.glossy_dielectric(n_tris, w, h, spp)
 elif which == "sponza": scene, args = scenes.sponza_scale(n_tris, w, h, spp, tex_size=1024)
 elif which == "five": scene, args = scenes.five_million(n_tris, w, h); args = args.replace(spp=spp)
 elif which == "cornell": scene, args = scenes.cornell_box(w, h, spp)
+elif which == "texture": scene, args = scenes.texture_heavy(n_tris, w, h, spp)
 print("scene gen %.2fs faces %d" % (time.time() - t, scene.n_faces))
 t = time.time(); model = Model(scene); print("host prepare %.2fs" % (time.time() - t))
 ctx = Context(0)

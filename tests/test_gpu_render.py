@@ -256,6 +256,31 @@ def test_interleaved_sample_shards_sum_to_the_single_pass(which):
     ctx.close()
 
 
+def test_checkpoint_resume_in_a_fresh_context_equals_one_render():
+    """stop after the first of two sample shards, save, tear the context down; a new context loads the blob, renders the
+    second shard and resolves to the frame of an uninterrupted render"""
+    from raym0nade_b200.api import RmError
+    scene, args = scenes.cornell_box(96, 96, 24)
+    model = Model(scene)
+    ctx = Context(0).upload(model)
+    ctx.render_samples(args, 0, 1, seed=8, reset=True)
+    whole = ctx.resolve(args)
+    ctx.render_samples(args, 0, 2, seed=8, reset=True)
+    blob = ctx.checkpoint_save(args)
+    ctx.close()
+    ctx = Context(0).upload(model)
+    with pytest.raises(RmError):
+        ctx.checkpoint_load(args.replace(spp=args.spp + 1), blob)          # a checkpoint only fits the args it was made for
+    ctx.checkpoint_load(args, blob)
+    ctx.render_samples(args, 1, 2, seed=8, reset=False)
+    resumed = ctx.resolve(args)
+    for k in ("Dd", "Ds", "Id", "Is"):
+        a, b = whole[k]["radiance"].astype(np.float64), resumed[k]["radiance"].astype(np.float64)
+        assert np.abs(a - b).max() <= 2e-4 * (1.0 + np.abs(a).max()), k
+        assert abs(a.sum() - b.sum()) <= 1e-5 * abs(a.sum()) + 1e-6, k
+    ctx.close()
+
+
 # --------------------------------------------------------------------------- FXAA + post pass
 def test_fxaa_bit_exact_random_and_edges(ref):
     ctx = Context(0)
