@@ -274,14 +274,22 @@ def run_ours(opt, rank, world, local_rank):
         per_kind["shade"] = {"ms_per_step": kinds["shade"]["ms"] / opt.steps, "launches_per_step": kinds["shade"]["launches"] / opt.steps}
         dom = max((k for k in per_kind if k != "shade"), key=lambda k: per_kind[k]["ms_per_step"])
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)
-        traffic = None
+        # per launch like `achieved`: the capture's DRAM bytes per ray x the rays of this run's average launch
+        traffic, traffic_note = None, None
+        rays_per_launch = counted[dom]["rays"] / max(kinds[dom]["launches"] / opt.steps, 1)
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {})
+            if "dram_bytes_per_ray" in tj:
+                traffic = tj["dram_bytes_per_ray"] * rays_per_launch
+                traffic_note = "ncu: %.1f DRAM bytes per ray on a %d-ray launch (profiles/traffic.json) x %.0f rays per launch here" % (
+                    tj["dram_bytes_per_ray"], tj["rays_per_launch"], rays_per_launch)
+            else:
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": {"primary": "k_trace<PrimaryJob>", "paths": "k_trace<PathJob>", "shadow": "k_trace<ShadowJob>"}[dom],
                     "achieved": per_kind[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kind[dom]["achieved_gbs"] / peak,
-                    "traffic": traffic, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_note": traffic_note, "rays_per_launch": rays_per_launch, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": 32.0 * counted[dom]["box"] / max(kinds[dom]["launches"] / opt.steps, 1) + 36.0 * counted[dom]["tri"] / max(kinds[dom]["launches"] / opt.steps, 1),
                     "note": "achieved = (32 B x box tests + 36 B x triangle tests) of this kernel's launches / its CUDA-event time; "
                             "the 1M-triangle scene (167 MB) is L2-resident, see DESIGN.md"}
@@ -306,7 +314,7 @@ def run_ours(opt, rank, world, local_rank):
                 "pixel_samples_per_s": npix * args.spp * opt.steps / (ms_total * 1e-3),
                 "time_to_spp_s": {str(args.spp): ms_total / opt.steps * 1e-3},
                 "rays_per_step": rays_total / opt.steps,
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ctx.scene_bytes()),
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ctx.scene_h2d_bytes()),
                         "d2h_bytes_per_step": int(npix * (HITINFO_DTYPE.itemsize + 4 * RADIANCE_DTYPE.itemsize)),
                         "ms_per_step": float(e2e_s.item()) * 1e3 / e2e_steps, "steps": e2e_steps,
                         "note": "rm_scene_upload + rm_render per step; outputs land in pinned host memory, the prepared scene is pageable"},

@@ -107,6 +107,9 @@ int rm_context_synchronize(RmContext *ctx);
 int rm_scene_upload(RmContext *ctx, const RmSceneDesc *scene);
 /* bytes of HBM the staged scene occupies */
 int64_t rm_scene_device_bytes(const RmContext *ctx);
+/* Bytes the last rm_scene_upload copied host -> device (the caller's arrays as they are; the traversal and shading
+ * records are formed from them on the device). */
+int64_t rm_scene_h2d_bytes(const RmContext *ctx);
 
 /* ---------------------------------------------------------------------------------
  * Per-ray seam: Model::rayHit / Model::rayHit_test (include/model.h:41-42,

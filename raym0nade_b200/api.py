@@ -54,7 +54,7 @@ class RmSceneDesc(C.Structure):
 # every symbol include/raym0nade_b200.h declares
 EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
-           "rm_scene_device_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
+           "rm_scene_device_bytes", "rm_scene_h2d_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
@@ -84,6 +84,8 @@ def lib():
     L.rm_scene_upload.argtypes = [vp, C.POINTER(RmSceneDesc)]
     L.rm_scene_device_bytes.restype = i64
     L.rm_scene_device_bytes.argtypes = [vp]
+    L.rm_scene_h2d_bytes.restype = i64
+    L.rm_scene_h2d_bytes.argtypes = [vp]
     L.rm_trace_closest.argtypes = [vp, i64, vp, vp, vp, vp]
     L.rm_trace_occluded.argtypes = [vp, i64, vp, vp, vp, vp]
     L.rm_trace_primary.argtypes = [vp, ARGS, vp, vp]
@@ -206,6 +208,9 @@ class Context:
 
     def scene_bytes(self):
         return lib().rm_scene_device_bytes(self.h)
+
+    def scene_h2d_bytes(self):
+        return lib().rm_scene_h2d_bytes(self.h)
 
     def set_option(self, name, value):
         _check(lib().rm_set_option(self.h, name.encode(), int(value)))

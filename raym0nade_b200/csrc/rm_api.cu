@@ -83,6 +83,35 @@ int rm_context_synchronize(RmContext *ctx) {
     return RM_OK;
 }
 
+// Per face: the traversal record {v0, e1, e2, |e1|, cut-out flag} - the fp32 values RayTriangleIntersection forms per test
+// (src/geometry.cpp:65-70), with the reference's operation order - and the shading record (positions, uvs, normals, material).
+__global__ void k_pack_faces(const float *__restrict__ pos, const float *__restrict__ uv, const float *__restrict__ nrm, const int *__restrict__ mat,
+                             const DevMaterial *__restrict__ mats, int n, float4 *__restrict__ tri, float4 *__restrict__ shade) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = pos + size_t(i) * 9;
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k] = p[k];
+    const V3 e1 = mk3(fsub(v[3], v[0]), fsub(v[4], v[1]), fsub(v[5], v[2])), e2 = mk3(fsub(v[6], v[0]), fsub(v[7], v[1]), fsub(v[8], v[2]));
+    const float len = length(e1);                                  // glm::length(edge1)
+    const int m = mat[i];
+    float4 *t = tri + size_t(i) * kTriStride;
+    t[0] = make_float4(v[0], v[1], v[2], e1.x);
+    t[1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    t[2] = make_float4(e2.z, len, mats[m].cutout ? 1.0f : 0.0f, 0.0f);
+    if (kTriStride > 3) t[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float *u = uv + size_t(i) * 6, *nn = nrm + size_t(i) * 9;
+    float4 *s = shade + size_t(i) * 7;
+    s[0] = make_float4(v[0], v[1], v[2], v[3]);
+    s[1] = make_float4(v[4], v[5], v[6], v[7]);
+    s[2] = make_float4(v[8], u[0], u[1], u[2]);
+    s[3] = make_float4(u[3], u[4], u[5], nn[0]);
+    s[4] = make_float4(nn[1], nn[2], nn[3], nn[4]);
+    s[5] = make_float4(nn[5], nn[6], nn[7], nn[8]);
+    s[6] = make_float4(__int_as_float(m), 0.0f, 0.0f, 0.0f);
+}
+
 int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if (!ctx || !sc) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: null argument");
     if (sc->n_faces <= 0 || sc->n_nodes < 2 || !sc->nodes || !sc->positions || !sc->uvs || !sc->normals || !sc->face_material)
@@ -118,31 +147,25 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     }
     if ((rc = upload(ctx->b_mats, mats.data(), mats.size() * sizeof(DevMaterial), st, total))) return rc;
 
-    // traversal records (48 B) and shading records (112 B)
-    std::vector<float> tri(size_t(n) * 4 * kTriStride, 0.0f), shade(size_t(n) * 28, 0.0f);
+    // traversal records (48 B) and shading records (112 B) are formed on the device from the caller's arrays as they
+    // are (k_pack_faces): the host only checks the material indices
     for (int i = 0; i < n; i++) {
-        const float *p = sc->positions + size_t(i) * 9;
-        int mat = sc->face_material[i];
+        const int mat = sc->face_material[i];
         if (mat < 0 || mat >= sc->n_materials) return rm_fail(RM_ERR_INVALID, "face %d: material index out of range", i);
-        float e1[3], e2[3];
-        for (int k = 0; k < 3; k++) { e1[k] = p[3 + k] - p[k]; e2[k] = p[6 + k] - p[k]; }
-        float len = std::sqrt((e1[0] * e1[0] + e1[1] * e1[1]) + e1[2] * e1[2]);   // glm::length(edge1)
-        float *t = &tri[size_t(i) * 4 * kTriStride];
-        t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = e1[0];
-        t[4] = e1[1]; t[5] = e1[2]; t[6] = e2[0]; t[7] = e2[1];
-        t[8] = e2[2]; t[9] = len; t[10] = mats[mat].cutout ? 1.0f : 0.0f; t[11] = 0.0f;
-        float *s = &shade[size_t(i) * 28];
-        std::memcpy(s, p, 36);
-        std::memcpy(s + 9, sc->uvs + size_t(i) * 6, 24);
-        std::memcpy(s + 15, sc->normals + size_t(i) * 9, 36);
-        std::memcpy(s + 24, &mat, 4);
     }
-    if ((rc = upload(ctx->b_tri, tri.data(), tri.size() * 4, st, total))) return rc;
-    if ((rc = upload(ctx->b_shade, shade.data(), shade.size() * 4, st, total))) return rc;
+    if ((rc = upload(ctx->b_raw[0], sc->positions, size_t(n) * 36, st, total))) return rc;
+    if ((rc = upload(ctx->b_raw[1], sc->uvs, size_t(n) * 24, st, total))) return rc;
+    if ((rc = upload(ctx->b_raw[2], sc->normals, size_t(n) * 36, st, total))) return rc;
+    if ((rc = upload(ctx->b_raw[3], sc->face_material, size_t(n) * 4, st, total))) return rc;
+    if ((rc = ctx->b_tri.alloc(size_t(n) * 16 * kTriStride)) || (rc = ctx->b_shade.alloc(size_t(n) * 112))) return rc;
+    k_pack_faces<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_raw[0].as<float>(), ctx->b_raw[1].as<float>(), ctx->b_raw[2].as<float>(), ctx->b_raw[3].as<int>(),
+                                                  ctx->b_mats.as<DevMaterial>(), n, ctx->b_tri.as<float4>(), ctx->b_shade.as<float4>());
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
 
-    // textures: one blob, each level 16-byte aligned
+    // textures: one blob, each level 16-byte aligned, copied level by level straight from the caller's memory
     std::vector<DevTexture> texs(std::max(sc->n_textures, 1));
-    std::vector<uint8_t> blob;
+    size_t blob_bytes = 0;
     for (int i = 0; i < sc->n_textures; i++) {
         const RmTextureDesc &t = sc->textures[i];
         if (t.map_depth < 1 || t.map_depth > 8 || (t.channels != 3 && t.channels != 4))
@@ -152,17 +175,24 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         for (int l = 0; l < 8; l++) {
             d.offset[l] = 0;
             if (l >= t.map_depth) continue;
-            size_t bytes = size_t(t.width >> l) * (t.height >> l) * t.channels;
-            size_t off = (blob.size() + 15) & ~size_t(15);
+            const size_t bytes = size_t(t.width >> l) * (t.height >> l) * t.channels;
+            const size_t off = (blob_bytes + 15) & ~size_t(15);
             if (off + bytes > 0xFFFFFFFFull) return rm_fail(RM_ERR_INVALID, "texture data exceeds 4 GiB");
-            blob.resize(off + bytes);
-            std::memcpy(blob.data() + off, t.levels[l], bytes);
+            blob_bytes = off + bytes;
             d.offset[l] = uint32_t(off);
         }
     }
-    blob.resize((blob.size() + 15) & ~size_t(15));
+    blob_bytes = (blob_bytes + 15) & ~size_t(15);
     if ((rc = upload(ctx->b_texs, texs.data(), texs.size() * sizeof(DevTexture), st, total))) return rc;
-    if ((rc = upload(ctx->b_texels, blob.data(), blob.size(), st, total))) return rc;
+    if ((rc = ctx->b_texels.alloc(blob_bytes))) return rc;
+    for (int i = 0; i < sc->n_textures; i++)
+        for (int l = 0; l < sc->textures[i].map_depth; l++) {
+            const RmTextureDesc &t = sc->textures[i];
+            const size_t bytes = size_t(t.width >> l) * (t.height >> l) * t.channels;
+            if (!bytes) continue;
+            RM_CUDA(cudaMemcpyAsync(ctx->b_texels.as<uint8_t>() + texs[i].offset[l], t.levels[l], bytes, cudaMemcpyHostToDevice, st));
+            total += int64_t(bytes);
+        }
 
     // lights
     std::vector<DevLight> lights(std::max(sc->n_lights, 1));
@@ -220,13 +250,18 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     int levels = 1;
     while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
     ctx->stack_levels = std::min(std::max(levels, 2), 40);
-    ctx->scene_bytes = total;
+    ctx->scene_h2d_bytes = total;
+    ctx->scene_bytes = 0;
+    for (const DevBuf *b : {&ctx->b_nodes, &ctx->b_tri, &ctx->b_shade, &ctx->b_mats, &ctx->b_texs, &ctx->b_texels, &ctx->b_lights, &ctx->b_lpos,
+                            &ctx->b_lnrm, &ctx->b_lcdf, &ctx->b_sky, &ctx->b_skycdf, &ctx->b_lut})
+        ctx->scene_bytes += int64_t(b->bytes);
     ctx->has_scene = true;
     ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
     return RM_OK;
 }
 
 int64_t rm_scene_device_bytes(const RmContext *ctx) { return ctx ? ctx->scene_bytes : 0; }
+int64_t rm_scene_h2d_bytes(const RmContext *ctx) { return ctx ? ctx->scene_h2d_bytes : 0; }
 
 // ------------------------------------------------------------------------ per-ray seam
 int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *dir, int32_t *tri_idx, float *t) {

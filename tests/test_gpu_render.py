@@ -256,6 +256,27 @@ def test_interleaved_sample_shards_sum_to_the_single_pass(which):
     ctx.close()
 
 
+@pytest.mark.parametrize("p_direct,spp", [(0.0, 8), (1.0, 8), (0.7, 1), (0.7, 0)])
+def test_render_degenerate_sample_splits(ref, p_direct, spp):
+    """spp_direct = int(spp * P_Direct) (src/render.cpp:500): all-indirect, all-direct, a single sample and no samples at all
+    must give finite planes whose empty halves are exactly zero, as the reference's do"""
+    scene, args = scenes.cornell_box(48, 48, spp)
+    args = args.replace(P_Direct=p_direct)
+    R, ctx = _setup(ref, scene)
+    out = ctx.render(args, seed=2)
+    ro = R.render(args, threads=4)
+    spp_d = int(np.float32(spp) * np.float32(p_direct))
+    for k in ("Dd", "Ds", "Id", "Is"):
+        assert np.isfinite(out[k]["radiance"]).all() and np.isfinite(out[k]["Var"]).all(), k
+        empty = (k[0] == "D" and spp_d == 0) or (k[0] == "I" and spp - spp_d == 0)
+        assert (np.abs(ro[k]["radiance"]).sum() == 0) == empty, k          # the reference agrees on which halves are empty
+        if empty:
+            assert not out[k]["radiance"].any() and not out[k]["Var"].any(), k
+        else:
+            assert out[k]["radiance"].sum() > 0 or k[1] == "s"
+    ctx.close()
+
+
 def test_checkpoint_resume_in_a_fresh_context_equals_one_render():
     """stop after the first of two sample shards, save, tear the context down; a new context loads the blob, renders the
     second shard and resolves to the frame of an uninterrupted render"""

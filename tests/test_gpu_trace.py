@@ -51,6 +51,34 @@ def test_primary_cutout_materials(ref):
     assert _compare_primary(ref, scene, args) > 0.3
 
 
+@pytest.mark.parametrize("size", [(1, 1), (7, 3), (37, 53), (130, 65)])
+def test_primary_ragged_frame_sizes(ref, size):
+    """frames that do not fill the 8x4 pixel tiles a warp fetches (K1): the partial tiles at the right and bottom edges"""
+    w, h = size
+    scene, args = scenes.heightfield_scene(3000, w, h, 0, with_sky=True)
+    _compare_primary(ref, scene, args)
+    scene, args = scenes.cornell_box(w, h, 0)
+    _compare_primary(ref, scene, args)
+
+
+def test_per_ray_seam_edge_cases(ref):
+    """empty batch, a single ray, a ray that starts far outside the scene and points away, axis-parallel rays"""
+    scene, _ = scenes.cornell_box()
+    ctx = Context(0).upload(Model(scene))
+    R = ref.RefScene(scene)
+    tri, t = ctx.trace_closest(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert tri.size == 0 and t.size == 0
+    org = np.array([[0, 1, 0], [50, 50, 50], [0, 1, 0], [0.3, 1.2, 0.1], [0, 1, 0]], np.float32)
+    d = np.array([[0, 0, -1], [0.57735, 0.57735, 0.57735], [1, 0, 0], [0, 1, 0], [0, -1, 0]], np.float32)
+    tri, t = ctx.trace_closest(org, d)
+    rtri, rt = R.trace_closest(org, d)
+    assert np.array_equal(tri, rtri)
+    assert np.array_equal(np.isnan(t), np.isnan(rt)) and np.array_equal(t[~np.isnan(t)].view(np.uint32), rt[~np.isnan(rt)].view(np.uint32))
+    tri1, t1 = ctx.trace_closest(org[:1], d[:1])
+    assert tri1[0] == tri[0] and t1[0] == t[0]
+    ctx.close()
+
+
 def test_primary_glossy_1m_1080p_full_size(ref):
     """BASELINE config 3's scene and frame at full size: every one of the 2 073 600 primary hits against the reference"""
     import os
