@@ -35,14 +35,38 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-WORKLOAD = "configs[2]: 1M-triangle glossy/dielectric synthetic scene (990,744 tris), 1920x1080"
+# The headline workload is configs[2]; --workload config2 / config4 run the same bench on BASELINE.json's other GPU configs.
+WORKLOADS = {
+    "config3": dict(name="configs[2]: 1M-triangle glossy/dielectric synthetic scene (990,744 tris), 1920x1080", spp=1024),
+    "config2": dict(name="configs[1]: Sponza-scale synthetic mesh (257,778 tris) with a 2048x1024 HDR sky, 1024^2 albedo maps, 1920x1080", spp=256),
+    "config4": dict(name="configs[3]: texture-heavy scene (491,368 tris, 32 materials x 2048^2 RGBA8 albedo + RGB8 normal maps with mips, alpha cut-outs), 3840x2160", spp=4096),
+}
+WORKLOAD = WORKLOADS["config3"]["name"]
 CPU_SAMPLE = dict(width=960, height=540, spp=16)     # bounded sample of the same scene/camera for the CPU legs (~10-20 s of host time)
 
 
-def build_workload(spp, width=1920, height=1080, n_tris=1_000_000):
+def build_workload(spp, workload="config3"):
+    """Scene + args of the workload.  Under torchrun the ranks of one box share one generated scene through a pickle in
+    /tmp (LOCAL_RANK 0 writes it): the texture-heavy scene takes a minute of numpy to generate."""
+    import pickle
     from raym0nade_b200 import scenes
-    scene, args = scenes.glossy_dielectric(n_tris, width, height, spp)
-    return scene, args
+    make = {"config3": lambda: scenes.glossy_dielectric(1_000_000, 1920, 1080, spp),
+            "config2": lambda: scenes.sponza_scale(260_000, 1920, 1080, spp, tex_size=1024),
+            "config4": lambda: scenes.texture_heavy(500_000, 3840, 2160, spp)}[workload]
+    world, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 or workload == "config3":
+        return make()
+    path = "/tmp/rm_bench_scene_%s_%d_%s.pkl" % (workload, spp, os.environ.get("MASTER_PORT", "0"))
+    if local_rank == 0:
+        scene, args = make()
+        with open(path + ".tmp", "wb") as f:
+            pickle.dump((scene, args), f, protocol=4)
+        os.replace(path + ".tmp", path)
+        return scene, args
+    while not os.path.exists(path):
+        time.sleep(0.5)
+    with open(path, "rb") as f:
+        return pickle.load(f)
 
 
 class ClockSampler(threading.Thread):
@@ -125,7 +149,7 @@ def run_reference(opt, rank, world):
         print(json.dumps(dict(base, unavailable="oracle/_ref not built (needs the reference sources: make -C oracle ref)")))
         return
     threads = os.cpu_count() or 1
-    scene, args = build_workload(opt.spp)
+    scene, args = build_workload(opt.spp, opt.workload)
     a = args.replace(**CPU_SAMPLE)
     rays, secs = 0, 0.0
     with StdoutToStderr():
@@ -166,7 +190,7 @@ def run_ours(opt, rank, world, local_rank):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    scene, args = build_workload(opt.spp)
+    scene, args = build_workload(opt.spp, opt.workload)
     npix = args.width * args.height
     model = Model(scene)
     stream = torch.cuda.current_stream().cuda_stream
@@ -332,9 +356,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=int(os.environ.get("RM_BENCH_SPP", "1024")))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=int(os.environ.get("RM_BENCH_SPP", "0")), help="samples per pixel of one step (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     opt = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[opt.workload]["name"]
+    if opt.spp <= 0:
+        opt.spp = WORKLOADS[opt.workload]["spp"]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if opt.warmup < 3 and opt.impl == "ours":

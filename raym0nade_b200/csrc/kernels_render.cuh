@@ -31,6 +31,13 @@ namespace rm {
 #ifndef RM_SHADE_CTAS
 #define RM_SHADE_CTAS 3
 #endif
+// CTA-wide lock step per batch / per phase of the shading stages: the warps of a CTA then run the same stretch of
+// these large, branchy kernels together and share its instruction-cache lines (see k_bounce)
+#ifdef RM_NO_LOCKSTEP
+#define RM_LOCKSTEP() ((void)0)
+#else
+#define RM_LOCKSTEP() __syncthreads()
+#endif
 constexpr int kShadeBlock = RM_SHADE_BLOCK;
 constexpr int kShadeCtasPerSm = RM_SHADE_CTAS;
 
@@ -117,7 +124,11 @@ RM_DI void medium_erase(Medium &m, int id) {       // multimap::erase(key): ever
     m.n = k;
 }
 
-// getAbsorb (src/render.cpp:83-87); pow_s lives in geometry.cpp where pow resolves to the double version
+// pow_s (src/geometry.cpp:22-28): there `pow` resolves to the double version.  Out of line: one copy of the (large)
+// double-precision pow per kernel instead of three - the shading stages are instruction-fetch sensitive.
+RM_NI float pow_s(float a, float k) { return (float)pow((double)a, (double)k); }
+
+// getAbsorb (src/render.cpp:83-87)
 RM_DI V3 get_absorb(V3 absorb, float dis) {
     float C = lum(absorb);
     if (!(C < fsub(1.0f, kEps))) return splat3(1.0f);
@@ -126,7 +137,7 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
     if (a.x < 0.0f) a.x = 0.0f;
     if (a.y < 0.0f) a.y = 0.0f;
     if (a.z < 0.0f) a.z = 0.0f;
-    return mk3((float)pow((double)a.x, (double)k), (float)pow((double)a.y, (double)k), (float)pow((double)a.z, (double)k));
+    return mk3(pow_s(a.x, k), pow_s(a.y, k), pow_s(a.z, k));
 }
 
 // device-side pipeline state (ints): queue lengths, cursors
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_direct_gen(Dev
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     for (int base = blockIdx.x * blockDim.x; base < npix; base += gridDim.x * blockDim.x) {
-        __syncthreads();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
+        RM_LOCKSTEP();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
         const int p = base + threadIdx.x;
         bool go = false;
         Bsdf B;
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_regen(DevScene
     const int n_items = C[C_PLAN_TAKE];
     const long long first = (long long)(unsigned)C[C_PLAN_LO] | ((long long)C[C_PLAN_HI] << 32);
     for (int base = blockIdx.x * blockDim.x; base < n_items; base += gridDim.x * blockDim.x) {
-        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        RM_LOCKSTEP();                       // CTA-wide lock step per batch (see k_bounce)
         const int i = base + threadIdx.x;
         bool want = false;
         int p = 0;
@@ -577,7 +588,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_surface(DevSce
       // live here: a hit, or a miss that returns the sky (src/render.cpp:129-133)
       const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Q.hit_t[i] != CUDART_INF_F || (sky && !(Q.flags[i] & 256)); });
       for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
-        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        RM_LOCKSTEP();                       // CTA-wide lock step per batch (see k_bounce)
         const int j = j0 + threadIdx.x;
         if (j >= n_live) continue;
         const int i = s_idx[j];
@@ -642,7 +653,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigne
       // live here: a hit on a non-emissive surface (k_surface marked the others finished)
       const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Qin.hit_t[i] != CUDART_INF_F; });
       for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
-        __syncthreads();
+        RM_LOCKSTEP();
         const int j = j0 + threadIdx.x;
         const int i = j < n_live ? s_idx[j] : -1;
         int mode = kBounceDead;
@@ -715,7 +726,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigne
                 } else mode = kBounceRefract;
             }
         }
-        __syncthreads();
+        RM_LOCKSTEP();
 
         // ---- phase 2: reflection (src/render.cpp:222-236)
         if (mode == kBounceReflect) {
@@ -732,7 +743,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigne
             next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
             next.dDdx = dDdx; next.dDdy = dDdy;
         }
-        __syncthreads();
+        RM_LOCKSTEP();
 
         // ---- phase 3: refraction (src/render.cpp:264-283); the incoming differentials pass through unchanged (268,273)
         if (mode == kBounceRefract) {
@@ -747,7 +758,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigne
             if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
             else medium_erase(med, B.s.id);
         }
-        __syncthreads();
+        RM_LOCKSTEP();
 
         // ---- phase 4: hand the vertex on
         const bool terminate = mode == kBounceNee;
@@ -792,7 +803,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_nee(DevScene S
     const int c = Q.cap;
     const int lane = threadIdx.x & 31;
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        __syncthreads();                       // CTA-wide lock step per batch (see k_bounce)
+        RM_LOCKSTEP();                       // CTA-wide lock step per batch (see k_bounce)
         const int r = base + threadIdx.x;
         int cnt = 0, i = 0;
         float4 q0 = make_float4(0, 0, 0, 0), q1 = q0;

@@ -532,10 +532,23 @@ def texture_heavy(n_tris=500_000, width=3840, height=2160, spp=4096, tex_size=20
     normal map; emissive quads for light."""
     b = SceneBuilder("texture_heavy")
     mats = []
-    for i in range(n_materials):
+
+    def make_pair(i):
         base = (120 + (i * 37) % 120, 110 + (i * 53) % 130, 100 + (i * 71) % 140)
-        d = b.texture(noise_albedo(tex_size, seed * 1000 + i, base, checker=4 + i % 5, cutout=(i % 4 == 3)))
-        n = b.texture(noise_normal_map(tex_size, seed * 2000 + i))
+        return (noise_albedo(tex_size, seed * 1000 + i, base, checker=4 + i % 5, cutout=(i % 4 == 3)),
+                noise_normal_map(tex_size, seed * 2000 + i))
+
+    # the textures are independent: large ones are generated on a thread pool (numpy releases the GIL), same arrays either way
+    if tex_size >= 512:
+        import concurrent.futures
+        import os
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            pairs = list(pool.map(make_pair, range(n_materials)))
+    else:
+        pairs = [make_pair(i) for i in range(n_materials)]
+    for alb, nrm in pairs:
+        d = b.texture(alb)
+        n = b.texture(nrm)
         mats.append(b.material(RawMaterial(tex_diffuse=d, tex_normals=n)))
     light = b.emissive(255)
     g = int(np.sqrt(n_tris * 0.4 / 2))
