@@ -248,6 +248,21 @@ RM_DI int cdf_sample(const float *cdf, int n, float u) {
     }
     return lo;
 }
+// The same lower_bound, started from the bracket a guide table gives: guide[j] = lower_bound(cdf, total * j / G).  Rounding
+// is monotone, so j/G <= u < (j+1)/G puts total*u between the two thresholds and the answer inside [guide[j], guide[j+1]]:
+// identical index, ~12 fewer dependent loads on a 2 M-entry sky CDF.
+RM_DI int cdf_sample_guided(const float *cdf, int n, float u, const int32_t *guide) {
+    float x = fmul(__ldg(cdf + n - 1), u);
+    int j = int(u * float(kSkyGuide));
+    j = j < 0 ? 0 : (j > kSkyGuide - 1 ? kSkyGuide - 1 : j);
+    int lo = __ldg(guide + j), len = __ldg(guide + j + 1) - lo;
+    while (len > 0) {
+        int half = len >> 1;
+        if (__ldg(cdf + lo + half) < x) { lo = lo + half + 1; len = len - half - 1; }
+        else len = half;
+    }
+    return lo;
+}
 RM_DI float cdf_pdf(const float *cdf, int n, int i) {
     float now = __ldg(cdf + i);
     if (i > 0) now = fsub(now, __ldg(cdf + i - 1));
@@ -311,7 +326,7 @@ RM_DI void sample_light_face(const DevScene &S, const DevLight &L, V3 pos, Rng &
 RM_DI void sample_sky(const DevScene &S, V3 shapeNormal, Rng &gen, V3 &Dir, V3 &light) {
     const int n = S.sky_width * S.sky_height;
     for (int T = 1; T <= kMaxTrys; T++) {
-        int idx = cdf_sample(S.sky_cdf, n, gen());
+        int idx = cdf_sample_guided(S.sky_cdf, n, gen(), S.sky_guide);
         int u = idx % S.sky_width, v = idx / S.sky_width;
         float phi = fdiv(fmul(kPi, fadd(float(v), 0.5f)), float(S.sky_height));
         float theta = fdiv(fmul(fmul(2.0f, kPi), fadd(float(u), 0.5f)), float(S.sky_width));

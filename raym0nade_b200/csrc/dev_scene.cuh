@@ -22,6 +22,8 @@ namespace rm {
 #endif
 constexpr int kTriStride = RM_TRI_STRIDE;
 
+constexpr int kSkyGuide = 4096;     // power of two: u * kSkyGuide is exact in fp32
+
 struct DevTexture {
     int32_t width, height, channels, map_depth;
     uint32_t offset[8];             // byte offset of each level in the texel blob
@@ -56,6 +58,7 @@ struct DevScene {
     const float *light_cdf;         // [total light faces]
     const float *sky_data;          // [h*w][3], premultiplied by texel solid angle
     const float *sky_cdf;           // [h*w]
+    const int32_t *sky_guide;       // [kSkyGuide + 1] lower_bound(sky_cdf, total * j / kSkyGuide): brackets of the CDF search
     const float *div255;            // [256] k / 255.0f, correctly rounded (RGBA8 decode without a division per channel)
     int32_t n_faces, n_nodes, n_materials, n_lights;
     int32_t sky_width, sky_height;

@@ -95,6 +95,7 @@ struct FrameBuffers {
     RmHitInfo *gbuffer;      // AoS, baseColor = nudged value the samplers use
     float *sav_base;         // [npix][3] un-nudged baseColor (restored at resolve, src/render.cpp:550)
     int *n_ind;              // [npix] spp_indirect of the pixel (0 when nothing is sampled)
+    int *dir_base;           // [npix] first shadow-queue slot of the pixel's direct samples in the current direct wave (-1: none)
 };
 
 struct Medium {
@@ -183,23 +184,26 @@ RM_DI int cta_compact(int base, int n, int *s_idx, int *s_n, Pred live_at) {
 }
 
 // ------------------------------------------------------------------ accumulation
+// LOCAL = false: r4 points at the pixel's accumulators in global memory, shared by many threads (atomicAdd);
+// LOCAL = true:  r4 is a running sum the calling thread owns (k_accum_direct)
+template <bool LOCAL>
 RM_DI void accum_basic(float *r4, V3 inrad, float weight) {          // accumulateInwardRadiance_basic, src/image.cpp:615-628
     if (!isfinite_any(inrad)) return;
     if (!isfinite(weight)) return;
-    atomicAdd(r4 + 0, fmul(inrad.x, weight));
-    atomicAdd(r4 + 1, fmul(inrad.y, weight));
-    atomicAdd(r4 + 2, fmul(inrad.z, weight));
-    atomicAdd(r4 + 3, fmul(dot(inrad, inrad), weight));
+    const float v0 = fmul(inrad.x, weight), v1 = fmul(inrad.y, weight), v2 = fmul(inrad.z, weight), v3 = fmul(dot(inrad, inrad), weight);
+    if (LOCAL) { r4[0] = fadd(r4[0], v0); r4[1] = fadd(r4[1], v1); r4[2] = fadd(r4[2], v2); r4[3] = fadd(r4[3], v3); }
+    else { atomicAdd(r4 + 0, v0); atomicAdd(r4 + 1, v1); atomicAdd(r4 + 2, v2); atomicAdd(r4 + 3, v3); }
 }
 
 // accumulateInwardRadiance (src/image.cpp:630-659): split into demodulated diffuse + specular
-RM_NI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) {
+template <bool LOCAL>
+RM_DI void accum_split_t(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) {
     if (length(l) < kEps) return;
     V3 base0 = normalize(baseColor);
-    if (length(baseColor) < kEps) { accum_basic(rs, l * b, w); return; }
+    if (length(baseColor) < kEps) { accum_basic<LOCAL>(rs, l * b, w); return; }
     const V3 White = normalize(splat3(1.0f));
     float XdotY = dot(base0, White);
-    if (XdotY > 0.99f) { accum_basic(rd, div_true(l * b, baseColor), w); return; }
+    if (XdotY > 0.99f) { accum_basic<LOCAL>(rd, div_true(l * b, baseColor), w); return; }
     V3 perp = normalize(cross(base0, White));
     V3 bp = b - perp * dot(perp, b);
     float d1 = dot(bp, White), d2 = dot(bp, base0);
@@ -207,9 +211,10 @@ RM_NI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) 
     float AminusB = fdiv(fsub(d1, d2), fsub(1.0f, XdotY));
     float Bc = fdiv(fsub(AplusB, AminusB), 2.0f);
     V3 base_part = Bc * base0;
-    accum_basic(rd, div_recip(l * Bc, length(baseColor)), w);
-    accum_basic(rs, l * (b - base_part), w);
+    accum_basic<LOCAL>(rd, div_recip(l * Bc, length(baseColor)), w);
+    accum_basic<LOCAL>(rs, l * (b - base_part), w);
 }
+RM_NI void accum_split(float *rd, float *rs, V3 baseColor, V3 b, V3 l, float w) { accum_split_t<false>(rd, rs, baseColor, b, l, w); }
 
 // One finished indirect LightSample of pixel p.  The reference drops a sample when it alone
 // exceeds 16/17 of the pixel's total luminance (src/render.cpp:534-547); at most one sample per
@@ -354,6 +359,7 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
 __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, int n_samples, int npix, int s_begin,
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+    const int lane = threadIdx.x & 31;
     for (int base = blockIdx.x * blockDim.x; base < npix; base += gridDim.x * blockDim.x) {
         RM_LOCKSTEP();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
         const int p = base + threadIdx.x;
@@ -371,20 +377,55 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_direct_gen(Dev
                 if (S.sky_width == 0) { total = light_weights(S, B, lw); if (total == 0.0f) go = false; }
             }
         }
+        // a pixel's n_samples items are one contiguous block of the shadow queue: k_accum_direct sums them per pixel in
+        // sample order without atomics, and a warp of the visibility pass gets rays that share their origin
+        const unsigned m = __ballot_sync(0xffffffffu, go);
+        int first = 0;
+        if (m) {
+            if (lane == __ffs(m) - 1) first = atomicAdd(s_count, __popc(m) * n_samples);
+            first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u)) * n_samples;
+        }
+        if (go && first + n_samples > s_cap) { atomicExch(overflow, 1); go = false; }
+        if (p < npix) Fb.dir_base[p] = go ? first : -1;
+        if (!go) continue;
 #pragma unroll 1
         for (int k = 0; k < n_samples; k++) {
             const int s = s_begin + k * s_stride;
-            bool want = false;
             NeeOut n;
-            if (go && s < spp_direct) {
+            n.valid = false;
+            if (s < spp_direct) {
                 Rng gen;
                 gen.init(seed, (unsigned)p, (unsigned)s, kStreamDirect);
                 n = nee_sample(S, B, gen, lw, total, spp_direct);
-                want = n.valid;
             }
-            push_shadow(sq, s_count, s_cap, overflow, want, p | 0x80000000, B.s.position, n, n.bsdf, n.light, n.weight);
+            if (!n.valid) { n.dir = splat3(0.0f); n.aim = CUDART_NAN_F; n.bsdf = n.light = splat3(0.0f); n.weight = 0.0f; }      // null item
+            write_shadow(sq + first + k, p | 0x80000000, B.s.position, n, n.bsdf, n.light, n.weight);
         }
     }
+}
+
+// accumulateInwardRadiance over a direct wave: one thread per pixel adds its visible samples in sample order into
+// running sums it owns and folds them into the pixel's Dd / Ds accumulators once (the same pixel is touched by no
+// other thread while this kernel runs) - 8 read-modify-writes per pixel and wave instead of 8 atomics per sample.
+__global__ void __launch_bounds__(256) k_accum_direct(FrameBuffers Fb, Accum Ac, const ShadowItem *__restrict__ sq, int n_samples, int npix) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int first = Fb.dir_base[p];
+    if (first < 0) return;
+    const float *gf = reinterpret_cast<const float *>(Fb.gbuffer + p);
+    const V3 base = mk3(gf[9], gf[10], gf[11]);
+    float rd[4] = {0.0f, 0.0f, 0.0f, 0.0f}, rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int k = 0; k < n_samples; k++) {
+        const float4 *src = reinterpret_cast<const float4 *>(sq + first + k);
+        const float4 d = src[3];
+        if (d.w == 0.0f) continue;
+        const float4 c = src[2];
+        accum_split_t<true>(rd, rs, base, mk3(c.x, c.y, c.z), mk3(d.x, d.y, d.z), c.w);
+    }
+    float *r = Ac.rad + 16 * size_t(p);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { r[j] = fadd(r[j], rd[j]); r[4 + j] = fadd(r[4 + j], rs[j]); }
 }
 
 // ------------------------------------------------------------------ path state I/O

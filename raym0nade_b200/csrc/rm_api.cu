@@ -218,6 +218,16 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if (nsky && (!sc->sky_data || !sc->sky_cdf)) return rm_fail(RM_ERR_INVALID, "sky size set but sky_data/sky_cdf missing");
     if ((rc = upload(ctx->b_sky, sc->sky_data, nsky * 12, st, total))) return rc;
     if ((rc = upload(ctx->b_skycdf, sc->sky_cdf, nsky * 4, st, total))) return rc;
+    // brackets for the sky CDF search (dev_bsdf.cuh cdf_sample_guided): guide[j] = lower_bound(cdf, total * (j / G))
+    std::vector<int32_t> guide(kSkyGuide + 1, 0);
+    if (nsky) {
+        const float *cdf = sc->sky_cdf, tot = cdf[nsky - 1];
+        for (int j = 0; j <= kSkyGuide; j++) {
+            const float x = tot * (float(j) / float(kSkyGuide));
+            guide[j] = int32_t(std::lower_bound(cdf, cdf + nsky, x) - cdf);
+        }
+    }
+    if ((rc = upload(ctx->b_skyguide, guide.data(), guide.size() * 4, st, total))) return rc;
     // k / 255.0f, correctly rounded: the RGBA8 decode table (dev_texture.cuh)
     float lut[256];
     for (int k = 0; k < 256; k++) lut[k] = float(k) / 255.0f;
@@ -237,6 +247,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     S.light_cdf = ctx->b_lcdf.as<float>();
     S.sky_data = ctx->b_sky.as<float>();
     S.sky_cdf = ctx->b_skycdf.as<float>();
+    S.sky_guide = ctx->b_skyguide.as<int32_t>();
     S.div255 = ctx->b_lut.as<float>();
     S.n_faces = n;
     S.n_nodes = sc->n_nodes;
@@ -253,7 +264,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     ctx->scene_h2d_bytes = total;
     ctx->scene_bytes = 0;
     for (const DevBuf *b : {&ctx->b_nodes, &ctx->b_tri, &ctx->b_shade, &ctx->b_mats, &ctx->b_texs, &ctx->b_texels, &ctx->b_lights, &ctx->b_lpos,
-                            &ctx->b_lnrm, &ctx->b_lcdf, &ctx->b_sky, &ctx->b_skycdf, &ctx->b_lut})
+                            &ctx->b_lnrm, &ctx->b_lcdf, &ctx->b_sky, &ctx->b_skycdf, &ctx->b_skyguide, &ctx->b_lut})
         ctx->scene_bytes += int64_t(b->bytes);
     ctx->has_scene = true;
     ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;

@@ -61,7 +61,7 @@ struct RmContext {
 
     // scene
     rm::DevScene scene{};
-    DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf, b_lut;
+    DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf, b_skyguide, b_lut;
     DevBuf b_raw[4];                       // the caller's positions / uvs / normals / face materials as uploaded (input of k_pack_faces)
     int64_t scene_bytes = 0;               // device-resident bytes of the uploaded scene
     int64_t scene_h2d_bytes = 0;           // bytes copied host -> device by the last rm_scene_upload
@@ -90,7 +90,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_lut, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };

@@ -18,7 +18,7 @@ namespace {
 struct RenderState {
     int npix = 0;
     // frame
-    DevBuf gbuffer, sav_base, n_ind, glass_list;
+    DevBuf gbuffer, sav_base, n_ind, glass_list, dir_base;
     // accumulators
     DevBuf rad, clum_sum, clum_max, hold_clum, hold, lock;
     bool accum_valid = false, hold_committed = false;
@@ -85,6 +85,7 @@ FrameBuffers frame(RenderState *R) {
     F.gbuffer = R->gbuffer.as<RmHitInfo>();
     F.sav_base = R->sav_base.as<float>();
     F.n_ind = R->n_ind.as<int>();
+    F.dir_base = R->dir_base.as<int>();
     return F;
 }
 
@@ -119,7 +120,7 @@ int spp_direct_of(const RmRenderArgs *a) { return int(float(a->spp) * a->P_Direc
 void rm_render_state_free(RmContext *ctx) {
     auto *R = static_cast<RenderState *>(ctx->render_state);
     if (!R) return;
-    for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
+    for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
                       &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1]})
         b->release();
@@ -145,7 +146,8 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
     const int npix = args->width * args->height;
     if ((rc = R->gbuffer.alloc(size_t(npix) * sizeof(RmHitInfo))) || (rc = R->sav_base.alloc(size_t(npix) * 12)) ||
-        (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(C_COUNT * 4)))
+        (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->dir_base.alloc(size_t(npix) * 4)) ||
+        (rc = R->counts.alloc(C_COUNT * 4)))
         return rc;
     R->npix = npix;
     cudaStream_t st = ctx->stream;
@@ -236,13 +238,14 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
     // (C_CUR_SHADOW must be 0)
-    auto trace_shadow = [&](const int *n_dev) {
+    auto trace_shadow = [&](const int *n_dev, int direct_samples) {
         ShadowJob job;
         job.sq = sq;
         ctx->timed_begin(RM_KIND_SHADOW);
         launch_trace(ctx->scene, ctx->stack_levels, ct, tgrid, st, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
         ctx->timed_end();
-        k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
+        if (direct_samples > 0) k_accum_direct<<<(npix + 255) / 256, 256, 0, st>>>(Fb, Ac, sq, direct_samples, npix);
+        else k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
         ctx->launches += 2;
     };
 
@@ -255,7 +258,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         k_direct_gen<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
                                            seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
-        trace_shadow(C + C_SQ);
+        trace_shadow(C + C_SQ, S);
     }
 
     // ---- indirect paths.  One round = every vertex in the path queue advances by one bounce:
@@ -293,7 +296,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
                 ctx->timed_end();
                 k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 0);
                 ctx->launches += 7;
-                trace_shadow(C + C_SQ_RUN);
+                trace_shadow(C + C_SQ_RUN, 0);
                 cur ^= 1;
             }
             RM_CUDA(cudaMemcpyAsync(R->h_counts, C, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -303,7 +306,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         }
         k_plan<<<1, 1, 0, st>>>(C, cur, R->q_cap, total_items);          // retires a queue traced in the last round
         k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 1);
-        trace_shadow(C + C_SQ_RUN);
+        trace_shadow(C + C_SQ_RUN, 0);
         ctx->launches += 2;
     }
     RM_CUDA(cudaGetLastError());
