@@ -40,6 +40,23 @@ namespace rm {
 #endif
 constexpr int kShadeBlock = RM_SHADE_BLOCK;
 constexpr int kShadeCtasPerSm = RM_SHADE_CTAS;
+// per stage (register budget vs resident warps is a per-kernel trade: profiles/r01e_ab14_per_stage_ctas.txt)
+#ifndef RM_CTAS_BOUNCE
+#define RM_CTAS_BOUNCE RM_SHADE_CTAS
+#endif
+#ifndef RM_CTAS_SURFACE
+#define RM_CTAS_SURFACE RM_SHADE_CTAS
+#endif
+#ifndef RM_CTAS_NEE
+#define RM_CTAS_NEE RM_SHADE_CTAS
+#endif
+#ifndef RM_CTAS_REGEN
+#define RM_CTAS_REGEN RM_SHADE_CTAS
+#endif
+#ifndef RM_CTAS_DIRECT
+#define RM_CTAS_DIRECT RM_SHADE_CTAS
+#endif
+constexpr int kCtasBounce = RM_CTAS_BOUNCE, kCtasSurface = RM_CTAS_SURFACE, kCtasNee = RM_CTAS_NEE, kCtasRegen = RM_CTAS_REGEN, kCtasDirect = RM_CTAS_DIRECT;
 
 constexpr int kMediumSlots = 6;     // nested-dielectric entries kept per path besides the air base entry
 constexpr int kMaxRayDepth = 16;    // maxRayDepth, src/render.cpp:125
@@ -356,7 +373,7 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
 // G-buffer record and the per-light-object weights (getLightObjectWeight, one BSDF evaluation per light object,
 // src/sampling.cpp:406-417) depend on the pixel only and are formed once instead of once per sample.  Every
 // sample keeps its own random stream, so the samples are the ones a per-sample loop draws.
-__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, int n_samples, int npix, int s_begin,
+__global__ void __launch_bounds__(kShadeBlock, kCtasDirect) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, int n_samples, int npix, int s_begin,
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int lane = threadIdx.x & 31;
@@ -489,7 +506,7 @@ __global__ void k_shadow_gate(int *C, int threshold, int cap, int flush) {
 
 // ------------------------------------------------------------------ first vertex of an indirect path
 // sampleIndirectLightFromFirstIntersection (src/render.cpp:314-423) up to the new ray.
-__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
+__global__ void __launch_bounds__(kShadeBlock, kCtasRegen) k_regen(DevScene S, DevArgs A, FrameBuffers Fb, ItemSpace I, const int *__restrict__ C, unsigned long long seed,
                                                PathQueue Q, int *q_count) {
     const int n_items = C[C_PLAN_TAKE];
     const long long first = (long long)(unsigned)C[C_PLAN_LO] | ((long long)C[C_PLAN_HI] << 32);
@@ -618,7 +635,7 @@ RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
 // sampleRay up to the surface (src/render.cpp:128-166): a miss returns the sky (unless direct light is
 // excluded), a hit builds the HitInfo, an emissive hit returns its emission.  Finished entries get
 // hit_t = INF.  Thread 0 also resets the counters the later stages of this round append to.
-__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
+__global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
     const int n = min(C[q_slot], Q.cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; }
     const int c = Q.cap;
@@ -684,7 +701,7 @@ __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4
 // instruction-cache lines instead of evicting each other's (the kernel was bound by instruction fetch).
 enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 };
 
-__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
+__global__ void __launch_bounds__(kShadeBlock, kCtasBounce) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
                                                 PathQueue Qout, int *out_count, NeeRequest *nq, int *nee_count) {
     const int n = min(*in_count, Qin.cap);
     const int c = Qin.cap;
@@ -838,7 +855,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_bounce(unsigne
 // sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every NeeRequest.
 // The request reserves its 1..6 shadow-queue slots up front; a sample that comes out invalid leaves a
 // null item (aim = NaN) that the visibility pass skips.
-__global__ void __launch_bounds__(kShadeBlock, kShadeCtasPerSm) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
+__global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
                                              const int *__restrict__ nee_count, int nq_cap, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int n = min(*nee_count, nq_cap);
     const int c = Q.cap;

@@ -233,7 +233,6 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     NeeRequest *nq = R->nee.as<NeeRequest>();
     const int grid = R->sm_count * 8;
     const int tgrid = R->sm_count * kTraceCtasPerSm;
-    const int sgrid = R->sm_count * kShadeCtasPerSm;             // shading stages: resident CTAs only, lock-stepped per batch
     const bool ct = ctx->count_tests;
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
@@ -255,7 +254,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         const int S = std::min(S_dir, n_d - k0);
         RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, 4, st));
         RM_CUDA(cudaMemsetAsync(C + C_CUR_SHADOW, 0, 4, st));
-        k_direct_gen<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+        k_direct_gen<<<R->sm_count * kCtasDirect, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
                                            seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
         trace_shadow(C + C_SQ, S);
@@ -283,16 +282,16 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
             for (int b = 0; b < batch && rounds < max_rounds; b++, rounds++) {
                 PathQueue Qin = make_queue(R, cur), Qout = make_queue(R, cur ^ 1);
                 k_plan<<<1, 1, 0, st>>>(C, cur, Qin.cap, total_items);
-                k_regen<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
+                k_regen<<<R->sm_count * kCtasRegen, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, I, C, seed, Qin, C + cur);
                 PathJob pj;
                 pj.Q = Qin;
                 ctx->timed_begin(RM_KIND_PATHS);
                 launch_trace(ctx->scene, ctx->stack_levels, ct, tgrid, st, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
                 ctx->timed_end();
                 ctx->timed_begin(RM_KIND_SHADE);
-                k_surface<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
-                k_bounce<<<sgrid, kShadeBlock, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
-                k_nee<<<sgrid, kShadeBlock, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+                k_surface<<<R->sm_count * kCtasSurface, kShadeBlock, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
+                k_bounce<<<R->sm_count * kCtasBounce, kShadeBlock, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
+                k_nee<<<R->sm_count * kCtasNee, kShadeBlock, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
                 ctx->timed_end();
                 k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 0);
                 ctx->launches += 7;
