@@ -3,7 +3,8 @@
 // renderPixel (src/render.cpp:448-551) is split into stages; every stage restates the
 // reference's procedure (including its idiosyncrasies) per sample:
 //   k_gbuffer        466-495   primary hit -> HitInfo, sky emission on a miss, red nudge
-//   k_direct_gen     425-437 + sampleDirectLight (src/sampling.cpp:467-527): one NEE sample -> shadow queue
+//   k_direct_gen     425-437 + sampleDirectLight (src/sampling.cpp:467-527): a pixel's direct NEE samples -> one contiguous
+//                              block of the shadow queue; k_accum_direct sums the visible ones per pixel
 //   k_regen          314-423   first vertex of an indirect path from the cached primary hit; tops the
 //                              path queue up with fresh (pixel, sample) items whenever paths have ended
 //   k_trace<PathJob> Model::rayHit over the path queue (closest hit)
