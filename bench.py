@@ -196,7 +196,18 @@ def run_ours(opt, rank, world, local_rank):
     stream = torch.cuda.current_stream().cuda_stream
     ctx = Context(local_rank, stream=stream).upload(model)
 
+    # the frame reduction runs inside the library (rm_reduce: NCCL on the context's stream); torch.distributed only
+    # carries the 128-byte unique id to the ranks and provides the barriers.  --reduce torch drives the same three steps
+    # through torch.distributed collectives on the library's device pointers instead.
+    if world > 1 and opt.reduce == "cabi":
+        uid = [Context.comm_unique_id().tobytes() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(np.frombuffer(uid[0], np.uint8), rank, world)
+
     def reduce_across_ranks():
+        if opt.reduce == "cabi":
+            ctx.reduce(0)
+            return
         from raym0nade_b200 import multi_gpu
         multi_gpu.reduce_frame(multi_gpu.ContextAccum(ctx), dist, rank, world,
                                lambda buf: torch.as_tensor(multi_gpu.DevPtr(buf), device=dev))
@@ -333,7 +344,7 @@ def run_ours(opt, rank, world, local_rank):
                 "ms_per_step": ms_total / opt.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "spp": args.spp, "spp_direct": spp_d, "P_Direct": args.P_Direct,
-                           "parallelism": "samples interleaved over %d GPU(s), NCCL reduce of fp32 accumulators per step" % world,
+                           "parallelism": "samples interleaved over %d GPU(s), NCCL reduce of fp32 accumulators per step (%s)" % (world, "rm_reduce" if opt.reduce == "cabi" else "torch.distributed"),
                            "l2_policy": "per-step working set (queues + accumulators, >3 GB) exceeds L2; accumulators re-zeroed each step"},
                 "pixel_samples_per_s": npix * args.spp * opt.steps / (ms_total * 1e-3),
                 "time_to_spp_s": {str(args.spp): ms_total / opt.steps * 1e-3},
@@ -359,6 +370,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=int(os.environ.get("RM_BENCH_SPP", "0")), help="samples per pixel of one step (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--reduce", default="cabi", choices=["cabi", "torch"], help="N > 1: rm_reduce (NCCL inside the library) or torch.distributed collectives")
     opt = ap.parse_args()
     global WORKLOAD
     WORKLOAD = WORKLOADS[opt.workload]["name"]

@@ -157,6 +157,16 @@ int rm_accum_view(RmContext *ctx, float **d_sum, int64_t *n_sum, float **d_max, 
 int rm_accum_after_reduce(RmContext *ctx, int32_t rank, int32_t world);
 int rm_accum_radiance(RmContext *ctx, float **d_rad, int64_t *n_rad);
 
+/* The same exchange done by the library over NCCL (bound at run time: libnccl.so.2), for hosts that do not bring their
+ * own collective layer.  One process per GPU, one context per process.  rm_comm_unique_id on rank 0 -> the host hands
+ * the 128 bytes to every rank (MPI, sockets, a file) -> rm_comm_init on every rank (collective) -> after each rank's
+ * rm_render_samples(ctx, args, rank, world, ...), rm_reduce(ctx, root) performs steps 1-3 on the context's stream
+ * (collective) and rank `root` calls rm_resolve.  Nothing like it exists in the reference (single process, threads). */
+int rm_comm_unique_id(uint8_t id[128]);
+int rm_comm_init(RmContext *ctx, const uint8_t id[128], int32_t rank, int32_t world);
+int rm_reduce(RmContext *ctx, int32_t root);
+int rm_comm_destroy(RmContext *ctx);
+
 /* Progressive checkpoint / resume (the reference has none): the un-finalised accumulators
  * of the current frame as one opaque blob of rm_checkpoint_bytes(args) bytes.  Save after any rm_render_samples call;
  * after rm_checkpoint_load (same scene uploaded, same args) further rm_render_samples calls with reset = 0 add the

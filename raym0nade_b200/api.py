@@ -57,7 +57,8 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_scene_device_bytes", "rm_scene_h2d_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved",
-           "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
+           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -100,6 +101,10 @@ def lib():
     L.rm_fxaa.argtypes = [vp, vp, vp, i32, i32]
     L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
+    L.rm_comm_unique_id.argtypes = [vp]
+    L.rm_comm_init.argtypes = [vp, vp, i32, i32]
+    L.rm_reduce.argtypes = [vp, i32]
+    L.rm_comm_destroy.argtypes = [vp]
     L.rm_checkpoint_bytes.restype = i64
     L.rm_checkpoint_bytes.argtypes = [ARGS]
     L.rm_checkpoint_save.argtypes = [vp, vp, i64]
@@ -315,6 +320,23 @@ class Context:
 
     def fxaa_device(self, d_in: int, d_out: int, width: int, height: int):
         _check(lib().rm_fxaa_device(self.h, C.c_void_p(d_in), C.c_void_p(d_out), width, height))
+
+    # ---- multi-GPU exchange inside the library (NCCL)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (call on rank 0, hand to every rank)"""
+        uid = np.zeros(128, np.uint8)
+        _check(lib().rm_comm_unique_id(_p(uid)))
+        return uid
+
+    def comm_init(self, uid, rank: int, world: int):
+        uid = np.ascontiguousarray(uid, np.uint8)
+        assert uid.size == 128
+        _check(lib().rm_comm_init(self.h, _p(uid), rank, world))
+
+    def reduce(self, root: int = 0):
+        """the three-step frame reduction over the context's communicator, on the context's stream"""
+        _check(lib().rm_reduce(self.h, root))
 
     def checkpoint_save(self, args: RenderArgs):
         """the un-finalised accumulators of the current frame as a byte blob"""

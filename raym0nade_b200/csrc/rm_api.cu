@@ -74,6 +74,7 @@ void rm_context_destroy(RmContext *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     rm_render_state_free(ctx);
+    rm_comm_state_free(ctx);
     delete ctx;
 }
 

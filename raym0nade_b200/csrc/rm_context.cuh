@@ -86,6 +86,9 @@ struct RmContext {
     DevBuf b_io[4];                        // staging for the batched per-ray seam / fxaa
     // wavefront + accumulators live in rm_render.cu's state
     void *render_state = nullptr;
+    // multi-GPU: NCCL communicator of this context (rm_comm.cu)
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -100,3 +103,5 @@ rm::DevArgs to_dev_args(const RmRenderArgs *a);
 int rm_check_args(const RmRenderArgs *a);
 // implemented in rm_render.cu
 void rm_render_state_free(RmContext *ctx);
+// implemented in rm_comm.cu
+void rm_comm_state_free(RmContext *ctx);

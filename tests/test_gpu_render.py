@@ -277,6 +277,22 @@ def test_render_degenerate_sample_splits(ref, p_direct, spp):
     ctx.close()
 
 
+def test_in_library_reduce_across_two_gpus():
+    """rm_comm_init + rm_reduce (NCCL inside the library): two ranks, one GPU each, against the single-GPU frame.  Needs two
+    GPUs; the protocol itself is also covered at world_size 2 over gloo on CPU (tests/test_cpu_host.py)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (NCCL does not put two ranks on one device)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "reduce_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rm_reduce over 2 ranks: OK" in r.stdout
+
+
 def test_checkpoint_resume_in_a_fresh_context_equals_one_render():
     """stop after the first of two sample shards, save, tear the context down; a new context loads the blob, renders the
     second shard and resolves to the frame of an uninterrupted render"""
