@@ -374,13 +374,18 @@ RM_DI void push_shadow(ShadowItem *q, int *count, int cap, int *overflow, bool w
 // G-buffer record and the per-light-object weights (getLightObjectWeight, one BSDF evaluation per light object,
 // src/sampling.cpp:406-417) depend on the pixel only and are formed once instead of once per sample.  Every
 // sample keeps its own random stream, so the samples are the ones a per-sample loop draws.
+// WARP = true (waves of >= 16 samples per pixel): one WARP per pixel, one lane per sample - the surface record, the
+// material branches of the BSDF and the light weights are uniform across the warp and the lanes' 64-byte items are
+// consecutive (coalesced).  WARP = false (few samples per pixel, e.g. previews): one THREAD per pixel loops over them.
+template <bool WARP>
 __global__ void __launch_bounds__(kShadeBlock, kCtasDirect) k_direct_gen(DevScene S, DevArgs A, FrameBuffers Fb, int n_samples, int npix, int s_begin,
                                                     int s_stride, int spp_direct, unsigned long long seed,
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int lane = threadIdx.x & 31;
-    for (int base = blockIdx.x * blockDim.x; base < npix; base += gridDim.x * blockDim.x) {
+    const int per_cta = WARP ? (blockDim.x >> 5) : blockDim.x;          // pixels a CTA takes per batch
+    for (int base = blockIdx.x * per_cta; base < npix; base += gridDim.x * per_cta) {
         RM_LOCKSTEP();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
-        const int p = base + threadIdx.x;
+        const int p = base + (WARP ? (threadIdx.x >> 5) : threadIdx.x);
         bool go = false;
         Bsdf B;
         B.s = default_surface();
@@ -397,17 +402,24 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasDirect) k_direct_gen(DevScen
         }
         // a pixel's n_samples items are one contiguous block of the shadow queue: k_accum_direct sums them per pixel in
         // sample order without atomics, and a warp of the visibility pass gets rays that share their origin
-        const unsigned m = __ballot_sync(0xffffffffu, go);
         int first = 0;
-        if (m) {
-            if (lane == __ffs(m) - 1) first = atomicAdd(s_count, __popc(m) * n_samples);
-            first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u)) * n_samples;
+        if (WARP) {                          // go is warp-uniform
+            if (go) {
+                if (lane == 0) first = atomicAdd(s_count, n_samples);
+                first = __shfl_sync(0xffffffffu, first, 0);
+            }
+        } else {
+            const unsigned m = __ballot_sync(0xffffffffu, go);
+            if (m) {
+                if (lane == __ffs(m) - 1) first = atomicAdd(s_count, __popc(m) * n_samples);
+                first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u)) * n_samples;
+            }
         }
         if (go && first + n_samples > s_cap) { atomicExch(overflow, 1); go = false; }
-        if (p < npix) Fb.dir_base[p] = go ? first : -1;
+        if (p < npix && (!WARP || lane == 0)) Fb.dir_base[p] = go ? first : -1;
         if (!go) continue;
 #pragma unroll 1
-        for (int k = 0; k < n_samples; k++) {
+        for (int k = WARP ? lane : 0; k < n_samples; k += WARP ? 32 : 1) {
             const int s = s_begin + k * s_stride;
             NeeOut n;
             n.valid = false;

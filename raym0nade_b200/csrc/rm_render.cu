@@ -254,8 +254,15 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         const int S = std::min(S_dir, n_d - k0);
         RM_CUDA(cudaMemsetAsync(C + C_SQ, 0, 4, st));
         RM_CUDA(cudaMemsetAsync(C + C_CUR_SHADOW, 0, 4, st));
-        k_direct_gen<<<R->sm_count * kCtasDirect, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
-                                           seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+        // environment-lit scenes: a warp per pixel (the sky CDF search dominates and the lanes share the surface);
+        // light objects: a thread per pixel (the per-light weights - one BSDF evaluation each - are formed once per pixel);
+        // A/B in profiles/r01e_ab15_direct_gen_mapping.txt
+        if (S >= 16 && ctx->scene.sky_width != 0)
+            k_direct_gen<true><<<R->sm_count * kCtasDirect, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+                                                                                 seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+        else
+            k_direct_gen<false><<<R->sm_count * kCtasDirect, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
+                                                                                  seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         ctx->launches++;
         trace_shadow(C + C_SQ, S);
     }
