@@ -327,7 +327,8 @@ def run_ours(opt, rank, world, local_rank):
                     "traffic": traffic, "traffic_note": traffic_note, "rays_per_launch": rays_per_launch, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": 32.0 * counted[dom]["box"] / max(kinds[dom]["launches"] / opt.steps, 1) + 36.0 * counted[dom]["tri"] / max(kinds[dom]["launches"] / opt.steps, 1),
                     "note": "achieved = (32 B x box tests + 36 B x triangle tests) of this kernel's launches / its CUDA-event time; "
-                            "the 1M-triangle scene (167 MB) is L2-resident, see DESIGN.md"}
+                            "the scene (%.0f MB in HBM, traversal streams %.0f MB) is largely L2-resident on B200 (126 MB L2), see DESIGN.md"
+                            % (ctx.scene_bytes() / 1e6, (scene.n_faces * 48 + model.desc.n_nodes * 32) / 1e6)}
         # reference CPU path on this box's host cores, bounded sample of the same workload
         cpu = None
         if world == 1 and not opt.no_cpu:
