@@ -195,6 +195,7 @@ def run_ours(opt, rank, world, local_rank):
     model = Model(scene)
     stream = torch.cuda.current_stream().cuda_stream
     ctx = Context(local_rank, stream=stream).upload(model)
+    ctx.set_option("exact_secondary", 1 if opt.exact_secondary else 0)
 
     # the frame reduction runs inside the library (rm_reduce: NCCL on the context's stream); torch.distributed only
     # carries the 128-byte unique id to the ranks and provides the barriers.  --reduce torch drives the same three steps
@@ -231,6 +232,13 @@ def run_ours(opt, rank, world, local_rank):
     ctx.stats_reset()
     step(1)
     counted = ctx.stats_kernels()
+    # the same rays through the reference's own tree in the reference's order: the B and T SURVEY.md section 8d defines the
+    # per-ray bytes on (bounce and shadow rays normally traverse the secondary-ray tree, which tests fewer boxes and triangles)
+    ctx.set_option("exact_secondary", 1)
+    ctx.stats_reset()
+    step(1)
+    counted_ref = ctx.stats_kernels()
+    ctx.set_option("exact_secondary", 1 if opt.exact_secondary else 0)
     ctx.set_option("count_tests", 0)
 
     for i in range(opt.warmup):
@@ -306,6 +314,12 @@ def run_ours(opt, rank, world, local_rank):
                            "box_tests_per_ray": c["box"] / c["rays"], "tri_tests_per_ray": c["tri"] / c["rays"],
                            "bytes_per_ray": bytes_per_step / c["rays"], "achieved_gbs": gbs,
                            "mrays_per_s_kernel_only": c["rays"] * opt.steps / (t["ms"] * 1e-3) / 1e6}
+            cr = counted_ref[k]
+            if cr["rays"]:
+                ref_bytes = 32.0 * cr["box"] + 36.0 * cr["tri"]
+                per_kind[k]["reference_order"] = {"box_tests_per_ray": cr["box"] / cr["rays"], "tri_tests_per_ray": cr["tri"] / cr["rays"],
+                                                  "bytes_per_ray": ref_bytes / cr["rays"],
+                                                  "equivalent_gbs": ref_bytes * opt.steps / (t["ms"] * 1e-3) / 1e9}
         per_kind["shade"] = {"ms_per_step": kinds["shade"]["ms"] / opt.steps, "launches_per_step": kinds["shade"]["launches"] / opt.steps}
         dom = max((k for k in per_kind if k != "shade"), key=lambda k: per_kind[k]["ms_per_step"])
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)
@@ -326,7 +340,10 @@ def run_ours(opt, rank, world, local_rank):
                     "achieved": per_kind[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kind[dom]["achieved_gbs"] / peak,
                     "traffic": traffic, "traffic_note": traffic_note, "rays_per_launch": rays_per_launch, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": 32.0 * counted[dom]["box"] / max(kinds[dom]["launches"] / opt.steps, 1) + 36.0 * counted[dom]["tri"] / max(kinds[dom]["launches"] / opt.steps, 1),
-                    "note": "achieved = (32 B x box tests + 36 B x triangle tests) of this kernel's launches / its CUDA-event time; "
+                    "tree": "reference tree, reference visit order" if (opt.exact_secondary or dom == "primary") else
+                            "secondary-ray tree (binned SAH over the same triangles, leaves <= 4): fewer box and triangle tests per ray than the "
+                            "reference order, whose figures are under kernels.*.reference_order",
+                    "note": "achieved = (32 B x box tests + 36 B x triangle tests) this kernel actually performed / its CUDA-event time; "
                             "the scene (%.0f MB in HBM, traversal streams %.0f MB) is largely L2-resident on B200 (126 MB L2), see DESIGN.md"
                             % (ctx.scene_bytes() / 1e6, (scene.n_faces * 48 + model.desc.n_nodes * 32) / 1e6)}
         # reference CPU path on this box's host cores, bounded sample of the same workload
@@ -346,6 +363,7 @@ def run_ours(opt, rank, world, local_rank):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "spp": args.spp, "spp_direct": spp_d, "P_Direct": args.P_Direct,
                            "parallelism": "samples interleaved over %d GPU(s), NCCL reduce of fp32 accumulators per step (%s)" % (world, "rm_reduce" if opt.reduce == "cabi" else "torch.distributed"),
+                           "secondary_rays": "reference tree and order" if opt.exact_secondary else "secondary-ray tree (same triangles, same tests, binned-SAH topology)",
                            "l2_policy": "per-step working set (queues + accumulators, >3 GB) exceeds L2; accumulators re-zeroed each step"},
                 "pixel_samples_per_s": npix * args.spp * opt.steps / (ms_total * 1e-3),
                 "time_to_spp_s": {str(args.spp): ms_total / opt.steps * 1e-3},
@@ -371,6 +389,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=int(os.environ.get("RM_BENCH_SPP", "0")), help="samples per pixel of one step (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exact-secondary", action="store_true", help="bounce and shadow rays through the reference's own tree in the reference's order (default: the secondary-ray tree)")
     ap.add_argument("--reduce", default="cabi", choices=["cabi", "torch"], help="N > 1: rm_reduce (NCCL inside the library) or torch.distributed collectives")
     opt = ap.parse_args()
     global WORKLOAD

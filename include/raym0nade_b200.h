@@ -218,6 +218,11 @@ int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_optio
  * Box/triangle counts are only collected when rm_set_option("count_tests", 1). */
 int rm_stats_reset(RmContext *ctx);
 int rm_stats_read(RmContext *ctx, uint64_t out[4]);
+/* Options (integers).  "exact_secondary" 0|1 (default 0): 1 sends the estimator's bounce and shadow rays through the
+ * reference's own BVH in the reference's visit order, like primary rays and the per-ray seam always are; 0 lets them use the
+ * library's second tree over the same triangles (same box / triangle tests, binned-SAH topology - the closest accepted hit is
+ * the same, far fewer tests per ray).  "count_tests", "time_kernels": counters / per-kind device timing.  The others
+ * ("trace_refill", "wave_paths", "stack_levels", ...) are tuning and test hooks, see rm_api.cu. */
 int rm_set_option(RmContext *ctx, const char *name, int64_t value);
 /* Per-kernel-kind breakdown.  Kinds: 0 primary / batched per-ray kernels, 1 closest hit over the
  * path queue, 2 occlusion over the shadow queue, 3 shading.  counters[3*kind + {0,1,2}] =

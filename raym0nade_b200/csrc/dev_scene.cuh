@@ -64,6 +64,10 @@ struct DevScene {
     int32_t sky_width, sky_height;
     int32_t any_cutout;             // some material has hasFullyTransparentPart
     int32_t root_is_leaf;
+    // Secondary-ray tree (fast_bvh.cpp): same record layout, but an inner record names the block of its children in faceL
+    // (explicit_children) and triangle indices are in the builder's order (face_map -> index into `shade` / the reference order)
+    int32_t explicit_children;
+    const int32_t *face_map;
 };
 
 // Camera / render arguments in device form (RenderArgs, include/render.h:8-15).

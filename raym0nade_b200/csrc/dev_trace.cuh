@@ -145,7 +145,7 @@ RM_DI V2 interp_uv(const FaceShade &F, V3 bary) {
 RM_DI bool transparent_test(const DevScene &S, const RaySetup &r, float t, int face) {
     float cut = __ldg(&S.tri[size_t(face) * kTriStride + 2].z);
     if (cut == 0.0f) return false;                       // material without hasFullyTransparentPart
-    FaceShade F = load_face(S, face);
+    FaceShade F = load_face(S, S.face_map ? __ldg(S.face_map + face) : face);
     V3 P = r.o + r.d * t;
     V3 bary = barycentric(F.v[0], F.v[1], F.v[2], P);
     V2 uv = interp_uv(F, bary);
@@ -199,6 +199,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
     // cut-outs: "the closest accepted t is < aim" <=> "some accepted t is < aim", and the traversal state is
     // identical up to that triangle, so the boolean is the reference's
     const bool anyhit = Job::kOcclusion && !S.any_cutout;
+    const bool expl = S.explicit_children != 0;
 
     bool active = false;
     int chunk_next = 0, chunk_end = 0;          // warp-uniform: rays of the current chunk not handed out yet
@@ -261,8 +262,10 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     else { ray_in_box_fast(r, a0, b0, tL0, tR0); ray_in_box_fast(r, a1, b1, tL1, tR1); }
                     if (COUNT) cnt.box += 2;
                     const int fr0 = __float_as_int(b0.w), fr1 = __float_as_int(b1.w);
-                    const int ref0 = fr0 ? leaf_ref(__float_as_int(b0.z), fr0) : (cur << 1);
-                    const int ref1 = fr1 ? leaf_ref(__float_as_int(b1.z), fr1) : (cur << 1 | 1);
+                    // an inner child's own children: blocks 2u, 2u+1 of the implicit heap (the reference's tree), or the
+                    // block its record names (the secondary-ray tree)
+                    const int ref0 = fr0 ? leaf_ref(__float_as_int(b0.z), fr0) : (expl ? __float_as_int(b0.z) : (cur << 1));
+                    const int ref1 = fr1 ? leaf_ref(__float_as_int(b1.z), fr1) : (expl ? __float_as_int(b1.z) : (cur << 1 | 1));
                     const bool ok0 = tL0 < tR0, ok1 = tL1 < tR1;
                     const bool zero_first = tL0 < tL1;
                     const int first = zero_first ? ref0 : ref1, second = zero_first ? ref1 : ref0;
@@ -345,7 +348,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                         t_min = fadd(t, kEps); t = CUDART_INF_F; face = -1; pass++;
                         again = pass < 8;
                     }
-                    if (!again) job.hit(idx, t, face);
+                    if (!again) job.hit(idx, t, (S.face_map && face >= 0) ? __ldg(S.face_map + face) : face);
                 } else {
                     bool occluded = !(t >= aim);
                     if (occluded && S.any_cutout && transparent_test(S, r, t, face)) {

@@ -113,6 +113,23 @@ __global__ void k_pack_faces(const float *__restrict__ pos, const float *__restr
     s[6] = make_float4(__int_as_float(m), 0.0f, 0.0f, 0.0f);
 }
 
+// the traversal records in the order of the secondary-ray tree's leaves
+__global__ void k_permute_tris(const float4 *__restrict__ tri, const int *__restrict__ order, int n, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *s = tri + size_t(order[i]) * kTriStride;
+    float4 *d = out + size_t(i) * kTriStride;
+#pragma unroll
+    for (int k = 0; k < kTriStride; k++) d[k] = s[k];
+}
+
+static uint64_t hash_words(const void *p, size_t bytes) {
+    const uint64_t *w = static_cast<const uint64_t *>(p);
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ bytes;
+    for (size_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+    return h;
+}
+
 int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if (!ctx || !sc) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: null argument");
     if (sc->n_faces <= 0 || sc->n_nodes < 2 || !sc->nodes || !sc->positions || !sc->uvs || !sc->normals || !sc->face_material)
@@ -163,6 +180,28 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
                                                   ctx->b_mats.as<DevMaterial>(), n, ctx->b_tri.as<float4>(), ctx->b_shade.as<float4>());
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
+
+    // the secondary-ray tree (fast_bvh.cpp): built on the host from the same positions, kept across uploads of the same
+    // geometry (a renderer re-stages materials and lights far more often than triangles)
+    {
+        const uint64_t key = hash_words(sc->positions, size_t(n) * 36);
+        if (!(ctx->fast_key_valid && ctx->fast_key == key && ctx->fast_n == n)) {
+            std::vector<RmBvhNode> fnodes;
+            std::vector<int32_t> forder;
+            int fdepth = 0;
+            if ((rc = rm_build_fast_bvh(sc->positions, n, ctx->fast_depth_cap, fnodes, forder, &fdepth))) return rc;
+            if ((rc = upload(ctx->b_nodes_fast, fnodes.data(), fnodes.size() * sizeof(RmBvhNode), st, total))) return rc;
+            if ((rc = upload(ctx->b_facemap, forder.data(), forder.size() * 4, st, total))) return rc;
+            RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die at scope exit
+            ctx->stack_levels_fast = std::min(std::max(fdepth, 2), 40);
+            ctx->fast_root_is_leaf = fnodes[1].faceR != 0;
+            ctx->fast_key = key; ctx->fast_n = n; ctx->fast_key_valid = true;
+        }
+        if ((rc = ctx->b_tri_fast.alloc(size_t(n) * 16 * kTriStride))) return rc;
+        k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap.as<int>(), n, ctx->b_tri_fast.as<float4>());
+        ctx->launches++;
+        RM_CUDA(cudaGetLastError());
+    }
 
     // textures: one blob, each level 16-byte aligned, copied level by level straight from the caller's memory
     std::vector<DevTexture> texs(std::max(sc->n_textures, 1));
@@ -258,10 +297,18 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     S.sky_height = sc->sky_height;
     S.any_cutout = any_cutout ? 1 : 0;
     S.root_is_leaf = sc->nodes[1].faceR != 0;
+    S.explicit_children = 0;
+    S.face_map = nullptr;
     // deferred children per ray <= inner levels of the heap-indexed tree (node indices < n_nodes)
     int levels = 1;
     while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
     ctx->stack_levels = std::min(std::max(levels, 2), 40);
+    ctx->scene_fast = S;
+    ctx->scene_fast.nodes = ctx->b_nodes_fast.as<float4>();
+    ctx->scene_fast.tri = ctx->b_tri_fast.as<float4>();
+    ctx->scene_fast.face_map = ctx->b_facemap.as<int32_t>();
+    ctx->scene_fast.explicit_children = 1;
+    ctx->scene_fast.root_is_leaf = ctx->fast_root_is_leaf ? 1 : 0;
     ctx->scene_h2d_bytes = total;
     ctx->scene_bytes = 0;
     for (const DevBuf *b : {&ctx->b_nodes, &ctx->b_tri, &ctx->b_shade, &ctx->b_mats, &ctx->b_texs, &ctx->b_texels, &ctx->b_lights, &ctx->b_lpos,
@@ -292,7 +339,8 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
     job.tri_idx = ctx->b_io[2].as<int>(); job.t_out = ctx->b_io[3].as<float>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    launch_trace(ctx->scene, ctx->stack_levels, ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(ctx->seam_secondary_tree ? ctx->scene_fast : ctx->scene, ctx->seam_secondary_tree ? ctx->stack_levels_fast : ctx->stack_levels, ctx->count_tests, grid, st, job,
+                 int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -318,7 +366,8 @@ int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *
     job.out = ctx->b_io[3].as<unsigned char>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    launch_trace(ctx->scene, ctx->stack_levels, ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(ctx->seam_secondary_tree ? ctx->scene_fast : ctx->scene, ctx->seam_secondary_tree ? ctx->stack_levels_fast : ctx->stack_levels, ctx->count_tests, grid, st, job,
+                 int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
@@ -403,6 +452,9 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return rm_fail(RM_ERR_INVALID, "rm_set_option: null argument");
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
+    // test hook: rm_trace_closest / rm_trace_occluded through the secondary-ray tree (the seam itself is the reference's tree)
+    if (!std::strcmp(name, "seam_secondary_tree")) { ctx->seam_secondary_tree = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "fast_depth_cap")) { ctx->fast_depth_cap = int(std::min<int64_t>(std::max<int64_t>(value, 8), 26)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
     if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
     if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }

@@ -39,7 +39,7 @@ struct RmContext {
     cudaStream_t stream = nullptr;
     bool has_scene = false;
     bool count_tests = false;
-    bool exact_secondary = true;
+    bool exact_secondary = false;      // true: bounce and shadow rays also traverse the reference's tree in the reference's order
     bool disable_clamp = false;        // debugging aid: never drop the held-back sample
     uint64_t launches = 0;
 
@@ -61,6 +61,13 @@ struct RmContext {
 
     // scene
     rm::DevScene scene{};
+    rm::DevScene scene_fast{};             // the same scene with the secondary-ray tree (fast_bvh.cpp) in place of the reference's
+    int stack_levels_fast = 24;
+    DevBuf b_nodes_fast, b_tri_fast, b_facemap, b_order;
+    int fast_depth_cap = 21;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
+    bool fast_root_is_leaf = false, fast_key_valid = false, seam_secondary_tree = false;
+    uint64_t fast_key = 0;
+    int fast_n = 0;
     DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf, b_skyguide, b_lut;
     DevBuf b_raw[4];                       // the caller's positions / uvs / normals / face materials as uploaded (input of k_pack_faces)
     int64_t scene_bytes = 0;               // device-resident bytes of the uploaded scene
@@ -93,7 +100,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_order, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };
@@ -103,5 +110,7 @@ rm::DevArgs to_dev_args(const RmRenderArgs *a);
 int rm_check_args(const RmRenderArgs *a);
 // implemented in rm_render.cu
 void rm_render_state_free(RmContext *ctx);
+// implemented in fast_bvh.cpp
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);

@@ -73,12 +73,13 @@ def _calc_var(rad, var, exposure):
     return rad, max(f32(var), f32(0))
 
 
-def _replay_scene(ref, scene, args, seed, direct):
+def _replay_scene(ref, scene, args, seed, direct, exact_secondary=0):
     """Render ONE sample per pixel on the GPU (clamp off), replay every pixel through the
     reference with the same draws, return (gpu planes, ref planes) as float64 arrays [npix, 2, 4]."""
     R, ctx = _setup(ref, scene)
     a = args.replace(spp=1, P_Direct=1.0 if direct else 0.0)
     ctx.set_option("disable_clamp", 1)
+    ctx.set_option("exact_secondary", exact_secondary)
     out = ctx.render(a, seed=seed)
     rg = R.gbuffer(a.replace(spp=0), threads=8)
     npix = a.width * a.height
@@ -133,28 +134,31 @@ def _assert_replay(gpu, refv, min_match):
     return match.mean()
 
 
+# exact = 0: bounce and shadow rays through the secondary-ray tree (the default); exact = 1: through the reference's own tree
+@pytest.mark.parametrize("exact", [0, 1])
 @pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
-def test_replay_indirect_sample_by_sample(ref, which):
+def test_replay_indirect_sample_by_sample(ref, which, exact):
     if which == "cornell":
         scene, args = scenes.cornell_box(64, 64, 1)
     elif which == "sky":
         scene, args = scenes.heightfield_scene(8_000, 80, 45, with_sky=True)
     else:
         scene, args = scenes.glossy_dielectric(30_000, 80, 45)
-    gpu, refv, exhausted = _replay_scene(ref, scene, args, seed=1234, direct=False)
+    gpu, refv, exhausted = _replay_scene(ref, scene, args, seed=1234, direct=False, exact_secondary=exact)
     assert exhausted == 0
     _assert_replay(gpu, refv, 0.97)
 
 
+@pytest.mark.parametrize("exact", [0, 1])
 @pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
-def test_replay_direct_sample_by_sample(ref, which):
+def test_replay_direct_sample_by_sample(ref, which, exact):
     if which == "cornell":
         scene, args = scenes.cornell_box(64, 64, 1)
     elif which == "sky":
         scene, args = scenes.heightfield_scene(8_000, 80, 45, with_sky=True)
     else:
         scene, args = scenes.glossy_dielectric(30_000, 80, 45)
-    gpu, refv, _ = _replay_scene(ref, scene, args, seed=77, direct=True)
+    gpu, refv, _ = _replay_scene(ref, scene, args, seed=77, direct=True, exact_secondary=exact)
     _assert_replay(gpu, refv, 0.99)
 
 
@@ -171,8 +175,9 @@ def _rel_mse(a, b, trim=0.01):
     return float(e[: max(1, int(len(e) * (1.0 - trim)))].mean())
 
 
+@pytest.mark.parametrize("exact", [0, 1])
 @pytest.mark.parametrize("which,spp", [("cornell", 128), ("sky", 64), ("glossy", 32)])
-def test_render_matches_reference_statistically(ref, which, spp):
+def test_render_matches_reference_statistically(ref, which, spp, exact):
     """relMSE(GPU, CPU seed A) <= 1.5 x relMSE(CPU seed A, CPU seed B) per plane; energy within 1.5 %."""
     if which == "cornell":
         scene, args = scenes.cornell_box(96, 96, spp)
@@ -181,6 +186,7 @@ def test_render_matches_reference_statistically(ref, which, spp):
     else:
         scene, args = scenes.glossy_dielectric(60_000, 128, 72, spp)
     R, ctx = _setup(ref, scene)
+    ctx.set_option("exact_secondary", exact)
     gpu = _planes(ctx.render(args, seed=5))
     gpu_b = _planes(ctx.render(args, seed=6))
     ca = _planes(R.render(args, threads=8, seed_base=100))

@@ -154,6 +154,45 @@ def test_closest_and_occluded_random_rays(ref, which):
     ctx.close()
 
 
+@pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout", "glossy"])
+def test_secondary_ray_tree_finds_the_reference_hits(ref, which):
+    """The estimator's bounce and shadow rays traverse a second tree over the same triangles (fast_bvh.cpp: binned SAH,
+    leaves <= 4) with the same box and triangle tests.  It must find the closest accepted triangle the reference finds:
+    checked here ray by ray against the compiled reference through a test hook that sends the per-ray seam through that
+    tree.  Equal-t ties between triangles (shared edges) are the only freedom a different visit order has: t is
+    bit-equal on every ray (with alpha cut-outs: on all but <= 0.02 %), the triangle index and the occlusion booleans on all
+    but a sliver."""
+    if which == "cornell":
+        scene, _ = scenes.cornell_box()
+    elif which == "heightfield":
+        scene, _ = scenes.heightfield_scene(20_000)
+    elif which == "cutout":
+        scene, _ = scenes.texture_heavy(40_000, tex_size=64, n_materials=8)
+    else:
+        scene, _ = scenes.glossy_dielectric(200_000, 64, 36, 0)
+    model = Model(scene)
+    R = ref.RefScene(scene)
+    ctx = Context(0).upload(model)
+    ctx.set_option("seam_secondary_tree", 1)
+    org, d = _random_rays(scene, 50_000, 23)
+    tri, t = ctx.trace_closest(org, d)
+    rtri, rt = R.trace_closest(org, d)
+    t_differs = t.view(np.uint32) != rt.view(np.uint32)
+    if which == "cutout":
+        # a tie at a shared edge can put the alpha test (and so the <= 8 re-traces) on the neighbouring triangle: 2 of 50 000 rays
+        assert t_differs.mean() <= 2e-4, t_differs.sum()
+    else:
+        assert not t_differs.any(), "closest t differs on %d rays" % t_differs.sum()
+    assert (tri != rtri).mean() <= 1e-3, (tri != rtri).mean()
+    hit = rtri >= 0
+    aim = np.full(org.shape[0], np.inf, np.float32)
+    aim[hit] = rt[hit] * np.where(np.arange(hit.sum()) % 3 == 0, 0.5, np.where(np.arange(hit.sum()) % 3 == 1, 1.0, 1.5)).astype(np.float32)
+    occ = ctx.trace_occluded(org, d, aim)
+    rocc = R.trace_occluded(org, d, aim)
+    assert (occ != rocc).mean() <= 1e-3, (occ != rocc).mean()
+    ctx.close()
+
+
 def test_work_counters_match_reference_traversal(ref):
     """box / triangle test counts come out identical because the traversal order is identical
     (these are the B and T of the bytes-per-ray roofline figure)"""
