@@ -32,7 +32,7 @@ struct Aabb {
     float area() const { float d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]}; return 2.0f * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]); }
 };
 
-constexpr int kBins = 16, kLeafMax = 4;
+constexpr int kBins = 16;
 
 struct Builder {
     const float *pos;                 // [n][9]
@@ -42,9 +42,10 @@ struct Builder {
     std::vector<RmBvhNode> &nodes;
     std::atomic<int> next_block{2};   // block 0 = {unused, whole-tree record}, block 1 = the root's children
     std::atomic<int> max_depth{0};
-    int depth_cap;
+    int depth_cap, kLeafMax;
 
-    Builder(const float *p, int n, std::vector<int32_t> &o, std::vector<RmBvhNode> &nd, int cap) : pos(p), order(o), nodes(nd), depth_cap(cap) {
+    Builder(const float *p, int n, std::vector<int32_t> &o, std::vector<RmBvhNode> &nd, int cap, int leaf_max)
+        : pos(p), order(o), nodes(nd), depth_cap(cap), kLeafMax(leaf_max) {
         tb.resize(n);
         cen.resize(size_t(n) * 3);
         for (int i = 0; i < n; i++) {
@@ -168,13 +169,14 @@ struct Builder {
 } // namespace
 
 // positions [n][9]; returns the node records (pairs), the triangle order and the tree depth (levels of inner nodes + 1)
-int rm_build_fast_bvh(const float *positions, int n, int depth_cap, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out) {
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out) {
+    const int kLeafMax = std::min(std::max(leaf_max, 1), 15);          // a leaf reference holds its count in 4 bits (dev_trace.cuh)
     if (!positions || n <= 0) return rm_fail(RM_ERR_INVALID, "rm_build_fast_bvh: no triangles");
     order.resize(n);
     for (int i = 0; i < n; i++) order[i] = i;
     nodes.assign(size_t(n + 2) * 2, RmBvhNode{});
     const int min_cap = int(std::ceil(std::log2(std::max(1.0, double(n) / kLeafMax)))) + 1;
-    Builder B(positions, n, order, nodes, std::max(depth_cap, min_cap));
+    Builder B(positions, n, order, nodes, std::max(depth_cap, min_cap), kLeafMax);
     RmBvhNode whole{};
     B.build(whole, 0, n, 0, 4, /*the root's children are block 1, where the engine starts*/ 1);
     nodes[1] = whole;          // only read when the whole scene is one leaf (root_is_leaf)

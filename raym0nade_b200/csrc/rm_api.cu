@@ -189,7 +189,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
             std::vector<RmBvhNode> fnodes;
             std::vector<int32_t> forder;
             int fdepth = 0;
-            if ((rc = rm_build_fast_bvh(sc->positions, n, ctx->fast_depth_cap, fnodes, forder, &fdepth))) return rc;
+            if ((rc = rm_build_fast_bvh(sc->positions, n, ctx->fast_depth_cap, ctx->fast_leaf_max, fnodes, forder, &fdepth))) return rc;
             if ((rc = upload(ctx->b_nodes_fast, fnodes.data(), fnodes.size() * sizeof(RmBvhNode), st, total))) return rc;
             if ((rc = upload(ctx->b_facemap, forder.data(), forder.size() * 4, st, total))) return rc;
             RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die at scope exit
@@ -454,6 +454,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
     // test hook: rm_trace_closest / rm_trace_occluded through the secondary-ray tree (the seam itself is the reference's tree)
     if (!std::strcmp(name, "seam_secondary_tree")) { ctx->seam_secondary_tree = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "fast_leaf_max")) { ctx->fast_leaf_max = int(std::min<int64_t>(std::max<int64_t>(value, 1), 15)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_depth_cap")) { ctx->fast_depth_cap = int(std::min<int64_t>(std::max<int64_t>(value, 8), 26)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
     if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }

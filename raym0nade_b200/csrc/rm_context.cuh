@@ -65,6 +65,7 @@ struct RmContext {
     int stack_levels_fast = 24;
     DevBuf b_nodes_fast, b_tri_fast, b_facemap, b_order;
     int fast_depth_cap = 21;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
+    int fast_leaf_max = 4;                 // triangles per leaf of the secondary-ray tree
     bool fast_root_is_leaf = false, fast_key_valid = false, seam_secondary_tree = false;
     uint64_t fast_key = 0;
     int fast_n = 0;
@@ -111,6 +112,6 @@ int rm_check_args(const RmRenderArgs *a);
 // implemented in rm_render.cu
 void rm_render_state_free(RmContext *ctx);
 // implemented in fast_bvh.cpp
-int rm_build_fast_bvh(const float *positions, int n, int depth_cap, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);

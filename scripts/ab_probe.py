@@ -19,8 +19,9 @@ else:
     try: pickle.dump((scene, args), open(cache, "wb"), protocol=4)
     except Exception as e: print("scene cache not written:", e)
 model = Model(scene)
-ctx = Context(0).upload(model)
-for k, v in opts.items(): ctx.set_option(k, int(v))
+ctx = Context(0)
+for k, v in opts.items(): ctx.set_option(k, int(v))         # before the upload: some options shape what is staged
+ctx.upload(model)
 ctx.trace_primary(args, download=False); ctx.gbuffer(args, download=False)
 ctx.render_samples(args, seed=1); ctx.synchronize()          # warm-up
 best = None
