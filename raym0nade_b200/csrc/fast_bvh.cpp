@@ -4,9 +4,9 @@
 // in the reference's own order: their triangle index is a bit-exact contract.  The rays of the estimator are held to
 // the north star's statistical bar instead, so they may use a better tree as long as the hit they find is the closest
 // accepted triangle under the same box and triangle tests.  This builder makes that tree:
-// binned SAH (16 bins per axis), leaves of at most 4 triangles (the reference: object median, 5-10 per leaf), depth capped
-// so the traversal stack still fits 8 resident CTAs per SM.  On the bench scene a bounce ray then tests 79 boxes and 11
-// triangles instead of 87 and 36 (prototype counts; the device counters report the real figures).
+// binned SAH (16 bins per axis), leaves of at most 3 triangles (the reference: object median, 5-10 per leaf), depth capped
+// so the traversal stack still fits 8 resident CTAs per SM.  On the bench scene a bounce ray then tests ~85 boxes and ~10
+// triangles instead of 98 and 36 (bench.py reports the device counters of both trees).
 //
 // Output, in the layout the traversal engine already reads (dev_trace.cuh): an array of 32-byte node records in PAIRS -
 // block b = records 2b, 2b+1 = the two children of one inner node, block 1 = the children of the root.  A leaf record

@@ -64,8 +64,8 @@ struct RmContext {
     rm::DevScene scene_fast{};             // the same scene with the secondary-ray tree (fast_bvh.cpp) in place of the reference's
     int stack_levels_fast = 24;
     DevBuf b_nodes_fast, b_tri_fast, b_facemap, b_order;
-    int fast_depth_cap = 21;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
-    int fast_leaf_max = 4;                 // triangles per leaf of the secondary-ray tree
+    int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
+    int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
     bool fast_root_is_leaf = false, fast_key_valid = false, seam_secondary_tree = false;
     uint64_t fast_key = 0;
     int fast_n = 0;
