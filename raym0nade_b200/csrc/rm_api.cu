@@ -457,9 +457,9 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "fast_leaf_max")) { ctx->fast_leaf_max = int(std::min<int64_t>(std::max<int64_t>(value, 1), 15)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_depth_cap")) { ctx->fast_depth_cap = int(std::min<int64_t>(std::max<int64_t>(value, 8), 26)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
-    if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
-    if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
-    if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = ctx->tune_fast.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = ctx->tune_fast.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = ctx->tune_fast.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
     if (!std::strcmp(name, "stack_levels")) {       // perf experiments only: never below the tree depth rm_scene_upload derived
         ctx->stack_levels = int(std::min<int64_t>(std::max<int64_t>(value, ctx->stack_levels), 40));
         return RM_OK;

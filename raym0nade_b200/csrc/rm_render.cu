@@ -237,6 +237,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     // bounce and shadow rays: the secondary-ray tree unless the caller asked for the reference's traversal order throughout
     const DevScene &sec_scene = ctx->exact_secondary ? ctx->scene : ctx->scene_fast;
     const int sec_levels = ctx->exact_secondary ? ctx->stack_levels : ctx->stack_levels_fast;
+    const TraceTune sec_tune = ctx->exact_secondary ? ctx->tune : ctx->tune_fast;
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
     // (C_CUR_SHADOW must be 0)
@@ -244,7 +245,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         ShadowJob job;
         job.sq = sq;
         ctx->timed_begin(RM_KIND_SHADOW);
-        launch_trace(sec_scene, sec_levels, ct, tgrid, st, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, ctx->tune);
+        launch_trace(sec_scene, sec_levels, ct, tgrid, st, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, sec_tune);
         ctx->timed_end();
         if (direct_samples > 0) k_accum_direct<<<(npix + 255) / 256, 256, 0, st>>>(Fb, Ac, sq, direct_samples, npix);
         else k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
@@ -296,7 +297,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
                 PathJob pj;
                 pj.Q = Qin;
                 ctx->timed_begin(RM_KIND_PATHS);
-                launch_trace(sec_scene, sec_levels, ct, tgrid, st, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, ctx->tune);
+                launch_trace(sec_scene, sec_levels, ct, tgrid, st, pj, Qin.cap, C + cur, C + C_CUR_PATH, cnt + 3, sec_tune);
                 ctx->timed_end();
                 ctx->timed_begin(RM_KIND_SHADE);
                 k_surface<<<R->sm_count * kCtasSurface, kShadeBlock, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
