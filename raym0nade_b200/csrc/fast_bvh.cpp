@@ -4,7 +4,7 @@
 // in the reference's own order: their triangle index is a bit-exact contract.  The rays of the estimator are held to
 // the north star's statistical bar instead, so they may use a better tree as long as the hit they find is the closest
 // accepted triangle under the same box and triangle tests.  This builder makes that tree:
-// binned SAH (16 bins per axis), leaves of at most 3 triangles (the reference: object median, 5-10 per leaf), depth capped
+// binned SAH (32 bins per axis), leaves of at most 3 triangles (the reference: object median, 5-10 per leaf), depth capped
 // so the traversal stack still fits 8 resident CTAs per SM.  On the bench scene a bounce ray then tests ~85 boxes and ~10
 // triangles instead of 98 and 36 (bench.py reports the device counters of both trees).
 //
@@ -32,7 +32,7 @@ struct Aabb {
     float area() const { float d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]}; return 2.0f * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]); }
 };
 
-constexpr int kBins = 16;
+constexpr int kBins = 32;
 
 struct Builder {
     const float *pos;                 // [n][9]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU call: parity suite, default bench line, ncu launch list, ncu --set full of the hot kernels (summarised on the box)
 mkdir -p gpurun_out
-TAG=${1:-r01f}
+TAG=${1:-r01g}
 ( timeout 1500 python -m pytest tests -m gpu -x -q; python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/pytest_gpu_${TAG}.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_${TAG}.log
 tail -5 gpurun_out/pytest_gpu_${TAG}.log
