@@ -182,7 +182,9 @@ constexpr int kTraceChunk = 64;
 struct TraceTune {
     int refill_live;     // refill idle lanes once fewer than this many lanes are busy
     int w_inner, w_leaf; // vote weights: the inner step runs when n_inner * w_inner >= n_leaf * w_leaf
+    int smem_levels;     // stack entries per thread held in shared memory; deeper ones (rare) go to a small local array
 };
+constexpr int kStackSpill = 28;   // local spill entries: smem_levels + kStackSpill >= any tree depth we build (<= 40)
 
 template <class Job, bool COUNT>
 RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt,
@@ -200,6 +202,13 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
     // identical up to that triangle, so the boolean is the reference's
     const bool anyhit = Job::kOcclusion && !S.any_cutout;
     const bool expl = S.explicit_children != 0;
+    // A ray's stack rarely holds more than ~14 deferred children even in a 23-level tree (scripts/bvh_quality_proto.cpp), so
+    // only the first tune.smem_levels entries live in shared memory - which leaves more of the SM's 256 KB as L1 - and the
+    // rest in a local array that is almost never touched.
+    const int cap = tune.smem_levels;
+    int2 spill[kStackSpill];
+    auto push = [&](int sp_, int2 e) { if (sp_ < cap) stack[sp_ * stride] = e; else spill[sp_ - cap] = e; };
+    auto peek = [&](int sp_) { return sp_ < cap ? stack[sp_ * stride] : spill[sp_ - cap]; };
 
     bool active = false;
     int chunk_next = 0, chunk_end = 0;          // warp-uniform: rays of the current chunk not handed out yet
@@ -272,14 +281,14 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     const bool okF = zero_first ? ok0 : ok1, okS = zero_first ? ok1 : ok0;
                     const float tLS = zero_first ? tL1 : tL0;
                     if (okF) {
-                        if (okS) { stack[sp * stride] = make_int2(second, __float_as_int(tLS)); sp++; }
+                        if (okS) { push(sp, make_int2(second, __float_as_int(tLS))); sp++; }
                         cur = first;
                     } else if (okS && tLS < t) cur = second;
                     else {
                         cur = kTraceDone;
                         while (sp > 0) {
                             sp--;
-                            const int2 e = stack[sp * stride];
+                            const int2 e = peek(sp);
                             if (__int_as_float(e.y) < t) { cur = e.x; break; }
                         }
                     }
@@ -331,7 +340,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     if (!stop)
                         while (sp > 0) {
                             sp--;
-                            const int2 e = stack[sp * stride];
+                            const int2 e = peek(sp);
                             if (__int_as_float(e.y) < t) { cur = e.x; break; }
                         }
                     ti = -1;

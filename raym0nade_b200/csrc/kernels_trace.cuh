@@ -3,6 +3,7 @@
 // All of them are persistent kernels around trace_engine (dev_trace.cuh): a fixed grid of
 // kTraceCtasPerSm CTAs per SM, each warp pulling chunks of rays from a device-side cursor.
 #pragma once
+#include <algorithm>
 #include "dev_trace.cuh"
 
 namespace rm {
@@ -107,9 +108,11 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene
 template <class Job>
 inline void launch_trace(const DevScene &S, int stack_levels, bool count, int grid, cudaStream_t st, const Job &job, int n_host, const int *n_dev,
                          int *cursor, unsigned long long *counters, const TraceTune &tune) {
-    const size_t smem = size_t(stack_levels) * kTraceBlock * sizeof(int2);
-    if (count) k_trace<Job, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, tune);
-    else k_trace<Job, false><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, tune);
+    TraceTune t = tune;
+    t.smem_levels = std::min(stack_levels, tune.smem_levels > 0 ? tune.smem_levels : stack_levels);
+    const size_t smem = size_t(t.smem_levels) * kTraceBlock * sizeof(int2);
+    if (count) k_trace<Job, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
+    else k_trace<Job, false><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
 }
 
 } // namespace rm

@@ -460,6 +460,10 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = ctx->tune_fast.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
     if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = ctx->tune_fast.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
     if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = ctx->tune_fast.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "smem_levels")) {        // stack entries per thread in shared memory (0 = the whole tree depth); deeper entries spill to local memory
+        ctx->tune.smem_levels = ctx->tune_fast.smem_levels = int(std::min<int64_t>(std::max<int64_t>(value, 0), 40));
+        return RM_OK;
+    }
     if (!std::strcmp(name, "stack_levels")) {       // perf experiments only: never below the tree depth rm_scene_upload derived
         ctx->stack_levels = int(std::min<int64_t>(std::max<int64_t>(value, ctx->stack_levels), 40));
         return RM_OK;
