@@ -80,7 +80,8 @@ struct RmContext {
     int sm_count = 148;
     int stack_levels = 24;                 // traversal stack entries per ray = tree depth of the uploaded scene (rm_scene_upload)
     rm::TraceTune tune{28, 1, 1, 0};          // see dev_trace.cuh; adjustable through rm_set_option for perf experiments
-    rm::TraceTune tune_fast{28, 1, 2, 0};     // the secondary-ray tree has short leaves: the vote leans towards the leaf step (profiles/r01g_ab17_votes.txt)
+    rm::TraceTune tune_fast{28, 1, 2, 14};    // the secondary-ray tree has short leaves: the vote leans towards the leaf step (profiles/r01g_ab17_votes.txt);
+                                           // 14 stack entries in shared memory, deeper ones (rare) in local memory (profiles/r01g_ab18_stack_spill.txt)
     int wave_paths = 1 << 25;              // path-queue capacity of the wavefront loop (vertices in flight per round).  32 M keeps every
                                            // launch long enough that kernel tails and launch gaps stay ~1 % (4 M: -10 %, 16 M: -1 %,
                                            // profiles/r01c_ab7_wave_size.txt, r01d_ab8_wave_size.txt) for 38 GB of queues out of 180 GB
