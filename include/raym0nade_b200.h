@@ -218,6 +218,9 @@ int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_optio
  * Box/triangle counts are only collected when rm_set_option("count_tests", 1). */
 int rm_stats_reset(RmContext *ctx);
 int rm_stats_read(RmContext *ctx, uint64_t out[4]);
+/* Host-only diagnostic (no GPU): build the secondary-ray tree (see "exact_secondary" below) for `positions` [n][9] and verify
+ * its invariants; out = {pair blocks, depth, leaves, largest leaf}. */
+int rm_secondary_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t leaf_max, int32_t out[4]);
 /* Options (integers).  "exact_secondary" 0|1 (default 0): 1 sends the estimator's bounce and shadow rays through the
  * reference's own BVH in the reference's visit order, like primary rays and the per-ray seam always are; 0 lets them use the
  * library's second tree over the same triangles (same box / triangle tests, binned-SAH topology - the closest accepted hit is

@@ -184,3 +184,56 @@ int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max
     if (depth_out) *depth_out = B.max_depth.load() + 1;
     return RM_OK;
 }
+
+// Host-only diagnostic behind the C ABI (no GPU needed): builds the secondary-ray tree for `positions` and checks its
+// invariants - every triangle in exactly one leaf, every leaf's box encloses its triangles and every inner box its
+// children, links in range, leaves within leaf_max, depth within the cap - before it reports the shape.
+extern "C" int rm_secondary_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t leaf_max, int32_t out[4]) {
+    std::vector<RmBvhNode> nodes;
+    std::vector<int32_t> order;
+    int depth = 0;
+    int rc = rm_build_fast_bvh(positions, n, depth_cap, leaf_max, nodes, order, &depth);
+    if (rc) return rc;
+    std::vector<uint8_t> seen(size_t(n), 0);
+    int leaves = 0, biggest = 0;
+    auto inside = [](const RmBvhNode &outer, const float *lo, const float *hi) {
+        for (int a = 0; a < 3; a++) if (lo[a] < outer.v0[a] || hi[a] > outer.v1[a]) return false;
+        return true;
+    };
+    auto check_leaf = [&](const RmBvhNode &c) {
+        const int cnt = c.faceR - c.faceL;
+        if (cnt < 1 || cnt > std::min(std::max(leaf_max, 1), 15) || c.faceL < 0 || c.faceR > n) return false;
+        for (int i = c.faceL; i < c.faceR; i++) {
+            const int t = order[i];
+            if (t < 0 || t >= n || seen[t]) return false;
+            seen[t] = 1;
+            for (int v = 0; v < 3; v++) { const float *p = positions + size_t(t) * 9 + v * 3; if (!inside(c, p, p)) return false; }
+        }
+        leaves++;
+        biggest = std::max(biggest, cnt);
+        return true;
+    };
+    bool ok = true;
+    if (nodes[1].faceR) ok = check_leaf(nodes[1]);
+    else {
+        std::vector<std::pair<int, int>> stack = {{1, 1}};           // (record index of the parent, its children's block)
+        if (nodes[1].faceL != 1) ok = false;
+        while (ok && !stack.empty()) {
+            auto [parent, block] = stack.back();
+            stack.pop_back();
+            for (int k = 0; k < 2 && ok; k++) {
+                const size_t ci = size_t(block) * 2 + k;
+                if (ci >= nodes.size()) { ok = false; break; }
+                const RmBvhNode &c = nodes[ci];
+                if (!inside(nodes[parent], c.v0, c.v1)) ok = false;
+                else if (c.faceR) ok = check_leaf(c);
+                else if (c.faceL < 2 || size_t(c.faceL) * 2 + 1 >= nodes.size()) ok = false;
+                else stack.push_back({int(ci), c.faceL});
+            }
+        }
+    }
+    for (int i = 0; ok && i < n; i++) ok = seen[i] != 0;
+    if (!ok) return rm_fail(RM_ERR_STATE, "rm_secondary_tree_stats: the tree violates an invariant");
+    if (out) { out[0] = int32_t(nodes.size() / 2); out[1] = depth; out[2] = leaves; out[3] = biggest; }
+    return RM_OK;
+}

@@ -194,3 +194,24 @@ def test_two_rank_reduction_equals_single_process_clamp():
     want = (clum * keep).sum(0)
     assert keep[3, ::4].sum() == 0 and keep[8].all()
     assert np.allclose(got, want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("which", ["one", "cornell", "heightfield", "glossy"])
+def test_secondary_ray_tree_invariants(which):
+    """the host builder of the secondary-ray tree (csrc/fast_bvh.cpp): every triangle in exactly one leaf, boxes enclose,
+    links in range, leaf size and depth within their bounds (checked inside rm_secondary_tree_stats)"""
+    from raym0nade_b200 import api
+    if which == "one":
+        pos = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    elif which == "cornell":
+        pos = scenes.cornell_box(8, 8, 0)[0].positions
+    elif which == "heightfield":
+        pos = scenes.heightfield_scene(20_000)[0].positions
+    else:
+        pos = scenes.glossy_dielectric(120_000, 8, 8, 0)[0].positions
+    n = np.asarray(pos).reshape(-1, 9).shape[0]
+    for leaf_max, cap in [(3, 22), (4, 21), (1, 26), (15, 8)]:
+        st = api.secondary_tree_stats(pos, cap, leaf_max)
+        assert st["largest_leaf"] <= leaf_max and st["leaves"] >= (n + leaf_max - 1) // leaf_max
+        min_depth = int(np.ceil(np.log2(max(1.0, n / leaf_max)))) + 1
+        assert st["depth"] <= max(cap, min_depth) + 1, st
