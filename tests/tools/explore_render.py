@@ -1,7 +1,7 @@
 """Exploratory: render a scene on the GPU and with the reference oracle, dump PNGs + stats."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from raym0nade_b200 import scenes
 from raym0nade_b200.api import Context, Model
 from oracle import refbind

@@ -4,7 +4,7 @@ Algorithmic bytes per pixel: clamp 4 planes x (16 B read +
 + variance pass 128 + 5 a-trous passes x (64 read + 36 G + 64 write) = 1072."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from raym0nade_b200 import scenes
 from raym0nade_b200.api import Context, Model
 
@@ -28,7 +28,7 @@ out["gpu_ms"]["filter"] = timed(lambda: ctx.filter(args))
 out["gpu_ms"]["postprocess_full_bloom_fxaa_incl_d2h"] = timed(lambda: ctx.postprocess(args, 63 | 256 | 512))
 out["gpu_ms"]["postprocess_full_incl_d2h"] = timed(lambda: ctx.postprocess(args, 63))
 npix = w * h
-peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 out["roofline"] = {"peak_gbs": peak,
                    "spatial_clamp": {"bytes": 128 * npix, "gbs": 128 * npix / out["gpu_ms"]["spatial_clamp"] / 1e6},
                    "filter": {"bytes": 1072 * npix, "gbs": 1072 * npix / out["gpu_ms"]["filter"] / 1e6}}
