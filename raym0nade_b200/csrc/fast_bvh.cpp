@@ -33,6 +33,10 @@ struct Aabb {
 };
 
 constexpr int kBins = 32;
+inline int bin_of(float c, float lo, float scale) {
+    const float f = (c - lo) * scale;
+    return f > 0.0f ? (f < float(kBins) ? int(f) : kBins - 1) : 0;      // also maps NaN to bin 0
+}
 
 struct Builder {
     const float *pos;                 // [n][9]
@@ -53,7 +57,10 @@ struct Builder {
             Aabb b;
             b.add(t); b.add(t + 3); b.add(t + 6);
             tb[i] = b;
-            for (int a = 0; a < 3; a++) cen[size_t(i) * 3 + a] = (t[a] + t[3 + a] + t[6 + a]) * (1.0f / 3.0f);
+            for (int a = 0; a < 3; a++) {
+                const float c = (t[a] + t[3 + a] + t[6 + a]) * (1.0f / 3.0f);
+                cen[size_t(i) * 3 + a] = std::isfinite(c) ? c : 0.0f;       // a non-finite triangle must not derail the sort / binning (it can never be hit)
+            }
         }
     }
 
@@ -103,7 +110,7 @@ struct Builder {
                     const int tr = order[i];
                     for (int ax = 0; ax < 3; ax++) {
                         if (!use[ax]) continue;
-                        const int k = std::min(kBins - 1, int((cen[size_t(tr) * 3 + ax] - lo3[ax]) * scale3[ax]));
+                        const int k = bin_of(cen[size_t(tr) * 3 + ax], lo3[ax], scale3[ax]);
                         P.bb[ax][k].add(tb[tr]);
                         P.cnt[ax][k]++;
                     }
@@ -136,7 +143,7 @@ struct Builder {
             if (best_axis >= 0) {
                 const float lo = cbox.lo[best_axis], scale = float(kBins) / (cbox.hi[best_axis] - cbox.lo[best_axis]);
                 auto mid = std::partition(order.begin() + L, order.begin() + R, [&](int32_t t) {
-                    return std::min(kBins - 1, int((cen[size_t(t) * 3 + best_axis] - lo) * scale)) <= best_bin;
+                    return bin_of(cen[size_t(t) * 3 + best_axis], lo, scale) <= best_bin;
                 });
                 M = int(mid - order.begin());
                 if (M == L || M == R) M = -1;

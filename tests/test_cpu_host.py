@@ -210,6 +210,9 @@ def test_secondary_ray_tree_invariants(which):
     else:
         pos = scenes.glossy_dielectric(120_000, 8, 8, 0)[0].positions
     n = np.asarray(pos).reshape(-1, 9).shape[0]
+    if which == "heightfield":          # coincident triangles (zero-extent centroid boxes) must still terminate and cover everything
+        pos = np.concatenate([np.asarray(pos).reshape(-1, 9), np.repeat(np.asarray(pos).reshape(-1, 9)[:1], 40, axis=0)])
+        n = pos.shape[0]
     for leaf_max, cap in [(3, 22), (4, 21), (1, 26), (15, 8)]:
         st = api.secondary_tree_stats(pos, cap, leaf_max)
         assert st["largest_leaf"] <= leaf_max and st["leaves"] >= (n + leaf_max - 1) // leaf_max
