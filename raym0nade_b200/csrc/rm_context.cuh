@@ -63,7 +63,7 @@ struct RmContext {
     rm::DevScene scene{};
     rm::DevScene scene_fast{};             // the same scene with the secondary-ray tree (fast_bvh.cpp) in place of the reference's
     int stack_levels_fast = 24;
-    DevBuf b_nodes_fast, b_tri_fast, b_facemap, b_order;
+    DevBuf b_nodes_fast, b_tri_fast, b_facemap;
     int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
     int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
     bool fast_root_is_leaf = false, fast_key_valid = false, seam_secondary_tree = false;
@@ -103,7 +103,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_order, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };
