@@ -5,6 +5,7 @@
 //   getWeight / filterRadiance         src/image.cpp:109-200   edge-stopping a-trous pass (5x5, dilated)
 //   Photo::filter                      src/image.cpp:193-213   variance pass + steps 1,2,4,8,16 per plane
 //   Photo::bloom                       src/image.cpp:248-283   bright-pass + 5 dilated 5x5 blurs
+//   Photo::depthFeildBlur              src/image.cpp:285-356   depth-ordered disc scatter with a 0.99 gain cap
 //
 // TEST INFRASTRUCTURE (see port_math.h).  Pinned against the compiled reference (oracle/_ref) by
 // tests/test_cpu_oracle.py.  Which libm flavour each unqualified call resolves to in the reference's
@@ -165,10 +166,74 @@ void bloomImage(vec3 *img, int width, int height) {
     }
 }
 
+// ---- depth of field ---------------------------------------------------------------------------------------
+// Photo::depthFeildBlur (src/image.cpp:285-356): pixels are visited nearest first (stable sort by camera distance); each
+// scatters its colour over a disc of radius CoC0 = min(CoC |1 - focus/depth| + eps, 96) with weights that fall off over
+// the last pixel of the radius, normalised by the disc's total weight; a destination stops accepting once it has
+// gathered 0.99.  The outcome depends on the visiting order, which is why this pass stays sequential.
+void depthOfField(const RmHitInfo *G, vec3 *img, int width, int height, vec3 cam, float focus, float CoC) {
+    const size_t n = size_t(width) * height;
+    struct Px { int x, y; float depth; };
+    std::vector<Px> px;
+    px.reserve(n);
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) px.push_back({x, y, length(v3(G[size_t(y) * width + x].position) - cam)});
+    std::stable_sort(px.begin(), px.end(), [](const Px &a, const Px &b) { return a.depth < b.depth; });
+    std::vector<vec3> out(n, v3(0.0f));
+    std::vector<float> gained(n, 0.0f);
+    for (size_t i = 0; i < n; i++) {
+        const Px &p = px[i];
+        const float spread = CoC * std::fabs(1.0f - focus / p.depth) + eps_zero;
+        const float c0 = (96.0f < spread) ? 96.0f : spread;                 // std::min(spread, MaxCoC)
+        const int radius = int(c0);
+        const vec3 colour = img[size_t(p.y) * width + p.x];
+        float total = 0.0f;
+        for (int dy = -radius; dy <= radius; dy++) {
+            const int xlen = int(std::sqrt(c0 * c0 - float(dy * dy)));
+            int xl, xr;
+            for (xl = -xlen; xl <= 0; xl++) {                                 // soft rim on the left ...
+                float w = c0 - sqrtf(float(xl * xl + dy * dy));
+                w = (1.0f < w) ? 1.0f : w;
+                if (w == 1.0f) break;
+                total += w;
+            }
+            for (xr = xlen; xr > 0; xr--) {                                   // ... and on the right
+                float w = c0 - sqrtf(float(xr * xr + dy * dy));
+                w = (1.0f < w) ? 1.0f : w;
+                if (w == 1.0f) break;
+                total += w;
+            }
+            total += float(xr - xl + 1);                                      // the full-weight span between them
+        }
+        for (int dy = -radius; dy <= radius; dy++) {
+            const int xlen = int(std::sqrt(c0 * c0 - float(dy * dy)));
+            for (int dx = -xlen; dx <= xlen; dx++) {
+                const int nx = p.x + dx, ny = p.y + dy;
+                if (nx < 0 || nx >= width || ny < 0 || ny >= height) continue;
+                float w = c0 - sqrtf(float(dx * dx + dy * dy));
+                w = ((1.0f < w) ? 1.0f : w) / total;
+                if (w < eps_zero) continue;
+                const size_t id = size_t(ny) * width + nx;
+                if (gained[id] + w > 0.99f) w = 0.99f - gained[id];
+                if (w < eps_zero) continue;
+                out[id] = out[id] + colour * w;
+                gained[id] += w;
+            }
+        }
+    }
+    for (size_t i = 0; i < n; i++) img[i] = div_scalar(out[i], gained[i]);
+}
+
 } // namespace
 } // namespace port
 
 extern "C" {
+
+// Photo::depthFeildBlur on an rgb frame, in place
+void port_depth_field_blur(const RmHitInfo *g, float *rgb, int width, int height, const float *camera_position, float focus, float CoC) {
+    port::depthOfField(g, reinterpret_cast<port::vec3 *>(rgb), width, height, port::v3(camera_position), focus, CoC);
+}
+
 
 // stages: bit 0 = Photo::spatialClamp, bit 1 = Photo::filter; planes are updated in place
 void port_denoise(const RmHitInfo *g, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is, int width, int height, int stages) {

@@ -39,6 +39,7 @@ def load():
     L.port_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
     L.port_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
     L.port_bloom.argtypes = [vp, i32, i32]
+    L.port_depth_field_blur.argtypes = [vp, vp, i32, i32, vp, C.c_float, C.c_float]
     L.port_kat_ray_in_box.argtypes = [i64, vp, vp, vp]
     L.port_kat_ray_triangle.argtypes = [i64, vp, vp, vp]
     L.port_kat_barycentric.argtypes = [i64, vp, vp, vp]
@@ -169,6 +170,15 @@ def fxaa(rgb):
     h, w = rgb.shape[:2]
     out = np.zeros_like(rgb)
     load().port_fxaa(_p(rgb), _p(out), w, h)
+    return out
+
+
+def depth_field_blur(gbuffer, rgb, camera_position, focus, coc):
+    """Photo::depthFeildBlur on an rgb frame [h][w][3] with the frame's G-buffer"""
+    out = _f32(rgb).copy()
+    h, w = out.shape[:2]
+    cam = _f32(np.asarray(camera_position, np.float32))
+    load().port_depth_field_blur(_p(gbuffer), _p(out), w, h, _p(cam), C.c_float(focus), C.c_float(coc))
     return out
 
 

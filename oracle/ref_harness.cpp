@@ -466,6 +466,22 @@ void ref_postprocess(const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRad
     photo.pixelarray = nullptr;
 }
 
+// Photo::depthFeildBlur (src/image.cpp:285-356) on a caller-supplied rgb frame and G-buffer
+void ref_depth_field_blur(const RmHitInfo *gbuffer, const float *rgb_in, float *rgb_out, int width, int height,
+                          const float *camera_position, float focus, float CoC) {
+    Photo photo(width, height);
+    size_t n = size_t(width) * height;
+    std::memcpy(static_cast<void *>(photo.Gbuffer), gbuffer, n * sizeof(RmHitInfo));
+    std::memcpy(static_cast<void *>(photo.pixelarray), rgb_in, n * sizeof(vec3));
+    photo.focus = focus;
+    photo.CoC = CoC;
+    photo.cameraPosition = vec3(camera_position[0], camera_position[1], camera_position[2]);
+    photo.depthFeildBlur();
+    std::memcpy(rgb_out, photo.pixelarray, n * sizeof(vec3));
+    delete[] photo.pixelarray;
+    photo.pixelarray = nullptr;
+}
+
 // Photo::spatialClamp (src/image.cpp:78-83) and Photo::filter (203-213) on caller-supplied planes, in place,
 // in the order render_multiThread applies them (src/render.cpp:645, 654).  stages: bit 0 clamp, bit 1 filter.
 void ref_denoise(const RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is,

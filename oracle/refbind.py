@@ -59,6 +59,7 @@ def load(flavour="plain"):
     L.ref_fxaa.argtypes = [vp, vp, i32, i32]
     L.ref_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
     L.ref_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
+    L.ref_depth_field_blur.argtypes = [vp, vp, vp, i32, i32, vp, C.c_float, C.c_float]
     L.ref_kat_ray_in_box.argtypes = [i64, vp, vp, vp]
     L.ref_kat_ray_triangle.argtypes = [i64, vp, vp, vp]
     L.ref_kat_barycentric.argtypes = [i64, vp, vp, vp]
@@ -291,6 +292,17 @@ def fxaa(rgb):
     h, w = rgb.shape[:2]
     out = np.zeros_like(rgb)
     L.ref_fxaa(_p(rgb), _p(out), w, h)
+    return out
+
+
+def depth_field_blur(gbuffer, rgb, camera_position, focus, coc):
+    """Photo::depthFeildBlur on an rgb frame [h][w][3] with the frame's G-buffer"""
+    L = load()
+    rgb = _f32(rgb)
+    h, w = rgb.shape[:2]
+    out = np.zeros_like(rgb)
+    cam = _f32(np.asarray(camera_position, np.float32))
+    L.ref_depth_field_blur(_p(gbuffer), _p(rgb), _p(out), w, h, _p(cam), C.c_float(focus), C.c_float(coc))
     return out
 
 

@@ -1,4 +1,4 @@
-"""Golden vectors for the image-space passes (spatialClamp, filter, bloom), produced by the compiled reference
+"""Golden vectors for the image-space passes (spatialClamp, filter, bloom, depthFeildBlur), produced by the compiled reference
 (oracle/_ref, i.e. the unmodified src/image.cpp).  Run in the build container (needs /root/reference):
 
     python tests/golden/make_golden_post.py
@@ -43,6 +43,13 @@ def main():
                 g["%s_s%d_%s" % (name, stages, k)] = d[k]
         for opts in (refbind.SHADE["Full"] | 256, refbind.SHADE["Full"] | 256 | 512):
             g["%s_post_%d" % (name, opts)] = refbind.postprocess(o["gbuffer"], *planes, w, h, args.exposure, opts)
+        # Photo::depthFeildBlur on the shaded frame (before gamma, as postProcessing orders it), two lens settings
+        shaded = refbind.postprocess(o["gbuffer"], *planes, w, h, args.exposure, refbind.SHADE["BaseColor"])
+        g[name + "_dof_in"] = shaded
+        g[name + "_dof_cam"] = np.asarray(args.position, np.float32)
+        for j, (focus, coc) in enumerate(((3.0, 4.0), (1.5, 24.0))):
+            g["%s_dof_%d_params" % (name, j)] = np.array([focus, coc], np.float32)
+            g["%s_dof_%d" % (name, j)] = refbind.depth_field_blur(o["gbuffer"], shaded, args.position, focus, coc)
     np.savez_compressed(os.path.join(OUT, "post_vectors.npz"), **g)
     print("wrote post_vectors.npz with", len(g), "arrays")
 

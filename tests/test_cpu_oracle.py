@@ -151,3 +151,14 @@ def test_post_golden_vectors_are_current(ref):
         inp = [GP["%s_in_%s" % (name, k)] for k in PLANES]
         got = ref.denoise(GP[name + "_gbuffer"], *inp, w, h, 3)
         assert same_planes(got, {k: GP["%s_s3_%s" % (name, k)] for k in PLANES})
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+def test_port_depth_of_field_matches_reference_vectors(name):
+    """Photo::depthFeildBlur: the depth-ordered disc scatter with its 0.99 gain cap, restated bit for bit (the pass itself
+    stays on the host - its result depends on the visiting order)"""
+    for j in (0, 1):
+        focus, coc = (float(v) for v in GP["%s_dof_%d_params" % (name, j)])
+        got = portbind.depth_field_blur(GP[name + "_gbuffer"], GP[name + "_dof_in"], GP[name + "_dof_cam"], focus, coc)
+        assert same(got, GP["%s_dof_%d" % (name, j)]), (name, j)
+        assert not same(got, GP[name + "_dof_in"])
