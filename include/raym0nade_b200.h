@@ -206,9 +206,13 @@ int rm_spatial_clamp(RmContext *ctx, const RmRenderArgs *args);
  * over each of the four planes, guided by the resolved G-buffer; in place on the context's planes (device).
  * Fetch the result with rm_download_resolved or shade it with rm_postprocess. */
 int rm_filter(RmContext *ctx, const RmRenderArgs *args);
-/* Photo::postProcessing (src/image.cpp:470-479) without depth-of-field: shade (215-246) [+ bloom (248-283) when
- * shade_options has DoBloom = 256] + gammaCorrection (454-468) [+ FXAA when it has DoFXAA = 512] on the
- * context's resolved planes -> host RGB. */
+/* Photo::depthFeildBlur (src/image.cpp:285-356) on an rgb frame (host buffers) with the context's resolved G-buffer; focus,
+ * CoC and the camera position come from `args` (src/render.cpp:665-668).  Every destination pixel replays, in the reference's
+ * depth order, the sources whose disc reaches it: same arithmetic, same order, no atomics. */
+int rm_depth_field_blur(RmContext *ctx, const RmRenderArgs *args, const float *rgb_in, float *rgb_out);
+/* Photo::postProcessing (src/image.cpp:470-479): shade (215-246) [+ depthFeildBlur (285-356) when shade_options has
+ * DoDepthFieldBlur = 1024] [+ bloom (248-283) when it has DoBloom = 256] + gammaCorrection (454-468) [+ FXAA when it has
+ * DoFXAA = 512] on the context's resolved planes -> host RGB. */
 int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_options, float *rgb_out);
 
 /* ---------------------------------------------------------------------------------

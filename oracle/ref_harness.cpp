@@ -466,6 +466,28 @@ void ref_postprocess(const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRad
     photo.pixelarray = nullptr;
 }
 
+// Photo::postProcessing with every stage available, depth of field included (focus / CoC / cameraPosition as
+// render_multiThread sets them, src/render.cpp:665-668)
+void ref_postprocess_full(const RmHitInfo *gbuffer, const RmRadiance *Dd, const RmRadiance *Ds, const RmRadiance *Id,
+                          const RmRadiance *Is, int width, int height, float exposure, int shade_options,
+                          const float *camera_position, float focus, float CoC, float *rgb_out) {
+    Photo photo(width, height);
+    size_t n = size_t(width) * height;
+    photo.exposure = exposure;
+    photo.focus = focus;
+    photo.CoC = CoC;
+    photo.cameraPosition = vec3(camera_position[0], camera_position[1], camera_position[2]);
+    std::memcpy(static_cast<void *>(photo.Gbuffer), gbuffer, n * sizeof(RmHitInfo));
+    std::memcpy(static_cast<void *>(photo.radiance_Dd), Dd, n * sizeof(RmRadiance));
+    std::memcpy(static_cast<void *>(photo.radiance_Ds), Ds, n * sizeof(RmRadiance));
+    std::memcpy(static_cast<void *>(photo.radiance_Id), Id, n * sizeof(RmRadiance));
+    std::memcpy(static_cast<void *>(photo.radiance_Is), Is, n * sizeof(RmRadiance));
+    photo.postProcessing(shade_options);
+    std::memcpy(rgb_out, photo.pixelarray, n * sizeof(vec3));
+    delete[] photo.pixelarray;
+    photo.pixelarray = nullptr;
+}
+
 // Photo::depthFeildBlur (src/image.cpp:285-356) on a caller-supplied rgb frame and G-buffer
 void ref_depth_field_blur(const RmHitInfo *gbuffer, const float *rgb_in, float *rgb_out, int width, int height,
                           const float *camera_position, float focus, float CoC) {

@@ -59,6 +59,7 @@ def load(flavour="plain"):
     L.ref_fxaa.argtypes = [vp, vp, i32, i32]
     L.ref_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
     L.ref_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
+    L.ref_postprocess_full.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp, C.c_float, C.c_float, vp]
     L.ref_depth_field_blur.argtypes = [vp, vp, vp, i32, i32, vp, C.c_float, C.c_float]
     L.ref_kat_ray_in_box.argtypes = [i64, vp, vp, vp]
     L.ref_kat_ray_triangle.argtypes = [i64, vp, vp, vp]
@@ -292,6 +293,16 @@ def fxaa(rgb):
     h, w = rgb.shape[:2]
     out = np.zeros_like(rgb)
     L.ref_fxaa(_p(rgb), _p(out), w, h)
+    return out
+
+
+def postprocess_full(gbuffer, Dd, Ds, Id, Is, width, height, exposure, shade_options, camera_position, focus, coc):
+    """Photo::postProcessing with depth of field available"""
+    L = load()
+    out = np.zeros((height, width, 3), np.float32)
+    cam = _f32(np.asarray(camera_position, np.float32))
+    L.ref_postprocess_full(_p(gbuffer), _p(Dd), _p(Ds), _p(Id), _p(Is), width, height, C.c_float(exposure), shade_options, _p(cam),
+                           C.c_float(focus), C.c_float(coc), _p(out))
     return out
 
 

@@ -56,7 +56,7 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_scene_h2d_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
-           "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved",
+           "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
            "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_secondary_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
@@ -111,6 +111,7 @@ def lib():
     L.rm_checkpoint_save.argtypes = [vp, vp, i64]
     L.rm_checkpoint_load.argtypes = [vp, ARGS, vp, i64]
     L.rm_upload_resolved.argtypes = [vp, ARGS, vp, vp, vp, vp, vp]
+    L.rm_depth_field_blur.argtypes = [vp, ARGS, vp, vp]
     L.rm_spatial_clamp.argtypes = [vp, ARGS]
     L.rm_filter.argtypes = [vp, ARGS]
     L.rm_stats_reset.argtypes = [vp]
@@ -376,6 +377,14 @@ class Context:
         planes = [np.zeros(n, RADIANCE_DTYPE) for _ in range(4)]
         self.download_resolved(g, planes)
         return dict(gbuffer=g, Dd=planes[0], Ds=planes[1], Id=planes[2], Is=planes[3])
+
+    def depth_field_blur(self, args: RenderArgs, rgb):
+        """Photo::depthFeildBlur on an rgb frame [h][w][3] with the resolved G-buffer; focus / CoC / position from args"""
+        a = args.to_c()
+        rgb = _f32(rgb)
+        out = np.zeros_like(rgb)
+        _check(lib().rm_depth_field_blur(self.h, C.byref(a), _p(rgb), _p(out)))
+        return out
 
     def postprocess(self, args: RenderArgs, shade_options: int):
         a = args.to_c()

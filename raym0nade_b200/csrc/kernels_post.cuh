@@ -350,4 +350,119 @@ __global__ void k_bloom_pass(const float *__restrict__ prev, float *__restrict__
     rgb[3 * i] = fadd(rgb[3 * i], add.x); rgb[3 * i + 1] = fadd(rgb[3 * i + 1], add.y); rgb[3 * i + 2] = fadd(rgb[3 * i + 2], add.z);
 }
 
+// ------------------------------------------------------------------ depth of field
+// Photo::depthFeildBlur (src/image.cpp:285-356).  The reference visits the pixels nearest first and lets each scatter its
+// colour over a disc; a destination stops accepting once it has gathered 0.99, so the result depends on the visiting
+// order.  Here every DESTINATION pixel replays, in that same order, the sources whose disc can reach it: the order
+// (a stable sort by camera distance) is made on the host with the reference's own comparator, k_dof_tile_lists filters
+// it per 32x32 tile (order kept), and k_dof_gather walks a tile's list once per destination - the same fp32 operations
+// in the same sequence per destination as the reference's scatter, without atomics.
+constexpr int kDofTile = 32;
+constexpr float kDofMaxCoC = 96.0f;
+
+// per source pixel: depth, CoC0 and the disc's total weight (the first pair of loops of the reference)
+__global__ void k_dof_prepare(const RmHitInfo *__restrict__ G, V3 cam, float focus, float CoC, int npix, float *__restrict__ depth,
+                              float2 *__restrict__ src) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float *g = reinterpret_cast<const float *>(G + p);
+    const float d = length(mk3(g[12], g[13], g[14]) - cam);
+    depth[p] = d;
+    const float spread = fadd(fmul(CoC, fabsf(fsub(1.0f, fdiv(focus, d)))), kEps);
+    const float c0 = (kDofMaxCoC < spread) ? kDofMaxCoC : spread;          // std::min(spread, MaxCoC); NaN stays NaN
+    float total = 0.0f;
+    if (c0 == c0) {
+        const int radius = int(c0);
+        for (int dy = -radius; dy <= radius; dy++) {
+            const int xlen = int(fsqrt(fsub(fmul(c0, c0), float(dy * dy))));
+            int xl, xr;
+            for (xl = -xlen; xl <= 0; xl++) {
+                float w = fsub(c0, fsqrt(float(xl * xl + dy * dy)));
+                w = (1.0f < w) ? 1.0f : w;
+                if (w == 1.0f) break;
+                total = fadd(total, w);
+            }
+            for (xr = xlen; xr > 0; xr--) {
+                float w = fsub(c0, fsqrt(float(xr * xr + dy * dy)));
+                w = (1.0f < w) ? 1.0f : w;
+                if (w == 1.0f) break;
+                total = fadd(total, w);
+            }
+            total = fadd(total, float(xr - xl + 1));
+        }
+    }
+    src[p] = make_float2(c0, total);
+}
+
+// For one tile: the sources of the depth-sorted order that lie within `reach` pixels of the tile, order kept.
+__global__ void __launch_bounds__(256) k_dof_tile_lists(const int *__restrict__ sorted, int npix, int width, int height, int reach, int tiles_x,
+                                                        int cap, int *__restrict__ lists, int *__restrict__ counts) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int tile = blockIdx.x;
+    const int x0 = (tile % tiles_x) * kDofTile - reach, x1 = (tile % tiles_x) * kDofTile + kDofTile - 1 + reach;
+    const int y0 = (tile / tiles_x) * kDofTile - reach, y1 = (tile / tiles_x) * kDofTile + kDofTile - 1 + reach;
+    int *out = lists + size_t(tile) * cap;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = 0; b < npix; b += blockDim.x) {
+        const int i = b + threadIdx.x;
+        int q = -1;
+        bool in = false;
+        if (i < npix) {
+            q = __ldg(sorted + i);
+            const int qx = q % width, qy = q / width;
+            in = qx >= x0 && qx <= x1 && qy >= y0 && qy <= y1;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        if (in) out[before + __popc(m & ((1u << lane) - 1u))] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[tile] = s_base;
+}
+
+// One thread per destination pixel: replay the tile's sources in order (the second pair of loops of the reference, seen
+// from the destination), then pixel = blurred / gained.
+__global__ void __launch_bounds__(kDofTile *kDofTile) k_dof_gather(const float *__restrict__ rgb_in, const float2 *__restrict__ src,
+                                                                     const int *__restrict__ lists, const int *__restrict__ counts, int cap,
+                                                                     int width, int height, int tiles_x, float *__restrict__ rgb_out) {
+    const int tile = blockIdx.x;
+    const int x = (tile % tiles_x) * kDofTile + threadIdx.x, y = (tile / tiles_x) * kDofTile + threadIdx.y;
+    const bool live = x < width && y < height;
+    const int *list = lists + size_t(tile) * cap;
+    const int n = counts[tile];
+    V3 acc = splat3(0.0f);
+    float gained = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const int q = __ldg(list + i);                       // the same source for the whole CTA
+        const float2 s = __ldg(src + q);
+        const float c0 = s.x;
+        if (!(c0 == c0) || !live) continue;                  // a source without a finite depth scatters nowhere
+        const int dx = x - q % width, dy = y - q / width;
+        const int radius = int(c0);
+        if (dy < -radius || dy > radius) continue;
+        const int xlen = int(fsqrt(fsub(fmul(c0, c0), float(dy * dy))));
+        if (dx < -xlen || dx > xlen) continue;
+        float w = fsub(c0, fsqrt(float(dx * dx + dy * dy)));
+        w = fdiv((1.0f < w) ? 1.0f : w, s.y);
+        if (w < kEps) continue;
+        if (fadd(gained, w) > 0.99f) w = fsub(0.99f, gained);
+        if (w < kEps) continue;
+        const float *c = rgb_in + size_t(q) * 3;
+        acc = acc + mk3(__ldg(c), __ldg(c + 1), __ldg(c + 2)) * w;
+        gained = fadd(gained, w);
+    }
+    if (!live) return;
+    const V3 r = div_recip(acc, gained);
+    float *o = rgb_out + (size_t(y) * width + x) * 3;
+    o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+
 } // namespace rm

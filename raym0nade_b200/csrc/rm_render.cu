@@ -6,6 +6,7 @@
 // between waves or bounces.
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "rm_context.cuh"
 #include "kernels_render.cuh"
@@ -33,6 +34,7 @@ struct RenderState {
     DevBuf planes_alt[4];     // second set of planes: every image-space pass reads one set and writes the other
     DevBuf f_pm, f_ns, f_op;  // packed neighbour fields of the G-buffer for the edge-stopping filter
     DevBuf glow[2];           // bloom
+    DevBuf dof_depth, dof_src, dof_sorted, dof_lists, dof_counts;      // depth of field
     int n_glass = 0;
     int sm_count = 148;
 };
@@ -122,7 +124,7 @@ void rm_render_state_free(RmContext *ctx) {
     if (!R) return;
     for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
-                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1]})
+                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts})
         b->release();
     for (int w = 0; w < 2; w++)
         for (int k = 0; k < 20; k++) R->q[w][k].release();
@@ -589,6 +591,46 @@ int rm_filter(RmContext *ctx, const RmRenderArgs *args) {
     return RM_OK;
 }
 
+// Photo::depthFeildBlur (src/image.cpp:285-356) with focus / CoC / cameraPosition from the render arguments
+// (src/render.cpp:665-668): d_in -> d_out, both device rgb frames of the resolved frame's size.
+static int dof_device(RmContext *ctx, RenderState *R, const RmRenderArgs *args, const float *d_in, float *d_out) {
+    int rc;
+    cudaStream_t st = ctx->stream;
+    const int npix = R->npix;
+    const int w = args->width, h = args->height;
+    if ((rc = R->dof_depth.alloc(size_t(npix) * 4)) || (rc = R->dof_src.alloc(size_t(npix) * 8)) || (rc = R->dof_sorted.alloc(size_t(npix) * 4))) return rc;
+    const V3 cam = {args->position[0], args->position[1], args->position[2]};
+    k_dof_prepare<<<(npix + 127) / 128, 128, 0, st>>>(R->g_out.as<RmHitInfo>(), cam, args->focus, args->CoC, npix, R->dof_depth.as<float>(), R->dof_src.as<float2>());
+    std::vector<float> depth(npix);
+    std::vector<float2> src(npix);
+    RM_CUDA(cudaMemcpyAsync(depth.data(), R->dof_depth.p, size_t(npix) * 4, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaMemcpyAsync(src.data(), R->dof_src.p, size_t(npix) * 8, cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    // the visiting order: the reference's own stable sort by camera distance (same comparator, same library routine)
+    struct Px { int idx; float depth; };
+    std::vector<Px> px(npix);
+    int reach = 0;
+    for (int i = 0; i < npix; i++) {
+        px[i] = {i, depth[i]};
+        if (src[i].x == src[i].x) reach = std::max(reach, int(src[i].x));
+    }
+    std::stable_sort(px.begin(), px.end(), [](const Px &a, const Px &b) { return a.depth < b.depth; });
+    std::vector<int> sorted(npix);
+    for (int i = 0; i < npix; i++) sorted[i] = px[i].idx;
+    RM_CUDA(cudaMemcpyAsync(R->dof_sorted.p, sorted.data(), size_t(npix) * 4, cudaMemcpyHostToDevice, st));
+    const int tiles_x = (w + kDofTile - 1) / kDofTile, tiles_y = (h + kDofTile - 1) / kDofTile, tiles = tiles_x * tiles_y;
+    const long long side = kDofTile + 2LL * reach;
+    const long long cap = std::min<long long>(npix, side * side);
+    if (cap * tiles > (1LL << 31)) return rm_fail(RM_ERR_INVALID, "depth of field: a reach of %d px needs %lld list entries", reach, cap * tiles);
+    if ((rc = R->dof_lists.alloc(size_t(cap) * tiles * 4)) || (rc = R->dof_counts.alloc(size_t(tiles) * 4))) return rc;
+    k_dof_tile_lists<<<tiles, 256, 0, st>>>(R->dof_sorted.as<int>(), npix, w, h, reach, tiles_x, int(cap), R->dof_lists.as<int>(), R->dof_counts.as<int>());
+    k_dof_gather<<<tiles, dim3(kDofTile, kDofTile), 0, st>>>(d_in, R->dof_src.as<float2>(), R->dof_lists.as<int>(), R->dof_counts.as<int>(), int(cap), w, h, tiles_x, d_out);
+    ctx->launches += 3;
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaStreamSynchronize(st));        // `sorted` dies at scope exit
+    return RM_OK;
+}
+
 // ------------------------------------------------------------------------ post pass
 int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int32_t width, int32_t height) {
     if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
@@ -618,6 +660,21 @@ int rm_fxaa(RmContext *ctx, const float *rgb_in, float *rgb_out, int32_t width, 
     return RM_OK;
 }
 
+// Photo::depthFeildBlur on a caller-supplied rgb frame (host buffers), with the context's resolved G-buffer
+int rm_depth_field_blur(RmContext *ctx, const RmRenderArgs *args, const float *rgb_in, float *rgb_out) {
+    RenderState *R = nullptr;
+    int rc = post_ready(ctx, args, "rm_depth_field_blur", &R);
+    if (rc) return rc;
+    if (!rgb_in || !rgb_out) return rm_fail(RM_ERR_INVALID, "rm_depth_field_blur: NULL buffer");
+    const size_t bytes = size_t(R->npix) * 12;
+    if ((rc = R->rgb[0].alloc(bytes)) || (rc = R->rgb[1].alloc(bytes))) return rc;
+    RM_CUDA(cudaMemcpyAsync(R->rgb[0].p, rgb_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = dof_device(ctx, R, args, R->rgb[0].as<float>(), R->rgb[1].as<float>()))) return rc;
+    RM_CUDA(cudaMemcpyAsync(rgb_out, R->rgb[1].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RM_OK;
+}
+
 int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_options, float *rgb_out) {
     if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_postprocess: nothing resolved yet");
     int rc = rm_check_args(args);
@@ -630,26 +687,35 @@ int rm_postprocess(RmContext *ctx, const RmRenderArgs *args, int32_t shade_optio
     const size_t bytes = size_t(npix) * 12;
     if ((rc = R->rgb[0].alloc(bytes)) || (rc = R->rgb[1].alloc(bytes))) return rc;
     cudaStream_t st = ctx->stream;
-    const bool bloom = (shade_options & 256) != 0;          // DoBloom sits between shade and gammaCorrection (src/image.cpp:470-479)
+    // Photo::postProcessing (src/image.cpp:470-479): shade -> [depth of field] -> [bloom] -> gamma -> [FXAA]
+    const bool bloom = (shade_options & 256) != 0, dof = (shade_options & 1024) != 0;
+    const bool gamma_later = bloom || dof;
     k_shade_gamma<<<(npix + 255) / 256, 256, 0, st>>>(R->g_out.as<RmHitInfo>(), R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
                                                        R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), npix, args->exposure, shade_options,
-                                                       !bloom, R->rgb[0].as<float>());
+                                                       !gamma_later, R->rgb[0].as<float>());
     ctx->launches++;
+    int out = 0;
+    if (dof) {
+        if ((rc = dof_device(ctx, R, args, R->rgb[0].as<float>(), R->rgb[1].as<float>()))) return rc;
+        out = 1;
+    }
     if (bloom) {
         if ((rc = R->glow[0].alloc(bytes)) || (rc = R->glow[1].alloc(bytes))) return rc;
-        float *img = R->rgb[0].as<float>();
+        float *img = R->rgb[out].as<float>();
         k_bloom_bright<<<(npix + 255) / 256, 256, 0, st>>>(img, R->glow[0].as<float>(), npix);
         dim3 block(32, 8), grid((args->width + 31) / 32, (args->height + 7) / 8);
         int cur = 0;
         for (int step = 1; step <= 16; step *= 2, cur ^= 1)
             k_bloom_pass<<<grid, block, 0, st>>>(R->glow[cur].as<float>(), R->glow[cur ^ 1].as<float>(), img, args->width, args->height, step);
-        k_gamma<<<(npix + 255) / 256, 256, 0, st>>>(img, npix);
-        ctx->launches += 7;
+        ctx->launches += 6;
     }
-    int out = 0;
+    if (gamma_later) {
+        k_gamma<<<(npix + 255) / 256, 256, 0, st>>>(R->rgb[out].as<float>(), npix);
+        ctx->launches++;
+    }
     if (shade_options & 512) {          // DoFXAA
-        if ((rc = rm_fxaa_device(ctx, R->rgb[0].as<float>(), R->rgb[1].as<float>(), args->width, args->height))) return rc;
-        out = 1;
+        if ((rc = rm_fxaa_device(ctx, R->rgb[out].as<float>(), R->rgb[out ^ 1].as<float>(), args->width, args->height))) return rc;
+        out ^= 1;
     }
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(rgb_out, R->rgb[out].p, bytes, cudaMemcpyDeviceToHost, st));

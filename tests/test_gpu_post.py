@@ -104,3 +104,67 @@ def test_post_passes_1080p_bench_scene(ref):
     ok = np.isfinite(want)
     assert (np.abs(img[ok] - want[ok]) > 2e-5).mean() < 1e-4
     ctx.close()
+
+
+# --------------------------------------------------------------------------- depth of field
+def test_depth_of_field_on_reference_made_frames():
+    """Photo::depthFeildBlur replayed per destination in the reference's depth order: + - * / sqrt only, so on a frame whose
+    pixels all have a finite depth (the closed box) the result is bit-equal to the golden vectors.  Pixels without a hit carry
+    a NaN depth, for which the reference's own loop bounds are int(NaN) - undefined behaviour; there (the height field under
+    a sky) the device treats such a pixel as scattering nowhere and the comparison is made where both sides are finite."""
+    for name in ("box", "hf"):
+        w, h = (int(v) for v in GP[name + "_wh"])
+        scene, args = (scenes.cornell_box(w, h, 1) if name == "box" else scenes.heightfield_scene(3000, w, h, 1, with_sky=True))
+        ctx = Context(0)
+        _render_small(ctx, scene, args)
+        ctx.upload_resolved(args, GP[name + "_gbuffer"], [GP["%s_in_%s" % (name, k)] for k in PLANES])
+        cam = tuple(float(v) for v in GP[name + "_dof_cam"])
+        for j in (0, 1):
+            focus, coc = (float(v) for v in GP["%s_dof_%d_params" % (name, j)])
+            got = ctx.depth_field_blur(args.replace(position=cam, focus=focus, CoC=coc), GP[name + "_dof_in"].reshape(h, w, 3))
+            want = GP["%s_dof_%d" % (name, j)].reshape(h, w, 3)
+            if name == "box":
+                assert np.array_equal(np.isnan(got), np.isnan(want))
+                assert np.array_equal(bits(np.nan_to_num(got)), bits(np.nan_to_num(want))), (name, j)
+                assert not np.array_equal(got, GP[name + "_dof_in"].reshape(h, w, 3))
+            else:
+                both = np.isfinite(got) & np.isfinite(want)
+                assert both.mean() > 0.5
+                assert (bits(got[both]) != bits(want[both])).mean() <= 0.02, (name, j)
+        ctx.close()
+
+
+def test_depth_of_field_cornell_512(ref):
+    """a 512x512 frame rendered on the GPU, blurred on the GPU and by the reference on the same frame and G-buffer"""
+    scene, args = scenes.cornell_box(512, 512, 8)
+    args = args.replace(focus=2.5, CoC=6.0)
+    ctx = Context(0).upload(Model(scene))
+    o = ctx.render(args, seed=4)
+    frame = ctx.postprocess(args, 1)                      # BaseColor, gamma-corrected: just an rgb frame for the pass
+    got = ctx.depth_field_blur(args, frame)
+    want = ref.depth_field_blur(o["gbuffer"], frame, args.position, args.focus, args.CoC)
+    both = np.isfinite(got) & np.isfinite(want)
+    assert both.mean() > 0.95
+    differ = (bits(got[both]) != bits(want[both])).mean()
+    if not np.isnan(o["gbuffer"]["position"]).any():
+        assert differ == 0.0 and np.array_equal(np.isnan(got), np.isnan(want))
+    else:       # a few pixels see past the box: NaN depth, int(NaN) loop bounds in the reference (see the test above)
+        assert differ <= 0.02, differ
+    assert np.abs(got[both] - frame[both]).max() > 1e-3
+    ctx.close()
+
+
+def test_postprocess_with_depth_of_field_and_bloom(ref):
+    """the whole Photo::postProcessing chain on the device: shade -> depth of field -> bloom -> gamma -> FXAA"""
+    scene, args = scenes.cornell_box(160, 160, 16)
+    args = args.replace(focus=2.5, CoC=5.0)
+    ctx = Context(0).upload(Model(scene))
+    o = ctx.render(args, seed=6)
+    for opts in (63 | 1024, 63 | 1024 | 256, 63 | 1024 | 256 | 512):
+        got = ctx.postprocess(args, opts)
+        want = ref.postprocess_full(o["gbuffer"], *[o[k] for k in PLANES], args.width, args.height, args.exposure, opts, args.position, args.focus, args.CoC)
+        ok = np.isfinite(got) & np.isfinite(want)
+        assert ok.mean() > 0.9
+        # gamma goes through powf (<= 2 ulp from glibc); with FXAA a 1-ulp difference can flip a tap choice on a few pixels
+        assert (np.abs(got[ok] - want[ok]) > 2e-5).mean() < (5e-3 if opts & 512 else 1e-3), opts
+    ctx.close()
