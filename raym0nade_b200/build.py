@@ -40,7 +40,46 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_OUT = os.path.join(HERE, "raym0nade")          # the console program (C++ host side above the C ABI)
+HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra"]
+
+
+def host_sources(with_main=True):
+    src = sorted(glob.glob(os.path.join(HOST_DIR, "*.cpp")))
+    return [s for s in src if with_main or os.path.basename(s) != "main.cpp"]
+
+
+def host_link_flags():
+    # $ORIGIN: the binary finds libraym0nade_b200.so next to itself wherever the tree is copied (the GPU box);
+    # zlib (PNG export) is linked statically
+    return ["-I", os.path.join(ROOT, "include"), "-I", HOST_DIR, "-L", HERE, "-lraym0nade_b200",
+            "-Wl,-rpath,$ORIGIN", "-l:libz.a"]
+
+
+def build_host(force=False, verbose=False):
+    """g++ the host side (raym0nade_b200/host) into the `raym0nade` console binary next to the library."""
+    deps = host_sources() + glob.glob(os.path.join(HOST_DIR, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [OUT]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    cmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + host_sources() + ["-o", HOST_OUT] + host_link_flags()
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("g++ failed on the host side (%d)" % r.returncode)
+    return HOST_OUT
+
+
 def build(force=False, verbose=False, extra=()):
+    build_library(force, verbose, extra)
+    build_host(force, verbose)
+    return OUT
+
+
+def build_library(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

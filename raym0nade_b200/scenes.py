@@ -59,6 +59,27 @@ class RawScene:
     def n_faces(self) -> int:
         return int(self.positions.shape[0])
 
+    def save(self, path: str) -> None:
+        """Write the `.rmscene` container the C++ host's Model reads (raym0nade_b200/host/model.cpp, loadRmScene):
+        the arrays of an RmRawScene, little-endian, in struct order."""
+        with open(path, "wb") as f:
+            sky = None if self.sky is None else np.ascontiguousarray(self.sky, dtype="<f4")
+            f.write(b"RMSCENE1")
+            f.write(np.array([self.n_faces, len(self.meshes), len(self.materials), len(self.textures),
+                              0 if sky is None else sky.shape[1], 0 if sky is None else sky.shape[0]], "<i4").tobytes())
+            for a in (self.positions, self.uvs, self.normals):
+                f.write(np.ascontiguousarray(a, dtype="<f4").tobytes())
+            f.write(np.array(self.meshes, "<i4").reshape(-1, 3).tobytes())
+            for m in self.materials:
+                f.write(np.array([m.tex_diffuse, m.tex_specular, m.tex_emissive, m.tex_normals], "<i4").tobytes())
+                f.write(np.array([m.opacity, m.ior, m.roughness, *m.transmitting_color], "<f4").tobytes())
+            for t in self.textures:
+                t = np.ascontiguousarray(t, dtype=np.uint8)
+                f.write(np.array([t.shape[1], t.shape[0], t.shape[2]], "<i4").tobytes())
+                f.write(t.tobytes())
+            if sky is not None:
+                f.write(sky.tobytes())
+
     def to_c(self) -> RmRawScene:
         """Build the C view (include/rm_types.h).  Arrays stay owned by this object."""
         pos = np.ascontiguousarray(self.positions, dtype=F32)
