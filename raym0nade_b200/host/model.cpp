@@ -145,6 +145,13 @@ bool Model::loadRmScene(const std::string &path) {
         std::cerr << "Error loading model: " << path << ": negative or inconsistent counts in the header" << std::endl;
         return false;
     }
+    // the header must not promise more than the file holds (a damaged file would otherwise ask for absurd allocations)
+    const std::streampos here = in.tellg();
+    in.seekg(0, std::ios::end);
+    const int64_t left = int64_t(in.tellg()) - int64_t(here);
+    in.seekg(here);
+    const int64_t fixed = nf * 96 + nm * int64_t(sizeof(RmRawMesh)) + nmat * int64_t(sizeof(RmRawMaterial)) + ntex * 12 + sw * sh * 12;
+    if (fixed > left) { std::cerr << "Error loading model: " << path << " is truncated or malformed" << std::endl; return false; }
     bool ok = readArray(in, positions, size_t(nf) * 9) && readArray(in, uvs, size_t(nf) * 6) && readArray(in, normals, size_t(nf) * 9) &&
               readArray(in, meshes, size_t(nm)) && readArray(in, materials, size_t(nmat));
     texturePixels.clear();
@@ -157,7 +164,9 @@ bool Model::loadRmScene(const std::string &path) {
         t.width = whc[0]; t.height = whc[1]; t.channels = whc[2];
         textures.push_back(t);
         texturePixels.emplace_back();
-        ok = readArray(in, texturePixels.back(), size_t(whc[0]) * size_t(whc[1]) * size_t(whc[2]));
+        const int64_t bytes = int64_t(whc[0]) * whc[1] * whc[2];
+        if (bytes > left) { ok = false; break; }
+        ok = readArray(in, texturePixels.back(), size_t(bytes));
     }
     if (ok && sw > 0) {
         ok = readArray(in, sky, size_t(sw) * size_t(sh) * 3);

@@ -102,6 +102,21 @@ def test_console_survives_bad_input(console, tmp_path):
     assert "was not created" in out and "Args (broken) does not exists." in out
 
 
+def test_damaged_scene_files_are_refused(console, tmp_path):
+    scene, _ = scenes.cornell_box(64, 64, 0)
+    scene.save(str(tmp_path / "ok.rmscene"))
+    good = open(tmp_path / "ok.rmscene", "rb").read()
+    open(tmp_path / "short.rmscene", "wb").write(good[: len(good) // 2])
+    open(tmp_path / "magic.rmscene", "wb").write(b"NOTSCENE" + good[8:])
+    open(tmp_path / "huge.rmscene", "wb").write(good[:8] + struct.pack("<6i", 2**30, 1, 1, 0, 0, 0) + good[32:])
+    open(tmp_path / "neg.rmscene", "wb").write(good[:8] + struct.pack("<6i", -5, 1, 1, 0, 0, 0) + good[32:])
+    script = "".join("create model %s\n%s/\n%s.rmscene\nnull\nview model %s\n" % (n, tmp_path, n, n) for n in ("short", "magic", "huge", "neg"))
+    rc, out, err = run_console(console, script + "exit\n")
+    assert rc == 0, err
+    assert out.count("Faces: 0") == 4
+    assert err.count("Error loading model") == 4
+
+
 def test_render_without_a_gpu_is_a_loud_no(console, tmp_path):
     import torch
     if torch.cuda.is_available():
