@@ -218,3 +218,29 @@ def test_secondary_ray_tree_invariants(which):
         assert st["largest_leaf"] <= leaf_max and st["leaves"] >= (n + leaf_max - 1) // leaf_max
         min_depth = int(np.ceil(np.log2(max(1.0, n / leaf_max)))) + 1
         assert st["depth"] <= max(cap, min_depth) + 1, st
+
+
+# --------------------------------------------------------------------------- static check of the compiled kernels
+def test_sass_has_the_fetch_widths_and_warp_primitives_the_design_states():
+    """DESIGN.md section 4 in the machine code (cuobjdump -sass, no GPU): every traversal kernel fetches nodes and triangles
+    with 128/256-bit global loads and refills idle lanes with vote + shuffle; no kernel uses a tensor-core instruction
+    (nothing on the path is a dense contraction); the image-space stencils stay free of local memory."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sass_mix
+    kernels = sass_mix.mix(api.LIB_PATH)
+    names = sass_mix.demangle(list(kernels))
+    by_name = {sass_mix.short(names[k]): c for k, c in kernels.items()}
+    assert len(by_name) >= 35
+    trace = {n: c for n, c in by_name.items() if "k_trace<" in n}
+    assert len(trace) == 10                                   # 5 jobs x {reference tree, secondary-ray tree}
+    for n, c in trace.items():
+        assert c["LDG.128"] + c["LDG.256"] >= 8, (n, dict(c))     # node pairs and triangle records, 16 B or 32 B per load
+        assert c["VOTE"] >= 3 and c["SHFL"] >= 8, (n, dict(c))    # ballot / shfl compaction of the ray queue
+        assert c["BAR"] == 0, n                                   # warps run independently: no CTA-wide barrier in traversal
+        assert c["inst"] < 2000, (n, c["inst"])                   # the loop stays inside the instruction cache
+    assert all(c["TENSOR"] == 0 for c in by_name.values())
+    for n in ("k_fxaa", "k_atrous", "k_shade_gamma", "k_bloom_pass", "k_dof_gather", "k_finalise"):
+        assert by_name[n]["LDL"] == 0 and by_name[n]["STL"] == 0, n
