@@ -101,6 +101,12 @@ int rm_context_create(int device, void *stream, RmContext **out);
 void rm_context_destroy(RmContext *ctx);
 int rm_context_synchronize(RmContext *ctx);
 
+/* Structural check of a post-load scene (host only, no GPU): every node reachable from the root lies inside the node
+ * array, leaf ranges inside the face array and together own every face (the tree as BVH::dfs_rayHit reads it,
+ * src/bvh.cpp:56-88), material / texture indices and slot-channel pairings (src/material.cpp:58), texture levels, light
+ * face lists and distributions, sky buffers.  rm_scene_upload runs it first; the reference trusts a loaded Model. */
+int rm_scene_validate(const RmSceneDesc *scene);
+
 /* Flatten a post-load scene into the SoA device layout and stage it to HBM.
  * Replaces nothing in the reference (it has no device); it is what `const Model&`
  * is to render_multiThread (src/render.cpp:593). */

@@ -53,7 +53,7 @@ class RmSceneDesc(C.Structure):
 
 # every symbol include/raym0nade_b200.h declares
 EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
-           "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_upload",
+           "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_validate", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_scene_h2d_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
@@ -83,6 +83,7 @@ def lib():
     L.rm_context_destroy.argtypes = [vp]
     L.rm_context_synchronize.argtypes = [vp]
     L.rm_scene_upload.argtypes = [vp, C.POINTER(RmSceneDesc)]
+    L.rm_scene_validate.argtypes = [C.POINTER(RmSceneDesc)]
     L.rm_scene_device_bytes.restype = i64
     L.rm_scene_device_bytes.argtypes = [vp]
     L.rm_scene_h2d_bytes.restype = i64
@@ -186,6 +187,10 @@ class Model:
 
     def material(self, i):
         return self.desc.materials[i]
+
+    def validate(self):
+        """rm_scene_validate on the prepared scene (host only); raises RmError naming the first inconsistency"""
+        _check(lib().rm_scene_validate(C.byref(self.desc)))
 
     def close(self):
         if getattr(self, "h", None):

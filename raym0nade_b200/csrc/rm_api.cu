@@ -132,13 +132,11 @@ static uint64_t hash_words(const void *p, size_t bytes) {
 
 int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if (!ctx || !sc) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: null argument");
-    if (sc->n_faces <= 0 || sc->n_nodes < 2 || !sc->nodes || !sc->positions || !sc->uvs || !sc->normals || !sc->face_material)
-        return rm_fail(RM_ERR_INVALID, "rm_scene_upload: scene is missing geometry");
-    if ((int64_t)sc->n_faces >= ((int64_t)1 << 27)) return rm_fail(RM_ERR_INVALID, "rm_scene_upload: more than 2^27 faces");
+    int rc = rm_scene_validate(sc);          // tree, index and pointer consistency (scene_check.cpp): nothing unchecked reaches the device
+    if (rc) return rc;
     RM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int64_t total = 0;
-    int rc;
     const int n = sc->n_faces;
 
     // nodes: same 32-byte images, heap-indexed; the array is padded to an even count so that
@@ -166,11 +164,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     if ((rc = upload(ctx->b_mats, mats.data(), mats.size() * sizeof(DevMaterial), st, total))) return rc;
 
     // traversal records (48 B) and shading records (112 B) are formed on the device from the caller's arrays as they
-    // are (k_pack_faces): the host only checks the material indices
-    for (int i = 0; i < n; i++) {
-        const int mat = sc->face_material[i];
-        if (mat < 0 || mat >= sc->n_materials) return rm_fail(RM_ERR_INVALID, "face %d: material index out of range", i);
-    }
+    // are (k_pack_faces); the material indices were checked by rm_scene_validate
     if ((rc = upload(ctx->b_raw[0], sc->positions, size_t(n) * 36, st, total))) return rc;
     if ((rc = upload(ctx->b_raw[1], sc->uvs, size_t(n) * 24, st, total))) return rc;
     if ((rc = upload(ctx->b_raw[2], sc->normals, size_t(n) * 36, st, total))) return rc;

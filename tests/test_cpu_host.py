@@ -244,3 +244,92 @@ def test_sass_has_the_fetch_widths_and_warp_primitives_the_design_states():
     assert all(c["TENSOR"] == 0 for c in by_name.values())
     for n in ("k_fxaa", "k_atrous", "k_shade_gamma", "k_bloom_pass", "k_dof_gather", "k_finalise"):
         assert by_name[n]["LDL"] == 0 and by_name[n]["STL"] == 0, n
+
+
+# --------------------------------------------------------------------------- rm_scene_validate (host only)
+def _scene_for(which):
+    if which == "cornell":
+        return scenes.cornell_box(64, 64, 0)[0]
+    if which == "sky":
+        return scenes.heightfield_scene(3000, 96, 54, 0, with_sky=True)[0]
+    if which == "textured":
+        return scenes.texture_heavy(4000, 96, 54, 4, tex_size=64, n_materials=4)[0]
+    return scenes.glossy_dielectric(20000, 96, 54, 0)[0]
+
+
+@pytest.mark.parametrize("which", ["cornell", "sky", "textured", "glossy"])
+def test_prepared_scenes_pass_validation(which):
+    Model(_scene_for(which)).validate()
+
+
+def test_validation_names_the_inconsistency():
+    """rm_scene_upload refuses, on the host and with a message, every scene whose indices would send a kernel out of bounds"""
+    import ctypes as C
+    model = Model(_scene_for("textured"))
+    L = api.lib()
+
+    def refused(mutate, needle):
+        d = api.RmSceneDesc.from_buffer_copy(model.desc)           # shallow copy: same arrays, private header
+        keep = mutate(d)                                            # noqa: F841  (keeps replacement arrays alive)
+        rc = L.rm_scene_validate(C.byref(d))
+        msg = L.rm_last_error().decode()
+        assert rc == -1 and needle in msg, (rc, msg)
+
+    def with_nodes(edit):
+        def f(d):
+            nodes = model.nodes().copy()
+            edit(nodes, d)
+            d.nodes = nodes.ctypes.data
+            return nodes
+        return f
+
+    first_leaf = int(np.nonzero(model.nodes()["faceR"] != 0)[0][0])
+    refused(with_nodes(lambda n, d: n["faceR"].__setitem__(first_leaf, d.n_faces + 7)), "leaf range")
+    refused(with_nodes(lambda n, d: n["faceL"].__setitem__(first_leaf, -3)), "leaf range")
+    refused(with_nodes(lambda n, d: n["faceR"].__setitem__(first_leaf, 0)), "children lie beyond")     # a leaf turned inner at the bottom level
+    refused(with_nodes(lambda n, d: n["faceL"].__setitem__(first_leaf, n["faceR"][first_leaf] - 1)), "leaves own")
+
+    def bad_face_material(d):
+        fm = np.ctypeslib.as_array(C.cast(d.face_material, C.POINTER(C.c_int32)), (d.n_faces,)).copy()
+        fm[5] = d.n_materials
+        d.face_material = fm.ctypes.data
+        return fm
+    refused(bad_face_material, "face 5: material index")
+
+    def bad_material_texture(d):
+        mats = (api.RmMaterialDesc * d.n_materials)(*[d.materials[i] for i in range(d.n_materials)])
+        mats[0].tex[0] = d.n_textures
+        d.materials = C.cast(mats, C.POINTER(api.RmMaterialDesc))
+        return mats
+    refused(bad_material_texture, "texture index out of range")
+
+    def swapped_slots(d):                                           # an RGB8 normal map in the diffuse slot
+        mats = (api.RmMaterialDesc * d.n_materials)(*[d.materials[i] for i in range(d.n_materials)])
+        i = next(i for i in range(d.n_materials) if mats[i].tex[3] >= 0)
+        mats[i].tex[0] = mats[i].tex[3]
+        d.materials = C.cast(mats, C.POINTER(api.RmMaterialDesc))
+        return mats
+    refused(swapped_slots, "channels in slot 0")
+
+    def null_level(d):
+        texs = (api.RmTextureDesc * d.n_textures)(*[d.textures[i] for i in range(d.n_textures)])
+        texs[0].levels[1] = None
+        d.textures = C.cast(texs, C.POINTER(api.RmTextureDesc))
+        return texs
+    refused(null_level, "level 1 is NULL")
+
+    refused(lambda d: setattr(d, "n_materials", 0), "at least one material")
+    refused(lambda d: setattr(d, "sky_width", 8), "bad sky size")
+    refused(lambda d: setattr(d, "positions", None), "missing geometry")
+
+    lit = Model(_scene_for("cornell"))
+
+    def empty_light(d):
+        lights = (api.RmLightDesc * d.n_lights)(*[d.lights[i] for i in range(d.n_lights)])
+        lights[0].n_faces = 0
+        d.lights = C.cast(lights, C.POINTER(api.RmLightDesc))
+        return lights
+    d = api.RmSceneDesc.from_buffer_copy(lit.desc)
+    keep = empty_light(d)                                           # noqa: F841
+    assert L.rm_scene_validate(C.byref(d)) == -1 and "light 0: no faces" in L.rm_last_error().decode()
+    assert L.rm_scene_validate(None) == -1
