@@ -124,9 +124,13 @@ __global__ void k_permute_tris(const float4 *__restrict__ tri, const int *__rest
 }
 
 static uint64_t hash_words(const void *p, size_t bytes) {
-    const uint64_t *w = static_cast<const uint64_t *>(p);
+    const unsigned char *b = static_cast<const unsigned char *>(p);
     uint64_t h = 0x9E3779B97F4A7C15ull ^ bytes;
-    for (size_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+    for (size_t i = 0; i < bytes; i += 8) {          // memcpy: float arrays are only 4-byte aligned; the tail word is zero-padded
+        uint64_t w = 0;
+        std::memcpy(&w, b + i, bytes - i < 8 ? bytes - i : 8);
+        h ^= w; h *= 0x100000001B3ull; h ^= h >> 29;
+    }
     return h;
 }
 
