@@ -10,7 +10,7 @@
 // The reference loads scenes through assimp and decodes images through an embedded Python interpreter; neither is part
 // of the hot path (and neither is installed here), so Model reads the raw post-import arrays - what processMesh /
 // processMaterial hand on - from a `.rmscene` container (raym0nade_b200/scenes.py writes one) or from a Wavefront
-// .obj/.mtl pair, and the sky from `.hdr` (Radiance RGBE) or `.pfm`.  Everything after that point - BVH build, mip
+// .obj/.mtl pair with PNG / DDS texture maps (image_io.cpp), and the sky from `.hdr` (Radiance RGBE) or `.pfm`.  Everything after that point - BVH build, mip
 // chains, light objects, sky CDF (rm_prepare_scene), the render and every image-space pass - is the library's.
 // There is no CPU renderer behind this interface: without a B200 the render prints the library's error and returns.
 #ifndef RAYM0NADE_B200_HOST_HPP
@@ -113,6 +113,8 @@ private:
     void syncPlanes();
 };
 
+// Decode a PNG or DDS (DXT1/3/5, uncompressed) file to 8-bit RGBA, top row first (image_io.cpp).  On failure `why` says why.
+bool loadImageRGBA(const std::string &path, int &width, int &height, std::vector<uint8_t> &rgba, std::string &why);
 // Encode an 8-bit RGB image as PNG (zlib deflate, filter 0 on every row).  Returns false if the file cannot be written.
 bool writePng(const char *file_name, const uint8_t *rgb, int width, int height);
 

@@ -182,7 +182,9 @@ bool Model::loadRmScene(const std::string &path) {
 // in order of first use (assimp splits an object per material; light objects are formed per mesh, src/model.cpp:121-123).
 // Materials: Kd and Ke become 1x1 RGBA8 textures (Kd stored through the inverse of the 2.2 decode that
 // Material::getDiffuseColor applies, src/material.cpp:337-352), d / Tr become the opacity that loadMaterialProperties
-// reads.  Image maps (map_Kd ...) need a decoder this host does not carry: bake them into a .rmscene instead.
+// reads.  map_Kd / map_Ks / map_Ke / map_Bump name PNG or DDS files (image_io.cpp), stored RGBA8 - RGB8 for normal maps -
+// so that the slot's fetch type matches the data (the reference keeps a PNG as RGB8 in every slot and then strides it
+// by four, src/material.cpp:58,273-281; that misread is not reproduced).
 bool Model::loadObj(const std::string &folder, const std::string &path) {
     std::ifstream in(path);
     if (!in) { std::cerr << "Error loading model: cannot open " << path << std::endl; return false; }
@@ -225,7 +227,30 @@ bool Model::loadObj(const std::string &folder, const std::string &path) {
             else if (key == "Ke") { float r = 0, g = 0, b = 0; ls >> r >> g >> b; if (r > 0 || g > 0 || b > 0) materials[cur].tex_emissive = texel(r, g, b, false); }
             else if (key == "d") { float d = 1; ls >> d; opacities[cur] = d; }
             else if (key == "Tr") { float tr = 0; ls >> tr; opacities[cur] = 1.0f - tr; }
-            else if (key.rfind("map_", 0) == 0) std::cerr << "- Texture path ignored (" << key << "): image maps need the .rmscene container" << std::endl;
+            else if (key.rfind("map_", 0) == 0 || key == "bump" || key == "norm") {
+                // slot: 0 diffuse, 1 specular (G = roughness, B = metallic, src/material.cpp:374-383), 2 emissive, 3 normals
+                const int slot = key == "map_Kd" ? 0 : key == "map_Ks" ? 1 : key == "map_Ke" ? 2
+                               : (key == "map_Bump" || key == "map_bump" || key == "bump" || key == "norm" || key == "map_Kn") ? 3 : -1;
+                std::string file, tok;
+                while (ls >> tok) file = tok;                     // options (-bm 1.0 ...) precede the file name
+                if (slot < 0 || file.empty()) continue;
+                std::replace(file.begin(), file.end(), '\\', '/');  // src/model.cpp:155
+                std::cout << "- Texture path (" << slot << "): " << file << std::endl;
+                int w = 0, h = 0;
+                std::vector<uint8_t> rgba;
+                std::string why;
+                if (!loadImageRGBA(folder + file, w, h, rgba, why)) { std::cerr << "Could not load " << folder + file << ": " << why << std::endl; continue; }
+                RmRawTexture t{};
+                t.width = w; t.height = h; t.channels = slot == 3 ? 3 : 4;      // the fetch type of the slot (src/material.cpp:58)
+                textures.push_back(t);
+                if (slot == 3) {
+                    std::vector<uint8_t> rgb(size_t(w) * h * 3);
+                    for (size_t i = 0; i < size_t(w) * h; i++) std::memcpy(&rgb[i * 3], &rgba[i * 4], 3);
+                    texturePixels.push_back(std::move(rgb));
+                } else texturePixels.push_back(std::move(rgba));
+                int32_t *slots[4] = {&materials[cur].tex_diffuse, &materials[cur].tex_specular, &materials[cur].tex_emissive, &materials[cur].tex_normals};
+                *slots[slot] = int(textures.size()) - 1;          // a map replaces the constant of the same slot (Kd / Ke)
+            }
         }
     };
 

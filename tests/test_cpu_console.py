@@ -287,3 +287,240 @@ def test_png_writer_round_trips(host_check, tmp_path):
         r = subprocess.run([host_check, "png", raw, str(w), str(h), png], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert np.array_equal(read_png(png), img)
+
+
+# --------------------------------------------------------------------------- texture file decoders (host/image_io.cpp)
+def _png_bytes(rows, width, height, depth, ctype, filters=None, palette=None, trns=None, idat_split=1, header_height=None, interlace=0):
+    """encode packed scanlines `rows` (h x stride uint8) as a PNG, applying the given filter type per row"""
+    def chunk(typ, data):
+        return struct.pack(">I", len(data)) + typ + data + struct.pack(">I", zlib.crc32(typ + data) & 0xFFFFFFFF)
+    samples = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    bpp = max(1, samples * depth // 8)
+    rows = np.asarray(rows, np.uint8)
+    out = bytearray()
+    prev = np.zeros(rows.shape[1], np.int32)
+    for y in range(height):
+        cur = rows[y].astype(np.int32)
+        ft = 0 if filters is None else filters[y % len(filters)]
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        b = prev
+        if ft == 0:
+            pred = 0
+        elif ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = b
+        elif ft == 3:
+            pred = (a + b) // 2
+        else:
+            p = a + b - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        out.append(ft)
+        out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+    z = zlib.compress(bytes(out), 6)
+    parts = [z[i * len(z) // idat_split:(i + 1) * len(z) // idat_split] for i in range(idat_split)]
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, header_height or height, depth, ctype, 0, 0, interlace))
+    if palette is not None:
+        png += chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    if trns is not None:
+        png += chunk(b"tRNS", bytes(trns))
+    png += chunk(b"tEXt", b"Comment\x00made by the test")          # an ancillary chunk the decoder must skip
+    for part in parts:
+        png += chunk(b"IDAT", part)
+    return png + chunk(b"IEND", b"")
+
+
+def _decode(host_check, tmp_path, name, data):
+    path, out = str(tmp_path / name), str(tmp_path / (name + ".bin"))
+    open(path, "wb").write(data)
+    r = subprocess.run([host_check, "image", path, out], capture_output=True, text=True)
+    if r.returncode != 0:
+        return None, r.stderr
+    b = open(out, "rb").read()
+    w, h = struct.unpack("<2i", b[:8])
+    return np.frombuffer(b, np.uint8, w * h * 4, 8).reshape(h, w, 4), ""
+
+
+def test_png_decoder_colour_types_depths_and_filters(host_check, tmp_path):
+    rng = np.random.default_rng(11)
+    w, h = 13, 9
+    # RGBA 8-bit, every filter type in turn, IDAT split in three
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    rgba[2:5] = rgba[2]                                         # rows that repeat: Up / Paeth do real work
+    got, err = _decode(host_check, tmp_path, "rgba.png", _png_bytes(rgba.reshape(h, -1), w, h, 8, 6, filters=[0, 1, 2, 3, 4], idat_split=3))
+    assert got is not None, err
+    assert np.array_equal(got, rgba)
+    # RGB 8-bit with a colour key (tRNS): the keyed colour turns transparent, everything else opaque
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    rgb[4, 5] = [10, 20, 30]
+    got, err = _decode(host_check, tmp_path, "rgb.png", _png_bytes(rgb.reshape(h, -1), w, h, 8, 2, filters=[4, 3], trns=[0, 10, 0, 20, 0, 30]))
+    assert got is not None, err
+    assert np.array_equal(got[..., :3], rgb)
+    assert got[4, 5, 3] == 0 and (np.delete(got[..., 3].ravel(), 4 * w + 5) == 255).all()
+    # RGB 16-bit: the high byte of every sample survives (png_set_strip_16, src/material.cpp:243-245)
+    rgb16 = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
+    got, err = _decode(host_check, tmp_path, "rgb16.png", _png_bytes(rgb16.astype(">u2").view(np.uint8).reshape(h, -1), w, h, 16, 2, filters=[1, 4]))
+    assert got is not None, err
+    assert np.array_equal(got[..., :3], (rgb16 >> 8).astype(np.uint8)) and (got[..., 3] == 255).all()
+    # grey + alpha 8-bit
+    ga = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+    got, err = _decode(host_check, tmp_path, "ga.png", _png_bytes(ga.reshape(h, -1), w, h, 8, 4, filters=[2, 3]))
+    assert got is not None, err
+    assert np.array_equal(got[..., 0], ga[..., 0]) and np.array_equal(got[..., 2], ga[..., 0]) and np.array_equal(got[..., 3], ga[..., 1])
+    # grey 4-bit and 1-bit: packed MSB first, expanded to the full 0..255 range
+    for depth in (4, 1):
+        g = rng.integers(0, 1 << depth, (h, w), dtype=np.uint8)
+        per = 8 // depth
+        padded = np.zeros((h, (w + per - 1) // per * per), np.uint8)
+        padded[:, :w] = g
+        packed = np.zeros((h, padded.shape[1] // per), np.uint8)
+        for k in range(per):
+            packed |= padded[:, k::per] << (8 - depth * (k + 1))
+        got, err = _decode(host_check, tmp_path, "g%d.png" % depth, _png_bytes(packed, w, h, depth, 0, filters=[0, 2]))
+        assert got is not None, err
+        assert np.array_equal(got[..., 1], (g.astype(np.int32) * 255 // ((1 << depth) - 1)).astype(np.uint8))
+    # palette 8-bit with per-entry alpha
+    pal = rng.integers(0, 256, (5, 3), dtype=np.uint8)
+    idx = rng.integers(0, 5, (h, w), dtype=np.uint8)
+    got, err = _decode(host_check, tmp_path, "pal.png", _png_bytes(idx, w, h, 8, 3, filters=[0, 1], palette=pal, trns=[255, 128, 0]))
+    assert got is not None, err
+    assert np.array_equal(got[..., :3], pal[idx])
+    assert np.array_equal(got[..., 3], np.array([255, 128, 0, 255, 255], np.uint8)[idx])
+
+
+def test_png_decoder_refuses_damaged_files(host_check, tmp_path):
+    img = np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 12)
+    good = _png_bytes(img, 4, 4, 8, 2)
+    flipped = bytearray(good)
+    flipped[-20] ^= 0x55                                        # inside the IDAT payload: its CRC no longer matches
+    for name, data, needle in [("crc.png", bytes(flipped), "CRC"), ("short.png", good[:40], ""),
+                               ("size.png", _png_bytes(img[:3], 4, 3, 8, 2, header_height=4), "zlib stream"),
+                               ("lace.png", _png_bytes(img, 4, 4, 8, 2, interlace=1), "interlaced")]:
+        got, err = _decode(host_check, tmp_path, name, data)
+        assert got is None and needle in err, (name, err)
+
+
+def _dxt_colours(c0, c1, punch):
+    def e(c):
+        r, g, b = (c >> 11) & 31, (c >> 5) & 63, c & 31
+        return np.array([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], np.int32)
+    p0, p1 = e(c0), e(c1)
+    if c0 > c1 or not punch:
+        return [(*p0, 255), (*p1, 255), (*((2 * p0 + p1) // 3), 255), (*((p0 + 2 * p1) // 3), 255)]
+    return [(*p0, 255), (*p1, 255), (*((p0 + p1) // 2), 255), (0, 0, 0, 0)]
+
+
+def _dds_header(w, h, fourcc=None, bits=0, masks=(0, 0, 0, 0)):
+    pf_flags = 0x4 if fourcc else (0x40 | (0x1 if masks[3] else 0))
+    pf = struct.pack("<II4sIIIII", 32, pf_flags, fourcc or b"\0\0\0\0", bits, *masks)
+    return b"DDS " + struct.pack("<IIIIIII", 124, 0x1007, h, w, 0, 0, 1) + b"\0" * 44 + pf + struct.pack("<IIIII", 0x1000, 0, 0, 0, 0)
+
+
+def test_dds_decoder_block_compression_and_masks(host_check, tmp_path):
+    rng = np.random.default_rng(5)
+    w, h = 10, 6                                                # not multiples of 4: edge blocks are cropped
+    bw, bh = (w + 3) // 4, (h + 3) // 4
+    assert len(_dds_header(w, h, b"DXT1")) == 128
+
+    def expected(blocks, alpha=None):
+        img = np.zeros((bh * 4, bw * 4, 4), np.uint8)
+        for by in range(bh):
+            for bx in range(bw):
+                c0, c1, idx, punch = blocks[by][bx]
+                pal = _dxt_colours(c0, c1, punch)
+                for i in range(16):
+                    img[by * 4 + i // 4, bx * 4 + i % 4] = pal[(idx >> (2 * i)) & 3]
+                if alpha is not None:
+                    img[by * 4:by * 4 + 4, bx * 4:bx * 4 + 4, 3] = alpha[by][bx]
+        return img[:h, :w]
+
+    # DXT1, both endpoint orders (four-colour and three-colour + transparent modes)
+    blocks = [[(int(rng.integers(0, 65536)), int(rng.integers(0, 65536)), int(rng.integers(0, 2**32)), True) for _ in range(bw)] for _ in range(bh)]
+    blocks[0][0] = (0x1234, 0xF00F, blocks[0][0][2], True)      # c0 < c1: index 3 is transparent black
+    blocks[0][1] = (0xF00F, 0x1234, blocks[0][1][2], True)
+    body = b"".join(struct.pack("<HHI", c0, c1, idx) for row in blocks for (c0, c1, idx, _) in row)
+    got, err = _decode(host_check, tmp_path, "a.dds", _dds_header(w, h, b"DXT1") + body)
+    assert got is not None, err
+    assert np.array_equal(got, expected(blocks))
+
+    # DXT5: interpolated alpha in both modes, colour always four-colour
+    alpha_blocks, body = [], b""
+    for by in range(bh):
+        arow = []
+        for bx in range(bw):
+            a0, a1 = (200, 40) if (bx + by) % 2 == 0 else (40, 200)
+            bits = int(rng.integers(0, 2**48))
+            if a0 > a1:
+                pal = [a0, a1] + [((7 - k) * a0 + k * a1) // 7 for k in range(1, 7)]
+            else:
+                pal = [a0, a1] + [((5 - k) * a0 + k * a1) // 5 for k in range(1, 5)] + [0, 255]
+            arow.append(np.array([pal[(bits >> (3 * i)) & 7] for i in range(16)], np.uint8).reshape(4, 4))
+            c0, c1, idx, _ = blocks[by][bx]
+            body += bytes([a0, a1]) + bits.to_bytes(6, "little") + struct.pack("<HHI", c0, c1, idx)
+        alpha_blocks.append(arow)
+    got, err = _decode(host_check, tmp_path, "b.dds", _dds_header(w, h, b"DXT5") + body)
+    assert got is not None, err
+    assert np.array_equal(got, expected([[(c0, c1, idx, False) for (c0, c1, idx, _) in row] for row in blocks], alpha_blocks))
+
+    # DXT3: explicit 4-bit alpha
+    alpha_blocks, body = [], b""
+    for by in range(bh):
+        arow = []
+        for bx in range(bw):
+            nib = rng.integers(0, 16, 16, dtype=np.uint8)
+            arow.append((nib * 17).reshape(4, 4))
+            packed = bytes(int(nib[2 * k]) | (int(nib[2 * k + 1]) << 4) for k in range(8))
+            c0, c1, idx, _ = blocks[by][bx]
+            body += packed + struct.pack("<HHI", c0, c1, idx)
+        alpha_blocks.append(arow)
+    got, err = _decode(host_check, tmp_path, "c.dds", _dds_header(w, h, b"DXT3") + body)
+    assert got is not None, err
+    assert np.array_equal(got, expected([[(c0, c1, idx, False) for (c0, c1, idx, _) in row] for row in blocks], alpha_blocks))
+
+    # uncompressed: 32-bit BGRA (the usual A8R8G8B8 masks) and 24-bit RGB without alpha
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    got, err = _decode(host_check, tmp_path, "d.dds", _dds_header(w, h, None, 32, (0x00FF0000, 0x0000FF00, 0x000000FF, 0xFF000000)) + rgba[..., [2, 1, 0, 3]].tobytes())
+    assert got is not None, err
+    assert np.array_equal(got, rgba)
+    got, err = _decode(host_check, tmp_path, "e.dds", _dds_header(w, h, None, 24, (0x0000FF, 0x00FF00, 0xFF0000, 0)) + rgba[..., :3].tobytes())
+    assert got is not None, err
+    assert np.array_equal(got[..., :3], rgba[..., :3]) and (got[..., 3] == 255).all()
+
+    # refused: a format outside the list, truncated data
+    got, err = _decode(host_check, tmp_path, "f.dds", _dds_header(w, h, b"DX10") + b"\0" * 64)
+    assert got is None and "DX10" in err
+    got, err = _decode(host_check, tmp_path, "g.dds", _dds_header(w, h, b"DXT1") + b"\0" * 8)
+    assert got is None and "truncated" in err
+
+
+def test_obj_materials_with_texture_maps(host_check, tmp_path):
+    """map_Kd / map_Bump / map_Ks in a .mtl: RGBA8 for colour slots, RGB8 for the normal map, constants replaced by maps"""
+    rng = np.random.default_rng(2)
+    albedo = rng.integers(0, 256, (4, 8, 4), dtype=np.uint8)
+    albedo[..., 3] = 255
+    albedo[0, 0, 3] = 0                                         # a cut-out texel -> hasFullyTransparentPart in the prepared scene
+    normal = rng.integers(0, 256, (2, 2, 3), dtype=np.uint8)
+    open(tmp_path / "albedo.png", "wb").write(_png_bytes(albedo.reshape(4, -1), 8, 4, 8, 6, filters=[4]))
+    open(tmp_path / "normal.dds", "wb").write(_dds_header(2, 2, None, 24, (0x0000FF, 0x00FF00, 0xFF0000, 0)) + normal.tobytes())
+    (tmp_path / "t.mtl").write_text("newmtl m\nKd 1 0 0\nmap_Kd albedo.png\nmap_Bump -bm 1.0 normal.dds\nmap_Ks missing.png\n")
+    (tmp_path / "t.obj").write_text("mtllib t.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl m\nf 1/1 2/2 3/3\n")
+    out = str(tmp_path / "dump.bin")
+    r = subprocess.run([host_check, "dump", str(tmp_path) + "/", "t.obj", "null", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "missing.png" in r.stderr                            # said so, carried on without the map
+    b = open(out, "rb").read()
+    nf, nmesh, nmat, ntex, sw, sh, nnodes, nlights = struct.unpack("<8i", b[:32])
+    assert (nf, nmat, ntex) == (1, 1, 3)                        # Kd texel, albedo map, normal map
+    off = 32 + nf * 96 + nmesh * 12
+    slots = np.frombuffer(b, "<i4", 4, off)
+    assert slots[0] == 1 and slots[3] == 2 and slots[1] == -1   # the map replaced the Kd constant; no specular map
+    off += nmat * 40 + (nnodes * 32) + nf * 36
+    texs = []
+    for _ in range(ntex):
+        w, h, c = struct.unpack("<3i", b[off:off + 12])
+        texs.append(np.frombuffer(b, np.uint8, w * h * c, off + 12).reshape(h, w, c))
+        off += 12 + w * h * c
+    assert np.array_equal(texs[1], albedo) and np.array_equal(texs[2], normal)

@@ -2,6 +2,7 @@
 // print so tests/test_cpu_console.py can compare them with the Python side.
 //   host_check png  <rgb.raw> <w> <h> <out.png>          writePng on raw 8-bit RGB
 //   host_check dump <folder> <model> <sky> <out.bin>     load a Model, write its raw arrays and prepared BVH nodes
+//   host_check image <file.png|.dds> <out.bin>           loadImageRGBA: int32 w, h, then w*h*4 bytes
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +46,17 @@ int main(int argc, char **argv) {
         }
         return o ? 0 : 1;
     }
-    std::cerr << "usage: host_check png|dump ..." << std::endl;
+    if (argc == 4 && !std::strcmp(argv[1], "image")) {
+        int w = 0, h = 0;
+        std::vector<uint8_t> rgba;
+        std::string why;
+        if (!loadImageRGBA(argv[2], w, h, rgba, why)) { std::cerr << why << std::endl; return 1; }
+        std::ofstream o(argv[3], std::ios::binary);
+        const int32_t wh[2] = {w, h};
+        put(o, wh, 2);
+        put(o, rgba.data(), rgba.size());
+        return o ? 0 : 1;
+    }
+    std::cerr << "usage: host_check png|dump|image ..." << std::endl;
     return 2;
 }
