@@ -6,7 +6,7 @@
 //   Model                 include/model.h:25-43   (constructor: src/model.cpp:172-215)
 //   Photo                 include/image.h:15-65
 //   render_multiThread    include/render.h:43     (src/render.cpp:593-676)
-//   MyConsole             include/myconsole.h, src/myconsole.cpp
+//   MyConsole             include/myconsole.h
 // The reference loads scenes through assimp and decodes images through an embedded Python interpreter; neither is part
 // of the hot path (and neither is installed here), so Model reads the raw post-import arrays - what processMesh /
 // processMaterial hand on - from a `.rmscene` container (raym0nade_b200/scenes.py writes one) or from a Wavefront
@@ -120,11 +120,12 @@ bool writePng(const char *file_name, const uint8_t *rgb, int width, int height);
 
 void render_multiThread(Model &model, const RenderArgs &args);
 
-class MyConsole {                 // include/myconsole.h
+class MyConsole {                 // include/myconsole.h: same commands; reads its dialogue from the stream it is given
 public:
     std::map<std::string, Model> models;
     std::map<std::string, RenderArgs> renderArgs;
-    MyConsole();
+    MyConsole();                                       // std::cin / std::cout
+    MyConsole(std::istream &in, std::ostream &out);
     void createModel(const std::string &model_id);
     void createRenderArgs(const std::string &str);
     void deleteModel(const std::string &str);
@@ -132,7 +133,14 @@ public:
     void viewModel(const std::string &str);
     void viewRenderArgs(const std::string &str);
     void render(const std::string &model_str, const std::string &args_str);
+    std::ostream &out() { return out_; }
+
+private:
+    std::istream &in_;
+    std::ostream &out_;
 };
 void parseCommand(MyConsole &console, const std::string &opt);
+// the read-dispatch loop of the console program: one command per line until `exit` or end of input
+int runConsole(MyConsole &console, std::istream &in, std::ostream &out);
 
 #endif

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
+#include <iterator>
 
 #include "host.hpp"
 
@@ -55,45 +56,38 @@ void render_multiThread(Model &model, const RenderArgs &args) {
     std::cout << "Rendering completed in " << renderMs << " ms." << std::endl;
     std::cout << "Rays traced: " << stats[0] << " (" << double(stats[0]) / (renderMs * 1e3) << " Mrays/s incl. scene upload and download)" << std::endl;
 
-    auto exportImage = [&](const std::string &tag, int shadeOptions) {
-        photo.postProcessing(shadeOptions);
-        photo.save((args.savePath + "(" + tag + ").png").c_str());
+    // The exports, as data: {file tag, shade options}, grouped by the state of the radiance planes they show - as
+    // rendered, after the firefly clamp, after the denoiser - and the depth-of-field set when the lens has a blur circle
+    // (the reference writes the same files in the same order, src/render.cpp:635-674).
+    struct Export { const char *tag; int options; };
+    constexpr int DD = Photo::Direct_Diffuse, DS = Photo::Direct_Specular, ID = Photo::Indirect_Diffuse, IS = Photo::Indirect_Specular;
+    constexpr int Full = Photo::Full, Bloom = Photo::DoBloom, Fxaa = Photo::DoFXAA, Dof = Photo::DoDepthFieldBlur;
+    static const Export gbufferViews[] = {{"DiffuseColor", Photo::BaseColor}, {"DiffuseColor_FXAA", Photo::BaseColor | Fxaa},
+                                          {"shapeNormal", Photo::shapeNormal}, {"surfaceNormal", Photo::surfaceNormal}};
+    static const Export clamped[] = {{"Direct_Diffuse", DD}, {"Direct_Specular", DS}, {"Indirect_Diffuse", ID}, {"Indirect_Specular", IS},
+                                     {"Raw", Full}, {"Raw_Bloom", Full | Bloom}, {"Raw_FXAA", Full | Fxaa}, {"Raw_Bloom_FXAA", Full | Bloom | Fxaa}};
+    static const Export filtered[] = {{"Direct_Diffuse_Filter", DD}, {"Direct_Specular_Filter", DS}, {"Indirect_Diffuse_Filter", ID},
+                                      {"Indirect_Specular_Filter", IS}, {"Filter", Full}, {"Filter_Bloom", Full | Bloom},
+                                      {"Filter_FXAA", Full | Fxaa}, {"Filter_Bloom_FXAA", Full | Bloom | Fxaa}};
+    static const Export withLens[] = {{"BaseColor_DepthFieldBlur", Photo::BaseColor | Dof}, {"Filter_DepthFieldBlur", Full | Dof},
+                                      {"Filter_DepthFieldBlur_Bloom", Full | Dof | Bloom}, {"Filter_DepthFieldBlur_FXAA", Full | Dof | Fxaa},
+                                      {"Filter_DepthFieldBlur_Bloom_FXAA", Full | Dof | Bloom | Fxaa}};
+    auto write = [&](const Export *list, size_t count) {
+        for (size_t i = 0; i < count; i++) {
+            photo.postProcessing(list[i].options);
+            photo.save((args.savePath + "(" + list[i].tag + ").png").c_str());
+        }
     };
-
-    // same exports, same order (src/render.cpp:635-674)
-    exportImage("DiffuseColor", Photo::BaseColor);
-    exportImage("DiffuseColor_FXAA", Photo::BaseColor | Photo::DoFXAA);
-    exportImage("shapeNormal", Photo::shapeNormal);
-    exportImage("surfaceNormal", Photo::surfaceNormal);
-
+    write(gbufferViews, std::size(gbufferViews));
     photo.spatialClamp();
-    exportImage("Direct_Diffuse", Photo::Direct_Diffuse);
-    exportImage("Direct_Specular", Photo::Direct_Specular);
-    exportImage("Indirect_Diffuse", Photo::Indirect_Diffuse);
-    exportImage("Indirect_Specular", Photo::Indirect_Specular);
-    exportImage("Raw", Photo::Full);
-    exportImage("Raw_Bloom", Photo::Full | Photo::DoBloom);
-    exportImage("Raw_FXAA", Photo::Full | Photo::DoFXAA);
-    exportImage("Raw_Bloom_FXAA", Photo::Full | Photo::DoBloom | Photo::DoFXAA);
+    write(clamped, std::size(clamped));
     photo.filter();
-    exportImage("Direct_Diffuse_Filter", Photo::Direct_Diffuse);
-    exportImage("Direct_Specular_Filter", Photo::Direct_Specular);
-    exportImage("Indirect_Diffuse_Filter", Photo::Indirect_Diffuse);
-    exportImage("Indirect_Specular_Filter", Photo::Indirect_Specular);
-    exportImage("Filter", Photo::Full);
-    exportImage("Filter_Bloom", Photo::Full | Photo::DoBloom);
-    exportImage("Filter_FXAA", Photo::Full | Photo::DoFXAA);
-    exportImage("Filter_Bloom_FXAA", Photo::Full | Photo::DoBloom | Photo::DoFXAA);
-
+    write(filtered, std::size(filtered));
     if (args.CoC > 1e-4f) {                                 // eps_zero, include/geometry.h:13
         photo.focus = args.focus;
         photo.CoC = args.CoC;
         photo.cameraPosition = args.position;
-        exportImage("BaseColor_DepthFieldBlur", Photo::BaseColor | Photo::DoDepthFieldBlur);
-        exportImage("Filter_DepthFieldBlur", Photo::Full | Photo::DoDepthFieldBlur);
-        exportImage("Filter_DepthFieldBlur_Bloom", Photo::Full | Photo::DoDepthFieldBlur | Photo::DoBloom);
-        exportImage("Filter_DepthFieldBlur_FXAA", Photo::Full | Photo::DoDepthFieldBlur | Photo::DoFXAA);
-        exportImage("Filter_DepthFieldBlur_Bloom_FXAA", Photo::Full | Photo::DoDepthFieldBlur | Photo::DoBloom | Photo::DoFXAA);
+        write(withLens, std::size(withLens));
     }
 
     std::cout << "Post processing finished. Total: " << msSince(startTime) << " ms." << std::endl;
