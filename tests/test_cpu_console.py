@@ -524,3 +524,60 @@ def test_obj_materials_with_texture_maps(host_check, tmp_path):
         texs.append(np.frombuffer(b, np.uint8, w * h * c, off + 12).reshape(h, w, c))
         off += 12 + w * h * c
     assert np.array_equal(texs[1], albedo) and np.array_equal(texs[2], normal)
+
+
+# --------------------------------------------------------------------------- render_multiThread against a mock device
+@pytest.fixture(scope="module")
+def mock_console(tmp_path_factory):
+    """the console linked with tests/tools/mock_device.cpp: the device entry points log their calls instead of rendering"""
+    out = str(tmp_path_factory.mktemp("mock") / "raym0nade_mock")
+    cmd = [os.environ.get("CXX", "g++")] + build.HOST_FLAGS + [os.path.join(ROOT, "tests", "tools", "mock_device.cpp")] + \
+        build.host_sources() + ["-o", out] + build.host_link_flags() + ["-Wl,-rpath," + os.path.dirname(build.OUT)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+@pytest.mark.parametrize("coc", [0.0, 4.0])
+def test_render_multithread_call_order_and_exports(mock_console, tmp_path, coc):
+    """the host's render_multiThread (src/render.cpp:593-676 in the reference): one upload, one render, then the exports
+    in the reference's order with the clamp and the denoiser between the groups; the depth-of-field group only with a
+    blur circle, and only it carries focus / CoC / camera position (src/render.cpp:664-668)"""
+    scene, _ = scenes.cornell_box(64, 64, 0)
+    scene.save(str(tmp_path / "cornell.rmscene"))
+    args = "0 0 -1\n1 0 0\n0 -1 0\n-3.5 0.25 0\n0.01 2.5 %g 8\n24 16\n5 3 0.7\n%s/frame\n" % (coc, tmp_path)
+    log = str(tmp_path / "calls.log")
+    r = subprocess.run([mock_console], input="create model box\n%s/\ncornell.rmscene\nnull\ncreate args a\n%srender box a\nexit\n" % (tmp_path, args),
+                       capture_output=True, text=True, timeout=120, env=dict(os.environ, RM_MOCK_LOG=log, RM_SEED="77", RM_DEVICE="0"))
+    assert r.returncode == 0, r.stderr
+    assert "Rendering completed in" in r.stdout and "Rays traced: 1000" in r.stdout and "Post processing finished." in r.stdout
+    calls = open(log).read().split("\n")[:-1]
+    kinds = [c.split()[0] for c in calls]
+    groups = ["postprocess"] * 4 + ["spatial_clamp", "download_resolved"] + ["postprocess"] * 8 + ["filter", "download_resolved"] + ["postprocess"] * 8
+    assert kinds == ["context_create", "stats_reset", "scene_upload", "render"] + groups + (["postprocess"] * 5 if coc > 0 else [])
+    assert calls[2] == "scene_upload faces=%d nodes=8 lights=1" % scene.n_faces
+    assert calls[3] == "render 24x16 spp=5 seed=77"
+    opts = [int(re.search(r"options=(\d+)", c).group(1)) for c in calls if c.startswith("postprocess")]
+    full = 63
+    want = [1, 1 | 512, 64, 128, 20, 36, 24, 40, full, full | 256, full | 512, full | 768, 20, 36, 24, 40, full, full | 256, full | 512, full | 768]
+    if coc > 0:
+        want += [1 | 1024, full | 1024, full | 1024 | 256, full | 1024 | 512, full | 1024 | 768]
+    assert opts == want
+    tags = ["DiffuseColor", "DiffuseColor_FXAA", "shapeNormal", "surfaceNormal", "Direct_Diffuse", "Direct_Specular", "Indirect_Diffuse",
+            "Indirect_Specular", "Raw", "Raw_Bloom", "Raw_FXAA", "Raw_Bloom_FXAA", "Direct_Diffuse_Filter", "Direct_Specular_Filter",
+            "Indirect_Diffuse_Filter", "Indirect_Specular_Filter", "Filter", "Filter_Bloom", "Filter_FXAA", "Filter_Bloom_FXAA"]
+    if coc > 0:
+        tags += ["BaseColor_DepthFieldBlur", "Filter_DepthFieldBlur", "Filter_DepthFieldBlur_Bloom", "Filter_DepthFieldBlur_FXAA",
+                 "Filter_DepthFieldBlur_Bloom_FXAA"]
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".png")) == sorted("frame(%s).png" % t for t in tags)
+    for tag, o in zip(tags, want):                         # each file holds the frame its own postprocess call returned, as byte(pixel * 255)
+        img = read_png(str(tmp_path / ("frame(%s).png" % tag)))
+        assert img.shape == (16, 24, 3)
+        assert (img[..., 0] == int(np.float32(o) / np.float32(2048) * np.float32(255))).all(), tag
+        assert np.array_equal(img[0, :, 1], (np.arange(24, dtype=np.float32) / np.float32(24) * np.float32(255)).astype(np.uint8))
+        assert (img[..., 2] == 255).all()
+    # the lens parameters reach the library only with the depth-of-field exports; exposure always
+    post = [c for c in calls if c.startswith("postprocess")]
+    assert all("focus=0 CoC=0 pos=0,0,0 exposure=8" in c for c in post[:20])
+    if coc > 0:
+        assert all("focus=2.5 CoC=4 pos=0.25,0,3.5 exposure=8" in c for c in post[20:])

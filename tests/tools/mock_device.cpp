@@ -1,0 +1,56 @@
+// mock_device.cpp — TEST-ONLY stand-ins for the device entry points of the C ABI, linked into a test build of the console
+// so that the host logic above the ABI (render_multiThread's call order, the export list, file names, PNG writing, the lens
+// parameters of the depth-of-field exports) can be exercised without a GPU.  It renders nothing: every call is appended to
+// the file named by RM_MOCK_LOG and the image calls return fixed patterns.  The host-only entry points (rm_prepare_scene,
+// rm_prepared_*, rm_last_error, rm_version) still come from the real library.  Never linked into the product.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "raym0nade_b200.h"
+
+namespace {
+void note(const char *fmt, ...) {
+    const char *path = std::getenv("RM_MOCK_LOG");
+    if (!path) return;
+    FILE *f = std::fopen(path, "a");
+    if (!f) return;
+    va_list ap;
+    va_start(ap, fmt);
+    std::vfprintf(f, fmt, ap);
+    va_end(ap);
+    std::fputc('\n', f);
+    std::fclose(f);
+}
+int g_npix = 0;
+}  // namespace
+
+struct RmContext { int device; };
+
+extern "C" {
+int rm_context_create(int device, void *, RmContext **out) { static RmContext c; c.device = device; *out = &c; note("context_create %d", device); return RM_OK; }
+int rm_stats_reset(RmContext *) { note("stats_reset"); return RM_OK; }
+int rm_stats_read(RmContext *, uint64_t out[4]) { out[0] = 1000; out[1] = out[2] = 0; out[3] = 7; return RM_OK; }
+int rm_scene_upload(RmContext *, const RmSceneDesc *s) { note("scene_upload faces=%d nodes=%d lights=%d", s->n_faces, s->n_nodes, s->n_lights); return rm_scene_validate(s); }
+int rm_render(RmContext *, const RmRenderArgs *a, uint64_t seed, RmHitInfo *g, RmRadiance *Dd, RmRadiance *, RmRadiance *, RmRadiance *) {
+    note("render %dx%d spp=%d seed=%llu", a->width, a->height, a->spp, (unsigned long long)seed);
+    g_npix = a->width * a->height;
+    if (g) g[0].id = 42;
+    if (Dd) Dd[0].Var = 0.5f;
+    return RM_OK;
+}
+int rm_download_resolved(RmContext *, RmHitInfo *g, RmRadiance *, RmRadiance *, RmRadiance *, RmRadiance *) { note("download_resolved"); if (g) g[0].id = 43; return RM_OK; }
+int rm_spatial_clamp(RmContext *, const RmRenderArgs *) { note("spatial_clamp"); return RM_OK; }
+int rm_filter(RmContext *, const RmRenderArgs *) { note("filter"); return RM_OK; }
+int rm_postprocess(RmContext *, const RmRenderArgs *a, int32_t options, float *rgb) {
+    note("postprocess options=%d focus=%g CoC=%g pos=%g,%g,%g exposure=%g", options, a->focus, a->CoC, a->position[0], a->position[1], a->position[2], a->exposure);
+    // a pattern that depends on the options, inside and outside [0, 1): red = options / 2048, green = x / width, blue = 1
+    for (int i = 0; i < g_npix; i++) {
+        rgb[i * 3] = float(options) / 2048.0f;
+        rgb[i * 3 + 1] = float(i % a->width) / float(a->width);
+        rgb[i * 3 + 2] = 1.0f;
+    }
+    return RM_OK;
+}
+}
