@@ -102,6 +102,8 @@ public:
 
     // The frame lives on the device after render(); these forward to the library and keep the host copies current.
     bool render(RmContext *ctx, const Model &model, const RenderArgs &args, uint64_t seed);
+    // the same frame rendered by `world` processes (one GPU each): this rank's sample shard + rm_reduce to rank 0
+    bool renderSharded(RmContext *ctx, const Model &model, const RenderArgs &args, uint64_t seed, int rank, int world);
     void spatialClamp();                      // src/image.cpp:30-82   -> rm_spatial_clamp
     void filter();                            // src/image.cpp:84-213  -> rm_filter
     void postProcessing(int shadeOptions);    // src/image.cpp:470-479 -> rm_postprocess

@@ -56,6 +56,26 @@ bool Photo::render(RmContext *ctx, const Model &model, const RenderArgs &args, u
     return true;
 }
 
+// One rank's share of a frame rendered by `world` processes, one GPU each: this rank's interleaved sample shard
+// (samples s with s mod world == rank, weighted with the global 1/spp), then the library's reduction to rank 0 over
+// NCCL (rm_reduce), which alone resolves and owns the frame afterwards.  The sequence is the one
+// scripts/reduce_check.py and bench.py run from Python.
+bool Photo::renderSharded(RmContext *ctx, const Model &model, const RenderArgs &args, uint64_t seed, int rank, int world) {
+    ctx_ = nullptr;
+    if (!model.desc()) { std::cerr << "Model is empty, nothing to render." << std::endl; return false; }
+    if (args.width != width || args.height != height) { std::cerr << "RenderArgs do not match the Photo size." << std::endl; return false; }
+    if (!ok(rm_scene_upload(ctx, model.desc()), "Scene upload failed")) return false;
+    const RmRenderArgs a = toC(args);
+    if (!ok(rm_trace_primary(ctx, &a, nullptr, nullptr), "Primary rays failed") || !ok(rm_gbuffer(ctx, &a, nullptr), "G-buffer failed") ||
+        !ok(rm_render_samples(ctx, &a, rank, world, seed, 1), "Rendering failed") || !ok(rm_reduce(ctx, 0), "Frame reduction failed")) return false;
+    if (rank != 0) return ok(rm_context_synchronize(ctx), "Synchronize failed");          // the shard is delivered; rank 0 has the frame
+    if (!ok(rm_resolve(ctx, &a, radiance_Dd, radiance_Ds, radiance_Id, radiance_Is), "Resolve failed") ||
+        !ok(rm_download_resolved(ctx, Gbuffer, nullptr, nullptr, nullptr, nullptr), "Download failed")) return false;
+    ctx_ = ctx;
+    args_ = args;
+    return true;
+}
+
 void Photo::syncPlanes() {
     ok(rm_download_resolved(ctx_, Gbuffer, radiance_Dd, radiance_Ds, radiance_Id, radiance_Is), "Download failed");
 }

@@ -581,3 +581,44 @@ def test_render_multithread_call_order_and_exports(mock_console, tmp_path, coc):
     assert all("focus=0 CoC=0 pos=0,0,0 exposure=8" in c for c in post[:20])
     if coc > 0:
         assert all("focus=2.5 CoC=4 pos=0.25,0,3.5 exposure=8" in c for c in post[20:])
+
+
+def test_two_process_launch_shards_samples_and_exports_on_rank_0(mock_console, tmp_path):
+    """one process per GPU (RM_RANK / RM_WORLD, or torchrun's RANK / WORLD_SIZE / LOCAL_RANK): the unique id travels through
+    a file, every rank renders its interleaved sample shard and joins rm_reduce, rank 0 alone resolves and writes the
+    exports.  The device calls are the mock's; their sequence is the one scripts/reduce_check.py runs on real GPUs."""
+    scene, _ = scenes.cornell_box(64, 64, 0)
+    scene.save(str(tmp_path / "cornell.rmscene"))
+    script = ("create model box\n%s/\ncornell.rmscene\nnull\ncreate args a\n0 0 -1\n1 0 0\n0 -1 0\n-3.5 0 0\n0.01 0 0 8\n24 16\n6 1 0.7\n%s/frame\n"
+              "render box a\nrender box a\nexit\n") % (tmp_path, tmp_path)               # two frames: the communicator is set up once
+    comm = str(tmp_path / "comm.id")
+    (tmp_path / "script.txt").write_text(script)
+    barrier = tmp_path / "barrier"
+    barrier.mkdir()
+    procs, logs, outs = [], [], []
+    for rank, env in [(1, dict(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")), (0, dict(RM_RANK="0", RM_WORLD="2", RM_DEVICE="0"))]:
+        logs.append(str(tmp_path / ("calls%d.log" % rank)))          # rank 1 starts first and has to wait for the id file
+        outs.append(str(tmp_path / ("stdout%d.txt" % rank)))
+        procs.append(subprocess.Popen([mock_console], stdin=open(tmp_path / "script.txt"), stdout=open(outs[-1], "w"), stderr=subprocess.STDOUT,
+                                      env=dict(os.environ, RM_MOCK_LOG=logs[-1], RM_MOCK_BARRIER=str(barrier), RM_COMM_FILE=comm, RM_SEED="5", **env)))
+    for p in procs:
+        p.wait(timeout=120)
+    outs = [(open(f).read(),) for f in outs]
+    assert all(p.returncode == 0 for p in procs), outs
+    calls1, calls0 = [open(f).read().split("\n")[:-1] for f in logs]
+    frame = ["scene_upload faces=%d nodes=8 lights=1" % scene.n_faces, "trace_primary 24x16 host=0", "gbuffer host=0"]
+    shard = lambda r: "render_samples begin=%d stride=2 spp=6 seed=5 reset=1" % r
+    idsum = sum((i * 7 + 3) & 255 for i in range(128))
+    assert calls1 == ["context_create 1", "comm_init rank=1 world=2 idsum=%d" % idsum] + \
+        2 * (["stats_reset"] + frame + [shard(1), "reduce root=0", "synchronize"])
+    head = ["context_create 0", "comm_unique_id", "comm_init rank=0 world=2 idsum=%d" % idsum]
+    assert calls0[:3] == head
+    per_frame = ["stats_reset"] + frame + [shard(0), "reduce root=0", "resolve host=1", "download_resolved gbuffer_only"]
+    rest = calls0[3:]
+    assert len(rest) % 2 == 0 and rest[:len(rest) // 2] == rest[len(rest) // 2:]          # both frames took the same path
+    assert rest[:len(per_frame)] == per_frame
+    assert [c.split()[0] for c in rest[len(per_frame):len(rest) // 2]] == \
+        ["postprocess"] * 4 + ["spatial_clamp", "download_resolved"] + ["postprocess"] * 8 + ["filter", "download_resolved"] + ["postprocess"] * 8
+    assert "Rank 1: sample shard rendered and reduced" in outs[0][0] and "rank 0 of 2" in outs[1][0]
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".png")]) == 20            # written once, by rank 0
+    assert not os.path.exists(comm)                                                      # the id file is gone once everybody has joined

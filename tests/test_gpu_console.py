@@ -38,7 +38,7 @@ def test_console_render_exports_match_the_python_host(tmp_path):
     args = scenes.RenderArgs.from_console(text)                 # the Python mirror parses the very same text
     assert np.allclose(args.position, a0.position, atol=1e-6) and args.CoC == 4.0 and args.spp == 8
     script = "create model box\n%s/\ncornell.rmscene\nnull\ncreate args a\n%s\nrender box a\nexit\n" % (tmp_path, text)
-    run = subprocess.run([console], input=script, capture_output=True, text=True, timeout=300, env=dict(os.environ, RM_SEED="0"))
+    run = subprocess.run([console], input=script, capture_output=True, text=True, timeout=300, env=dict(os.environ, RM_SEED="0", RM_RANK="0", RM_WORLD="1", RM_DEVICE="0"))       # one process, one GPU, whatever the launcher of the test run set
     assert run.returncode == 0, run.stderr
     assert "Rendering completed in" in run.stdout and "Post processing finished." in run.stdout, run.stdout + run.stderr
     png = {}

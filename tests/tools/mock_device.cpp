@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "raym0nade_b200.h"
 
@@ -40,7 +41,48 @@ int rm_render(RmContext *, const RmRenderArgs *a, uint64_t seed, RmHitInfo *g, R
     if (Dd) Dd[0].Var = 0.5f;
     return RM_OK;
 }
-int rm_download_resolved(RmContext *, RmHitInfo *g, RmRadiance *, RmRadiance *, RmRadiance *, RmRadiance *) { note("download_resolved"); if (g) g[0].id = 43; return RM_OK; }
+int rm_context_synchronize(RmContext *) { note("synchronize"); return RM_OK; }
+int rm_comm_unique_id(uint8_t id[128]) { for (int i = 0; i < 128; i++) id[i] = uint8_t(i * 7 + 3); note("comm_unique_id"); return RM_OK; }
+int rm_comm_init(RmContext *, const uint8_t id[128], int32_t rank, int32_t world) {
+    unsigned sum = 0;
+    for (int i = 0; i < 128; i++) sum += id[i];
+    note("comm_init rank=%d world=%d idsum=%u", rank, world, sum);
+    // ncclCommInitRank is a collective: nobody returns before everybody has arrived.  Emulated with one marker file per
+    // rank in the directory RM_MOCK_BARRIER names (the host relies on it: rank 0 removes the id file right after).
+    if (const char *dir = std::getenv("RM_MOCK_BARRIER")) {
+        char path[512];
+        std::snprintf(path, sizeof path, "%s/rank%d", dir, rank);
+        if (FILE *f = std::fopen(path, "w")) std::fclose(f);
+        for (int waited = 0; waited < 6000; waited++) {
+            int present = 0;
+            for (int r = 0; r < world; r++) {
+                std::snprintf(path, sizeof path, "%s/rank%d", dir, r);
+                if (FILE *f = std::fopen(path, "r")) { std::fclose(f); present++; }
+            }
+            if (present == world) return RM_OK;
+            struct timespec ts = {0, 10 * 1000 * 1000};
+            nanosleep(&ts, nullptr);
+        }
+        return RM_ERR_STATE;
+    }
+    return RM_OK;
+}
+int rm_trace_primary(RmContext *, const RmRenderArgs *a, int32_t *tri, float *t) { note("trace_primary %dx%d host=%d", a->width, a->height, int(tri || t)); g_npix = a->width * a->height; return RM_OK; }
+int rm_gbuffer(RmContext *, const RmRenderArgs *, RmHitInfo *g) { note("gbuffer host=%d", int(g != nullptr)); return RM_OK; }
+int rm_render_samples(RmContext *, const RmRenderArgs *a, int32_t begin, int32_t stride, uint64_t seed, int32_t reset) {
+    note("render_samples begin=%d stride=%d spp=%d seed=%llu reset=%d", begin, stride, a->spp, (unsigned long long)seed, reset);
+    return RM_OK;
+}
+int rm_reduce(RmContext *, int32_t root) { note("reduce root=%d", root); return RM_OK; }
+int rm_resolve(RmContext *, const RmRenderArgs *, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is) {
+    note("resolve host=%d", int(Dd && Ds && Id && Is));
+    return RM_OK;
+}
+int rm_download_resolved(RmContext *, RmHitInfo *g, RmRadiance *Dd, RmRadiance *, RmRadiance *, RmRadiance *) {
+    note(Dd ? "download_resolved" : "download_resolved gbuffer_only");
+    if (g) g[0].id = 43;
+    return RM_OK;
+}
 int rm_spatial_clamp(RmContext *, const RmRenderArgs *) { note("spatial_clamp"); return RM_OK; }
 int rm_filter(RmContext *, const RmRenderArgs *) { note("filter"); return RM_OK; }
 int rm_postprocess(RmContext *, const RmRenderArgs *a, int32_t options, float *rgb) {
