@@ -45,9 +45,14 @@ HOST_OUT = os.path.join(HERE, "raym0nade")          # the console program (C++ h
 HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra"]
 
 
-def host_sources(with_main=True):
+HOST_FXAA_OUT = os.path.join(HERE, "raym0nade_fxaa")  # the stand-alone FXAA program (the reference's fxaa.cpp)
+HOST_MAINS = {"main.cpp": HOST_OUT, "fxaa_tool.cpp": HOST_FXAA_OUT}
+
+
+def host_sources(with_main=True, main="main.cpp"):
+    """the host translation units shared by every program, plus the one holding `main` if asked for"""
     src = sorted(glob.glob(os.path.join(HOST_DIR, "*.cpp")))
-    return [s for s in src if with_main or os.path.basename(s) != "main.cpp"]
+    return [s for s in src if os.path.basename(s) not in HOST_MAINS or (with_main and os.path.basename(s) == main)]
 
 
 def host_link_flags():
@@ -58,18 +63,19 @@ def host_link_flags():
 
 
 def build_host(force=False, verbose=False):
-    """g++ the host side (raym0nade_b200/host) into the `raym0nade` console binary next to the library."""
-    deps = host_sources() + glob.glob(os.path.join(HOST_DIR, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [OUT]
-    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
-        return HOST_OUT
-    cmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + host_sources() + ["-o", HOST_OUT] + host_link_flags()
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode:
-        raise RuntimeError("g++ failed on the host side (%d)" % r.returncode)
+    """g++ the host side (raym0nade_b200/host) into the `raym0nade` console and `raym0nade_fxaa` next to the library."""
+    deps = glob.glob(os.path.join(HOST_DIR, "*.cpp")) + glob.glob(os.path.join(HOST_DIR, "*.hpp")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + [OUT]
+    for main, out in HOST_MAINS.items():
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+            continue
+        cmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + host_sources(main=main) + ["-o", out] + host_link_flags()
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("g++ failed on the host side (%d)" % r.returncode)
     return HOST_OUT
 
 

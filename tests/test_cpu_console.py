@@ -622,3 +622,44 @@ def test_two_process_launch_shards_samples_and_exports_on_rank_0(mock_console, t
     assert "Rank 1: sample shard rendered and reduced" in outs[0][0] and "rank 0 of 2" in outs[1][0]
     assert len([f for f in os.listdir(tmp_path) if f.endswith(".png")]) == 20            # written once, by rank 0
     assert not os.path.exists(comm)                                                      # the id file is gone once everybody has joined
+
+
+def test_fxaa_program_sequence_against_the_mock_device(tmp_path):
+    """raym0nade_fxaa (the reference's fxaa.cpp): PNG -> linear light -> rm_fxaa -> gammaCorrection through rm_postprocess ->
+    PNG.  The device calls are the mock's: what is checked is the decoding table, the staging of the frame as the only
+    radiance plane, the shade options that pass it through, and the file that comes out."""
+    tool = str(tmp_path / "fxaa_mock")
+    cmd = [os.environ.get("CXX", "g++")] + build.HOST_FLAGS + [os.path.join(ROOT, "tests", "tools", "mock_device.cpp")] + \
+        build.host_sources(main="fxaa_tool.cpp") + ["-o", tool] + build.host_link_flags() + ["-Wl,-rpath," + os.path.dirname(build.OUT)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (6, 10, 3), dtype=np.uint8)
+    open(tmp_path / "in.png", "wb").write(_png_bytes(img.reshape(6, -1), 10, 6, 8, 2, filters=[1, 4]))
+    log = str(tmp_path / "calls.log")
+    r = subprocess.run([tool, str(tmp_path / "in.png"), str(tmp_path / "out.png")], capture_output=True, text=True, env=dict(os.environ, RM_MOCK_LOG=log))
+    assert r.returncode == 0, r.stderr
+    assert "width: 10 height: 6" in r.stdout
+    calls = open(log).read().split("\n")[:-1]
+    assert [c.split()[0] for c in calls] == ["context_create", "fxaa", "upload_resolved", "postprocess", "context_destroy"]
+    lin = lambda k: float(np.float32(np.float32(k) / np.float32(255)) ** np.float32(2.2))
+    first = [float(x) for x in re.search(r"first=(\S+),(\S+),(\S+)", calls[1]).groups()]
+    assert calls[1].startswith("fxaa 10x6") and np.allclose(first, [lin(k) for k in img[0, 0]], rtol=2e-6)
+    staged = [float(x) for x in re.search(r"Dd0=(\S+),(\S+),(\S+)", calls[2]).groups()]
+    assert np.allclose(staged, first, rtol=1e-7) and "Ds0=0 base0=0" in calls[2]          # the frame is the only thing in the Photo
+    assert "options=20 " in calls[3] and "exposure=1" in calls[3]                        # Direct_Diffuse without BaseColor / Emission
+    out = read_png(str(tmp_path / "out.png"))
+    assert out.shape == (6, 10, 3) and (out[..., 0] == int(np.float32(20) / np.float32(2048) * np.float32(255))).all() and (out[..., 2] == 255).all()
+    # a missing input is reported, nothing is written
+    r = subprocess.run([tool, str(tmp_path / "nope.png"), str(tmp_path / "o2.png")], capture_output=True, text=True, env=dict(os.environ, RM_MOCK_LOG=log))
+    assert r.returncode == 1 and "Could not open file for reading" in r.stderr and not os.path.exists(tmp_path / "o2.png")
+
+
+def test_fxaa_program_without_a_gpu_is_a_loud_no(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    build.build_host()
+    open(tmp_path / "in.png", "wb").write(_png_bytes(np.zeros((2, 6), np.uint8), 2, 2, 8, 2))
+    r = subprocess.run([build.HOST_FXAA_OUT, str(tmp_path / "in.png"), str(tmp_path / "out.png")], capture_output=True, text=True)
+    assert r.returncode == 1 and "No CUDA context" in r.stderr and not os.path.exists(tmp_path / "out.png")

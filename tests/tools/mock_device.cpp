@@ -41,6 +41,18 @@ int rm_render(RmContext *, const RmRenderArgs *a, uint64_t seed, RmHitInfo *g, R
     if (Dd) Dd[0].Var = 0.5f;
     return RM_OK;
 }
+void rm_context_destroy(RmContext *) { note("context_destroy"); }
+int rm_fxaa(RmContext *, const float *in, float *out, int32_t w, int32_t h) {
+    note("fxaa %dx%d first=%.9g,%.9g,%.9g last=%.9g", w, h, in[0], in[1], in[2], in[size_t(w) * h * 3 - 1]);
+    std::memcpy(out, in, size_t(w) * h * 12);
+    return RM_OK;
+}
+int rm_upload_resolved(RmContext *, const RmRenderArgs *a, const RmHitInfo *g, const RmRadiance *Dd, const RmRadiance *Ds, const RmRadiance *, const RmRadiance *) {
+    g_npix = a->width * a->height;
+    note("upload_resolved %dx%d Dd0=%.9g,%.9g,%.9g Ds0=%g base0=%g", a->width, a->height, Dd[0].radiance[0], Dd[0].radiance[1], Dd[0].radiance[2],
+         Ds[0].radiance[0], g[0].baseColor[0]);
+    return RM_OK;
+}
 int rm_context_synchronize(RmContext *) { note("synchronize"); return RM_OK; }
 int rm_comm_unique_id(uint8_t id[128]) { for (int i = 0; i < 128; i++) id[i] = uint8_t(i * 7 + 3); note("comm_unique_id"); return RM_OK; }
 int rm_comm_init(RmContext *, const uint8_t id[128], int32_t rank, int32_t world) {
