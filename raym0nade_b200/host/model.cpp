@@ -213,9 +213,9 @@ bool Model::loadObj(const std::string &folder, const std::string &path) {
         texturePixels.push_back({q(r), q(g), q(b), 255});
         return int(textures.size()) - 1;
     };
-    auto loadMtl = [&](const std::string &file) {
-        std::ifstream m(file);
-        if (!m) { std::cerr << "Could not open material library " << file << std::endl; return; }
+    auto loadMtl = [&](const std::string &library) {
+        std::ifstream m(library);
+        if (!m) { std::cerr << "Could not open material library " << library << std::endl; return; }
         std::string line, key;
         int cur = -1;
         while (std::getline(m, line)) {
