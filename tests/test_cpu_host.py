@@ -333,3 +333,27 @@ def test_validation_names_the_inconsistency():
     keep = empty_light(d)                                           # noqa: F841
     assert L.rm_scene_validate(C.byref(d)) == -1 and "light 0: no faces" in L.rm_last_error().decode()
     assert L.rm_scene_validate(None) == -1
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/raym0nade_b200.h compiles as pedantic C99 and a C program links against the
+    library and calls a host-only entry point (what a cgo / JNI / ctypes binding relies on)"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "raym0nade_b200.h"\n'
+                   "int main(void) {\n"
+                   "    RmSceneDesc d; memset(&d, 0, sizeof d);\n"
+                   "    int rc = rm_scene_validate(&d);\n"
+                   '    printf("%d|%s|%s|%d %d %d %d\\n", rc, rm_last_error(), rm_version(), (int)sizeof(RmHitInfo), (int)sizeof(RmRadiance), (int)sizeof(RmBvhNode), (int)sizeof(RmRenderArgs));\n'
+                   "    return 0;\n}\n")
+    exe = str(tmp_path / "abi")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                        "-L", os.path.dirname(api.LIB_PATH), "-lraym0nade_b200", "-Wl,-rpath," + os.path.dirname(api.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True).stdout.strip().split("|")
+    assert out[0] == "-1" and "missing geometry" in out[1] and "sm_100a" in out[2]
+    assert out[3] == "88 16 32 80"                          # HitInfo, RadianceData, BVH_Node of the reference; RenderArgs minus threads / savePath
