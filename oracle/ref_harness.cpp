@@ -224,6 +224,8 @@ void *ref_scene_create(const RmRawScene *raw) {
 }
 
 void ref_scene_destroy(void *h) { delete static_cast<RefScene *>(h); }
+// the reference Model behind a scene handle (for oracle/bridge_harness.cpp)
+const void *ref_scene_model(void *h) { return &static_cast<RefScene *>(h)->model; }
 
 int ref_node_count(void *h) { return static_cast<RefScene *>(h)->node_count; }
 int ref_light_count(void *h) { return int(static_cast<RefScene *>(h)->model.lightObjects.size()); }

@@ -21,7 +21,9 @@ SLOT_DIFFUSE, SLOT_SPECULAR, SLOT_EMISSIVE, SLOT_NORMALS = 1, 2, 4, 6
 
 
 def lib_path(flavour="plain"):
-    return os.path.join(_HERE, "_ref", "libraym_ref.so" if flavour == "plain" else "libraym_ref_count.so")
+    """'plain' / 'count': the reference + harness; 'bridge': the same plus the reference-tree binding
+    (raym0nade_b200/host/reference_tree), linked against the product library (make -C oracle bridge)"""
+    return os.path.join(_HERE, "_ref", {"plain": "libraym_ref.so", "count": "libraym_ref_count.so", "bridge": "libraym_bridge.so"}[flavour])
 
 
 def available(flavour="plain") -> bool:
@@ -71,6 +73,13 @@ def load(flavour="plain"):
     L.ref_kat_accumulate.argtypes = [i64, vp, vp, vp]
     L.ref_kat_absorb.argtypes = [i64, vp, vp, vp]
     L.ref_build_flavour.restype = C.c_char_p
+    if flavour == "bridge":
+        L.ref_bridge_create.restype = vp
+        L.ref_bridge_create.argtypes = [vp]
+        L.ref_bridge_desc.restype = vp
+        L.ref_bridge_desc.argtypes = [vp]
+        L.ref_bridge_destroy.argtypes = [vp]
+        L.ref_bridge_render.argtypes = [vp, C.POINTER(RmRenderArgs), i32, vp, vp]
     _LIBS[flavour] = L
     return L
 

@@ -357,3 +357,66 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True).stdout.strip().split("|")
     assert out[0] == "-1" and "missing geometry" in out[1] and "sm_100a" in out[2]
     assert out[3] == "88 16 32 80"                          # HitInfo, RadianceData, BVH_Node of the reference; RenderArgs minus threads / savePath
+
+
+# --------------------------------------------------------------------------- the binding a maintainer adds to the reference tree
+@pytest.mark.parametrize("which", ["cornell", "sky", "textured", "glossy"])
+def test_reference_tree_binding_fills_the_same_scene(which):
+    """raym0nade_b200/host/reference_tree/gpu_bridge.cpp, compiled against the unmodified reference: the RmSceneDesc it fills
+    from a Model the reference built equals the one rm_prepare_scene derives from the same raw scene - nodes, triangle order,
+    materials, mip chains, light objects, sky - bit for bit, and passes rm_scene_validate"""
+    import ctypes as C
+    from oracle import refbind
+    if not refbind.available("bridge"):
+        pytest.skip("oracle/_ref/libraym_bridge.so not built (make -C oracle bridge, needs /root/reference)")
+    scene = _scene_for(which)
+    R = refbind.RefScene(scene, flavour="bridge")
+    b = R.L.ref_bridge_create(R.h)
+    d = api.RmSceneDesc.from_address(R.L.ref_bridge_desc(b))
+    m = Model(scene)
+    p = m.desc
+    assert api.lib().rm_scene_validate(C.byref(d)) == 0, api.lib().rm_last_error()
+
+    def arr(addr, dtype, count):
+        return np.frombuffer((C.c_char * (np.dtype(dtype).itemsize * count)).from_address(addr), dtype) if count else np.zeros(0, dtype)
+
+    def pv(ptr):
+        return ptr if isinstance(ptr, int) or ptr is None else C.cast(ptr, C.c_void_p).value
+
+    for f in ("n_faces", "n_nodes", "n_materials", "n_textures", "n_lights", "sky_width", "sky_height"):
+        assert getattr(d, f) == getattr(p, f), f
+    nf = d.n_faces
+    for f, per in (("positions", 9), ("uvs", 6), ("normals", 9)):
+        assert np.array_equal(arr(pv(getattr(d, f)), np.uint32, nf * per), arr(pv(getattr(p, f)), np.uint32, nf * per)), f
+    assert np.array_equal(arr(pv(d.face_material), np.int32, nf), arr(pv(p.face_material), np.int32, nf))
+    # every node the traversal can reach (slots the build never wrote are garbage in the reference, zero in ours)
+    dn, pn = arr(pv(d.nodes), np.uint8, d.n_nodes * 32).reshape(-1, 32), arr(pv(p.nodes), np.uint8, p.n_nodes * 32).reshape(-1, 32)
+    face_r = pn.view(np.int32).reshape(-1, 8)[:, 7]
+    stack, seen = [1], 0
+    while stack:
+        u = stack.pop()
+        assert np.array_equal(dn[u], pn[u]), u
+        seen += 1
+        if face_r[u] == 0:
+            stack += [2 * u, 2 * u + 1]
+    assert seen > 0
+    for i in range(d.n_materials):
+        a, c = d.materials[i], p.materials[i]
+        assert list(a.tex) == list(c.tex) and a.has_fully_transparent_part == c.has_fully_transparent_part
+        assert (a.opacity, a.ior, a.roughness, list(a.transmitting_color)) == (c.opacity, c.ior, c.roughness, list(c.transmitting_color))
+    for i in range(d.n_textures):
+        a, c = d.textures[i], p.textures[i]
+        assert (a.width, a.height, a.channels, a.map_depth) == (c.width, c.height, c.channels, c.map_depth), i
+        for l in range(a.map_depth):
+            n = (a.width >> l) * (a.height >> l) * a.channels
+            assert np.array_equal(arr(a.levels[l], np.uint8, n), arr(c.levels[l], np.uint8, n)), (i, l)
+    for i in range(d.n_lights):
+        a, c = d.lights[i], p.lights[i]
+        assert (list(a.center), list(a.color), a.power, a.n_faces) == (list(c.center), list(c.color), c.power, c.n_faces)
+        for f, per in (("face_positions", 9), ("face_normals", 9), ("face_cdf", 1)):
+            assert np.array_equal(arr(getattr(a, f), np.uint32, a.n_faces * per), arr(getattr(c, f), np.uint32, a.n_faces * per)), (i, f)
+    ns = d.sky_width * d.sky_height
+    assert np.array_equal(arr(pv(d.sky_data), np.uint32, ns * 3), arr(pv(p.sky_data), np.uint32, ns * 3))
+    assert np.array_equal(arr(pv(d.sky_cdf), np.uint32, ns), arr(pv(p.sky_cdf), np.uint32, ns))
+    R.L.ref_bridge_destroy(b)
+    R.close()
