@@ -420,3 +420,22 @@ def test_reference_tree_binding_fills_the_same_scene(which):
     assert np.array_equal(arr(pv(d.sky_cdf), np.uint32, ns), arr(pv(p.sky_cdf), np.uint32, ns))
     R.L.ref_bridge_destroy(b)
     R.close()
+
+
+def test_reference_tree_binding_without_a_gpu_leaves_the_photo_alone():
+    """render_multiThread_b200 on a box without a B200: the library's error is printed, the reference's Photo is not touched,
+    and nothing falls back to the CPU renderer"""
+    import ctypes as C
+    import torch
+    from oracle import refbind
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not refbind.available("bridge"):
+        pytest.skip("oracle/_ref/libraym_bridge.so not built (make -C oracle bridge, needs /root/reference)")
+    scene, args = scenes.cornell_box(16, 16, 2)
+    R = refbind.RefScene(scene, flavour="bridge")
+    rgb = np.zeros((16, 16, 3), np.float32)
+    a = args.to_c()
+    assert R.L.ref_bridge_render(R.h, C.byref(a), 63, rgb.ctypes.data_as(C.c_void_p), None) == -1
+    assert not rgb.any()
+    R.close()
