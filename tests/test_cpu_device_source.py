@@ -1,0 +1,135 @@
+"""The kernels' own source on the CPU: tests/tools/device_on_host.cpp compiles the device headers of raym0nade_b200/csrc
+(dev_math / dev_trace / dev_surface / dev_bsdf / dev_texture .cuh) with g++ through a small shim and runs their deterministic
+functions against the golden vectors the compiled reference produced (tests/golden/reference_vectors.npz).  The GPU suite
+checks the same functions where they really run; this file keeps an arithmetic regression from slipping through a CPU-only
+run.  Bars: bit-equal for the arithmetic that is + - * / sqrt only; a few ulp where libm (powf, atan2f, acosf, sinf) is
+involved - on the host that is glibc, the reference's own libm, and in this container every one of these comparisons comes
+out bit-equal (0 ulp)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from raym0nade_b200 import scenes
+from raym0nade_b200.api import Model, RmSceneDesc
+from raym0nade_b200.ctypes_defs import HITINFO_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+
+
+@pytest.fixture(scope="module")
+def doh(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    out = str(tmp_path_factory.mktemp("doh") / "libdoh.so")
+    cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "raym0nade_b200", "csrc"), "-I", os.path.join(ROOT, "tests", "tools"),
+           os.path.join(ROOT, "tests", "tools", "device_on_host.cpp"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(out)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.doh_ray_in_box.argtypes = [i64, vp, vp, vp, i32]
+    L.doh_ray_triangle.argtypes = [i64, vp, vp, vp]
+    L.doh_barycentric.argtypes = [i64, vp, vp, vp]
+    L.doh_bsdf.argtypes = [i32, i64, vp, vp, vp, vp]
+    L.doh_uniform_from_u32.argtypes = [vp, i32, vp]
+    L.doh_material_fetch.argtypes = [C.POINTER(RmSceneDesc), i32, i32, i64, vp, vp]
+    L.doh_sky_get.argtypes = [C.POINTER(RmSceneDesc), i64, vp, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def same(a, b):
+    """bit-equal, NaNs in the same places"""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a, nan=0.0).view(np.uint32), np.nan_to_num(b, nan=0.0).view(np.uint32))
+
+
+def ulps(a, b):
+    """largest distance in units of the last place between two finite float32 arrays"""
+    a, b = np.asarray(a, np.float32).ravel(), np.asarray(b, np.float32).ravel()
+    ia, ib = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    ia, ib = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia), np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return int(np.abs(ia - ib).max()) if a.size else 0
+
+
+def test_slab_test_both_paths(doh):
+    """rayInBox (src/geometry.cpp:40-61) as slab_axis emulates it - early return, partial tL and all - and the fast path for
+    rays without a parallel axis; the golden rays include 256 exactly axis-parallel ones and infinite tR"""
+    rays, boxes = _f32(G["box_rays"]), _f32(G["box_boxes"])
+    for variant in (0, 1):
+        tlr = _f32(G["box_tlr_in"]).copy()
+        doh.doh_ray_in_box(len(rays), _p(rays), _p(boxes), _p(tlr), variant)
+        # the reference's early return leaves tR untouched where the emulation parks -1 (slab_axis `kill`): both mean "missed",
+        # and every caller only asks tL < tR; compare tL bit for bit and tR wherever the box was entered
+        want = G["box_tlr_out"]
+        hit_ref, hit_dev = want[:, 0] < want[:, 1], tlr[:, 0] < tlr[:, 1]
+        assert np.array_equal(hit_ref, hit_dev), variant
+        assert same(tlr[hit_ref], want[hit_ref]), variant
+        assert same(tlr[:, 0], want[:, 0]), variant          # the partial tL a missed box leaves decides the child order (bvh.cpp:75-87)
+        assert hit_ref.sum() > 100 and (~hit_ref).sum() > 100
+
+
+def test_triangle_test_and_barycentrics(doh):
+    rays, tris = _f32(G["tri_rays"]), _f32(G["tri_tris"])
+    t = np.zeros(len(rays), np.float32)
+    doh.doh_ray_triangle(len(rays), _p(rays), _p(tris), _p(t))
+    assert same(t, G["tri_t"])                                 # includes the 128 degenerate-edge triangles and the misses (+inf)
+    assert np.isfinite(G["tri_t"]).mean() > 0.02
+    tri, p = _f32(G["bary_tris"]), _f32(G["bary_p"])
+    out = np.zeros((len(p), 3), np.float32)
+    doh.doh_barycentric(len(p), _p(tri), _p(p), _p(out))
+    assert same(out, G["bary_out"])
+
+
+def test_bsdf_evaluation(doh):
+    surf = np.ascontiguousarray(G["bsdf_surf"], HITINFO_DTYPE)
+    V, Ldir = _f32(G["bsdf_V"]), _f32(G["bsdf_L"])
+    for which, name in [(0, "bsdf_out"), (1, "brdf_out"), (2, "btdf_out")]:
+        out = np.zeros((len(surf), 3), np.float32)
+        doh.doh_bsdf(which, len(surf), _p(surf), _p(V), _p(Ldir), _p(out))
+        want = G[name]
+        assert np.array_equal(np.isnan(out), np.isnan(want)) and np.array_equal(out == 0, want == 0), name
+        ok = np.isfinite(want) & (want != 0)
+        assert np.allclose(out[ok], want[ok], rtol=2e-6, atol=0), (name, ulps(out[ok], want[ok]))
+        assert (out.view(np.uint32)[ok] == want.view(np.uint32)[ok]).mean() > 0.9, name     # almost everywhere to the bit
+
+
+def test_rng_float_mapping(doh):
+    u32 = np.ascontiguousarray(G["rng_u32"], np.uint32)
+    out = np.zeros(len(u32), np.float32)
+    doh.doh_uniform_from_u32(_p(u32), len(u32), _p(out))
+    assert same(out, G["rng_out"])
+
+
+def test_material_fetches_and_sky_lookup(doh):
+    scene, _ = scenes.texture_heavy(6000, 96, 54, 0, tex_size=32, n_materials=8)
+    m = Model(scene)
+    uvd = _f32(G["tex_uvd"])                                   # includes NaN footprints (no mip selection) and far out-of-range uv
+    for which in range(4):
+        out = np.zeros((len(uvd), 4), np.float32)
+        doh.doh_material_fetch(C.byref(m.desc), 1, which, len(uvd), _p(uvd), _p(out))
+        want = G["tex_fetch%d" % which]
+        assert np.array_equal(np.isnan(out), np.isnan(want)), which
+        ok = np.isfinite(want)
+        assert ulps(out[ok], want[ok]) <= 2, (which, ulps(out[ok], want[ok]))
+    scene, _ = scenes.heightfield_scene(3000, 96, 54, 0, with_sky=True)
+    m = Model(scene)
+    dirs = _f32(G["sky_dirs"])
+    out = np.zeros((len(dirs), 3), np.float32)
+    doh.doh_sky_get(C.byref(m.desc), len(dirs), _p(dirs), _p(out))
+    assert ulps(out, G["sky_out"]) <= 2, ulps(out, G["sky_out"])

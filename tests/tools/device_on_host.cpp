@@ -1,0 +1,134 @@
+// device_on_host.cpp — TEST-ONLY: the device headers of raym0nade_b200/csrc compiled as host code (cuda_on_host.h) and
+// exposed with the signatures of the oracle's known-answer functions, so that the CPU suite holds the kernels' own source
+// for the deterministic stages - rayInBox, RayTriangleIntersection, barycentric, BRDF / BTDF evaluation, the RNG float
+// mapping, trilinear material fetches, the sky lookup - to the golden vectors the compiled reference produced
+// (tests/golden/reference_vectors.npz).  The GPU suite checks the same functions as they run on the device; this copy
+// catches an arithmetic regression in every CPU-only test run.  Built with -ffp-contract=off, no fast-math.
+#include "cuda_on_host.h"
+#include "raym0nade_b200.h"
+namespace rm { struct Philox4; static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1); }
+#include "dev_bsdf.cuh"
+#include "dev_texture.cuh"
+namespace rm { static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); } }
+
+#include <vector>
+
+using namespace rm;
+
+namespace {
+V3 ld(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+// the scene streams of dev_scene.cuh formed on the host the way rm_scene_upload forms them (rm_api.cu): texture table +
+// one texel blob with 16-byte aligned levels, materials, the k/255 table, the sky
+struct HostScene {
+    std::vector<DevTexture> textures;
+    std::vector<uint8_t> texels;
+    std::vector<DevMaterial> materials;
+    float lut[256];
+    DevScene S{};
+    explicit HostScene(const RmSceneDesc *sc) {
+        textures.resize(std::max(sc->n_textures, 1));
+        size_t bytes = 0;
+        for (int i = 0; i < sc->n_textures; i++) {
+            const RmTextureDesc &t = sc->textures[i];
+            DevTexture &d = textures[i];
+            d.width = t.width; d.height = t.height; d.channels = t.channels; d.map_depth = t.map_depth;
+            for (int l = 0; l < 8; l++) {
+                d.offset[l] = 0;
+                if (l >= t.map_depth) continue;
+                const size_t n = size_t(t.width >> l) * (t.height >> l) * t.channels, off = (bytes + 15) & ~size_t(15);
+                d.offset[l] = uint32_t(off);
+                bytes = off + n;
+                texels.resize(bytes);
+                if (n) std::memcpy(&texels[off], t.levels[l], n);
+            }
+        }
+        texels.resize(((bytes + 15) & ~size_t(15)) + 16);
+        materials.resize(std::max(sc->n_materials, 1));
+        for (int i = 0; i < sc->n_materials; i++) {
+            const RmMaterialDesc &m = sc->materials[i];
+            DevMaterial &d = materials[i];
+            for (int k = 0; k < 4; k++) d.tex[k] = m.tex[k] < 0 ? -1 : m.tex[k];
+            d.opacity = m.opacity; d.ior = m.ior; d.roughness = m.roughness;
+            for (int k = 0; k < 3; k++) d.tc[k] = m.transmitting_color[k];
+            d.cutout = m.has_fully_transparent_part ? 1 : 0;
+            d._pad = 0;
+        }
+        for (int k = 0; k < 256; k++) lut[k] = float(k) / 255.0f;
+        S.textures = textures.data(); S.texels = texels.data(); S.materials = materials.data(); S.div255 = lut;
+        S.n_materials = sc->n_materials;
+        S.sky_width = sc->sky_width; S.sky_height = sc->sky_height; S.sky_data = sc->sky_data; S.sky_cdf = sc->sky_cdf;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// variant 0: the general slab test; 1: the fast path the engine takes for rays without a parallel axis (others: general)
+void doh_ray_in_box(int64_t n, const float *rays, const float *boxes, float *tlr, int variant) {
+    for (int64_t i = 0; i < n; i++) {
+        const RaySetup r = setup_ray(ld(rays + i * 6), ld(rays + i * 6 + 3));
+        const float *b = boxes + i * 6;
+        const float4 a = make_float4(b[0], b[1], b[2], b[3]), c = make_float4(b[4], b[5], 0.0f, 0.0f);
+        if (variant == 1 && (r.flags & 7u) == 0) ray_in_box_fast(r, a, c, tlr[i * 2], tlr[i * 2 + 1]);
+        else ray_in_box(r, a, c, tlr[i * 2], tlr[i * 2 + 1]);
+    }
+}
+
+// the traversal record of a triangle as k_pack_faces forms it (rm_api.cu): {v0, e1.x} {e1.yz, e2.xy} {e2.z, |e1|, cutout, 0}
+void doh_ray_triangle(int64_t n, const float *rays, const float *tris, float *t) {
+    for (int64_t i = 0; i < n; i++) {
+        const float *v = tris + i * 9;
+        const V3 e1 = mk3(fsub(v[3], v[0]), fsub(v[4], v[1]), fsub(v[5], v[2])), e2 = mk3(fsub(v[6], v[0]), fsub(v[7], v[1]), fsub(v[8], v[2]));
+        const float4 q0 = make_float4(v[0], v[1], v[2], e1.x), q1 = make_float4(e1.y, e1.z, e2.x, e2.y), q2 = make_float4(e2.z, length(e1), 0.0f, 0.0f);
+        t[i] = ray_triangle(setup_ray(ld(rays + i * 6), ld(rays + i * 6 + 3)), q0, q1, q2);
+    }
+}
+
+void doh_barycentric(int64_t n, const float *tris, const float *p, float *out) {
+    for (int64_t i = 0; i < n; i++) {
+        const V3 b = barycentric(ld(tris + i * 9), ld(tris + i * 9 + 3), ld(tris + i * 9 + 6), ld(p + i * 3));
+        out[i * 3] = b.x; out[i * 3 + 1] = b.y; out[i * 3 + 2] = b.z;
+    }
+}
+
+// which: 0 getBSDF, 1 getBRDF, 2 getBTDF (src/sampling.cpp:49-199)
+void doh_bsdf(int which, int64_t n, const RmHitInfo *surf, const float *in_dirs, const float *out_dirs, float *out) {
+    for (int64_t i = 0; i < n; i++) {
+        Bsdf B;
+        B.inDir = ld(in_dirs + i * 3);
+        B.s = load_hitinfo(surf + i);
+        const V3 L = ld(out_dirs + i * 3);
+        const V3 c = which == 0 ? get_bsdf(B, L) : (which == 1 ? get_brdf(B, L) : get_btdf(B, L));
+        out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
+    }
+}
+
+void doh_uniform_from_u32(const uint32_t *u32, int n, float *out) {
+    for (int i = 0; i < n; i++) out[i] = uniform_from_u32(u32[i]);
+}
+
+// which: 0 getDiffuseColor, 1 getEmissiveColor, 2 getNormal, 3 getSurfaceData (src/material.cpp:349-383); uvd = (u, v, duv)
+void doh_material_fetch(const RmSceneDesc *sc, int material, int which, int64_t n, const float *uvd, float *out) {
+    HostScene H(sc);
+    const DevMaterial &m = H.materials[material];
+    for (int64_t i = 0; i < n; i++) {
+        const float u = uvd[i * 3], v = uvd[i * 3 + 1], d = uvd[i * 3 + 2];
+        float *o = out + i * 4;
+        o[0] = o[1] = o[2] = o[3] = 0.0f;
+        if (which == 0) { const V4 c = mat_diffuse(H.S, m, u, v, d); o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+        else if (which == 1) { const V3 c = mat_emissive(H.S, m, u, v, d); o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+        else if (which == 2) { const V3 c = mat_normal(H.S, m, u, v, d); o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+        else mat_surface(H.S, m, u, v, o[0], o[1]);
+    }
+}
+
+void doh_sky_get(const RmSceneDesc *sc, int64_t n, const float *dirs, float *out) {
+    HostScene H(sc);
+    for (int64_t i = 0; i < n; i++) {
+        const V3 c = sky_get(H.S, ld(dirs + i * 3));
+        out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
+    }
+}
+
+}
