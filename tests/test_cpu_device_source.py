@@ -2,7 +2,9 @@
 (dev_math / dev_trace / dev_surface / dev_bsdf / dev_texture .cuh) with g++ through a small shim and runs their deterministic
 functions against the golden vectors the compiled reference produced (tests/golden/reference_vectors.npz).  The GPU suite
 checks the same functions where they really run; this file keeps an arithmetic regression from slipping through a CPU-only
-run.  Bars: bit-equal for the arithmetic that is + - * / sqrt only; a few ulp where libm (powf, atan2f, acosf, sinf) is
+run.  The image-space kernels (FXAA, spatial clamp, filterVar + a-trous, shade / bloom / gamma) are run whole: launched on the
+host thread by thread with the launch shapes of rm_render.cu - kernels with a shared-memory tile as real threads meeting at a
+barrier - against tests/golden/post_vectors.npz.  Bars: bit-equal for the arithmetic that is + - * / sqrt only; a few ulp where libm (powf, atan2f, acosf, sinf) is
 involved - on the host that is glibc, the reference's own libm, and in this container every one of these comparisons comes
 out bit-equal (0 ulp)."""
 import ctypes as C
@@ -28,7 +30,7 @@ def doh(tmp_path_factory):
         pytest.skip("CUDA headers not found")
     cxx = os.environ.get("CXX") or shutil.which("g++")
     out = str(tmp_path_factory.mktemp("doh") / "libdoh.so")
-    cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"),
+    cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread", "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "raym0nade_b200", "csrc"), "-I", os.path.join(ROOT, "tests", "tools"),
            os.path.join(ROOT, "tests", "tools", "device_on_host.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -133,3 +135,64 @@ def test_material_fetches_and_sky_lookup(doh):
     out = np.zeros((len(dirs), 3), np.float32)
     doh.doh_sky_get(C.byref(m.desc), len(dirs), _p(dirs), _p(out))
     assert ulps(out, G["sky_out"]) <= 2, ulps(out, G["sky_out"])
+
+
+# --------------------------------------------------------------------------- whole kernels, run on the host thread by thread
+GP = np.load(os.path.join(os.path.dirname(__file__), "golden", "post_vectors.npz"))
+PLANES = ("Dd", "Ds", "Id", "Is")
+
+
+def _kernels(doh):
+    vp, i32 = C.c_void_p, C.c_int32
+    doh.doh_fxaa.argtypes = [vp, vp, i32, i32]
+    doh.doh_denoise.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
+    doh.doh_postprocess.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
+    return doh
+
+
+def test_fxaa_kernel(doh):
+    """k_fxaa - shared-memory luma tile, one barrier - run as 256 real threads per block: bit-equal to Photo::FXAA"""
+    L = _kernels(doh)
+    src = _f32(G["fxaa_in"])
+    out = np.zeros_like(src)
+    L.doh_fxaa(_p(src), _p(out), src.shape[1], src.shape[0])
+    assert same(out, G["fxaa_out"])
+    assert not same(out, src)
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+@pytest.mark.parametrize("stages", [1, 2, 3])
+def test_clamp_and_filter_kernels(doh, name, stages):
+    """k_spatial_clamp (1), k_filter_pack + k_filter_var + five k_atrous passes (2), both in the reference's order (3), with the
+    launch shapes of rm_spatial_clamp / rm_filter"""
+    L = _kernels(doh)
+    w, h = (int(v) for v in GP[name + "_wh"])
+    planes = [np.ascontiguousarray(GP["%s_in_%s" % (name, k)]).copy() for k in PLANES]
+    g = np.ascontiguousarray(GP[name + "_gbuffer"])
+    L.doh_denoise(_p(g), *[_p(p) for p in planes], w, h, stages)
+    for k, got in zip(PLANES, planes):
+        want = GP["%s_s%d_%s" % (name, stages, k)]
+        if stages == 1:
+            assert same(got["radiance"], want["radiance"]) and same(got["Var"], want["Var"]), k       # + - * / only: to the bit
+        else:                                                  # powf(x, 1024) and expf in the weights: libm's on the host
+            for f in ("radiance", "Var"):
+                a, b = got[f].astype(np.float64), want[f].astype(np.float64)
+                assert np.array_equal(np.isnan(a), np.isnan(b)), (k, f)
+                ok = np.isfinite(b)
+                assert (np.abs(a[ok] - b[ok]) <= 2e-6 * (1.0 + np.abs(b[ok]))).all(), (k, f, np.abs(a[ok] - b[ok]).max())
+    assert any(not same(p["radiance"], GP["%s_in_%s" % (name, k)]["radiance"]) for k, p in zip(PLANES, planes))
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+def test_shade_bloom_gamma_fxaa_kernels(doh, name):
+    L = _kernels(doh)
+    w, h = (int(v) for v in GP[name + "_wh"])
+    planes = [np.ascontiguousarray(GP["%s_in_%s" % (name, k)]) for k in PLANES]
+    g = np.ascontiguousarray(GP[name + "_gbuffer"])
+    for opts in (63 | 256, 63 | 256 | 512):
+        out = np.zeros((h, w, 3), np.float32)
+        L.doh_postprocess(_p(g), *[_p(p) for p in planes], w, h, float(GP[name + "_exposure"][0]), opts, _p(out))
+        want = GP["%s_post_%d" % (name, opts)]
+        assert np.array_equal(np.isnan(out), np.isnan(want)), opts
+        ok = np.isfinite(want)
+        assert np.abs(out[ok] - want[ok]).max() <= 2e-6, (opts, np.abs(out[ok] - want[ok]).max())

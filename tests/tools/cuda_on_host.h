@@ -11,8 +11,50 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cuda_runtime.h>            // float2 / float4 / int2 / make_float4 ... (host-includable)
-#include <device_launch_parameters.h>
+#include <cuda_runtime.h>            // float2 / float4 / int2 / dim3 / make_float4 ... (host-includable)
+
+// The launch geometry a kernel body reads.  On the host a kernel without barriers, shared memory or warp primitives is an
+// ordinary function of (blockIdx, threadIdx): rm_host_launch below calls it once per thread of the grid, in order.
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+#define __launch_bounds__(...)
+
+// Kernels that stage a tile in shared memory and meet at __syncthreads(): `__shared__` becomes one static array per
+// process and rm_host_launch_blocks runs the blocks one after the other, each as blockDim real threads that meet at a
+// barrier (a thread that leaves the kernel early drops out of it, as on the device).
+#ifdef __shared__
+#undef __shared__
+#endif
+#define __shared__ static
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+struct RmBlockBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int expected = 0, waiting = 0;
+    unsigned generation = 0;
+    void arrive(bool leave) {
+        std::unique_lock<std::mutex> l(m);
+        if (leave) expected--; else waiting++;
+        if (waiting >= expected) { waiting = 0; generation++; cv.notify_all(); return; }
+        if (leave) return;
+        const unsigned g = generation;
+        cv.wait(l, [&] { return g != generation; });
+    }
+};
+static RmBlockBarrier *rm_block_barrier = nullptr;
+
+template <class Kernel, class... Args>
+static void rm_host_launch(Kernel kernel, dim3 grid, dim3 block, Args... args) {
+    gridDim = grid; blockDim = block;
+    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++)
+        for (unsigned tz = 0; tz < block.z; tz++) for (unsigned ty = 0; ty < block.y; ty++) for (unsigned tx = 0; tx < block.x; tx++) {
+            blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz};
+            kernel(args...);
+        }
+}
 
 #ifdef __noinline__
 #undef __noinline__
@@ -43,7 +85,27 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __ballot_sync(unsigned, int) { rm_gpu_only(); }
 static inline unsigned __activemask() { rm_gpu_only(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { rm_gpu_only(); }
-static inline void __syncthreads() { rm_gpu_only(); }
+static inline void __syncthreads() { if (rm_block_barrier) rm_block_barrier->arrive(false); else rm_gpu_only(); }
+
+template <class Kernel, class... Args>
+static void rm_host_launch_blocks(Kernel kernel, dim3 grid, dim3 block, Args... args) {
+    RmBlockBarrier barrier;
+    rm_block_barrier = &barrier;
+    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+        barrier.expected = int(block.x * block.y * block.z);
+        barrier.waiting = 0;
+        std::vector<std::thread> threads;
+        for (unsigned tz = 0; tz < block.z; tz++) for (unsigned ty = 0; ty < block.y; ty++) for (unsigned tx = 0; tx < block.x; tx++)
+            threads.emplace_back([=, &barrier] {
+                gridDim = grid; blockDim = block;
+                blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz};
+                kernel(args...);
+                barrier.arrive(true);
+            });
+        for (auto &t : threads) t.join();
+    }
+    rm_block_barrier = nullptr;
+}
 template <class T> static inline T __shfl_sync(unsigned, T, int, int = 32) { rm_gpu_only(); }
 template <class T> static inline T __shfl_down_sync(unsigned, T, unsigned, int = 32) { rm_gpu_only(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T, int, int = 32) { rm_gpu_only(); }

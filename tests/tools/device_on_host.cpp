@@ -11,6 +11,8 @@ namespace rm { struct Philox4; static Philox4 philox_block(uint32_t c0, uint32_t
 #include "dev_texture.cuh"
 namespace rm { static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); } }
 
+#include "kernels_post.cuh"
+
 #include <vector>
 
 using namespace rm;
@@ -129,6 +131,59 @@ void doh_sky_get(const RmSceneDesc *sc, int64_t n, const float *dirs, float *out
         const V3 c = sky_get(H.S, ld(dirs + i * 3));
         out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
     }
+}
+
+// ---- whole kernels, launched on the host thread by thread (cuda_on_host.h) with the launch shapes of rm_render.cu
+
+void doh_fxaa(const float *in, float *out, int w, int h) {                 // rm_fxaa_device
+    rm_host_launch_blocks(k_fxaa, dim3((w + kFxTileW - 1) / kFxTileW, (h + kFxTileH - 1) / kFxTileH), dim3(kFxTileW, kFxTileH), in, out, w, h);
+}
+
+// stages: bit 0 Photo::spatialClamp (rm_spatial_clamp), bit 1 Photo::filter (rm_filter), in the reference's order; planes in place
+void doh_denoise(const RmHitInfo *G, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is, int w, int h, int stages) {
+    const int npix = w * h;
+    std::vector<RmRadiance> alt[4];
+    Planes4 cur{{Dd, Ds, Id, Is}}, other;
+    for (int k = 0; k < 4; k++) { alt[k].resize(npix); other.p[k] = alt[k].data(); }
+    auto swap = [&] { std::swap(cur, other); };
+    if (stages & 1) {
+        rm_host_launch_blocks(k_spatial_clamp, dim3((w + kClW - 1) / kClW, (h + kClH - 1) / kClH, 4), dim3(kClW, kClH), cur, other, w, h);
+        swap();
+    }
+    if (stages & 2) {
+        std::vector<float4> pm(npix), ns(npix);
+        std::vector<float> op(npix);
+        FilterG F{pm.data(), ns.data(), op.data()};
+        rm_host_launch(k_filter_pack, dim3((npix + 255) / 256), dim3(256), G, F, npix);
+        const dim3 block(32, 4);
+        rm_host_launch(k_filter_var, dim3((w + 31) / 32, (h + 3) / 4, 4), block, cur, other, w, h);
+        swap();
+        for (int step = 1; step <= 16; step *= 2) {
+            rm_host_launch(k_atrous, dim3((w + 31) / 32, (h + 3) / 4, 1), block, G, F, cur, other, w, h, step);
+            swap();
+        }
+    }
+    if (cur.p[0] != Dd)                                                     // an odd number of passes: the result sits in the scratch set
+        for (int k = 0; k < 4; k++) std::memcpy(other.p[k], cur.p[k], size_t(npix) * sizeof(RmRadiance));
+}
+
+// Photo::postProcessing without depth of field (rm_postprocess): shade -> [bloom] -> gamma -> [FXAA]
+void doh_postprocess(const RmHitInfo *G, const RmRadiance *Dd, const RmRadiance *Ds, const RmRadiance *Id, const RmRadiance *Is, int w, int h,
+                     float exposure, int options, float *rgb_out) {
+    const int npix = w * h;
+    const bool bloom = (options & 256) != 0;
+    std::vector<float> rgb(size_t(npix) * 3), tmp(size_t(npix) * 3);
+    rm_host_launch(k_shade_gamma, dim3((npix + 255) / 256), dim3(256), G, Dd, Ds, Id, Is, npix, exposure, options, !bloom, rgb.data());
+    if (bloom) {
+        std::vector<float> glow[2] = {std::vector<float>(size_t(npix) * 3), std::vector<float>(size_t(npix) * 3)};
+        rm_host_launch(k_bloom_bright, dim3((npix + 255) / 256), dim3(256), (const float *)rgb.data(), glow[0].data(), npix);
+        int cur = 0;
+        for (int step = 1; step <= 16; step *= 2, cur ^= 1)
+            rm_host_launch(k_bloom_pass, dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), (const float *)glow[cur].data(), glow[cur ^ 1].data(), rgb.data(), w, h, step);
+        rm_host_launch(k_gamma, dim3((npix + 255) / 256), dim3(256), rgb.data(), npix);
+    }
+    if (options & 512) { doh_fxaa(rgb.data(), tmp.data(), w, h); rgb.swap(tmp); }
+    std::memcpy(rgb_out, rgb.data(), rgb.size() * sizeof(float));
 }
 
 }
