@@ -20,9 +20,13 @@ struct TraceCounters { unsigned long long rays, box, tri; };
 
 // One 256-bit read-only load (sm_100 LDG.E.256): half the L1 lookups of two 128-bit loads.  p is 32-byte aligned.
 RM_DI void ldg256(const float4 *p, float4 &a, float4 &b) {
+#ifdef __CUDA_ARCH__
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
+#else
+    a = p[0]; b = p[1];          // the headers compiled as host code (tests/tools/cuda_on_host.h)
+#endif
 }
 
 // A reference to a BVH child: inner node index u >= 1, or a leaf encoded as ~(faceL<<4 | count).

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene
     flush_counters(cnt, counters, COUNT);
 }
 
+#ifdef __CUDACC__       // (the launch syntax below is nvcc's; tests/tools/cuda_on_host.h compiles this header with g++)
 // Launch geometry of every trace kernel: kTraceCtasPerSm CTAs per SM, stack sized by the tree depth.
 template <class Job>
 inline void launch_trace(const DevScene &S, int stack_levels, bool count, int grid, cudaStream_t st, const Job &job, int n_host, const int *n_dev,
@@ -114,5 +115,6 @@ inline void launch_trace(const DevScene &S, int stack_levels, bool count, int gr
     if (count) k_trace<Job, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
     else k_trace<Job, false><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
 }
+#endif
 
 } // namespace rm

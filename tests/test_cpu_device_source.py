@@ -4,7 +4,8 @@ functions against the golden vectors the compiled reference produced (tests/gold
 checks the same functions where they really run; this file keeps an arithmetic regression from slipping through a CPU-only
 run.  The image-space kernels (FXAA, spatial clamp, filterVar + a-trous, shade / bloom / gamma) are run whole: launched on the
 host thread by thread with the launch shapes of rm_render.cu - kernels with a shared-memory tile as real threads meeting at a
-barrier - against tests/golden/post_vectors.npz.  Bars: bit-equal for the arithmetic that is + - * / sqrt only; a few ulp where libm (powf, atan2f, acosf, sinf) is
+barrier - against tests/golden/post_vectors.npz; and the traversal engine runs as one emulated warp (32 real threads meeting at
+every vote and shuffle) against the golden primary hits, closest hits and occlusion answers.  Bars: bit-equal for the arithmetic that is + - * / sqrt only; a few ulp where libm (powf, atan2f, acosf, sinf) is
 involved - on the host that is glibc, the reference's own libm, and in this container every one of these comparisons comes
 out bit-equal (0 ulp)."""
 import ctypes as C
@@ -196,3 +197,43 @@ def test_shade_bloom_gamma_fxaa_kernels(doh, name):
         assert np.array_equal(np.isnan(out), np.isnan(want)), opts
         ok = np.isfinite(want)
         assert np.abs(out[ok] - want[ok]).max() <= 2e-6, (opts, np.abs(out[ok] - want[ok]).max())
+
+
+# --------------------------------------------------------------------------- the traversal engine itself, as one emulated warp
+def _scene(name):
+    return {"cornell": lambda: scenes.cornell_box(64, 64, 0), "hf": lambda: scenes.heightfield_scene(3000, 96, 54, 0, with_sky=True),
+            "tex": lambda: scenes.texture_heavy(6000, 96, 54, 0, tex_size=32, n_materials=8)}[name]()
+
+
+@pytest.mark.parametrize("name", ["cornell", "hf", "tex"])
+def test_trace_engine_as_an_emulated_warp(doh, name):
+    """trace_engine (dev_trace.cuh) - persistent warp, ballot / popc lane refill, vote between the inner and the leaf step,
+    per-lane stack, alpha cut-out re-traces - run as 32 real threads that meet at every __ballot_sync / __shfl_sync, on the
+    reference's own tree: primary hits, closest hits and occlusion answers equal the compiled reference's golden vectors,
+    triangle index for triangle index and t to the bit (the north star's first correctness bar, here without a GPU)"""
+    from raym0nade_b200.ctypes_defs import RmRenderArgs
+    L = doh
+    vp, i32 = C.c_void_p, C.c_int32
+    L.doh_trace_primary.argtypes = [C.POINTER(RmSceneDesc), C.POINTER(RmRenderArgs), vp, vp, vp]
+    L.doh_trace_closest.argtypes = [C.POINTER(RmSceneDesc), i32, vp, vp, vp, vp]
+    L.doh_trace_occluded.argtypes = [C.POINTER(RmSceneDesc), i32, vp, vp, vp, vp]
+    scene, args = _scene(name)
+    m = Model(scene)
+    a = args.to_c()
+    n = args.width * args.height
+    tri, t, counts = np.full(n, -7, np.int32), np.zeros(n, np.float32), np.zeros(3, np.uint64)
+    L.doh_trace_primary(C.byref(m.desc), C.byref(a), _p(tri), _p(t), _p(counts))
+    assert np.array_equal(tri, G[name + "_tri"])
+    assert same(t, G[name + "_t"])
+    rays, box, tests = (int(c) for c in counts)
+    assert rays >= n and box > rays and tests > 0              # cut-out re-traces count as rays again
+    if name == "tex":
+        assert rays > n                                        # the cut-out materials of this scene were re-traced through
+    o, d = _f32(G[name + "_rays_o"]), _f32(G[name + "_rays_d"])
+    ctri, ct = np.zeros(len(o), np.int32), np.zeros(len(o), np.float32)
+    L.doh_trace_closest(C.byref(m.desc), len(o), _p(o), _p(d), _p(ctri), _p(ct))
+    assert np.array_equal(ctri, G[name + "_rays_tri"]) and same(ct, G[name + "_rays_t"])
+    aim = _f32(G[name + "_rays_aim"])
+    occ = np.zeros(len(o), np.uint8)
+    L.doh_trace_occluded(C.byref(m.desc), len(o), _p(o), _p(d), _p(aim), _p(occ))
+    assert np.array_equal(occ, G[name + "_rays_occ"])

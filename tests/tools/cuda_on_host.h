@@ -26,6 +26,7 @@ static thread_local dim3 blockDim, gridDim;
 #undef __shared__
 #endif
 #define __shared__ static
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -82,9 +83,59 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 
 // GPU-only primitives: present for the parser, never executed on the host
 [[noreturn]] static inline void rm_gpu_only() { std::abort(); }
-static inline unsigned __ballot_sync(unsigned, int) { rm_gpu_only(); }
+// One warp = 32 real threads in lock step wherever they vote or shuffle.  Full-mask collectives only (all the engine uses):
+// every collective call is one barrier; results travel through three rotating slots so that a fast lane's next call can
+// never overwrite what a slow lane has not read yet.  rm_host_launch_warp sets it up.
+struct RmWarp {
+    RmBlockBarrier barrier;
+    std::atomic<unsigned> votes[3];
+    uint64_t slots[3][32];
+};
+static RmWarp *rm_warp = nullptr;
+static thread_local unsigned rm_warp_votes = 0, rm_warp_shuffles = 0;      // per-lane call counts: the rotation index of each kind
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    if (!rm_warp || mask != 0xffffffffu) rm_gpu_only();
+    const unsigned k = rm_warp_votes++ % 3, lane = threadIdx.x & 31;
+    if (pred) rm_warp->votes[k].fetch_or(1u << lane);
+    rm_warp->barrier.arrive(false);
+    const unsigned v = rm_warp->votes[k].load();
+    if (lane == 0) rm_warp->votes[(k + 2) % 3].store(0);      // the slot of the vote after next: nobody is in it yet, or still
+    return v;
+}
+template <class T> static inline T __shfl_sync(unsigned mask, T value, int src, int = 32) {
+    static_assert(sizeof(T) <= 8, "shuffle of a 32- or 64-bit value");
+    if (!rm_warp || mask != 0xffffffffu) rm_gpu_only();
+    const unsigned k = rm_warp_shuffles++ % 3, lane = threadIdx.x & 31;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &value, sizeof(T));
+    rm_warp->slots[k][lane] = bits;
+    rm_warp->barrier.arrive(false);
+    T out;
+    std::memcpy(&out, &rm_warp->slots[k][src & 31], sizeof(T));
+    return out;
+}
 static inline unsigned __activemask() { rm_gpu_only(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { rm_gpu_only(); }
+
+// `body(lane)` on the 32 lanes of one emulated warp
+template <class Body>
+static void rm_host_launch_warp(Body body) {
+    RmWarp warp;
+    for (auto &v : warp.votes) v.store(0);
+    warp.barrier.expected = 32;
+    rm_warp = &warp;
+    std::vector<std::thread> lanes;
+    for (unsigned lane = 0; lane < 32; lane++)
+        lanes.emplace_back([&, lane] {
+            gridDim = dim3(1); blockDim = dim3(32);
+            blockIdx = {0, 0, 0}; threadIdx = {lane, 0, 0};
+            rm_warp_votes = rm_warp_shuffles = 0;
+            body(int(lane));
+            warp.barrier.arrive(true);
+        });
+    for (auto &t : lanes) t.join();
+    rm_warp = nullptr;
+}
 static inline void __syncthreads() { if (rm_block_barrier) rm_block_barrier->arrive(false); else rm_gpu_only(); }
 
 template <class Kernel, class... Args>
@@ -106,10 +157,9 @@ static void rm_host_launch_blocks(Kernel kernel, dim3 grid, dim3 block, Args... 
     }
     rm_block_barrier = nullptr;
 }
-template <class T> static inline T __shfl_sync(unsigned, T, int, int = 32) { rm_gpu_only(); }
 template <class T> static inline T __shfl_down_sync(unsigned, T, unsigned, int = 32) { rm_gpu_only(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T, int, int = 32) { rm_gpu_only(); }
-template <class T, class U> static inline T atomicAdd(T *, U) { rm_gpu_only(); }
+template <class T, class U> static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, T(v), __ATOMIC_SEQ_CST); }
 template <class T, class U> static inline T atomicMax(T *, U) { rm_gpu_only(); }
 template <class T, class U> static inline T atomicExch(T *, U) { rm_gpu_only(); }
 template <class T, class U, class W> static inline T atomicCAS(T *, U, W) { rm_gpu_only(); }

@@ -12,6 +12,9 @@ namespace rm { struct Philox4; static Philox4 philox_block(uint32_t c0, uint32_t
 namespace rm { static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); } }
 
 #include "kernels_post.cuh"
+#undef __shared__
+#define __shared__                   // k_trace's `extern __shared__` stack: declared, never defined - the engine is called directly
+#include "kernels_trace.cuh"
 
 #include <vector>
 
@@ -26,6 +29,8 @@ struct HostScene {
     std::vector<DevTexture> textures;
     std::vector<uint8_t> texels;
     std::vector<DevMaterial> materials;
+    std::vector<float4> nodes, tri, shade;
+    int levels = 2;                          // traversal stack entries = tree depth (rm_scene_upload)
     float lut[256];
     DevScene S{};
     explicit HostScene(const RmSceneDesc *sc) {
@@ -57,12 +62,62 @@ struct HostScene {
             d._pad = 0;
         }
         for (int k = 0; k < 256; k++) lut[k] = float(k) / 255.0f;
+        // traversal: node pairs as they are (padded to an even count), the 48-byte triangle records and the 112-byte shading
+        // records of k_pack_faces (rm_api.cu), restated here with the same fp32 operations
+        nodes.assign((size_t(sc->n_nodes + 2) & ~size_t(1)) * 2, make_float4(0, 0, 0, 0));
+        std::memcpy(nodes.data(), sc->nodes, sizeof(RmBvhNode) * sc->n_nodes);
+        tri.resize(size_t(sc->n_faces) * kTriStride);
+        shade.resize(size_t(sc->n_faces) * 7);
+        bool any_cutout = false;
+        for (int i = 0; i < sc->n_faces; i++) {
+            const float *v = sc->positions + size_t(i) * 9, *u = sc->uvs + size_t(i) * 6, *nn = sc->normals + size_t(i) * 9;
+            const int m = sc->face_material[i];
+            const V3 e1 = mk3(fsub(v[3], v[0]), fsub(v[4], v[1]), fsub(v[5], v[2])), e2 = mk3(fsub(v[6], v[0]), fsub(v[7], v[1]), fsub(v[8], v[2]));
+            float4 *t = &tri[size_t(i) * kTriStride];
+            t[0] = make_float4(v[0], v[1], v[2], e1.x);
+            t[1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+            t[2] = make_float4(e2.z, length(e1), materials[m].cutout ? 1.0f : 0.0f, 0.0f);
+            any_cutout |= materials[m].cutout != 0;
+            float4 *s = &shade[size_t(i) * 7];
+            s[0] = make_float4(v[0], v[1], v[2], v[3]);
+            s[1] = make_float4(v[4], v[5], v[6], v[7]);
+            s[2] = make_float4(v[8], u[0], u[1], u[2]);
+            s[3] = make_float4(u[3], u[4], u[5], nn[0]);
+            s[4] = make_float4(nn[1], nn[2], nn[3], nn[4]);
+            s[5] = make_float4(nn[5], nn[6], nn[7], nn[8]);
+            s[6] = make_float4(__int_as_float(m), 0.0f, 0.0f, 0.0f);
+        }
+        S.nodes = nodes.data(); S.tri = tri.data(); S.shade = shade.data();
+        S.n_faces = sc->n_faces; S.n_nodes = sc->n_nodes;
+        S.any_cutout = any_cutout ? 1 : 0;
+        S.root_is_leaf = sc->nodes[1].faceR != 0;
+        S.explicit_children = 0; S.face_map = nullptr;
+        levels = 1;
+        while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
+        levels = std::min(std::max(levels, 2), 40);
         S.textures = textures.data(); S.texels = texels.data(); S.materials = materials.data(); S.div255 = lut;
         S.n_materials = sc->n_materials;
         S.sky_width = sc->sky_width; S.sky_height = sc->sky_height; S.sky_data = sc->sky_data; S.sky_cdf = sc->sky_cdf;
     }
 };
 }  // namespace
+
+template <class Job>
+void run_engine(const HostScene &H, Job job, int n, unsigned long long *out_counts) {
+    int cursor = 0;
+    std::vector<int2> stack(size_t(H.levels) * 32);
+    TraceTune tune{28, 1, 1, H.levels};
+    unsigned long long total[3] = {0, 0, 0};
+    std::mutex m;
+    rm_host_launch_warp([&](int lane) {
+        TraceCounters cnt = {0, 0, 0};
+        Job mine = job;
+        trace_engine<Job, true>(H.S, mine, n, &cursor, stack.data() + lane, 32, cnt, tune);
+        std::lock_guard<std::mutex> l(m);
+        total[0] += cnt.rays; total[1] += cnt.box; total[2] += cnt.tri;
+    });
+    if (out_counts) for (int k = 0; k < 3; k++) out_counts[k] = total[k];
+}
 
 extern "C" {
 
@@ -184,6 +239,34 @@ void doh_postprocess(const RmHitInfo *G, const RmRadiance *Dd, const RmRadiance 
     }
     if (options & 512) { doh_fxaa(rgb.data(), tmp.data(), w, h); rgb.swap(tmp); }
     std::memcpy(rgb_out, rgb.data(), rgb.size() * sizeof(float));
+}
+
+// ---- the traversal engine itself: one emulated warp (32 real threads voting and shuffling through cuda_on_host.h) pulls all
+// the rays from the cursor, exactly as each warp of k_trace does on the device.  out_counts = {rays, box tests, triangle tests}.
+// rm_trace_primary: the primary ray of every pixel as renderPixel forms it + Model::rayHit
+void doh_trace_primary(const RmSceneDesc *sc, const RmRenderArgs *a, int32_t *tri_idx, float *t, unsigned long long *counts) {
+    HostScene H(sc);
+    PrimaryJob job;
+    job.A.position = ld(a->position); job.A.direction = ld(a->direction); job.A.up = ld(a->up); job.A.right = ld(a->right);
+    job.A.accuracy = a->accuracy; job.A.exposure = a->exposure; job.A.P_Direct = a->P_Direct;
+    job.A.width = a->width; job.A.height = a->height; job.A.spp = a->spp;
+    job.tiles_x = (a->width + 7) / 8;
+    job.tri_idx = tri_idx; job.t_out = t;
+    run_engine(H, job, job.tiles_x * ((a->height + 3) / 4) * 32, counts);
+}
+
+// rm_trace_closest / rm_trace_occluded: Model::rayHit / rayHit_test over a list of rays
+void doh_trace_closest(const RmSceneDesc *sc, int n, const float *org, const float *dir, int32_t *tri_idx, float *t) {
+    HostScene H(sc);
+    ClosestJob job;
+    job.org = org; job.dir = dir; job.aim_in = nullptr; job.tri_idx = tri_idx; job.t_out = t;
+    run_engine(H, job, n, nullptr);
+}
+void doh_trace_occluded(const RmSceneDesc *sc, int n, const float *org, const float *dir, const float *aim, uint8_t *out) {
+    HostScene H(sc);
+    OccludedJob job;
+    job.org = org; job.dir = dir; job.aim_in = aim; job.out = out;
+    run_engine(H, job, n, nullptr);
 }
 
 }
