@@ -33,7 +33,9 @@ def doh(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("doh") / "libdoh.so")
     cmd = [cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread", "-I", CUDA_INC, "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "raym0nade_b200", "csrc"), "-I", os.path.join(ROOT, "tests", "tools"),
-           os.path.join(ROOT, "tests", "tools", "device_on_host.cpp"), "-o", out]
+           os.path.join(ROOT, "tests", "tools", "device_on_host.cpp"),
+           os.path.join(ROOT, "raym0nade_b200", "csrc", "fast_bvh.cpp"), os.path.join(ROOT, "raym0nade_b200", "csrc", "rm_error.cpp"),      # the secondary-ray tree builder, as it is
+           "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     L = C.CDLL(out)
@@ -236,4 +238,40 @@ def test_trace_engine_as_an_emulated_warp(doh, name):
     aim = _f32(G[name + "_rays_aim"])
     occ = np.zeros(len(o), np.uint8)
     L.doh_trace_occluded(C.byref(m.desc), len(o), _p(o), _p(d), _p(aim), _p(occ))
+    assert np.array_equal(occ, G[name + "_rays_occ"])
+
+
+@pytest.mark.parametrize("name", ["cornell", "hf", "tex"])
+@pytest.mark.parametrize("smem_levels", [14, 3])
+def test_secondary_ray_tree_finds_the_reference_hits(doh, name, smem_levels):
+    """The estimator's bounce and shadow rays traverse the library's second tree (fast_bvh.cpp: binned SAH, leaves <= 3, explicit
+    child blocks, its own triangle order).  Same box test, same triangle test, same engine: the closest accepted hit is the
+    reference's - t to the bit, the same triangle unless two triangles tie at that t - and so is every occlusion answer.
+    smem_levels 14 is the context's setting; 3 forces deferred children into the engine's local spill array."""
+    L = doh
+    vp, i32 = C.c_void_p, C.c_int32
+    L.doh_trace_closest_secondary.argtypes = [C.POINTER(RmSceneDesc), i32, vp, vp, vp, vp, i32, vp]
+    L.doh_trace_occluded_secondary.argtypes = [C.POINTER(RmSceneDesc), i32, vp, vp, vp, vp, i32]
+    scene, _ = _scene(name)
+    m = Model(scene)
+    o, d = _f32(G[name + "_rays_o"]), _f32(G[name + "_rays_d"])
+    tri, t, shape = np.zeros(len(o), np.int32), np.zeros(len(o), np.float32), np.zeros(4, np.int32)
+    assert L.doh_trace_closest_secondary(C.byref(m.desc), len(o), _p(o), _p(d), _p(tri), _p(t), smem_levels, _p(shape)) == 0
+    assert same(t, G[name + "_rays_t"])
+    differ = tri != G[name + "_rays_tri"]
+    assert differ.mean() < 0.01                                # only exact ties may name another triangle of the same surface point
+    if differ.any():
+        pos = np.float32(scene.positions)[m.permutation()]
+        for i in np.nonzero(differ)[0]:                        # both triangles contain the hit point: re-test the other one on the host
+            assert tri[i] >= 0 and G[name + "_rays_tri"][i] >= 0
+            hit = o[i].astype(np.float64) + d[i].astype(np.float64) * float(t[i])
+            for f in (tri[i], G[name + "_rays_tri"][i]):
+                v = pos[f].astype(np.float64)
+                nrm = np.cross(v[1] - v[0], v[2] - v[0])
+                assert abs(np.dot(hit - v[0], nrm)) <= 1e-3 * np.linalg.norm(nrm) * (1.0 + np.abs(hit).max())
+    if name != "cornell":
+        assert shape[1] > 3                                    # deeper than the small stack: the spill array was really in play
+    aim = _f32(G[name + "_rays_aim"])
+    occ = np.zeros(len(o), np.uint8)
+    assert L.doh_trace_occluded_secondary(C.byref(m.desc), len(o), _p(o), _p(d), _p(aim), _p(occ), smem_levels) == 0
     assert np.array_equal(occ, G[name + "_rays_occ"])

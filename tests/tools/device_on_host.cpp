@@ -18,6 +18,9 @@ namespace rm { static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2
 
 #include <vector>
 
+// the secondary-ray tree builder of the product (raym0nade_b200/csrc/fast_bvh.cpp, compiled into this test library as it is)
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
+
 using namespace rm;
 
 namespace {
@@ -31,6 +34,25 @@ struct HostScene {
     std::vector<DevMaterial> materials;
     std::vector<float4> nodes, tri, shade;
     int levels = 2;                          // traversal stack entries = tree depth (rm_scene_upload)
+    std::vector<RmBvhNode> fast_nodes;
+    std::vector<int32_t> fast_order;
+    std::vector<float4> fast_tri;
+    // scene_fast of rm_scene_upload: the secondary-ray tree (pair blocks, explicit children), the triangle records in the
+    // builder's order, face_map back to the reference order; depth cap 22, leaves <= 3 as the context's defaults
+    bool use_secondary_tree(const RmSceneDesc *sc, int depth_cap = 22, int leaf_max = 3) {
+        int depth = 0;
+        if (rm_build_fast_bvh(sc->positions, sc->n_faces, depth_cap, leaf_max, fast_nodes, fast_order, &depth) != RM_OK) return false;
+        fast_tri.resize(size_t(sc->n_faces) * kTriStride);
+        for (int i = 0; i < sc->n_faces; i++)                      // k_permute_tris
+            for (int k = 0; k < kTriStride; k++) fast_tri[size_t(i) * kTriStride + k] = tri[size_t(fast_order[i]) * kTriStride + k];
+        S.nodes = reinterpret_cast<const float4 *>(fast_nodes.data());
+        S.tri = fast_tri.data();
+        S.face_map = fast_order.data();
+        S.explicit_children = 1;
+        S.root_is_leaf = fast_nodes[1].faceR != 0;
+        levels = std::min(std::max(depth, 2), 40);
+        return true;
+    }
     float lut[256];
     DevScene S{};
     explicit HostScene(const RmSceneDesc *sc) {
@@ -103,10 +125,10 @@ struct HostScene {
 }  // namespace
 
 template <class Job>
-void run_engine(const HostScene &H, Job job, int n, unsigned long long *out_counts) {
+void run_engine(const HostScene &H, Job job, int n, unsigned long long *out_counts, int smem_levels = 0, int w_leaf = 1) {
     int cursor = 0;
-    std::vector<int2> stack(size_t(H.levels) * 32);
-    TraceTune tune{28, 1, 1, H.levels};
+    TraceTune tune{28, 1, w_leaf, std::min(H.levels, smem_levels > 0 ? smem_levels : H.levels)};      // launch_trace's clamp
+    std::vector<int2> stack(size_t(tune.smem_levels) * 32);
     unsigned long long total[3] = {0, 0, 0};
     std::mutex m;
     rm_host_launch_warp([&](int lane) {
@@ -267,6 +289,27 @@ void doh_trace_occluded(const RmSceneDesc *sc, int n, const float *org, const fl
     OccludedJob job;
     job.org = org; job.dir = dir; job.aim_in = aim; job.out = out;
     run_engine(H, job, n, nullptr);
+}
+
+// The same per-ray seam through the SECONDARY-RAY tree (what the estimator's bounce and shadow rays traverse): tune_fast of
+// the context - vote weight 2 for the leaf step, 14 stack entries in "shared memory", deeper ones in the local spill array.
+int doh_trace_closest_secondary(const RmSceneDesc *sc, int n, const float *org, const float *dir, int32_t *tri_idx, float *t, int smem_levels,
+                                int32_t *shape4) {
+    HostScene H(sc);
+    if (!H.use_secondary_tree(sc)) return -1;
+    ClosestJob job;
+    job.org = org; job.dir = dir; job.aim_in = nullptr; job.tri_idx = tri_idx; job.t_out = t;
+    run_engine(H, job, n, nullptr, smem_levels, 2);
+    if (shape4) { shape4[0] = int32_t(H.fast_nodes.size() / 2); shape4[1] = H.levels; shape4[2] = smem_levels; shape4[3] = H.S.root_is_leaf; }
+    return 0;
+}
+int doh_trace_occluded_secondary(const RmSceneDesc *sc, int n, const float *org, const float *dir, const float *aim, uint8_t *out, int smem_levels) {
+    HostScene H(sc);
+    if (!H.use_secondary_tree(sc)) return -1;
+    OccludedJob job;
+    job.org = org; job.dir = dir; job.aim_in = aim; job.out = out;
+    run_engine(H, job, n, nullptr, smem_levels, 2);
+    return 0;
 }
 
 }
