@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include <cuda_runtime.h>            // float2 / float4 / int2 / dim3 / make_float4 ... (host-includable)
 
@@ -159,7 +160,15 @@ static void rm_host_launch_blocks(Kernel kernel, dim3 grid, dim3 block, Args... 
 }
 template <class T> static inline T __shfl_down_sync(unsigned, T, unsigned, int = 32) { rm_gpu_only(); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T, int, int = 32) { rm_gpu_only(); }
-template <class T, class U> static inline T atomicAdd(T *p, U v) { return __atomic_fetch_add(p, T(v), __ATOMIC_SEQ_CST); }
+template <class T, class U> static inline T atomicAdd(T *p, U v) {
+    if constexpr (std::is_floating_point<T>::value) {          // fp32 atomic add: compare-and-swap on the bits
+        T seen;
+        __atomic_load(p, &seen, __ATOMIC_SEQ_CST);
+        for (;;) { T want = seen + T(v); if (__atomic_compare_exchange(p, &seen, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return seen; }
+    } else return __atomic_fetch_add(p, T(v), __ATOMIC_SEQ_CST);
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> static inline T __shfl_up_sync(unsigned, T, unsigned, int = 32) { rm_gpu_only(); }
 template <class T, class U> static inline T atomicMax(T *, U) { rm_gpu_only(); }
 template <class T, class U> static inline T atomicExch(T *, U) { rm_gpu_only(); }
 template <class T, class U, class W> static inline T atomicCAS(T *, U, W) { rm_gpu_only(); }

@@ -15,6 +15,9 @@ namespace rm { static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2
 #undef __shared__
 #define __shared__                   // k_trace's `extern __shared__` stack: declared, never defined - the engine is called directly
 #include "kernels_trace.cuh"
+#undef __shared__
+#define __shared__ static
+#include "kernels_render.cuh"
 
 #include <vector>
 
@@ -310,6 +313,20 @@ int doh_trace_occluded_secondary(const RmSceneDesc *sc, int n, const float *org,
     job.org = org; job.dir = dir; job.aim_in = aim; job.out = out;
     run_engine(H, job, n, nullptr, smem_levels, 2);
     return 0;
+}
+
+// rm_gbuffer: k_gbuffer over the primary hits {tri_idx, t} - getHitInfo with ray differentials, normal mapping, trilinear
+// material fetches, sky emission on a miss, the red nudge.  gbuffer = what the samplers read; sav_base = the un-nudged base colour.
+void doh_gbuffer(const RmSceneDesc *sc, const RmRenderArgs *a, const int32_t *tri_idx, const float *t, RmHitInfo *gbuffer, float *sav_base, int32_t *n_ind) {
+    HostScene H(sc);
+    DevArgs A;
+    A.position = ld(a->position); A.direction = ld(a->direction); A.up = ld(a->up); A.right = ld(a->right);
+    A.accuracy = a->accuracy; A.exposure = a->exposure; A.P_Direct = a->P_Direct; A.width = a->width; A.height = a->height; A.spp = a->spp;
+    const int npix = a->width * a->height;
+    FrameBuffers Fb{gbuffer, sav_base, n_ind, nullptr};
+    int glass = 0;
+    const int spp_d = int(float(a->spp) * a->P_Direct);                    // src/render.cpp:500
+    rm_host_launch(k_gbuffer, dim3((npix + 127) / 128), dim3(128), H.S, A, (const int *)tri_idx, t, Fb, spp_d, a->spp - spp_d, &glass);
 }
 
 }
