@@ -306,3 +306,13 @@ def test_gbuffer_kernel(doh, name):
     if name == "cornell":
         assert (d[:, 0] != 0).any()                            # grey walls: the nudge is in play
     assert (n_ind == 0).all()                                  # spp 0: nothing to sample
+
+
+def test_radiance_split(doh):
+    """accum_split, the device's accumulateInwardRadiance: the projection of a sample's bsdf onto {white, base colour} that
+    separates demodulated diffuse from specular, with its three special cases (black light, black base, near-white base)"""
+    doh.doh_accumulate.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    base, s7 = _f32(G["acc_base"]), _f32(G["acc_s7"])
+    out = np.zeros((len(s7), 8), np.float32)
+    doh.doh_accumulate(len(s7), _p(base), _p(s7), _p(out))
+    assert same(out, G["acc_out"])

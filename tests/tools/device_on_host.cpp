@@ -329,4 +329,14 @@ void doh_gbuffer(const RmSceneDesc *sc, const RmRenderArgs *a, const int32_t *tr
     rm_host_launch(k_gbuffer, dim3((npix + 127) / 128), dim3(128), H.S, A, (const int *)tri_idx, t, Fb, spp_d, a->spp - spp_d, &glass);
 }
 
+// accumulateInwardRadiance (src/image.cpp:615-659) as the shading kernels apply it to one sample: accum_split into a zeroed
+// {diffuse, specular} pair of {rgb, second moment}; s7 = {bsdfPdf rgb, light rgb, weight}
+void doh_accumulate(int64_t n, const float *base, const float *s7, float *out) {
+    for (int64_t i = 0; i < n; i++) {
+        float *o = out + i * 8;
+        for (int k = 0; k < 8; k++) o[k] = 0.0f;
+        accum_split(o, o + 4, ld(base + i * 3), ld(s7 + i * 7), ld(s7 + i * 7 + 3), s7[i * 7 + 6]);
+    }
+}
+
 }
