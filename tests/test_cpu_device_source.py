@@ -316,3 +316,44 @@ def test_radiance_split(doh):
     out = np.zeros((len(s7), 8), np.float32)
     doh.doh_accumulate(len(s7), _p(base), _p(s7), _p(out))
     assert same(out, G["acc_out"])
+
+
+# --------------------------------------------------------------------------- next-event estimation, sample by sample
+@pytest.mark.parametrize("secondary_tree", [0, 1])
+@pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
+def test_direct_light_samples_replay_the_reference(doh, ref, which, secondary_tree):
+    """One direct-light sample per pixel drawn by the device code (light-object pick by lum(bsdf)*power/d^2, face pick from the
+    area*luminance CDF, uniform point + cosine rejection - or an environment texel through the guided CDF search -, BSDF
+    evaluation and clamp, then rayHit_test on the shadow ray through the emulated engine) against the reference's own
+    sampleDirectLight fed the same 32-bit draws through its pre-loaded mt19937 (oracle/ref_harness.cpp): every pixel agrees on
+    whether a sample arrives, and every arriving sample equals the reference's LightSample to the bit."""
+    from raym0nade_b200 import rng
+    from raym0nade_b200.ctypes_defs import RmRenderArgs
+    doh.doh_replay_direct.argtypes = [C.POINTER(RmSceneDesc), C.POINTER(RmRenderArgs), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32]
+    if which == "cornell":
+        scene, args = scenes.cornell_box(40, 40, 1)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(8_000, 48, 27, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(30_000, 48, 27)
+    R = ref.RefScene(scene)
+    m = Model(scene)
+    g = np.ascontiguousarray(R.gbuffer(args, threads=4))
+    n = args.width * args.height
+    out7, status = np.zeros((n, 7), np.float32), np.zeros(n, np.uint8)
+    a = args.to_c()
+    seed = 77
+    assert doh.doh_replay_direct(C.byref(m.desc), C.byref(a), _p(g), seed, _p(out7), _p(status), secondary_tree) == 0
+    arrived = 0
+    for p in range(n):
+        if not np.isfinite(g[p]["position"]).any() or np.linalg.norm(g[p]["emission"]) > 0:
+            assert status[p] == 0                              # a miss or an emissive surface draws nothing (src/render.cpp:425-437)
+            continue
+        s, used = R.replay_direct(args, g[p], rng.stream_u32(seed, p, 0, rng.STREAM_DIRECT, 624))
+        assert used < 624
+        assert (s is not None) == (status[p] == 2), p
+        if s is not None:
+            assert np.array_equal(s.view(np.uint32), out7[p].view(np.uint32)), (p, s, out7[p])
+            arrived += 1
+    assert arrived > n // 4 and (status == 1).sum() > 20       # lit and shadowed pixels both occur
+    R.close()

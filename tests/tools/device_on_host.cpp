@@ -36,6 +36,9 @@ struct HostScene {
     std::vector<uint8_t> texels;
     std::vector<DevMaterial> materials;
     std::vector<float4> nodes, tri, shade;
+    std::vector<DevLight> lights;
+    std::vector<float> lpos, lnrm, lcdf;
+    std::vector<int32_t> guide;
     int levels = 2;                          // traversal stack entries = tree depth (rm_scene_upload)
     std::vector<RmBvhNode> fast_nodes;
     std::vector<int32_t> fast_order;
@@ -120,6 +123,25 @@ struct HostScene {
         levels = 1;
         while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
         levels = std::min(std::max(levels, 2), 40);
+        // lights and the sky-CDF brackets, as rm_scene_upload stages them
+        lights.resize(std::max(sc->n_lights, 1));
+        for (int i = 0; i < sc->n_lights; i++) {
+            const RmLightDesc &L = sc->lights[i];
+            DevLight &d = lights[i];
+            for (int k = 0; k < 3; k++) { d.center[k] = L.center[k]; d.color[k] = L.color[k]; }
+            d.power = L.power; d.n_faces = L.n_faces; d.face_offset = int32_t(lcdf.size());
+            lpos.insert(lpos.end(), L.face_positions, L.face_positions + size_t(L.n_faces) * 9);
+            lnrm.insert(lnrm.end(), L.face_normals, L.face_normals + size_t(L.n_faces) * 9);
+            lcdf.insert(lcdf.end(), L.face_cdf, L.face_cdf + L.n_faces);
+        }
+        guide.assign(kSkyGuide + 1, 0);
+        const size_t nsky = size_t(sc->sky_width) * sc->sky_height;
+        if (nsky) {
+            const float *cdf = sc->sky_cdf, tot = cdf[nsky - 1];
+            for (int j = 0; j <= kSkyGuide; j++) guide[j] = int32_t(std::lower_bound(cdf, cdf + nsky, tot * (float(j) / float(kSkyGuide))) - cdf);
+        }
+        S.lights = lights.data(); S.light_pos = lpos.data(); S.light_nrm = lnrm.data(); S.light_cdf = lcdf.data();
+        S.n_lights = sc->n_lights; S.sky_guide = guide.data();
         S.textures = textures.data(); S.texels = texels.data(); S.materials = materials.data(); S.div255 = lut;
         S.n_materials = sc->n_materials;
         S.sky_width = sc->sky_width; S.sky_height = sc->sky_height; S.sky_data = sc->sky_data; S.sky_cdf = sc->sky_cdf;
@@ -337,6 +359,49 @@ void doh_accumulate(int64_t n, const float *base, const float *s7, float *out) {
         for (int k = 0; k < 8; k++) o[k] = 0.0f;
         accum_split(o, o + 4, ld(base + i * 3), ld(s7 + i * 7), ld(s7 + i * 7 + 3), s7[i * 7 + 6]);
     }
+}
+
+// One direct-light sample per pixel (sample 0 of spp_direct = 1) exactly as k_direct_gen draws it - the pixel's surface
+// record from the G-buffer, the per-light weights, nee_sample on the pixel's own Philox stream - then Model::rayHit_test on
+// the shadow ray through the engine (ShadowJob over the items, on the reference's tree or the secondary-ray tree).
+// out7[p] = {bsdfPdf rgb, light rgb, weight}; status[p]: 0 = no sample (miss, emissive pixel, no light, rejected), 1 = drawn
+// but occluded, 2 = visible.
+int doh_replay_direct(const RmSceneDesc *sc, const RmRenderArgs *a, const RmHitInfo *gbuffer, unsigned long long seed, float *out7, uint8_t *status,
+                      int secondary_tree) {
+    HostScene H(sc);
+    const V3 cam = ld(a->position);
+    const int npix = a->width * a->height;
+    std::vector<ShadowItem> items(npix);
+    for (int p = 0; p < npix; p++) {
+        status[p] = 0;
+        NeeOut n;
+        n.valid = false;
+        Bsdf B;
+        B.s = load_hitinfo(gbuffer + p);
+        if (isfinite_any(B.s.position) && !(length(B.s.emission) > 0.0f)) {
+            B.inDir = -normalize(B.s.position - cam);
+            float lw[kMaxLights], total = 0.0f;
+            bool go = true;
+            if (H.S.sky_width == 0) { total = light_weights(H.S, B, lw); go = total != 0.0f; }
+            if (go) {
+                Rng gen;
+                gen.init(seed, unsigned(p), 0u, kStreamDirect);
+                n = nee_sample(H.S, B, gen, lw, total, 1);
+            }
+        }
+        if (!n.valid) { n.dir = splat3(0.0f); n.aim = CUDART_NAN_F; n.bsdf = n.light = splat3(0.0f); n.weight = 0.0f; }
+        else status[p] = 1;
+        write_shadow(&items[p], p | 0x80000000, B.s.position, n, n.bsdf, n.light, n.weight);
+        float *o = out7 + size_t(p) * 7;
+        o[0] = n.bsdf.x; o[1] = n.bsdf.y; o[2] = n.bsdf.z; o[3] = n.light.x; o[4] = n.light.y; o[5] = n.light.z; o[6] = n.weight;
+    }
+    if (secondary_tree && !H.use_secondary_tree(sc)) return -1;
+    ShadowJob job;
+    job.sq = items.data();
+    run_engine(H, job, npix, nullptr, secondary_tree ? 14 : 0, secondary_tree ? 2 : 1);
+    for (int p = 0; p < npix; p++)
+        if (status[p] == 1 && items[p].vis != 0.0f) status[p] = 2;
+    return 0;
 }
 
 }
