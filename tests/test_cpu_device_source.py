@@ -20,6 +20,8 @@ from raym0nade_b200 import scenes
 from raym0nade_b200.api import Model, RmSceneDesc
 from raym0nade_b200.ctypes_defs import HITINFO_DTYPE
 
+pytestmark = pytest.mark.timeout(600)          # the emulated warps and blocks are real threads meeting at barriers: never hang the suite
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
