@@ -359,3 +359,64 @@ def test_direct_light_samples_replay_the_reference(doh, ref, which, secondary_tr
             arrived += 1
     assert arrived > n // 4 and (status == 1).sum() > 20       # lit and shadowed pixels both occur
     R.close()
+
+
+# --------------------------------------------------------------------------- the direct-light kernels, launched as on the device
+def _calc_var(rad, var, exposure):
+    """calcVar of renderPixel (src/render.cpp:510-516), fp32"""
+    f32 = np.float32
+    rad = (rad * f32(exposure)).astype(f32)
+    var = (var * f32(exposure * exposure)).astype(f32)
+    var = var - ((rad[0] * rad[0] + rad[1] * rad[1]) + rad[2] * rad[2])
+    return rad, max(f32(var), f32(0))
+
+
+@pytest.mark.parametrize("which,spp,warp_per_pixel", [("cornell", 1, 0), ("glossy", 1, 0), ("sky", 3, 1), ("sky", 3, 0), ("cornell", 3, 0)])
+def test_direct_light_kernels_resolve_to_the_reference_planes(doh, ref, which, spp, warp_per_pixel):
+    """k_direct_gen (both mappings: a thread or a warp per pixel) -> ShadowJob through the engine -> k_accum_direct ->
+    k_finalise, launched block by block as real threads with a CTA barrier and a warp context per 32 lanes: the resolved
+    direct-diffuse and direct-specular planes equal what the reference's own sampleDirectLight / accumulateInwardRadiance /
+    calcVar give for the same draws - to the bit where the sample weights are formed identically (one sample per pixel, or an
+    environment-lit scene), to 2e-6 where the reference harness's 1/(fails+1) * 1/spp is the kernel's 1/(spp*(fails+1))"""
+    from raym0nade_b200 import rng
+    from raym0nade_b200.ctypes_defs import RADIANCE_DTYPE, RmRenderArgs
+    f32 = np.float32
+    doh.doh_direct_planes.argtypes = [C.POINTER(RmSceneDesc), C.POINTER(RmRenderArgs), C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p]
+    if which == "cornell":
+        scene, args = scenes.cornell_box(32, 32, 1)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(8_000, 40, 24, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(30_000, 40, 24)
+    R = ref.RefScene(scene)
+    m = Model(scene)
+    g = np.ascontiguousarray(R.gbuffer(args, threads=4))
+    n = args.width * args.height
+    Dd, Ds = np.zeros(n, RADIANCE_DTYPE), np.zeros(n, RADIANCE_DTYPE)
+    a = args.to_c()
+    seed = 91
+    items = doh.doh_direct_planes(C.byref(m.desc), C.byref(a), _p(g), seed, spp, warp_per_pixel, 0, _p(Dd), _p(Ds))
+    assert items > 0 and items % spp == 0                      # one contiguous block of spp items per sampled pixel
+    exact = spp == 1 or which == "sky"
+    lit = 0
+    for p in range(n):
+        acc = np.zeros(8, f32)
+        if np.isfinite(g[p]["position"]).any() and not np.linalg.norm(g[p]["emission"]) > 0:
+            for si in range(spp):
+                s, _ = R.replay_direct(args, g[p], rng.stream_u32(seed, p, si, rng.STREAM_DIRECT, 624))
+                if s is not None:
+                    s = s.copy()
+                    s[6] = f32(s[6]) * (f32(1.0) / f32(spp))           # mulWeight(samples, 1 / spp_direct), src/render.cpp:505
+                    acc = acc + ref.accumulate(g[p]["baseColor"][None], s[None])[0]
+        lit += bool(acc[:3].any())
+        for j, plane in enumerate((Dd, Ds)):
+            rad, var = _calc_var(acc[4 * j:4 * j + 3], acc[4 * j + 3], args.exposure)
+            if exact:
+                assert np.array_equal(rad.view(np.uint32), plane["radiance"][p].view(np.uint32)), (p, j, rad, plane["radiance"][p])
+                assert f32(var).view(np.uint32) == plane["Var"][p].view(np.uint32), (p, j)
+            else:
+                assert np.allclose(plane["radiance"][p], rad, rtol=2e-6, atol=1e-9), (p, j, rad, plane["radiance"][p])
+                assert abs(float(plane["Var"][p]) - float(var)) <= 1e-5 * (1.0 + abs(float(var))), (p, j)
+    assert lit > n // 5
+    R.close()

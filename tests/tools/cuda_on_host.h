@@ -29,6 +29,7 @@ static thread_local dim3 blockDim, gridDim;
 #define __shared__ static
 #include <atomic>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -92,11 +93,12 @@ struct RmWarp {
     std::atomic<unsigned> votes[3];
     uint64_t slots[3][32];
 };
-static RmWarp *rm_warp = nullptr;
+static thread_local RmWarp *rm_warp = nullptr;          // the warp this host thread is a lane of
 static thread_local unsigned rm_warp_votes = 0, rm_warp_shuffles = 0;      // per-lane call counts: the rotation index of each kind
+static inline unsigned rm_lane() { return (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u; }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
     if (!rm_warp || mask != 0xffffffffu) rm_gpu_only();
-    const unsigned k = rm_warp_votes++ % 3, lane = threadIdx.x & 31;
+    const unsigned k = rm_warp_votes++ % 3, lane = rm_lane();
     if (pred) rm_warp->votes[k].fetch_or(1u << lane);
     rm_warp->barrier.arrive(false);
     const unsigned v = rm_warp->votes[k].load();
@@ -105,8 +107,8 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
 }
 template <class T> static inline T __shfl_sync(unsigned mask, T value, int src, int = 32) {
     static_assert(sizeof(T) <= 8, "shuffle of a 32- or 64-bit value");
-    if (!rm_warp || mask != 0xffffffffu) rm_gpu_only();
-    const unsigned k = rm_warp_shuffles++ % 3, lane = threadIdx.x & 31;
+    if (!rm_warp || mask == 0u) rm_gpu_only();              // any mask: in this code base every lane of the warp makes every call
+    const unsigned k = rm_warp_shuffles++ % 3, lane = rm_lane();
     uint64_t bits = 0;
     std::memcpy(&bits, &value, sizeof(T));
     rm_warp->slots[k][lane] = bits;
@@ -114,6 +116,11 @@ template <class T> static inline T __shfl_sync(unsigned mask, T value, int src, 
     T out;
     std::memcpy(&out, &rm_warp->slots[k][src & 31], sizeof(T));
     return out;
+}
+template <class T> static inline T __shfl_up_sync(unsigned mask, T value, unsigned delta, int = 32) {
+    const unsigned lane = rm_lane();
+    const T from = __shfl_sync(mask, value, int(lane >= delta ? lane - delta : lane));
+    return lane >= delta ? from : value;
 }
 static inline unsigned __activemask() { rm_gpu_only(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { rm_gpu_only(); }
@@ -124,10 +131,10 @@ static void rm_host_launch_warp(Body body) {
     RmWarp warp;
     for (auto &v : warp.votes) v.store(0);
     warp.barrier.expected = 32;
-    rm_warp = &warp;
     std::vector<std::thread> lanes;
     for (unsigned lane = 0; lane < 32; lane++)
         lanes.emplace_back([&, lane] {
+            rm_warp = &warp;
             gridDim = dim3(1); blockDim = dim3(32);
             blockIdx = {0, 0, 0}; threadIdx = {lane, 0, 0};
             rm_warp_votes = rm_warp_shuffles = 0;
@@ -135,7 +142,6 @@ static void rm_host_launch_warp(Body body) {
             warp.barrier.arrive(true);
         });
     for (auto &t : lanes) t.join();
-    rm_warp = nullptr;
 }
 static inline void __syncthreads() { if (rm_block_barrier) rm_block_barrier->arrive(false); else rm_gpu_only(); }
 
@@ -144,14 +150,25 @@ static void rm_host_launch_blocks(Kernel kernel, dim3 grid, dim3 block, Args... 
     RmBlockBarrier barrier;
     rm_block_barrier = &barrier;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-        barrier.expected = int(block.x * block.y * block.z);
+        const unsigned nthreads = block.x * block.y * block.z;
+        barrier.expected = int(nthreads);
         barrier.waiting = 0;
+        std::vector<std::unique_ptr<RmWarp>> warps;             // the block's warps: lanes vote and shuffle within their own
+        for (unsigned w = 0; w * 32 < nthreads; w++) {
+            warps.emplace_back(new RmWarp());
+            for (auto &v : warps.back()->votes) v.store(0);
+            warps.back()->barrier.expected = int(std::min(32u, nthreads - w * 32));
+        }
         std::vector<std::thread> threads;
         for (unsigned tz = 0; tz < block.z; tz++) for (unsigned ty = 0; ty < block.y; ty++) for (unsigned tx = 0; tx < block.x; tx++)
-            threads.emplace_back([=, &barrier] {
+            threads.emplace_back([=, &barrier, &warps] {
                 gridDim = grid; blockDim = block;
                 blockIdx = {bx, by, bz}; threadIdx = {tx, ty, tz};
+                RmWarp *mine = warps[(tx + block.x * (ty + block.y * tz)) / 32].get();
+                rm_warp = mine;
+                rm_warp_votes = rm_warp_shuffles = 0;
                 kernel(args...);
+                mine->barrier.arrive(true);
                 barrier.arrive(true);
             });
         for (auto &t : threads) t.join();
@@ -168,7 +185,11 @@ template <class T, class U> static inline T atomicAdd(T *p, U v) {
     } else return __atomic_fetch_add(p, T(v), __ATOMIC_SEQ_CST);
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-template <class T> static inline T __shfl_up_sync(unsigned, T, unsigned, int = 32) { rm_gpu_only(); }
+
 template <class T, class U> static inline T atomicMax(T *, U) { rm_gpu_only(); }
-template <class T, class U> static inline T atomicExch(T *, U) { rm_gpu_only(); }
-template <class T, class U, class W> static inline T atomicCAS(T *, U, W) { rm_gpu_only(); }
+template <class T, class U> static inline T atomicExch(T *p, U v) { T want = T(v), old; __atomic_exchange(p, &want, &old, __ATOMIC_SEQ_CST); return old; }
+template <class T, class U, class W> static inline T atomicCAS(T *p, U compare, W value) {
+    T expected = T(compare), want = T(value);
+    __atomic_compare_exchange(p, &expected, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;                                           // the value seen: `compare` when the swap happened
+}

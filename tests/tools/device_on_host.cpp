@@ -404,4 +404,41 @@ int doh_replay_direct(const RmSceneDesc *sc, const RmRenderArgs *a, const RmHitI
     return 0;
 }
 
+// The direct-light half of rm_render_samples + rm_resolve as KERNELS, with the launch sequence of rm_render.cu: k_direct_gen
+// (thread per pixel, or - `warp_per_pixel` - a warp per pixel as on environment-lit scenes) fills one contiguous block of the
+// shadow queue per pixel, the engine runs ShadowJob over the queue, k_accum_direct folds the visible samples into the pixel's
+// accumulators in sample order, k_finalise applies exposure and the variance formula.  Blocks are emulated as real threads with
+// a CTA barrier and one warp context per 32 lanes.  spp direct samples per pixel in one wave.
+int doh_direct_planes(const RmSceneDesc *sc, const RmRenderArgs *a, const RmHitInfo *gbuffer_in, unsigned long long seed, int spp, int warp_per_pixel,
+                      int secondary_tree, RmRadiance *Dd, RmRadiance *Ds) {
+    HostScene H(sc);
+    DevArgs A;
+    A.position = ld(a->position); A.direction = ld(a->direction); A.up = ld(a->up); A.right = ld(a->right);
+    A.accuracy = a->accuracy; A.exposure = a->exposure; A.P_Direct = a->P_Direct; A.width = a->width; A.height = a->height; A.spp = spp;
+    const int npix = a->width * a->height;
+    std::vector<RmHitInfo> g(gbuffer_in, gbuffer_in + npix), g_out(npix);
+    std::vector<float> sav(size_t(npix) * 3, 0.0f), rad(size_t(npix) * 16, 0.0f), clum_sum(size_t(npix) * 2, 0.0f), clum_max(npix, 0.0f), hold_clum(npix, -1.0f),
+        hold(size_t(npix) * 8, 0.0f);
+    std::vector<int> n_ind(npix, 0), dir_base(npix, -1), lock(npix, 0);
+    FrameBuffers Fb{g.data(), sav.data(), n_ind.data(), dir_base.data()};
+    Accum Ac{rad.data(), clum_sum.data(), clum_max.data(), hold_clum.data(), hold.data(), lock.data()};
+    const int s_cap = npix * spp;
+    std::vector<ShadowItem> sq(size_t(s_cap) + 1);
+    int s_count = 0, overflow = 0;
+    const dim3 grid(2), block(kShadeBlock);
+    if (warp_per_pixel)
+        rm_host_launch_blocks(k_direct_gen<true>, grid, block, H.S, A, Fb, spp, npix, 0, 1, spp, seed, sq.data(), &s_count, s_cap, &overflow);
+    else
+        rm_host_launch_blocks(k_direct_gen<false>, grid, block, H.S, A, Fb, spp, npix, 0, 1, spp, seed, sq.data(), &s_count, s_cap, &overflow);
+    if (overflow || s_count > s_cap) return -2;
+    if (secondary_tree && !H.use_secondary_tree(sc)) return -1;
+    ShadowJob job;
+    job.sq = sq.data();
+    run_engine(H, job, s_count, nullptr, secondary_tree ? 14 : 0, secondary_tree ? 2 : 1);
+    rm_host_launch(k_accum_direct, dim3((npix + 255) / 256), dim3(256), Fb, Ac, (const ShadowItem *)sq.data(), spp, npix);
+    std::vector<RmRadiance> Id(npix), Is(npix);
+    rm_host_launch(k_finalise, dim3((npix + 255) / 256), dim3(256), Ac, Fb, npix, a->exposure, Dd, Ds, Id.data(), Is.data(), g_out.data());
+    return s_count;
+}
+
 }
