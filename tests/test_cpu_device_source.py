@@ -420,3 +420,68 @@ def test_direct_light_kernels_resolve_to_the_reference_planes(doh, ref, which, s
                 assert abs(float(plane["Var"][p]) - float(var)) <= 1e-5 * (1.0 + abs(float(var))), (p, j)
     assert lit > n // 5
     R.close()
+
+
+# --------------------------------------------------------------------------- the whole indirect estimator, kernels and round loop
+@pytest.mark.parametrize("secondary_tree", [0, 1])
+@pytest.mark.parametrize("which", ["cornell", "sky", "glossy"])
+def test_indirect_wavefront_replays_the_reference(doh, ref, which, secondary_tree):
+    """The wavefront estimator itself on the CPU: primary hits -> k_gbuffer -> rounds of [k_plan, k_regen, PathJob through the
+    engine, k_surface, k_bounce, k_nee, k_shadow_gate, ShadowJob through the engine, k_accum_shadow] with the round loop of
+    rm_render_samples restated around the kernels -> k_publish_max, k_commit_hold, k_finalise; every block a set of real threads
+    with a CTA barrier and a warp context per 32 lanes.  One indirect sample per opaque pixel, sixteen on glass.  Each pixel is
+    then replayed through the reference's own sampleIndirectLightFromFirstIntersection fed the pixel's Philox draws
+    (recursion, Russian roulette into NEE, nested dielectrics, absorption, rejection sampling - src/render.cpp:121-423): every
+    pixel's indirect-diffuse and indirect-specular radiance agrees to 2e-3 of the pixel's scale (the bar of the GPU replay test,
+    which asks it of 97 % of the pixels) and nearly all to the bit - the rest differ in the order several samples of one pixel
+    were added (atomics)."""
+    from raym0nade_b200 import rng
+    from raym0nade_b200.ctypes_defs import RADIANCE_DTYPE, RmRenderArgs
+    f32 = np.float32
+    doh.doh_indirect_planes.argtypes = [C.POINTER(RmSceneDesc), C.POINTER(RmRenderArgs), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    if which == "cornell":
+        scene, args = scenes.cornell_box(24, 24, 1)
+    elif which == "sky":
+        scene, args = scenes.heightfield_scene(8_000, 32, 18, with_sky=True)
+    else:
+        scene, args = scenes.glossy_dielectric(30_000, 32, 18)
+    a1 = args.replace(spp=1, P_Direct=0.0)
+    R = ref.RefScene(scene)
+    m = Model(scene)
+    n = a1.width * a1.height
+    Id, Is, g_out, rounds = np.zeros(n, RADIANCE_DTYPE), np.zeros(n, RADIANCE_DTYPE), np.zeros(n, HITINFO_DTYPE), np.zeros(1, np.int32)
+    a = a1.to_c()
+    seed = 1234
+    n_glass = doh.doh_indirect_planes(C.byref(m.desc), C.byref(a), seed, 1, secondary_tree, _p(g_out), _p(Id), _p(Is), _p(rounds))
+    assert n_glass >= 0 and 2 <= rounds[0] <= 40
+    rg = R.gbuffer(a1.replace(spp=0), threads=4)
+    if which == "glossy":
+        assert n_glass > 0 and n_glass == int((rg["opacity"][np.isfinite(rg["position"][:, 0])] <= 1 - 1e-4).sum())
+    pixels = exact = 0
+    for p in range(n):
+        g = rg[p]
+        if np.isnan(g["position"][0]):
+            assert not Id["radiance"][p].any() and not Is["radiance"][p].any()
+            continue
+        n_s = 1 if g["opacity"] > 1 - 1e-4 else 16             # src/render.cpp:498-501
+        acc = np.zeros(8, f32)
+        base = np.zeros(3, f32) if g["opacity"] < 1e-4 else g["baseColor"]
+        for si in range(n_s):
+            samples, used = R.replay_indirect(a1, p % a1.width, p // a1.width, g, rng.stream_u32(seed, p, si, rng.STREAM_INDIRECT, 624))
+            assert used < 624
+            for s in samples:
+                s = s.copy()
+                s[6] = f32(s[6]) * (f32(1.0) / f32(n_s))       # mulWeight(samples, 1 / spp_indirect)
+                acc = acc + ref.accumulate(base[None], s[None])[0]
+        same_bits = True
+        for j, plane in enumerate((Id, Is)):
+            rad = (acc[4 * j:4 * j + 3] * f32(a1.exposure)).astype(f32)
+            err = np.abs(plane["radiance"][p] - rad).max() / (np.abs(rad).max() + 1e-6)
+            assert err < 2e-3, (p, j, rad, plane["radiance"][p])
+            same_bits = same_bits and np.array_equal(rad.view(np.uint32), plane["radiance"][p].view(np.uint32))
+        pixels += 1
+        exact += same_bits
+    assert pixels > n // 2 and exact >= 0.9 * pixels, (pixels, exact)
+    assert Id["radiance"].sum() > 0
+    R.close()

@@ -88,8 +88,23 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 // One warp = 32 real threads in lock step wherever they vote or shuffle.  Full-mask collectives only (all the engine uses):
 // every collective call is one barrier; results travel through three rotating slots so that a fast lane's next call can
 // never overwrite what a slow lane has not read yet.  rm_host_launch_warp sets it up.
+// meeting point of the lanes named by a partial mask (a shuffle among the lanes that took a branch): `n` lanes per meeting
+struct RmGroupBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned generation = 0;
+    void arrive(int n) {
+        std::unique_lock<std::mutex> l(m);
+        if (++waiting >= n) { waiting = 0; generation++; cv.notify_all(); return; }
+        const unsigned g = generation;
+        cv.wait(l, [&] { return g != generation; });
+    }
+};
 struct RmWarp {
     RmBlockBarrier barrier;
+    RmGroupBarrier group;
+    uint64_t group_slots[32];
     std::atomic<unsigned> votes[3];
     uint64_t slots[3][32];
 };
@@ -107,10 +122,19 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
 }
 template <class T> static inline T __shfl_sync(unsigned mask, T value, int src, int = 32) {
     static_assert(sizeof(T) <= 8, "shuffle of a 32- or 64-bit value");
-    if (!rm_warp || mask == 0u) rm_gpu_only();              // any mask: in this code base every lane of the warp makes every call
-    const unsigned k = rm_warp_shuffles++ % 3, lane = rm_lane();
+    if (!rm_warp || mask == 0u) rm_gpu_only();
     uint64_t bits = 0;
     std::memcpy(&bits, &value, sizeof(T));
+    if (mask != 0xffffffffu) {                                 // only the lanes of `mask` are here (alloc_slot): they meet among themselves,
+        const int n = __builtin_popcount(mask);                // once to publish and once more before anyone may publish again
+        rm_warp->group_slots[rm_lane()] = bits;
+        rm_warp->group.arrive(n);
+        T got;
+        std::memcpy(&got, &rm_warp->group_slots[src & 31], sizeof(T));
+        rm_warp->group.arrive(n);
+        return got;
+    }
+    const unsigned k = rm_warp_shuffles++ % 3, lane = rm_lane();
     rm_warp->slots[k][lane] = bits;
     rm_warp->barrier.arrive(false);
     T out;

@@ -4,6 +4,7 @@
 // mapping, trilinear material fetches, the sky lookup - to the golden vectors the compiled reference produced
 // (tests/golden/reference_vectors.npz).  The GPU suite checks the same functions as they run on the device; this copy
 // catches an arithmetic regression in every CPU-only test run.  Built with -ffp-contract=off, no fast-math.
+#include <cstdio>
 #include "cuda_on_host.h"
 #include "raym0nade_b200.h"
 namespace rm { struct Philox4; static Philox4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1); }
@@ -439,6 +440,126 @@ int doh_direct_planes(const RmSceneDesc *sc, const RmRenderArgs *a, const RmHitI
     std::vector<RmRadiance> Id(npix), Is(npix);
     rm_host_launch(k_finalise, dim3((npix + 255) / 256), dim3(256), Ac, Fb, npix, a->exposure, Dd, Ds, Id.data(), Is.data(), g_out.data());
     return s_count;
+}
+
+// glass pixels of the frame (rm_render.cu, k_glass_list): the pixels whose indirect sample count is 16x the base
+static __global__ void k_glass_list_host(const int *n_ind, int npix, int base, int *list, int *count) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool glass = p < npix && base > 0 && n_ind[p] > base;
+    int slot = alloc_slot(count, glass);
+    if (glass) list[slot] = p;
+}
+
+// The indirect half of rm_render_samples + rm_resolve with the round loop of rm_render.cu restated around the kernels
+// themselves: primary hits -> k_gbuffer -> [k_plan, k_regen, PathJob through the engine, k_surface, k_bounce, k_nee, k_shadow_gate,
+// ShadowJob through the engine, k_accum_shadow]* -> k_publish_max, k_commit_hold (hold-back never dropped, like the
+// "disable_clamp" option of the replay tests), k_finalise.  `spp` indirect samples per opaque pixel (16x on glass), no direct ones.
+int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned long long seed, int spp, int secondary_tree, RmHitInfo *g_out,
+                        RmRadiance *Id, RmRadiance *Is, int32_t *rounds_out) {
+    HostScene H(sc);
+    DevArgs A;
+    A.position = ld(a->position); A.direction = ld(a->direction); A.up = ld(a->up); A.right = ld(a->right);
+    A.accuracy = a->accuracy; A.exposure = a->exposure; A.P_Direct = 0.0f; A.width = a->width; A.height = a->height; A.spp = spp;
+    const int npix = a->width * a->height;
+    // frame: primary hits and G-buffer
+    std::vector<int> tri(npix, -1);
+    std::vector<float> t(npix, 0.0f);
+    {
+        PrimaryJob job;
+        job.A = A; job.tiles_x = (a->width + 7) / 8; job.tri_idx = tri.data(); job.t_out = t.data();
+        run_engine(H, job, job.tiles_x * ((a->height + 3) / 4) * 32, nullptr);
+    }
+    std::vector<RmHitInfo> g(npix);
+    std::vector<float> sav(size_t(npix) * 3, 0.0f);
+    std::vector<int> n_ind(npix, 0), dir_base(npix, -1), glass_list(npix, 0);
+    FrameBuffers Fb{g.data(), sav.data(), n_ind.data(), dir_base.data()};
+    int C[C_COUNT] = {0};
+    const int base = spp;                                                   // spp_direct = 0
+    rm_host_launch(k_gbuffer, dim3((npix + 127) / 128), dim3(128), H.S, A, (const int *)tri.data(), (const float *)t.data(), Fb, 0, base, C + 4);
+    rm_host_launch_blocks(k_glass_list_host, dim3((npix + 127) / 128), dim3(128), (const int *)n_ind.data(), npix, base, glass_list.data(), C + 5);
+    const int n_glass = C[5];
+    // accumulators (reset_accum)
+    std::vector<float> rad(size_t(npix) * 16, 0.0f), clum_sum(size_t(npix) * 2, 0.0f), clum_max(npix, 0.0f), hold_clum(npix, -1.0f), hold(size_t(npix) * 8, 0.0f);
+    std::vector<int> lock(npix, 0);
+    Accum Ac{rad.data(), clum_sum.data(), clum_max.data(), hold_clum.data(), hold.data(), lock.data()};
+    // item space and queues (rm_render_samples)
+    const int n_a = base, n_b_total = n_glass > 0 ? 16 * base : 0;
+    const long long items_a = (long long)npix * n_a, items_b = n_b_total > n_a ? (long long)n_glass * (n_b_total - n_a) : 0, total_items = items_a + items_b;
+    const int q_cap = int(std::max(1024LL, total_items)), s_cap = 6 * q_cap;
+    const size_t words[17] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6};
+    std::vector<std::vector<uint32_t>> store[2];
+    PathQueue Q[2];
+    for (int w = 0; w < 2; w++) {
+        store[w].resize(17);
+        for (int k = 0; k < 17; k++) store[w][k].assign(size_t(q_cap) * words[k], 0u);
+        auto at = [&](int k) { return static_cast<void *>(store[w][k].data()); };
+        PathQueue &q = Q[w];
+        q.cap = q_cap;
+        q.pixel = (int *)at(0); q.sample = (unsigned *)at(1); q.drawn = (unsigned *)at(2);
+        q.o = (float *)at(3); q.d = (float *)at(4); q.diff = (float *)at(5);
+        q.T = (float *)at(6); q.B0 = (float *)at(7); q.W = (float *)at(8); q.rough = (float *)at(9);
+        q.flags = (int *)at(10); q.med_id = (int *)at(11); q.med = (float *)at(12);
+        q.hit_t = (float *)at(13); q.hit_face = (int *)at(14);
+        q.surf = (float *)at(15); q.hdP = (float *)at(16);
+    }
+    std::vector<NeeRequest> nq(q_cap);
+    std::vector<ShadowItem> sq(size_t(s_cap) + 1);
+    ItemSpace I;
+    I.items_a = items_a; I.total = total_items; I.npix = npix; I.n_glass = std::max(n_glass, 1); I.n_a = n_a;
+    I.glass_list = glass_list.data(); I.s_begin = 0; I.s_stride = 1;
+    // the tree the bounce and shadow rays traverse
+    HostScene Hsec(sc);
+    if (secondary_tree && !Hsec.use_secondary_tree(sc)) return -1;
+    const HostScene &T = secondary_tree ? Hsec : H;
+    const int sl = secondary_tree ? 14 : 0, wl = secondary_tree ? 2 : 1;
+    auto trace_shadow = [&] {
+        ShadowJob job;
+        job.sq = sq.data();
+        run_engine(T, job, std::min(C[C_SQ_RUN], s_cap), nullptr, sl, wl);
+        rm_host_launch_blocks(k_accum_shadow, dim3(2), dim3(256), Fb, Ac, (const ShadowItem *)sq.data(), (const int *)(C + C_SQ_RUN), s_cap);
+    };
+    const dim3 grid(2), block(kShadeBlock);
+    const int shadow_threshold = std::max(1, q_cap / 2);
+    int cur = 0, rounds = 0;
+    const bool trace = std::getenv("RM_DOH_TRACE") != nullptr;
+#define DOH_STEP(name) do { if (trace) std::fprintf(stderr, "round %d %s: q=%d/%d nee=%d sq=%d run=%d\n", rounds, name, C[0], C[1], C[C_NEE], C[C_SQ], C[C_SQ_RUN]); } while (0)
+    if (total_items > 0) {
+        for (;;) {
+            PathQueue Qin = Q[cur], Qout = Q[cur ^ 1];
+            rm_host_launch(k_plan, dim3(1), dim3(1), C, cur, Qin.cap, total_items);
+            DOH_STEP("planned");
+            rm_host_launch_blocks(k_regen, grid, block, H.S, A, Fb, I, (const int *)C, seed, Qin, C + cur);
+            DOH_STEP("regenerated");
+            PathJob pj;
+            pj.Q = Qin;
+            run_engine(T, pj, std::min(C[cur], Qin.cap), nullptr, sl, wl);
+            DOH_STEP("traced");
+            rm_host_launch_blocks(k_surface, grid, block, H.S, Fb, Ac, Qin, C, cur);
+            DOH_STEP("surfaced");
+            rm_host_launch_blocks(k_bounce, grid, block, seed, Qin, (const int *)(C + cur), Qout, C + (cur ^ 1), nq.data(), C + C_NEE);
+            DOH_STEP("bounced");
+            rm_host_launch_blocks(k_nee, grid, block, H.S, Fb, seed, Qin, (const NeeRequest *)nq.data(), (const int *)(C + C_NEE), Qin.cap, sq.data(), C + C_SQ, s_cap,
+                                  C + C_OVERFLOW);
+            DOH_STEP("nee drawn");
+            rm_host_launch(k_shadow_gate, dim3(1), dim3(1), C, shadow_threshold, s_cap, 0);
+            trace_shadow();
+            DOH_STEP("shadows");
+            cur ^= 1;
+            rounds++;
+            const long long handed = (long long)(unsigned)C[C_ITEM_LO] | ((long long)C[C_ITEM_HI] << 32);
+            if ((handed >= total_items && C[cur] == 0) || rounds > 64) break;
+        }
+        rm_host_launch(k_plan, dim3(1), dim3(1), C, cur, q_cap, total_items);
+        rm_host_launch(k_shadow_gate, dim3(1), dim3(1), C, shadow_threshold, s_cap, 1);
+        trace_shadow();
+    }
+    if (C[C_OVERFLOW]) return -2;
+    rm_host_launch(k_publish_max, dim3((npix + 255) / 256), dim3(256), Ac, npix);
+    rm_host_launch(k_commit_hold, dim3((npix + 255) / 256), dim3(256), Ac, Fb, npix, true);
+    std::vector<RmRadiance> Dd(npix), Ds(npix);
+    rm_host_launch(k_finalise, dim3((npix + 127) / 128), dim3(128), Ac, Fb, npix, a->exposure, Dd.data(), Ds.data(), Id, Is, g_out);
+    if (rounds_out) *rounds_out = rounds;
+    return n_glass;
 }
 
 }
