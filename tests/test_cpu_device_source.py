@@ -485,3 +485,29 @@ def test_indirect_wavefront_replays_the_reference(doh, ref, which, secondary_tre
     assert pixels > n // 2 and exact >= 0.9 * pixels, (pixels, exact)
     assert Id["radiance"].sum() > 0
     R.close()
+
+
+@pytest.mark.parametrize("name", ["box", "hf"])
+def test_depth_of_field_kernels(doh, name):
+    """k_dof_prepare -> the reference's stable sort by camera distance -> k_dof_tile_lists -> k_dof_gather, as dof_device chains
+    them: every destination replays, in the reference's visiting order, the sources whose disc reaches it.  + - * / sqrt only:
+    bit-equal to Photo::depthFeildBlur wherever every pixel has a finite depth (the closed box); a pixel without a hit carries
+    a NaN depth, for which the reference's own loop bounds are int(NaN) - there the frames agree on the pixels no such source
+    can reach (the same bar as tests/test_gpu_post.py)."""
+    doh.doh_depth_field_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]
+    w, h = (int(v) for v in GP[name + "_wh"])
+    g = np.ascontiguousarray(GP[name + "_gbuffer"])
+    src, cam = _f32(GP[name + "_dof_in"]), _f32(GP[name + "_dof_cam"])
+    finite = np.isfinite(g["position"][:, 0]).all()
+    for j in (0, 1):
+        focus, coc = (float(v) for v in GP["%s_dof_%d_params" % (name, j)])
+        out = np.zeros_like(src)
+        reach = doh.doh_depth_field_blur(_p(g), _p(src), _p(cam), focus, coc, w, h, _p(out))
+        want = GP["%s_dof_%d" % (name, j)]
+        assert reach >= 1
+        if finite:
+            assert same(out, want), (name, j)
+        else:
+            agree = np.isclose(out, want, rtol=0, atol=1e-6).all(-1)
+            assert agree.mean() > 0.5, (name, j, agree.mean())
+        assert not same(out, src)

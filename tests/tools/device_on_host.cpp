@@ -562,4 +562,31 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
     return n_glass;
 }
 
+// Photo::depthFeildBlur as dof_device runs it (rm_render.cu): k_dof_prepare, the reference's stable sort by camera distance on
+// the host, k_dof_tile_lists (per-tile source lists, order kept), k_dof_gather (every destination replays its sources in order)
+int doh_depth_field_blur(const RmHitInfo *G, const float *rgb_in, const float *cam3, float focus, float CoC, int w, int h, float *rgb_out) {
+    const int npix = w * h;
+    std::vector<float> depth(npix);
+    std::vector<float2> src(npix);
+    rm_host_launch(k_dof_prepare, dim3((npix + 127) / 128), dim3(128), G, ld(cam3), focus, CoC, npix, depth.data(), src.data());
+    struct Px { int idx; float depth; };
+    std::vector<Px> px(npix);
+    int reach = 0;
+    for (int i = 0; i < npix; i++) {
+        px[i] = {i, depth[i]};
+        if (src[i].x == src[i].x) reach = std::max(reach, int(src[i].x));
+    }
+    std::stable_sort(px.begin(), px.end(), [](const Px &a, const Px &b) { return a.depth < b.depth; });
+    std::vector<int> sorted(npix);
+    for (int i = 0; i < npix; i++) sorted[i] = px[i].idx;
+    const int tiles_x = (w + kDofTile - 1) / kDofTile, tiles_y = (h + kDofTile - 1) / kDofTile, tiles = tiles_x * tiles_y;
+    const long long side = kDofTile + 2LL * reach;
+    const long long cap = std::min<long long>(npix, side * side);
+    std::vector<int> lists(size_t(cap) * tiles), counts(tiles, 0);
+    rm_host_launch_blocks(k_dof_tile_lists, dim3(tiles), dim3(256), (const int *)sorted.data(), npix, w, h, reach, tiles_x, int(cap), lists.data(), counts.data());
+    rm_host_launch(k_dof_gather, dim3(tiles), dim3(kDofTile, kDofTile), rgb_in, (const float2 *)src.data(), (const int *)lists.data(), (const int *)counts.data(),
+                   int(cap), w, h, tiles_x, rgb_out);
+    return reach;
+}
+
 }
