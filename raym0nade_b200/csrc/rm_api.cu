@@ -142,6 +142,9 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     cudaStream_t st = ctx->stream;
     int64_t total = 0;
     const int n = sc->n_faces;
+    // the buffers of the previous scene are reused (and reallocated on growth) from here on: until this upload has
+    // finished there is no scene, so a failure half-way cannot leave a later call traversing freed or half-written memory
+    ctx->has_scene = ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
 
     // nodes: same 32-byte images, heap-indexed; the array is padded to an even count so that
     // every child pair (2u, 2u+1) is a whole 64-byte block

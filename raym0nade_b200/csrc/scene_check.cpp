@@ -35,6 +35,10 @@ extern "C" int rm_scene_validate(const RmSceneDesc *sc) {
             if (nd.faceR != 0) {
                 if (nd.faceL < 0 || nd.faceL >= nd.faceR || nd.faceR > sc->n_faces)
                     return rm_fail(RM_ERR_INVALID, "BVH node %d: leaf range [%d, %d) is outside the %d faces", u, nd.faceL, nd.faceR, sc->n_faces);
+                // a leaf reference carries its face count in 4 bits (dev_trace.cuh leaf_ref); the reference's builder stops
+                // splitting at <= 10 faces (src/bvh.cpp:22), so a longer leaf is not a tree it could have produced
+                if (nd.faceR - nd.faceL > 15)
+                    return rm_fail(RM_ERR_INVALID, "BVH node %d: leaf of %d faces (at most 15 are supported)", u, nd.faceR - nd.faceL);
                 owned += nd.faceR - nd.faceL;
             } else {
                 if (2 * int64_t(u) + 1 >= sc->n_nodes)
@@ -64,8 +68,11 @@ extern "C" int rm_scene_validate(const RmSceneDesc *sc) {
         if (t.map_depth < 1 || t.map_depth > 8 || (t.channels != 3 && t.channels != 4))
             return rm_fail(RM_ERR_INVALID, "texture %d: bad map_depth/channels", i);
         if (t.width <= 0 || t.height <= 0) return rm_fail(RM_ERR_INVALID, "texture %d: bad size %d x %d", i, t.width, t.height);
+        // every level the mip selection can reach must have texels: a level with a zero dimension would be fetched modulo 0
+        if ((t.width >> (t.map_depth - 1)) == 0 || (t.height >> (t.map_depth - 1)) == 0)
+            return rm_fail(RM_ERR_INVALID, "texture %d: %d levels of a %d x %d image (level %d is empty)", i, t.map_depth, t.width, t.height, t.map_depth - 1);
         for (int l = 0; l < t.map_depth; l++)
-            if ((t.width >> l) > 0 && (t.height >> l) > 0 && !t.levels[l]) return rm_fail(RM_ERR_INVALID, "texture %d: level %d is NULL", i, l);
+            if (!t.levels[l]) return rm_fail(RM_ERR_INVALID, "texture %d: level %d is NULL", i, l);
     }
     for (int i = 0; i < sc->n_lights; i++) {
         const RmLightDesc &L = sc->lights[i];

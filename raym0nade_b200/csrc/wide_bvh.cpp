@@ -1,0 +1,154 @@
+// wide_bvh.cpp — the secondary-ray tree in its traversal form: 4-wide nodes with 8-bit quantised child boxes.
+//
+// fast_bvh.cpp builds a binned-SAH binary tree over the scene's triangles.  The traversal engine of the estimator's
+// bounce and shadow rays (dev_trace4.cuh) is bound by instruction issue and by the L1 data pipe - one wavefront per lane
+// and load, the rays being incoherent - not by DRAM, so what it needs is FEWER, FATTER steps: this file collapses the
+// binary tree into nodes of up to four children and stores each node in ONE 64-byte record (two 256-bit loads per lane and
+// step instead of two per binary node, for about half the steps per ray):
+//
+//   bytes  0..11  o[3]        the node's lower corner (origin of the quantisation grid)
+//         12..23  s[3]        grid step per axis: (extent / 255) rounded up
+//         24..35  qlo[3][4]   per axis, per child: lower plane in grid units, rounded DOWN
+//         36..47  qhi[3][4]   per axis, per child: upper plane in grid units, rounded UP
+//         48..51  child_base  index of the node's first inner child (its inner children are consecutive records)
+//         52..55  tri_base    first triangle of the node's leaf children (consecutive in the tree's triangle order)
+//         56..59  meta[4]     per child: 0 = empty slot, 0x80 | k = the k-th inner child, (offset << 2) | count = a leaf of
+//                             `count` (1..3) triangles starting `offset` (< 32) after tri_base
+//         60..63  unused
+//
+// A decoded box o + s * q always ENCLOSES the child's true box (checked here in double precision), so a ray that meets a
+// triangle meets the boxes above it: the tree returns the same closest accepted triangle as any other valid hierarchy
+// over the same triangles under the same triangle test (the reference's RayTriangleIntersection, src/geometry.cpp:63-87).
+// Only the work per ray differs.  There is no reference counterpart: the reference's tree (src/bvh.cpp:18-54) is what
+// primary rays and the per-ray seam traverse, in its own order.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "rm_internal.h"
+#include "raym0nade_b200.h"
+#include "wide_bvh.h"
+
+namespace {
+
+struct Box3 { float lo[3], hi[3]; };
+
+inline Box3 box_of(const RmBvhNode &r) { return {{r.v0[0], r.v0[1], r.v0[2]}, {r.v1[0], r.v1[1], r.v1[2]}}; }
+inline float half_area(const Box3 &b) {
+    const float d[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
+    return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+}
+
+struct Collapser {
+    const std::vector<RmBvhNode> &bin;      // the binary tree: pair blocks (fast_bvh.cpp)
+    const std::vector<int32_t> &order_in;   // its triangle order
+    std::vector<RmWideNode> &out;
+    std::vector<int32_t> &order_out;
+    int max_depth = 0;
+    bool ok = true;
+
+    // fills out[self] for the binary inner record `rec` (children in pair block rec.faceL)
+    void emit(int self, const RmBvhNode &rec, int depth) {
+        max_depth = std::max(max_depth, depth);
+        // gather up to four children: open the inner child with the largest surface until four are held or none is inner
+        const RmBvhNode *ch[4];
+        int n = 0;
+        ch[n++] = &bin[size_t(rec.faceL) * 2];
+        ch[n++] = &bin[size_t(rec.faceL) * 2 + 1];
+        while (n < 4) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int i = 0; i < n; i++)
+                if (ch[i]->faceR == 0) {
+                    const float a = half_area(box_of(*ch[i]));
+                    if (a > best_area || best < 0) { best_area = a; best = i; }
+                }
+            if (best < 0) break;
+            const RmBvhNode *open = ch[best];
+            ch[best] = &bin[size_t(open->faceL) * 2];
+            ch[n++] = &bin[size_t(open->faceL) * 2 + 1];
+        }
+        fill(self, ch, n, depth);
+    }
+
+    void fill(int self, const RmBvhNode *const *ch, int n, int depth) {
+        RmWideNode w;
+        std::memset(&w, 0, sizeof(w));
+        Box3 u = box_of(*ch[0]);
+        for (int i = 1; i < n; i++)
+            for (int a = 0; a < 3; a++) { u.lo[a] = std::min(u.lo[a], ch[i]->v0[a]); u.hi[a] = std::max(u.hi[a], ch[i]->v1[a]); }
+        for (int a = 0; a < 3; a++) {
+            w.o[a] = u.lo[a];
+            // grid step: o + 255 s must reach the upper corner (in exact arithmetic: o, s are floats, the check is in double)
+            float s = float((double(u.hi[a]) - double(u.lo[a])) / 255.0);
+            if (!(s > 0.0f)) s = 0.0f;
+            while (double(u.lo[a]) + 255.0 * double(s) < double(u.hi[a])) s = std::nextafter(s, INFINITY);
+            w.s[a] = s;
+        }
+        int n_inner = 0, n_tris = 0;
+        for (int i = 0; i < n; i++) (ch[i]->faceR == 0 ? n_inner : n_tris) += ch[i]->faceR == 0 ? 1 : ch[i]->faceR - ch[i]->faceL;
+        w.child_base = n_inner ? int32_t(out.size()) : 0;
+        w.tri_base = int32_t(order_out.size());
+        if (n_inner) out.resize(out.size() + n_inner);         // the inner children's records: consecutive
+        int k_inner = 0, tri_off = 0;
+        const RmBvhNode *inner[4];
+        for (int i = 0; i < n; i++) {
+            const RmBvhNode &c = *ch[i];
+            for (int a = 0; a < 3; a++) {
+                const double o = w.o[a], s = w.s[a];
+                int lo = 0, hi = 255;
+                if (s > 0.0) {
+                    lo = int(std::floor((double(c.v0[a]) - o) / s));
+                    hi = int(std::ceil((double(c.v1[a]) - o) / s));
+                    lo = std::min(std::max(lo, 0), 255);
+                    hi = std::min(std::max(hi, 0), 255);
+                    while (lo > 0 && o + s * lo > double(c.v0[a])) lo--;
+                    while (hi < 255 && o + s * hi < double(c.v1[a])) hi++;
+                    if (o + s * lo > double(c.v0[a]) || o + s * hi < double(c.v1[a])) ok = false;
+                } else {
+                    lo = hi = 0;                                // flat node along this axis: every child plane is o itself
+                    if (double(c.v0[a]) < o || double(c.v1[a]) > o) ok = false;
+                }
+                w.qlo[a][i] = uint8_t(lo);
+                w.qhi[a][i] = uint8_t(hi);
+            }
+            if (c.faceR == 0) {
+                w.meta[i] = uint8_t(0x80 | k_inner);
+                inner[k_inner++] = &c;
+            } else {
+                const int cnt = c.faceR - c.faceL;
+                if (cnt < 1 || cnt > 3 || tri_off > 31) { ok = false; continue; }
+                w.meta[i] = uint8_t((tri_off << 2) | cnt);
+                for (int t = c.faceL; t < c.faceR; t++) order_out.push_back(order_in[t]);
+                tri_off += cnt;
+            }
+        }
+        const int base = w.child_base;
+        out[self] = w;
+        for (int k = 0; k < k_inner; k++) emit(base + k, *inner[k], depth + 1);
+    }
+};
+
+} // namespace
+
+int rm_build_wide_bvh(const std::vector<RmBvhNode> &bin, const std::vector<int32_t> &order_in, int n_tris, std::vector<RmWideNode> &out,
+                      std::vector<int32_t> &order_out, int *depth_out) {
+    if (bin.size() < 2 || n_tris <= 0 || int(order_in.size()) != n_tris) return rm_fail(RM_ERR_INVALID, "rm_build_wide_bvh: no tree");
+    out.clear();
+    order_out.clear();
+    out.reserve(size_t(n_tris));
+    order_out.reserve(size_t(n_tris));
+    Collapser C{bin, order_in, out, order_out};
+    out.resize(1);
+    const RmBvhNode &whole = bin[1];
+    if (whole.faceR != 0) {                    // the whole scene is one leaf: a root with that single leaf child
+        if (whole.faceR - whole.faceL > 3) return rm_fail(RM_ERR_INVALID, "rm_build_wide_bvh: leaves hold at most 3 triangles");
+        const RmBvhNode *one[1] = {&whole};
+        C.fill(0, one, 1, 0);
+    } else C.emit(0, whole, 0);
+    if (!C.ok || int(order_out.size()) != n_tris) return rm_fail(RM_ERR_STATE, "rm_build_wide_bvh: the collapse lost a triangle or a box");
+    if (depth_out) *depth_out = C.max_depth + 1;
+    return RM_OK;
+}

@@ -8,6 +8,7 @@
 // Two private members are read: BVH::node (include/bvh.h:13) and RandomDistribution::prefixSums (include/component.h:38).
 // In the reference tree add `friend struct B200Bridge;` to `BVH` and `RandomDistribution`; this repository leaves the
 // reference untouched and compiles this file with -fno-access-control instead.
+#include <algorithm>
 #include <iostream>
 
 #include "gpu_bridge.h"
@@ -20,7 +21,7 @@ static_assert(sizeof(vec3) == 3 * sizeof(float), "SkyBox::data is handed over as
 const RmSceneDesc *B200Bridge::fill(const Model &m) {
     const int n = int(m.faces.size());
     positions.clear(); uvs.clear(); normals.clear(); faceMaterial.clear();
-    materials.clear(); textures.clear(); lights.clear(); lightArrays.clear();
+    materials.clear(); textures.clear(); lights.clear(); lightArrays.clear(); texelStorage.clear();
     positions.reserve(size_t(n) * 9); uvs.reserve(size_t(n) * 6); normals.reserve(size_t(n) * 9);
     for (const Face &f : m.faces) {                       // already in post-build order: BVH::build permuted Model::faces (bvh.cpp:38)
         for (int c = 0; c < 3; c++) {
@@ -42,7 +43,19 @@ const RmSceneDesc *B200Bridge::fill(const Model &m) {
             t.width = img.width; t.height = img.height;
             t.channels = k == 3 ? 3 : 4;                  // the stride of the slot's fetch type, not ImageData::channels (src/material.cpp:58)
             t.map_depth = img.map_depth;
-            for (int l = 0; l < img.map_depth; l++) t.levels[l] = img.data[l].data();
+            // The slot's fetch strides by its own type (vec4 for diffuse / specular / emissive, vec3 for normals,
+            // src/material.cpp:48-79) whatever ImageData::channels says; a PNG is stored as packed RGB8
+            // (src/material.cpp:273-281), so a PNG in an RGBA slot is SHORTER than the w*h*4 bytes the fetch (and
+            // rm_scene_upload) walks: the reference reads past the end of its vector there.  Such a level is handed over
+            // as a bridge-owned copy of the claimed size - the bytes the reference owns verbatim (so every in-bounds
+            // fetch returns what the reference's returns), zeros where the reference would over-read.
+            for (int l = 0; l < img.map_depth; l++) {
+                const size_t need = size_t(img.width >> l) * size_t(img.height >> l) * size_t(t.channels);
+                if (img.data[l].size() >= need) { t.levels[l] = img.data[l].data(); continue; }
+                texelStorage.emplace_back(need, uint8_t(0));
+                std::copy(img.data[l].begin(), img.data[l].end(), texelStorage.back().begin());
+                t.levels[l] = texelStorage.back().data();
+            }
             d.tex[k] = int32_t(textures.size());
             textures.push_back(t);
         }

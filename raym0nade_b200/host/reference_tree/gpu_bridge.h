@@ -17,6 +17,7 @@ struct B200Bridge {
     std::vector<RmTextureDesc> textures;
     std::vector<RmLightDesc> lights;
     std::vector<std::vector<float>> lightArrays;
+    std::vector<std::vector<uint8_t>> texelStorage;     // levels whose ImageData buffer is shorter than the slot's fetch stride needs (see fill)
     RmSceneDesc desc{};
 
     // view a loaded Model as the library's post-load scene; valid while both the Model and this object live

@@ -472,6 +472,29 @@ def cornell_box(width=512, height=512, spp=64):
     return scene, args
 
 
+def nested_glass(width=96, height=96, spp=16, shells=9):
+    """Not a BASELINE config: the Cornell room with `shells` concentric glass spheres (each its own material, so each its
+    own entry of the reference's Medium multimap, src/render.cpp:13-42) around a small diffuse core - a ray towards the
+    core is inside `shells` nested dielectrics at once."""
+    b = SceneBuilder("nested_glass")
+    white, red, green = b.diffuse(200, 200, 200), b.diffuse(200, 30, 30), b.diffuse(30, 200, 30)
+    light = b.emissive(255)
+    b.quad((-1, -1, -1), (1, -1, -1), (1, -1, 1), (-1, -1, 1), white)
+    b.quad((-1, 1, -1), (-1, 1, 1), (1, 1, 1), (1, 1, -1), white)
+    b.quad((-1, -1, -1), (-1, 1, -1), (1, 1, -1), (1, -1, -1), white)
+    b.quad((-1, -1, -1), (-1, -1, 1), (-1, 1, 1), (-1, 1, -1), red)
+    b.quad((1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1), green)
+    b.quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25), light)
+    for k in range(shells):
+        tint = (1.0 - 0.01 * (k % 3), 1.0 - 0.012 * ((k + 1) % 3), 1.0 - 0.008 * ((k + 2) % 3))
+        m = b.material(RawMaterial(opacity=0.0, ior=1.05 + 0.03 * k, roughness=5e-3, transmitting_color=tint))
+        b.cube_sphere((0.0, -0.2, 0.0), 0.75 - 0.06 * k, 10, m)
+    b.cube_sphere((0.0, -0.2, 0.0), 0.75 - 0.06 * shells - 0.05, 6, b.diffuse(220, 160, 60))
+    scene = b.build()
+    args = camera((0.0, 0.0, 3.4), (0.0, 0.0, 0.0), width, height, hfov_tan=0.41, exposure=8.0, P_Direct=0.7, spp=spp)
+    return scene, args
+
+
 # --------------------------------------------------------------------------- config 2
 def _terrain(seed, amp=1.0, freq=0.35):
     return lambda X, Z: amp * (fbm(X * freq + 37.0, Z * freq + 11.0, seed, 5) - 0.5) * 2.0

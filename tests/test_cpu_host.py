@@ -289,6 +289,11 @@ def test_validation_names_the_inconsistency():
     refused(with_nodes(lambda n, d: n["faceR"].__setitem__(first_leaf, 0)), "children lie beyond")     # a leaf turned inner at the bottom level
     refused(with_nodes(lambda n, d: n["faceL"].__setitem__(first_leaf, n["faceR"][first_leaf] - 1)), "leaves own")
 
+    # a leaf reference holds its face count in 4 bits: a root leaf of 16 faces must not reach the device
+    def long_leaf(n, d):
+        n["faceL"][1], n["faceR"][1] = 0, d.n_faces
+    refused(with_nodes(long_leaf), "at most 15")
+
     def bad_face_material(d):
         fm = np.ctypeslib.as_array(C.cast(d.face_material, C.POINTER(C.c_int32)), (d.n_faces,)).copy()
         fm[5] = d.n_materials
@@ -317,6 +322,13 @@ def test_validation_names_the_inconsistency():
         d.textures = C.cast(texs, C.POINTER(api.RmTextureDesc))
         return texs
     refused(null_level, "level 1 is NULL")
+
+    def empty_level(d):                                             # more levels than the image has (a level of zero width)
+        texs = (api.RmTextureDesc * d.n_textures)(*[d.textures[i] for i in range(d.n_textures)])
+        texs[0].width, texs[0].height, texs[0].map_depth = 4, 64, 4
+        d.textures = C.cast(texs, C.POINTER(api.RmTextureDesc))
+        return texs
+    refused(empty_level, "is empty")
 
     refused(lambda d: setattr(d, "n_materials", 0), "at least one material")
     refused(lambda d: setattr(d, "sky_width", 8), "bad sky size")
