@@ -231,10 +231,15 @@ int rm_stats_read(RmContext *ctx, uint64_t out[4]);
 /* Host-only diagnostic (no GPU): build the secondary-ray tree (see "exact_secondary" below) for `positions` [n][9] and verify
  * its invariants; out = {pair blocks, depth, leaves, largest leaf}. */
 int rm_secondary_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t leaf_max, int32_t out[4]);
+/* The same for the 4-wide, 8-bit quantised form of that tree that bounce and shadow rays traverse by default
+ * (csrc/wide_bvh.cpp): every triangle in one leaf, every decoded child box encloses the vertices beneath it;
+ * out = {nodes (64-byte records), levels, leaves, children per node x 100}. */
+int rm_wide_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t out[4]);
 /* Options (integers).  "exact_secondary" 0|1 (default 0): 1 sends the estimator's bounce and shadow rays through the
  * reference's own BVH in the reference's visit order, like primary rays and the per-ray seam always are; 0 lets them use the
  * library's second tree over the same triangles (same box / triangle tests, binned-SAH topology - the closest accepted hit is
- * the same, far fewer tests per ray).  "count_tests", "time_kernels": counters / per-kind device timing.  The others
+ * the same, far fewer tests per ray) - "secondary_tree" 1: as the binary tree, 2 (default): collapsed to 4-wide nodes with
+ * quantised child boxes and a conservative slab test.  "count_tests", "time_kernels": counters / per-kind device timing.  The others
  * ("trace_refill", "wave_paths", "stack_levels", ...) are tuning and test hooks, see rm_api.cu. */
 int rm_set_option(RmContext *ctx, const char *name, int64_t value);
 /* Per-kernel-kind breakdown.  Kinds: 0 primary / batched per-ray kernels, 1 closest hit over the

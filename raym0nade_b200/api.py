@@ -58,7 +58,7 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
-           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_secondary_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -103,6 +103,7 @@ def lib():
     L.rm_fxaa_device.argtypes = [vp, vp, vp, i32, i32]
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
     L.rm_secondary_tree_stats.argtypes = [vp, i32, i32, i32, vp]
+    L.rm_wide_tree_stats.argtypes = [vp, i32, i32, vp]
     L.rm_comm_unique_id.argtypes = [vp]
     L.rm_comm_init.argtypes = [vp, vp, i32, i32]
     L.rm_reduce.argtypes = [vp, i32]
@@ -415,6 +416,14 @@ def secondary_tree_stats(positions, depth_cap=22, leaf_max=3):
     out = np.zeros(4, np.int32)
     _check(lib().rm_secondary_tree_stats(_p(pos), pos.shape[0], depth_cap, leaf_max, _p(out)))
     return dict(blocks=int(out[0]), depth=int(out[1]), leaves=int(out[2]), largest_leaf=int(out[3]))
+
+
+def wide_tree_stats(positions, depth_cap=22):
+    """build + verify the 4-wide secondary-ray tree on the host; returns dict(nodes, levels, leaves, children_per_node)"""
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 9)
+    out = np.zeros(4, np.int32)
+    _check(lib().rm_wide_tree_stats(_p(pos), pos.shape[0], depth_cap, _p(out)))
+    return dict(nodes=int(out[0]), levels=int(out[1]), leaves=int(out[2]), children_per_node=out[3] / 100.0)
 
 
 def render_multiThread(model: Model, args: RenderArgs, device: int = 0, seed: int = 0):

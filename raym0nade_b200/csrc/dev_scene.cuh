@@ -68,6 +68,8 @@ struct DevScene {
     // (explicit_children) and triangle indices are in the builder's order (face_map -> index into `shade` / the reference order)
     int32_t explicit_children;
     const int32_t *face_map;
+    // 4-wide form of the secondary-ray tree (wide_bvh.cpp): `nodes` then holds 64-byte RmWideNode records, record 0 = the root
+    int32_t wide;
 };
 
 // Camera / render arguments in device form (RenderArgs, include/render.h:8-15).

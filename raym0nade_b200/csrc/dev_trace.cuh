@@ -86,6 +86,35 @@ RM_DI void ray_in_box_fast(const RaySetup &r, float4 a, float4 b, float &tL, flo
     slab_fast(r.o.z, r.inv[2], nz ? b.y : a.z, nz ? a.z : b.y, tL, tR, live);
 }
 
+// ------------------------------------------------------------------------------------------
+// The 4-wide secondary-ray tree (wide_bvh.cpp): one 64-byte record per node = two 256-bit loads, holding the node's
+// quantisation grid (origin o, step s) and, per child, its box in 8-bit grid units.  A child plane is o + s*q; along the
+// ray that is t = q * (s * inv) + (o - org) * inv: one fused multiply-add per plane after a per-node, per-axis setup.
+// This is NOT the reference's rayInBox - it has no counterpart there - it is a conservative slab test (the decoded box
+// encloses the child's true box, the interval is widened by a few ulps and by rayInBox's own 1e-4), so every triangle the ray can hit is still
+// reached and tested with the reference's RayTriangleIntersection.
+struct WideRay {
+    float inv[3];      // 1 / d[i], with |d[i]| clamped away from zero (box test only)
+};
+RM_DI WideRay setup_wide_ray(V3 d) {
+    // rayInBox calls an axis with |d| < eps_zero "parallel" and only asks whether the origin lies inside the slab
+    // (src/geometry.cpp:42-47).  A huge reciprocal says the same thing through the ordinary slab arithmetic: both planes map
+    // to -huge / +huge when the origin is between them, to two values of one sign (an empty interval) when it is not.
+    WideRay w;
+    const float dx = fabsf(d.x) < kEps ? copysignf(1e-30f, d.x) : d.x, dy = fabsf(d.y) < kEps ? copysignf(1e-30f, d.y) : d.y,
+                dz = fabsf(d.z) < kEps ? copysignf(1e-30f, d.z) : d.z;
+    w.inv[0] = __frcp_rn(dx); w.inv[1] = __frcp_rn(dy); w.inv[2] = __frcp_rn(dz);
+    return w;
+}
+// byte c of w as a float: the byte is dropped into the mantissa of 2^23 (one PRMT), then 2^23 is subtracted (exact)
+RM_DI float q8(unsigned w, int c) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | unsigned(c))) - 8388608.0f;
+#else
+    return float((w >> (8 * c)) & 0xffu);
+#endif
+}
+
 // returns t or +INF.  Straight-line: the early returns of the reference become one select at the end.  Under SIMT
 // an early return only saves work when every lane of the warp takes it, and the divergent returns cost more than
 // the arithmetic they skip; the value is a pure function of the inputs, so the result is the reference's.
@@ -189,15 +218,17 @@ struct TraceTune {
     int smem_levels;     // stack entries per thread held in shared memory; deeper ones (rare) go to a small local array
 };
 constexpr int kStackSpill = 28;   // local spill entries: smem_levels + kStackSpill >= any tree depth we build (<= 40)
+constexpr int kStackSpillWide = 56; // the 4-wide tree defers up to three children per level (rm_scene_upload checks 3 * levels against it)
 
-template <class Job, bool COUNT>
+template <class Job, bool COUNT, bool WIDE = false>
 RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt,
                         const TraceTune tune) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     int root;
-    if (S.root_is_leaf) {
+    if (WIDE) root = 0;                          // record 0; a scene that is one leaf still has a root record with that one child
+    else if (S.root_is_leaf) {
         float4 rb = __ldg(S.nodes + 3);
         root = leaf_ref(__float_as_int(rb.z), __float_as_int(rb.w));
     } else root = 1;
@@ -210,7 +241,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
     // only the first tune.smem_levels entries live in shared memory - which leaves more of the SM's 256 KB as L1 - and the
     // rest in a local array that is almost never touched.
     const int cap = tune.smem_levels;
-    int2 spill[kStackSpill];
+    int2 spill[WIDE ? kStackSpillWide : kStackSpill];
     auto push = [&](int sp_, int2 e) { if (sp_ < cap) stack[sp_ * stride] = e; else spill[sp_ - cap] = e; };
     auto peek = [&](int sp_) { return sp_ < cap ? stack[sp_ * stride] : spill[sp_ - cap]; };
 
@@ -218,6 +249,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
     int chunk_next = 0, chunk_end = 0;          // warp-uniform: rays of the current chunk not handed out yet
     bool exhausted = false;                     // warp-uniform: the global cursor ran past n
     RaySetup r;
+    WideRay wr;
     float t_min = kEps, t = CUDART_INF_F, aim = CUDART_INF_F, t_reset = CUDART_INF_F;
     int face = -1, cur = kTraceDone, sp = 0, pass = 0, idx = 0, ti = -1, tend = 0;
 
@@ -241,6 +273,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                 V3 o, d;
                 if (job.load(idx, o, d, aim)) {
                     r = setup_ray(o, d);
+                    if (WIDE) wr = setup_wide_ray(d);
                     t_min = kEps;
                     t_reset = Job::kOcclusion ? fadd(aim, kEps) : CUDART_INF_F;
                     t = t_reset;
@@ -265,7 +298,59 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
             const int nI = __popc(__ballot_sync(FULL, wantI));
             const int nL = __popc(live) - nI;
             if (nI * tune.w_inner >= nL * tune.w_leaf) {
-                if (wantI) {
+                if (WIDE) {
+                  if (wantI) {
+                    // ---- one 4-wide node: 64 bytes, up to four children
+                    const float4 *nd = S.nodes + (size_t(cur) << 2);
+                    float4 h0, h1, h2, h3;
+                    ldg256(nd, h0, h1);
+                    ldg256(nd + 2, h2, h3);
+                    // per axis: t(q) = q * a + b with a = s * inv, b = (o - org) * inv
+                    const float ax = h0.w * wr.inv[0], ay = h1.x * wr.inv[1], az = h1.y * wr.inv[2];
+                    // (o - org) first: the difference is formed at the precision of the coordinates, as the reference's (b - o) * inv is;
+                    // o * inv - org * inv would carry the rounding of two large products into a small t
+                    const float bx = (h0.x - r.o.x) * wr.inv[0], by = (h0.y - r.o.y) * wr.inv[1], bz = (h0.z - r.o.z) * wr.inv[2];
+                    const unsigned qlx = __float_as_uint(h1.z), qly = __float_as_uint(h1.w), qlz = __float_as_uint(h2.x);
+                    const unsigned qhx = __float_as_uint(h2.y), qhy = __float_as_uint(h2.z), qhz = __float_as_uint(h2.w);
+                    // the near plane of an axis is the lower one when the ray runs upwards along it
+                    const bool ux = wr.inv[0] >= 0.0f, uy = wr.inv[1] >= 0.0f, uz = wr.inv[2] >= 0.0f;
+                    const unsigned nx = ux ? qlx : qhx, fx = ux ? qhx : qlx, ny = uy ? qly : qhy, fy = uy ? qhy : qly, nz = uz ? qlz : qhz, fz = uz ? qhz : qlz;
+                    const unsigned meta = __float_as_uint(h3.z);
+                    const int child_base = __float_as_int(h3.x), tri_base = __float_as_int(h3.y);
+                    unsigned key[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float tn = fmaxf(fmaxf(fmaf(q8(nx, c), ax, bx), fmaf(q8(ny, c), ay, by)), fmaxf(fmaf(q8(nz, c), az, bz), t_min));
+                        const float tf = fminf(fminf(fmaf(q8(fx, c), ax, bx), fmaf(q8(fy, c), ay, by)), fminf(fmaf(q8(fz, c), az, bz), t));
+                        const bool hitc = ((meta >> (8 * c)) & 0xffu) != 0u && tn * 0.999998f <= tf * 1.000002f + kEps;      // a few ulps, and the slack rayInBox gives its far plane
+                        // sort key: the entry distance (positive, so its bit pattern orders like the float) with the slot in the low bits
+                        key[c] = hitc ? ((__float_as_uint(tn) & ~3u) | unsigned(c)) : 0xffffffffu;
+                    }
+                    if (COUNT) cnt.box += 4;
+                    // 5-comparator network: ascending by entry distance, misses last
+#define RM_CSWAP(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
+                    RM_CSWAP(0, 1) RM_CSWAP(2, 3) RM_CSWAP(0, 2) RM_CSWAP(1, 3) RM_CSWAP(1, 2)
+#undef RM_CSWAP
+                    auto ref_of = [&](unsigned k) {
+                        const unsigned m = (meta >> (8 * (k & 3u))) & 0xffu;
+                        return (m & 0x80u) ? child_base + int(m & 0x7fu) : ~(((tri_base + int(m >> 2)) << 4) | int(m & 3u));
+                    };
+                    // far children first onto the stack, the nearest one is visited next
+#pragma unroll
+                    for (int c = 3; c >= 1; c--)
+                        if (key[c] != 0xffffffffu) { push(sp, make_int2(ref_of(key[c]), int(key[c] & ~3u))); sp++; }
+                    if (key[0] != 0xffffffffu) cur = ref_of(key[0]);
+                    else {
+                        cur = kTraceDone;
+                        while (sp > 0) {
+                            sp--;
+                            const int2 e = peek(sp);
+                            if (__int_as_float(e.y) < t) { cur = e.x; break; }
+                        }
+                    }
+                    ti = -1;
+                  }
+                } else if (wantI) {
                     const float4 *nd = S.nodes + (size_t(cur) << 2);        // children 2u, 2u+1: one 64-byte block
                     float4 a0, b0, a1, b1;
                     ldg256(nd, a0, b0);

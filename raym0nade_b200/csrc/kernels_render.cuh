@@ -59,7 +59,8 @@ constexpr int kShadeCtasPerSm = RM_SHADE_CTAS;
 #endif
 constexpr int kCtasBounce = RM_CTAS_BOUNCE, kCtasSurface = RM_CTAS_SURFACE, kCtasNee = RM_CTAS_NEE, kCtasRegen = RM_CTAS_REGEN, kCtasDirect = RM_CTAS_DIRECT;
 
-constexpr int kMediumSlots = 6;     // nested-dielectric entries kept per path besides the air base entry
+constexpr int kMediumSlots = 16;    // nested-dielectric entries per path besides the implicit air entry: a path gains at most one per level,
+                                    // maxRayDepth levels (the reference's multimap is unbounded, src/render.cpp:13-42)
 constexpr int kMaxRayDepth = 16;    // maxRayDepth, src/render.cpp:125
 
 // ------------------------------------------------------------------ path queue (SoA)
@@ -71,23 +72,15 @@ struct PathQueue {
     float *diff;             // [12][cap]
     float *T, *B0;           // [3][cap]
     float *W, *rough;
-    int *flags;              // depth | exclude << 8 | n_medium << 16
-    int *med_id;             // [kMediumSlots][cap]
+    int *flags;              // depth | exclude << 8 | n_medium << 16 | (k_decide:) mode << 24 | doDirect << 26 | nee_pass_absorb << 27
+    int *med_id;             // [kMediumSlots][cap]   the medium stack lives here, in insertion order; the kernels walk it in place
     float *med;              // [4][kMediumSlots][cap]  ior, absorb rgb
-    float *hit_t;            // INF = this entry is finished (miss, emissive hit) - k_bounce skips it
+    float *hit_t;            // INF = this entry is finished (miss, emissive hit) - the later stages skip it
     int *hit_face;
     float *surf;             // [22][cap]  the vertex's HitInfo (written by k_surface), field order of RmHitInfo
     float *hdP;              // [6][cap]   dPdx, dPdy at the hit (calc_dPdxy)
-};
-
-// a path that ended in next-event estimation (src/render.cpp:207-221, 249-263): k_nee draws its light samples
-struct __align__(16) NeeRequest {
-    int src;                 // index into the path queue the vertex lives in
-    int count;               // sampleCount[depth] | pass_absorb << 8
-    float factor;            // the `scaling` of the terminating branch: 1/P_reflect [/(1-P_RR)] or 1/(1-P_reflect) [...]
-    unsigned drawn;          // position of the sample's random stream
-    float absorb[3];
-    int _pad;
+    float *dec;              // [7][cap]   decision record of k_decide: P_reflect | NEE scaling, P_RR, F, absorb rgb, relative eta
+    int *skey, *srank;       // sort key of the vertex and its position inside the key's bin
 };
 
 // one NEE / terminal sample waiting for its visibility test
@@ -116,33 +109,6 @@ struct FrameBuffers {
     int *dir_base;           // [npix] first shadow-queue slot of the pixel's direct samples in the current direct wave (-1: none)
 };
 
-struct Medium {
-    int n;
-    int id[kMediumSlots];
-    float ior[kMediumSlots];
-    V3 ab[kMediumSlots];
-};
-
-RM_DI float medium_ior(const Medium &m) {          // Medium::ior, src/render.cpp:26-31
-    float v = 1.0f;
-    for (int i = 0; i < m.n; i++) v = fmaxf(v, m.ior[i]);
-    return v;
-}
-RM_DI V3 medium_absorb(const Medium &m) {          // Medium::absorb, 33-38
-    V3 a = splat3(1.0f);
-    for (int i = 0; i < m.n; i++) a = a * m.ab[i];
-    return a;
-}
-RM_DI void medium_insert(Medium &m, int id, float ior, V3 ab) {
-    if (m.n < kMediumSlots) { m.id[m.n] = id; m.ior[m.n] = ior; m.ab[m.n] = ab; m.n++; }
-}
-RM_DI void medium_erase(Medium &m, int id) {       // multimap::erase(key): every entry with that id
-    int k = 0;
-    for (int i = 0; i < m.n; i++)
-        if (m.id[i] != id) { m.id[k] = m.id[i]; m.ior[k] = m.ior[i]; m.ab[k] = m.ab[i]; k++; }
-    m.n = k;
-}
-
 // pow_s (src/geometry.cpp:22-28): there `pow` resolves to the double version.  Out of line: one copy of the (large)
 // double-precision pow per kernel instead of three - the shading stages are instruction-fetch sensitive.
 RM_NI float pow_s(float a, float k) { return (float)pow((double)a, (double)k); }
@@ -162,6 +128,13 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
 // device-side pipeline state (ints): queue lengths, cursors
 enum { C_Q0 = 0, C_Q1 = 1, C_SQ = 2, C_OVERFLOW = 3, C_GLASS = 4, C_GLASS_LIST = 5, C_CUR_PATH = 6, C_CUR_SHADOW = 7,
        C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_SQ_RUN = 14, C_COUNT = 16 };
+
+// the sort of a round's live vertices by (mode, material), see k_decide
+constexpr int kSortClasses = 32;                      // material id modulo this
+constexpr int kKeyReflect = 0, kKeyRefract = kSortClasses, kKeyNee = 2 * kSortClasses;
+constexpr int kSortBins = 8 * kSortClasses;           // reflect | refract | NEE with 1..6 light samples
+// pipeline state beyond C_COUNT: per-bin counts of this round, then the exclusive offsets (kSortBins + 1)
+enum { C_BINS = C_COUNT, C_OFFS = C_COUNT + kSortBins, C_TOTAL = C_COUNT + 2 * kSortBins + 16 };
 
 // warp-aggregated slot allocation
 RM_DI int alloc_slot(int *counter, bool want) {
@@ -460,7 +433,7 @@ __global__ void __launch_bounds__(256) k_accum_direct(FrameBuffers Fb, Accum Ac,
 
 // ------------------------------------------------------------------ path state I/O
 RM_DI void store_path(const PathQueue &Q, int i, int pixel, unsigned sample, unsigned drawn, V3 o, V3 d, const RayDiff &df,
-                      V3 T, V3 B0, float W, float rough, int depth, bool exclude, const Medium &m) {
+                      V3 T, V3 B0, float W, float rough, int depth, bool exclude, int n_medium) {
     const int c = Q.cap;
     Q.pixel[i] = pixel; Q.sample[i] = sample; Q.drawn[i] = drawn;
     Q.o[i] = o.x; Q.o[c + i] = o.y; Q.o[2 * c + i] = o.z;
@@ -471,12 +444,7 @@ RM_DI void store_path(const PathQueue &Q, int i, int pixel, unsigned sample, uns
     Q.T[i] = T.x; Q.T[c + i] = T.y; Q.T[2 * c + i] = T.z;
     Q.B0[i] = B0.x; Q.B0[c + i] = B0.y; Q.B0[2 * c + i] = B0.z;
     Q.W[i] = W; Q.rough[i] = rough;
-    Q.flags[i] = depth | (exclude ? 256 : 0) | (m.n << 16);
-    for (int k = 0; k < m.n; k++) {
-        Q.med_id[k * c + i] = m.id[k];
-        Q.med[(4 * k) * c + i] = m.ior[k];
-        Q.med[(4 * k + 1) * c + i] = m.ab[k].x; Q.med[(4 * k + 2) * c + i] = m.ab[k].y; Q.med[(4 * k + 3) * c + i] = m.ab[k].z;
-    }
+    Q.flags[i] = depth | (exclude ? 256 : 0) | (n_medium << 16);       // the caller writes the n_medium entries of the medium stack
 }
 
 // ------------------------------------------------------------------ work items of the indirect sample loop
@@ -533,8 +501,10 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasRegen) k_regen(DevScene S, D
         V3 newDir = splat3(0.0f), bsdfPdf = splat3(CUDART_NAN_F), pos = splat3(0.0f);
         RayDiff next;
         float W = 1.0f, rough = 0.0f;
-        Medium med;
-        med.n = 0;
+        bool entered = false;                 // the first vertex refracted into a dielectric: the path starts with one medium entry
+        int med_id = 0;
+        float med_ior = 1.0f;
+        V3 med_ab = splat3(1.0f);
         if (i < n_items) {
             const long long j = first + i;
             int k;
@@ -574,8 +544,8 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasRegen) k_regen(DevScene S, D
                     bsdfPdf = bsdfPdf * fsub(1.0f, F);
                     bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
                     next = bd;
-                    if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
-                    else medium_erase(med, B.s.id);
+                    // (leaving a dielectric here erases from an empty stack: nothing to do)
+                    if (B.s.entering) { entered = true; med_id = B.s.id; med_ior = ior; med_ab = B.s.baseColor; }
                 }
                 if (isfinite_any(newDir)) {
                     want = true;
@@ -585,8 +555,14 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasRegen) k_regen(DevScene S, D
             }
         }
         int slot = alloc_slot(q_count, want);
-        if (want && slot < Q.cap)
-            store_path(Q, slot, p, s, gen.drawn, pos, newDir, next, splat3(1.0f), bsdfPdf, W, rough, 1, true, med);
+        if (want && slot < Q.cap) {
+            store_path(Q, slot, p, s, gen.drawn, pos, newDir, next, splat3(1.0f), bsdfPdf, W, rough, 1, true, entered ? 1 : 0);
+            if (entered) {
+                const int c = Q.cap;
+                Q.med_id[slot] = med_id;
+                Q.med[slot] = med_ior; Q.med[c + slot] = med_ab.x; Q.med[2 * c + slot] = med_ab.y; Q.med[3 * c + slot] = med_ab.z;
+            }
+        }
     }
 }
 
@@ -635,14 +611,12 @@ RM_DI Surface load_surface(const PathQueue &Q, int i) {
     return s;
 }
 
-RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
+// Medium::absorb() (src/render.cpp:33-38) over the path's medium stack
+RM_DI V3 medium_absorb(const PathQueue &Q, int i, int n) {
     const int c = Q.cap;
-    med.n = n;
-    for (int k = 0; k < n; k++) {
-        med.id[k] = Q.med_id[k * c + i];
-        med.ior[k] = Q.med[(4 * k) * c + i];
-        med.ab[k] = mk3(Q.med[(4 * k + 1) * c + i], Q.med[(4 * k + 2) * c + i], Q.med[(4 * k + 3) * c + i]);
-    }
+    V3 a = splat3(1.0f);
+    for (int k = 0; k < n; k++) a = a * mk3(Q.med[(4 * k + 1) * c + i], Q.med[(4 * k + 2) * c + i], Q.med[(4 * k + 3) * c + i]);
+    return a;
 }
 
 // sampleRay up to the surface (src/render.cpp:128-166): a miss returns the sky (unless direct light is
@@ -650,7 +624,10 @@ RM_DI void load_medium(const PathQueue &Q, int i, int n, Medium &med) {
 // hit_t = INF.  Thread 0 also resets the counters the later stages of this round append to.
 __global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene S, FrameBuffers Fb, Accum Ac, PathQueue Q, int *C, int q_slot) {
     const int n = min(C[q_slot], Q.cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; }
+    if (blockIdx.x == 0) {                   // the counters the later stages of this round append to
+        if (threadIdx.x == 0) { C[q_slot ^ 1] = 0; C[C_NEE] = 0; }
+        for (int k = threadIdx.x; k < kSortBins; k += blockDim.x) C[C_BINS + k] = 0;
+    }
     const int c = Q.cap;
     __shared__ int s_idx[kWindow];
     __shared__ int s_n;
@@ -687,9 +664,7 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene 
             if (length(sf.emission) > kEps) {
                 // emissive surface (src/render.cpp:162-166)
                 if (!exclude) {
-                    Medium med;
-                    load_medium(Q, i, fl >> 16, med);
-                    light = sf.emission * get_absorb(medium_absorb(med), t);
+                    light = sf.emission * get_absorb(medium_absorb(Q, i, (fl >> 16) & 31), t);
                     add = true;
                 }
                 Q.hit_t[i] = CUDART_INF_F;
@@ -707,184 +682,266 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene 
 // ------------------------------------------------------------------ one sampleRay level
 __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6};
 
-// sampleRay from the surface on (src/render.cpp:143-312): roughness regularisation, Russian roulette,
-// Fresnel split, then either a NEE termination (-> NeeRequest) or a sampled continuation (-> Qout).
-// The body is cut into phases (decide / reflect / refract / store) with a CTA barrier between them: the
-// warps of a CTA then run the same stretch of this large, branchy kernel at the same time and share its
-// instruction-cache lines instead of evicting each other's (the kernel was bound by instruction fetch).
+// sampleRay from the surface on (src/render.cpp:143-312) is three kinds of work that share nothing but the vertex:
+// a reflected continuation (sample_reflection), a refracted one (sample_btdf) or a termination in next-event estimation
+// (sampleDirectLight, 1..6 light samples).  Which one a vertex takes is decided by its Fresnel term and two draws.  Run
+// together in one kernel the three leave most lanes of a warp idle (ncu, round 1: 12.6 of 32 lanes per instruction), so
+// the level is split the way the reference branches (src/render.cpp:172-284):
+//   k_decide     roughness regularisation, medium scan + calcEta, Fresnel, Russian roulette -> the vertex's MODE, written
+//                with the few numbers the next stage needs (the decision record), and a sort key
+//   k_sort_*     counting sort of the live vertices by key = (mode, material) - NEE vertices also by their sample count
+//   k_continue   <reflect> and <refract>: dense over their segment of the sorted queue -> the next path queue
+//   k_nee        dense over the NEE segment -> shadow items
+// Every warp of the dense kernels then runs one mode on one material (full warps up to the rejection-loop tails), and
+// the surviving paths land in the next queue grouped by the object they left - the next closest-hit pass gets rays whose
+// origins are neighbours.
 enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 };
+// PathQueue::flags: depth | exclude << 8 | n_medium << 16 | mode << 24 | doDirect << 26 | nee_pass_absorb << 27
+// decision record PathQueue::dec [7][cap]: P_reflect (NEE: the `scaling` factor), P_RR, F, absorb rgb, relative eta
 
-__global__ void __launch_bounds__(kShadeBlock, kCtasBounce) k_bounce(unsigned long long seed, PathQueue Qin, const int *__restrict__ in_count,
-                                                PathQueue Qout, int *out_count, NeeRequest *nq, int *nee_count) {
-    const int n = min(*in_count, Qin.cap);
-    const int c = Qin.cap;
+#ifndef RM_CTAS_DECIDE
+#define RM_CTAS_DECIDE 4
+#endif
+__global__ void __launch_bounds__(kShadeBlock, RM_CTAS_DECIDE) k_decide(unsigned long long seed, PathQueue Q, const int *__restrict__ in_count, int *bins) {
+    const int n = min(*in_count, Q.cap);
+    const int c = Q.cap;
+    const int lane = threadIdx.x & 31;
     __shared__ int s_idx[kWindow];
     __shared__ int s_n;
     for (int base = blockIdx.x * kWindow; base < n; base += gridDim.x * kWindow) {
       // live here: a hit on a non-emissive surface (k_surface marked the others finished)
-      const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Qin.hit_t[i] != CUDART_INF_F; });
+      const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Q.hit_t[i] != CUDART_INF_F; });
       for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
-        RM_LOCKSTEP();
         const int j = j0 + threadIdx.x;
         const int i = j < n_live ? s_idx[j] : -1;
-        int mode = kBounceDead;
-        int p = 0, depth = 0, fails = 0;
+        int key = -1;
+        if (i >= 0) {
+            const int p = Q.pixel[i];
+            const int fl = Q.flags[i];
+            const int depth = fl & 255, n_med = (fl >> 16) & 31;
+            const float t = Q.hit_t[i];
+            Rng gen;
+            gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, Q.drawn[i]);
+            const float *f = Q.surf + i;
+            const float s_rough = f[16 * c], opacity = f[18 * c], s_eta = f[19 * c];
+            const int id = __float_as_int(f[20 * c]);
+            const bool entering = __float_as_int(f[21 * c]) != 0;
+            // the medium stack as the reference's Medium::ior() / absorb() see it, and as they would after erase(id)
+            float eta_all = 1.0f, eta_excl = 1.0f;
+            V3 ab = splat3(1.0f);
+            int n_excl = 0;
+            for (int k = 0; k < n_med; k++) {
+                const float ior = Q.med[(4 * k) * c + i];
+                eta_all = fmaxf(eta_all, ior);
+                ab = ab * mk3(Q.med[(4 * k + 1) * c + i], Q.med[(4 * k + 2) * c + i], Q.med[(4 * k + 3) * c + i]);
+                if (Q.med_id[k * c + i] != id) { eta_excl = fmaxf(eta_excl, ior); n_excl++; }
+            }
+            // roughness regularisation along the path (src/render.cpp:143-146): both the carried factor and the vertex take the maximum
+            const float rough = fmaxf(fmaxf(Q.rough[i], fmul(1.0f, s_rough)), s_rough);
+            const float P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(rough)));
+            bool doDirect = P_RR < 0.9f;
+            const V3 absorb = get_absorb(ab, t);
+            float P_reflect = 1.0f, F = 0.0f, eta_rel = s_eta;
+            int n_after = n_med;
+            if (opacity < kEps) {
+                // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
+                const float eta2 = entering ? fmaxf(eta_all, s_eta) : eta_excl;
+                if (!entering) n_after = n_excl + 1;            // erase(id) then insert(id, ...)
+                eta_rel = fdiv(eta_all, eta2);
+                Bsdf B;
+                B.s = default_surface();
+                B.inDir = -mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
+                B.s.surfaceNormal = mk3(f[3 * c], f[4 * c], f[5 * c]);
+                B.s.eta = eta_rel;
+                V3 refr;
+                precise_refraction(B, refr, F);
+                if (n_after == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
+                else P_reflect = F;
+                P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
+            }
+            int mode;
+            float first = P_reflect;                            // decision record slot 0
+            bool pass_absorb = false;
+            if (gen() <= P_reflect) {
+                doDirect = doDirect && entering && n_after == 0;
+                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                    mode = kBounceNee;
+                    first = fdiv(1.0f, P_reflect);
+                    if (depth < kMaxRayDepth) first = fdiv(first, fsub(1.0f, P_RR));
+                } else mode = kBounceReflect;
+            } else {
+                doDirect = doDirect && !entering && n_after == 1;
+                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
+                    mode = kBounceNee;
+                    pass_absorb = true;
+                    first = fdiv(1.0f, fsub(1.0f, P_reflect));
+                    if (depth < kMaxRayDepth) first = fdiv(first, fsub(1.0f, P_RR));
+                } else mode = kBounceRefract;
+            }
+            Q.flags[i] = (fl & 0x00ffffff) | (mode << 24) | (doDirect ? 1 << 26 : 0) | (pass_absorb ? 1 << 27 : 0);
+            Q.drawn[i] = gen.drawn;
+            Q.rough[i] = rough;
+            float *d = Q.dec + i;
+            d[0] = first; d[c] = P_RR; d[2 * c] = F; d[3 * c] = absorb.x; d[4 * c] = absorb.y; d[5 * c] = absorb.z; d[6 * c] = eta_rel;
+            const int cls = id & (kSortClasses - 1);
+            key = mode == kBounceReflect ? kKeyReflect + cls : (mode == kBounceRefract ? kKeyRefract + cls : kKeyNee + (c_sampleCount[depth] - 1) * kSortClasses + cls);
+        }
+        // position inside the key's bin: the lanes of a warp that share a key share one atomic
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(grp) - 1;
+        int first_rank = 0;
+        if (key >= 0 && lane == leader) first_rank = atomicAdd(bins + key, __popc(grp));
+        first_rank = __shfl_sync(0xffffffffu, first_rank, leader);
+        if (key >= 0) { Q.skey[i] = key; Q.srank[i] = first_rank + __popc(grp & ((1u << lane) - 1u)); }
+      }
+    }
+}
+
+// exclusive offsets of the bins (one block)
+__global__ void __launch_bounds__(kSortBins) k_sort_offsets(const int *__restrict__ bins, int *offs) {
+    __shared__ int s[kSortBins];
+    const int k = threadIdx.x;
+    const int v = bins[k];
+    s[k] = v;
+    __syncthreads();
+    for (int o = 1; o < kSortBins; o <<= 1) {
+        const int add = k >= o ? s[k - o] : 0;
+        __syncthreads();
+        s[k] += add;
+        __syncthreads();
+    }
+    offs[k] = s[k] - v;
+    if (k == kSortBins - 1) offs[kSortBins] = s[k];
+}
+
+// the sorted queue: position -> path-queue slot
+__global__ void __launch_bounds__(256) k_sort_scatter(PathQueue Q, const int *__restrict__ in_count, const int *__restrict__ offs, int *__restrict__ sorted) {
+    const int n = min(*in_count, Q.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (Q.hit_t[i] != CUDART_INF_F) sorted[offs[Q.skey[i]] + Q.srank[i]] = i;
+}
+
+// A sampled continuation: reflection (src/render.cpp:222-236) or refraction (264-283), dense over its segment of the
+// sorted queue; the surviving vertex goes into the next path queue.
+template <bool REFRACT>
+__global__ void __launch_bounds__(kShadeBlock, kCtasBounce) k_continue(unsigned long long seed, PathQueue Qin, PathQueue Qout, int *out_count,
+                                                                        const int *__restrict__ sorted, const int *__restrict__ offs) {
+    const int lo = offs[REFRACT ? kKeyRefract : kKeyReflect], hi = offs[REFRACT ? kKeyNee : kKeyRefract];
+    const int c = Qin.cap;
+    for (int base = lo + blockIdx.x * blockDim.x; base < hi; base += gridDim.x * blockDim.x) {
+        RM_LOCKSTEP();
+        const int j = base + threadIdx.x;
+        bool cont = false;
+        int i = 0, p = 0, depth = 0, fl = 0, fails = 0;
         unsigned sample = 0;
         Rng gen;
-        V3 T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f), absorb = splat3(1.0f), dir = splat3(0.0f);
-        V3 bsdfPdf = splat3(CUDART_NAN_F);
-        float W = 1.0f, rough = 0.0f, nee_factor = 1.0f, ior = 1.0f, P_reflect = 1.0f, P_RR = 1.0f, F = 0.0f;
-        bool nee_pass_absorb = false, doDirect = false;
+        V3 T = splat3(1.0f), B0 = splat3(0.0f), newDir = splat3(0.0f);
+        float W = 1.0f, rough = 0.0f, ior = 1.0f;
         RayDiff next;
-        Medium med;
-        med.n = 0;
         Bsdf B;
         B.s = default_surface();
         B.inDir = splat3(0.0f);
-        const float t = i >= 0 ? Qin.hit_t[i] : CUDART_INF_F;
-
-        // ---- phase 1: load the vertex, Fresnel and roulette decisions
-        if (t != CUDART_INF_F) {
+        if (j < hi) {
+            i = sorted[j];
             p = Qin.pixel[i];
             sample = Qin.sample[i];
-            const int fl = Qin.flags[i];
+            fl = Qin.flags[i];
             depth = fl & 255;
-            load_medium(Qin, i, fl >> 16, med);
-            dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
+            const V3 dir = mk3(Qin.d[i], Qin.d[c + i], Qin.d[2 * c + i]);
             T = mk3(Qin.T[i], Qin.T[c + i], Qin.T[2 * c + i]);
             B0 = mk3(Qin.B0[i], Qin.B0[c + i], Qin.B0[2 * c + i]);
             W = Qin.W[i];
             rough = Qin.rough[i];
             gen.init(seed, (unsigned)p, sample, kStreamIndirect, Qin.drawn[i]);
+            const float *d = Qin.dec + i;
+            const float P_reflect = d[0], P_RR = d[c], F = d[2 * c];
+            const V3 absorb = mk3(d[3 * c], d[4 * c], d[5 * c]);
             B.inDir = -dir;
             B.s = load_surface(Qin, i);
             ior = B.s.eta;
-            rough = fmaxf(rough, fmul(1.0f, B.s.roughness));
-            B.s.roughness = fmaxf(B.s.roughness, rough);
-            P_RR = fadd(1.0f, fmul(fsub(0.5f, 1.0f), fsqrt(B.s.roughness)));
-            doDirect = P_RR < 0.9f;
-            absorb = get_absorb(medium_absorb(med), t);
-            if (B.s.opacity < kEps) {
-                // calcEta (src/render.cpp:89-99); the base air entry is implicit (ior 1, absorb 1)
-                float eta1 = medium_ior(med), eta2;
-                if (B.s.entering) eta2 = fmaxf(eta1, B.s.eta);
-                else {
-                    medium_erase(med, B.s.id);
-                    eta2 = medium_ior(med);
-                    medium_insert(med, B.s.id, B.s.eta, B.s.baseColor);
-                }
-                B.s.eta = fdiv(eta1, eta2);
-                V3 refr;
-                precise_refraction(B, refr, F);
-                if (med.n == 0) P_reflect = fadd(0.24f, fmul(fsub(1.0f, 0.24f), F));
-                else P_reflect = F;
-                P_reflect = fmaxf(fsub(P_reflect, 1e-3f), 0.0f);
-            }
-            if (gen() <= P_reflect) {
-                doDirect = doDirect && B.s.entering && med.n == 0;
-                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                    mode = kBounceNee;
-                    nee_factor = fdiv(1.0f, P_reflect);
-                    if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                } else mode = kBounceReflect;
+            B.s.roughness = rough;
+            B.s.eta = d[6 * c];
+            const bool doDirect = (fl >> 26) & 1;
+            V3 bsdfPdf = splat3(CUDART_NAN_F);
+            if (!REFRACT) {
+                sample_reflection(B, gen, newDir, bsdfPdf, fails);
+                bsdfPdf = div_true(bsdfPdf, P_reflect);
+                if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
+                RayDiff bd;                                   // only the direction differentials enter calc_dDdxy
+                bd.dPdx = bd.dPdy = splat3(0.0f);
+                bd.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
+                bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
+                V3 dDdx, dDdy;
+                calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
+                next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
+                next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
+                next.dDdx = dDdx; next.dDdy = dDdy;
             } else {
-                doDirect = doDirect && !B.s.entering && med.n == 1;
-                if (doDirect && (depth >= kMaxRayDepth || gen() > P_RR)) {
-                    mode = kBounceNee;
-                    nee_pass_absorb = true;
-                    nee_factor = fdiv(1.0f, fsub(1.0f, P_reflect));
-                    if (depth < kMaxRayDepth) nee_factor = fdiv(nee_factor, fsub(1.0f, P_RR));
-                } else mode = kBounceRefract;
+                // the incoming differentials pass through a refraction unchanged (src/render.cpp:268,273)
+                if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
+                else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
+                next.dPdx = mk3(Qin.diff[0 * c + i], Qin.diff[1 * c + i], Qin.diff[2 * c + i]);
+                next.dPdy = mk3(Qin.diff[3 * c + i], Qin.diff[4 * c + i], Qin.diff[5 * c + i]);
+                next.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
+                next.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
+                bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
+                if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
             }
-        }
-        RM_LOCKSTEP();
-
-        // ---- phase 2: reflection (src/render.cpp:222-236)
-        if (mode == kBounceReflect) {
-            sample_reflection(B, gen, newDir, bsdfPdf, fails);
-            bsdfPdf = div_true(bsdfPdf, P_reflect);
-            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-            RayDiff bd;                                   // only the direction differentials enter calc_dDdxy
-            bd.dPdx = bd.dPdy = splat3(0.0f);
-            bd.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
-            bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
-            V3 dDdx, dDdy;
-            calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
-            next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
-            next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
-            next.dDdx = dDdx; next.dDdy = dDdy;
-        }
-        RM_LOCKSTEP();
-
-        // ---- phase 3: refraction (src/render.cpp:264-283); the incoming differentials pass through unchanged (268,273)
-        if (mode == kBounceRefract) {
-            if (fabsf(fsub(B.s.eta, 1.0f)) < kEps) { newDir = dir; bsdfPdf = splat3(1.0f); }
-            else { sample_btdf(B, gen, newDir, bsdfPdf, fails); bsdfPdf = bsdfPdf * fsub(1.0f, F); }
-            next.dPdx = mk3(Qin.diff[0 * c + i], Qin.diff[1 * c + i], Qin.diff[2 * c + i]);
-            next.dPdy = mk3(Qin.diff[3 * c + i], Qin.diff[4 * c + i], Qin.diff[5 * c + i]);
-            next.dDdx = mk3(Qin.diff[6 * c + i], Qin.diff[7 * c + i], Qin.diff[8 * c + i]);
-            next.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
-            bsdfPdf = div_true(bsdfPdf, fsub(1.0f, P_reflect));
-            if (doDirect) bsdfPdf = div_true(bsdfPdf, P_RR);
-            if (B.s.entering) medium_insert(med, B.s.id, ior, B.s.baseColor);
-            else medium_erase(med, B.s.id);
-        }
-        RM_LOCKSTEP();
-
-        // ---- phase 4: hand the vertex on
-        const bool terminate = mode == kBounceNee;
-        bool cont = false;
-        if (terminate) {
-            // the light samples see the regularised roughness and the relative eta of this vertex
-            Qin.surf[16 * c + i] = B.s.roughness;
-            Qin.surf[19 * c + i] = B.s.eta;
-        } else if (mode != kBounceDead && isfinite_any(newDir) && depth != kMaxRayDepth) {
-            cont = true;
-            bsdfPdf = bsdfPdf * absorb;
-            T = T * bsdfPdf;
-            if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
-        }
-        const int ns = alloc_slot(nee_count, terminate);
-        if (terminate) {
-            NeeRequest rq;
-            rq.src = i;
-            rq.count = c_sampleCount[depth] | (nee_pass_absorb ? 256 : 0);
-            rq.factor = nee_factor;
-            rq.drawn = gen.drawn;
-            rq.absorb[0] = absorb.x; rq.absorb[1] = absorb.y; rq.absorb[2] = absorb.z;
-            rq._pad = 0;
-            float4 *dst = reinterpret_cast<float4 *>(nq + ns);
-            const float4 *src = reinterpret_cast<const float4 *>(&rq);
-            dst[0] = src[0]; dst[1] = src[1];
+            if (isfinite_any(newDir) && depth != kMaxRayDepth) {
+                cont = true;
+                bsdfPdf = bsdfPdf * absorb;
+                T = T * bsdfPdf;
+                if (fails > 0) W = fmul(W, fdiv(1.0f, float(1 + fails)));
+            }
         }
         const int slot = alloc_slot(out_count, cont);
-        if (cont && slot < Qout.cap)
-            store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, doDirect, med);
-      }
+        if (cont && slot < Qout.cap) {
+            // the medium stack the continuing path carries: calcEta's erase(id) + insert(id, ...) on leaving a dielectric, then
+            // the refraction's own insert (entering) or erase (leaving)
+            const bool glass = B.s.opacity < kEps;
+            const bool drop = glass && !B.s.entering;
+            const bool append = glass && (REFRACT ? B.s.entering : !B.s.entering);
+            const int n_med = (fl >> 16) & 31;
+            const int oc = Qout.cap;
+            int n_out = 0;
+            for (int k = 0; k < n_med; k++) {
+                const int mid = Qin.med_id[k * c + i];
+                if (drop && mid == B.s.id) continue;
+                Qout.med_id[n_out * oc + slot] = mid;
+#pragma unroll
+                for (int q = 0; q < 4; q++) Qout.med[(4 * n_out + q) * oc + slot] = Qin.med[(4 * k + q) * c + i];
+                n_out++;
+            }
+            if (append && n_out < kMediumSlots) {
+                Qout.med_id[n_out * oc + slot] = B.s.id;
+                Qout.med[(4 * n_out) * oc + slot] = ior;
+                Qout.med[(4 * n_out + 1) * oc + slot] = B.s.baseColor.x; Qout.med[(4 * n_out + 2) * oc + slot] = B.s.baseColor.y; Qout.med[(4 * n_out + 3) * oc + slot] = B.s.baseColor.z;
+                n_out++;
+            }
+            store_path(Qout, slot, p, sample, gen.drawn, B.s.position, newDir, next, T, B0, W, rough, depth + 1, (fl >> 26) & 1, n_out);
+        }
     }
 }
 
 // ------------------------------------------------------------------ NEE at a terminating vertex
-// sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every NeeRequest.
-// The request reserves its 1..6 shadow-queue slots up front; a sample that comes out invalid leaves a
-// null item (aim = NaN) that the visibility pass skips.
-__global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const NeeRequest *__restrict__ nq,
-                                             const int *__restrict__ nee_count, int nq_cap, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
-    const int n = min(*nee_count, nq_cap);
+// sampleDirectLight(bsdf, model, gen, sampleCount[depth]) (src/sampling.cpp:467-527) for every vertex of the NEE segment of
+// the sorted queue (ordered by sample count, then material).  A vertex reserves its 1..6 shadow-queue slots up front; a
+// sample that comes out invalid leaves a null item (aim = NaN) that the visibility pass skips.
+__global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, FrameBuffers Fb, unsigned long long seed, PathQueue Q, const int *__restrict__ sorted,
+                                             const int *__restrict__ offs, ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
+    const int lo = offs[kKeyNee], hi = offs[kSortBins];
     const int c = Q.cap;
     const int lane = threadIdx.x & 31;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        RM_LOCKSTEP();                       // CTA-wide lock step per batch (see k_bounce)
+    for (int base = lo + blockIdx.x * blockDim.x; base < hi; base += gridDim.x * blockDim.x) {
+        RM_LOCKSTEP();                       // CTA-wide lock step per batch: the warps share the kernel's instruction-cache lines
         const int r = base + threadIdx.x;
-        int cnt = 0, i = 0;
-        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0;
-        if (r < n) {
-            const float4 *src = reinterpret_cast<const float4 *>(nq + r);
-            q0 = __ldg(src); q1 = __ldg(src + 1);
-            i = __float_as_int(q0.x);
-            cnt = __float_as_int(q0.y) & 255;
+        int cnt = 0, i = 0, fl = 0;
+        if (r < hi) {
+            i = sorted[r];
+            fl = Q.flags[i];
+            cnt = c_sampleCount[fl & 255];
         }
-        // reserve cnt consecutive shadow slots per request: warp scan + one atomic per warp
+        // reserve cnt consecutive shadow slots per vertex: warp scan + one atomic per warp
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -892,15 +949,19 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, Frame
         if (lane == 31 && incl > 0) first = atomicAdd(s_count, incl);
         first = __shfl_sync(0xffffffffu, first, 31) + incl - cnt;
         if (cnt == 0) continue;
-        const bool pass_absorb = (__float_as_int(q0.y) & 256) != 0;
-        const float nee_factor = q0.z;
-        const V3 absorb = mk3(q1.x, q1.y, q1.z);
+        const bool pass_absorb = (fl >> 27) & 1;
+        const float *d = Q.dec + i;
+        const float nee_factor = d[0];
+        const V3 absorb = mk3(d[3 * c], d[4 * c], d[5 * c]);
         const int p = Q.pixel[i];
         Rng gen;
-        gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, __float_as_uint(q0.w));
+        gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, Q.drawn[i]);
         Bsdf B;
         B.inDir = -mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
         B.s = load_surface(Q, i);
+        // the light samples see the regularised roughness and the relative eta of this vertex
+        B.s.roughness = Q.rough[i];
+        B.s.eta = d[6 * c];
         const V3 T = mk3(Q.T[i], Q.T[c + i], Q.T[2 * c + i]), B0 = mk3(Q.B0[i], Q.B0[c + i], Q.B0[2 * c + i]);
         const float W = Q.W[i];
         const float inv_spp = fdiv(1.0f, float(Fb.n_ind[p]));

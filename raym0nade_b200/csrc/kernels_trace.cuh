@@ -92,7 +92,7 @@ struct OccludedJob : RayListJob {
     RM_DI void visibility(int i, bool occluded) const { out[i] = occluded ? 1 : 0; }
 };
 
-template <class Job, bool COUNT>
+template <class Job, bool COUNT, bool WIDE = false>
 __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene S, Job job, int n_host, const int *__restrict__ n_dev,
                                                                                 int *cursor, unsigned long long *counters, TraceTune tune) {
     // one deferred child per tree level and thread: [levels][kTraceBlock] int2, sized by the launcher from the scene's
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceCtasPerSm) k_trace(DevScene
     extern __shared__ int2 stack[];
     TraceCounters cnt = {0, 0, 0};
     const int n = n_dev ? min(*n_dev, n_host) : n_host;          // queue kernels read their length on the device
-    trace_engine<Job, COUNT>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt, tune);
+    trace_engine<Job, COUNT, WIDE>(S, job, n, cursor, stack + threadIdx.x, kTraceBlock, cnt, tune);
     flush_counters(cnt, counters, COUNT);
 }
 
@@ -112,6 +112,11 @@ inline void launch_trace(const DevScene &S, int stack_levels, bool count, int gr
     TraceTune t = tune;
     t.smem_levels = std::min(stack_levels, tune.smem_levels > 0 ? tune.smem_levels : stack_levels);
     const size_t smem = size_t(t.smem_levels) * kTraceBlock * sizeof(int2);
+    if (S.wide) {          // the 4-wide secondary-ray tree (wide_bvh.cpp)
+        if (count) k_trace<Job, true, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
+        else k_trace<Job, false, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
+        return;
+    }
     if (count) k_trace<Job, true><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
     else k_trace<Job, false><<<grid, kTraceBlock, smem, st>>>(S, job, n_host, n_dev, cursor, counters, t);
 }

@@ -9,6 +9,7 @@
 
 #include "rm_context.cuh"
 #include "kernels_trace.cuh"
+#include "wide_bvh.h"
 
 using namespace rm;
 
@@ -41,6 +42,18 @@ static int upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st, int
     if (bytes) RM_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
     total += (int64_t)bytes;
     return RM_OK;
+}
+
+// test hook "seam_secondary_tree": the per-ray seam through the binary (1) or the 4-wide (2) secondary-ray tree; the seam
+// itself (0) is the reference's tree in the reference's order
+static const DevScene &seam_scene(const RmContext *ctx) {
+    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->scene_wide : (ctx->seam_tree ? ctx->scene_fast : ctx->scene);
+}
+static int seam_levels(const RmContext *ctx) {
+    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->stack_levels_wide : (ctx->seam_tree ? ctx->stack_levels_fast : ctx->stack_levels);
+}
+static TraceTune seam_tune(const RmContext *ctx) {
+    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->tune_wide : (ctx->seam_tree ? ctx->tune_fast : ctx->tune);
 }
 
 extern "C" {
@@ -196,11 +209,31 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
             RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die at scope exit
             ctx->stack_levels_fast = std::min(std::max(fdepth, 2), 40);
             ctx->fast_root_is_leaf = fnodes[1].faceR != 0;
+            // ... and its 4-wide, 8-bit quantised form (wide_bvh.cpp): what bounce and shadow rays traverse by default
+            ctx->have_wide = false;
+            if (ctx->fast_leaf_max <= 3) {
+                std::vector<RmWideNode> wnodes;
+                std::vector<int32_t> worder;
+                int wdepth = 0;
+                if ((rc = rm_build_wide_bvh(fnodes, forder, n, wnodes, worder, &wdepth))) return rc;
+                if (3 * wdepth <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {       // up to three deferred children per level
+                    if ((rc = upload(ctx->b_nodes_wide, wnodes.data(), wnodes.size() * sizeof(RmWideNode), st, total))) return rc;
+                    if ((rc = upload(ctx->b_facemap_wide, worder.data(), worder.size() * 4, st, total))) return rc;
+                    RM_CUDA(cudaStreamSynchronize(st));
+                    ctx->stack_levels_wide = std::max(3 * wdepth, 2);
+                    ctx->have_wide = true;
+                }
+            }
             ctx->fast_key = key; ctx->fast_n = n; ctx->fast_key_valid = true;
         }
         if ((rc = ctx->b_tri_fast.alloc(size_t(n) * 16 * kTriStride))) return rc;
         k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap.as<int>(), n, ctx->b_tri_fast.as<float4>());
         ctx->launches++;
+        if (ctx->have_wide) {
+            if ((rc = ctx->b_tri_wide.alloc(size_t(n) * 16 * kTriStride))) return rc;
+            k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide.as<int>(), n, ctx->b_tri_wide.as<float4>());
+            ctx->launches++;
+        }
         RM_CUDA(cudaGetLastError());
     }
 
@@ -300,6 +333,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     S.root_is_leaf = sc->nodes[1].faceR != 0;
     S.explicit_children = 0;
     S.face_map = nullptr;
+    S.wide = 0;
     // deferred children per ray <= inner levels of the heap-indexed tree (node indices < n_nodes)
     int levels = 1;
     while ((int64_t(1) << levels) < int64_t(sc->n_nodes)) levels++;
@@ -310,6 +344,14 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     ctx->scene_fast.face_map = ctx->b_facemap.as<int32_t>();
     ctx->scene_fast.explicit_children = 1;
     ctx->scene_fast.root_is_leaf = ctx->fast_root_is_leaf ? 1 : 0;
+    ctx->scene_wide = S;
+    if (ctx->have_wide) {
+        ctx->scene_wide.nodes = ctx->b_nodes_wide.as<float4>();
+        ctx->scene_wide.tri = ctx->b_tri_wide.as<float4>();
+        ctx->scene_wide.face_map = ctx->b_facemap_wide.as<int32_t>();
+        ctx->scene_wide.root_is_leaf = 0;
+        ctx->scene_wide.wide = 1;
+    }
     ctx->scene_h2d_bytes = total;
     ctx->scene_bytes = 0;
     for (const DevBuf *b : {&ctx->b_nodes, &ctx->b_tri, &ctx->b_shade, &ctx->b_mats, &ctx->b_texs, &ctx->b_texels, &ctx->b_lights, &ctx->b_lpos,
@@ -340,8 +382,7 @@ int rm_trace_closest(RmContext *ctx, int64_t n, const float *org, const float *d
     job.tri_idx = ctx->b_io[2].as<int>(); job.t_out = ctx->b_io[3].as<float>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    launch_trace(ctx->seam_secondary_tree ? ctx->scene_fast : ctx->scene, ctx->seam_secondary_tree ? ctx->stack_levels_fast : ctx->stack_levels, ctx->count_tests, grid, st, job,
-                 int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(seam_scene(ctx), seam_levels(ctx), ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, seam_tune(ctx));
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(tri_idx, ctx->b_io[2].p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -367,8 +408,7 @@ int rm_trace_occluded(RmContext *ctx, int64_t n, const float *org, const float *
     job.out = ctx->b_io[3].as<unsigned char>();
     RM_CUDA(cudaMemsetAsync(ctx->b_cursor.p, 0, 4, st));
     const int grid = ctx->sm_count * kTraceCtasPerSm;
-    launch_trace(ctx->seam_secondary_tree ? ctx->scene_fast : ctx->scene, ctx->seam_secondary_tree ? ctx->stack_levels_fast : ctx->stack_levels, ctx->count_tests, grid, st, job,
-                 int(n), nullptr, ctx->b_cursor.as<int>(), cnt, ctx->tune);
+    launch_trace(seam_scene(ctx), seam_levels(ctx), ctx->count_tests, grid, st, job, int(n), nullptr, ctx->b_cursor.as<int>(), cnt, seam_tune(ctx));
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(out, ctx->b_io[3].p, n, cudaMemcpyDeviceToHost, st));
@@ -454,15 +494,17 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
     // test hook: rm_trace_closest / rm_trace_occluded through the secondary-ray tree (the seam itself is the reference's tree)
-    if (!std::strcmp(name, "seam_secondary_tree")) { ctx->seam_secondary_tree = value != 0; return RM_OK; }
+    if (!std::strcmp(name, "seam_secondary_tree")) { ctx->seam_tree = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); return RM_OK; }
+    // bounce and shadow rays: 1 = the binary secondary-ray tree, 2 = its 4-wide quantised form (default)
+    if (!std::strcmp(name, "secondary_tree")) { ctx->secondary_tree = value == 1 ? 1 : 2; return RM_OK; }
     if (!std::strcmp(name, "fast_leaf_max")) { ctx->fast_leaf_max = int(std::min<int64_t>(std::max<int64_t>(value, 1), 15)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_depth_cap")) { ctx->fast_depth_cap = int(std::min<int64_t>(std::max<int64_t>(value, 8), 26)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }
-    if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = ctx->tune_fast.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
-    if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = ctx->tune_fast.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
-    if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = ctx->tune_fast.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "trace_refill")) { ctx->tune.refill_live = ctx->tune_fast.refill_live = ctx->tune_wide.refill_live = int(std::min<int64_t>(std::max<int64_t>(value, 1), 32)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_inner")) { ctx->tune.w_inner = ctx->tune_fast.w_inner = ctx->tune_wide.w_inner = int(std::max<int64_t>(value, 1)); return RM_OK; }
+    if (!std::strcmp(name, "trace_w_leaf")) { ctx->tune.w_leaf = ctx->tune_fast.w_leaf = ctx->tune_wide.w_leaf = int(std::max<int64_t>(value, 1)); return RM_OK; }
     if (!std::strcmp(name, "smem_levels")) {        // stack entries per thread in shared memory (0 = the whole tree depth); deeper entries spill to local memory
-        ctx->tune.smem_levels = ctx->tune_fast.smem_levels = int(std::min<int64_t>(std::max<int64_t>(value, 0), 40));
+        ctx->tune.smem_levels = ctx->tune_fast.smem_levels = ctx->tune_wide.smem_levels = int(std::min<int64_t>(std::max<int64_t>(value, 0), 40));
         return RM_OK;
     }
     if (!std::strcmp(name, "stack_levels")) {       // perf experiments only: never below the tree depth rm_scene_upload derived

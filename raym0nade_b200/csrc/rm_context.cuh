@@ -62,11 +62,16 @@ struct RmContext {
     // scene
     rm::DevScene scene{};
     rm::DevScene scene_fast{};             // the same scene with the secondary-ray tree (fast_bvh.cpp) in place of the reference's
-    int stack_levels_fast = 24;
+    rm::DevScene scene_wide{};             // ... and with that tree collapsed to 4-wide quantised nodes (wide_bvh.cpp): what bounce and shadow rays traverse
+    int stack_levels_fast = 24, stack_levels_wide = 42;
+    int secondary_tree = 2;                // 1: the binary secondary-ray tree, 2: its 4-wide form (rm_set_option "secondary_tree")
+    bool have_wide = false;
     DevBuf b_nodes_fast, b_tri_fast, b_facemap;
+    DevBuf b_nodes_wide, b_tri_wide, b_facemap_wide;
     int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
     int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
-    bool fast_root_is_leaf = false, fast_key_valid = false, seam_secondary_tree = false;
+    bool fast_root_is_leaf = false, fast_key_valid = false;
+    int seam_tree = 0;                     // test hook: which tree rm_trace_closest / rm_trace_occluded traverse (0 = the reference's)
     uint64_t fast_key = 0;
     int fast_n = 0;
     DevBuf b_nodes, b_tri, b_shade, b_mats, b_texs, b_texels, b_lights, b_lpos, b_lnrm, b_lcdf, b_sky, b_skycdf, b_skyguide, b_lut;
@@ -80,6 +85,7 @@ struct RmContext {
     int sm_count = 148;
     int stack_levels = 24;                 // traversal stack entries per ray = tree depth of the uploaded scene (rm_scene_upload)
     rm::TraceTune tune{28, 1, 1, 0};          // see dev_trace.cuh; adjustable through rm_set_option for perf experiments
+    rm::TraceTune tune_wide{28, 1, 2, 14};    // the 4-wide tree: same vote, same shared-memory stack share
     rm::TraceTune tune_fast{28, 1, 2, 14};    // the secondary-ray tree has short leaves: the vote leans towards the leaf step (profiles/r01g_ab17_votes.txt);
                                            // 14 stack entries in shared memory, deeper ones (rare) in local memory (profiles/r01g_ab18_stack_spill.txt)
     int wave_paths = 1 << 25;              // path-queue capacity of the wavefront loop (vertices in flight per round).  32 M keeps every
@@ -103,7 +109,7 @@ struct RmContext {
     ~RmContext() {
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
-                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
+                          &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_nodes_wide, &b_tri_wide, &b_facemap_wide, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
     }
 };
@@ -115,5 +121,6 @@ int rm_check_args(const RmRenderArgs *a);
 void rm_render_state_free(RmContext *ctx);
 // implemented in fast_bvh.cpp
 int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
+// implemented in wide_bvh.cpp (declared in wide_bvh.h)
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);

@@ -26,7 +26,7 @@ struct RenderState {
     // queues
     int q_cap = 0, s_cap = 0;
     DevBuf q[2][20];
-    DevBuf shadow, nee;
+    DevBuf shadow, sorted;    // shadow items; the round's live vertices ordered by (mode, material) (k_decide / k_sort_*)
     DevBuf counts;            // int[C_COUNT]: device-side pipeline state, see the C_* indices in kernels_render.cuh
     int *h_counts = nullptr;  // pinned mirror of `counts`
     // resolved planes + output images
@@ -61,6 +61,7 @@ PathQueue make_queue(RenderState *R, int which) {
     Q.flags = b[10].as<int>(); Q.med_id = b[11].as<int>(); Q.med = b[12].as<float>();
     Q.hit_t = b[13].as<float>(); Q.hit_face = b[14].as<int>();
     Q.surf = b[15].as<float>(); Q.hdP = b[16].as<float>();
+    Q.dec = b[17].as<float>(); Q.skey = b[18].as<int>(); Q.srank = b[19].as<int>();
     return Q;
 }
 
@@ -68,11 +69,11 @@ int alloc_queues(RenderState *R, int q_cap, int s_cap) {
     int rc;
     if (q_cap > R->q_cap) {
         const size_t c = size_t(q_cap);
-        const size_t words[17] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6};
+        const size_t words[20] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6, 7, 1, 1};
         for (int w = 0; w < 2; w++)
-            for (int k = 0; k < 17; k++)
+            for (int k = 0; k < 20; k++)
                 if ((rc = R->q[w][k].alloc(c * words[k] * 4))) return rc;
-        if ((rc = R->nee.alloc(c * sizeof(NeeRequest)))) return rc;
+        if ((rc = R->sorted.alloc(c * sizeof(int)))) return rc;
         R->q_cap = q_cap;
     }
     if (s_cap > R->s_cap) {
@@ -128,7 +129,7 @@ void rm_render_state_free(RmContext *ctx) {
         b->release();
     for (int w = 0; w < 2; w++)
         for (int k = 0; k < 20; k++) R->q[w][k].release();
-    R->nee.release();
+    R->sorted.release();
     if (R->h_counts) cudaFreeHost(R->h_counts);
     delete R;
     ctx->render_state = nullptr;
@@ -149,11 +150,11 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     const int npix = args->width * args->height;
     if ((rc = R->gbuffer.alloc(size_t(npix) * sizeof(RmHitInfo))) || (rc = R->sav_base.alloc(size_t(npix) * 12)) ||
         (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->dir_base.alloc(size_t(npix) * 4)) ||
-        (rc = R->counts.alloc(C_COUNT * 4)))
+        (rc = R->counts.alloc(C_TOTAL * 4)))
         return rc;
     R->npix = npix;
     cudaStream_t st = ctx->stream;
-    RM_CUDA(cudaMemsetAsync(R->counts.p, 0, C_COUNT * 4, st));
+    RM_CUDA(cudaMemsetAsync(R->counts.p, 0, C_TOTAL * 4, st));
     const int spp_d = spp_direct_of(args), base = args->spp - spp_d;
     int *counts = R->counts.as<int>();
     k_gbuffer<<<(npix + 127) / 128, 128, 0, st>>>(ctx->scene, to_dev_args(args), ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), frame(R), spp_d, base, counts + 4);
@@ -232,14 +233,15 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const FrameBuffers Fb = frame(R);
     const Accum Ac = accum(R);
     ShadowItem *sq = R->shadow.as<ShadowItem>();
-    NeeRequest *nq = R->nee.as<NeeRequest>();
+    int *sorted = R->sorted.as<int>();
     const int grid = R->sm_count * 8;
     const int tgrid = R->sm_count * kTraceCtasPerSm;
     const bool ct = ctx->count_tests;
     // bounce and shadow rays: the secondary-ray tree unless the caller asked for the reference's traversal order throughout
-    const DevScene &sec_scene = ctx->exact_secondary ? ctx->scene : ctx->scene_fast;
-    const int sec_levels = ctx->exact_secondary ? ctx->stack_levels : ctx->stack_levels_fast;
-    const TraceTune sec_tune = ctx->exact_secondary ? ctx->tune : ctx->tune_fast;
+    const bool use_wide = !ctx->exact_secondary && ctx->secondary_tree == 2 && ctx->have_wide;
+    const DevScene &sec_scene = ctx->exact_secondary ? ctx->scene : (use_wide ? ctx->scene_wide : ctx->scene_fast);
+    const int sec_levels = ctx->exact_secondary ? ctx->stack_levels : (use_wide ? ctx->stack_levels_wide : ctx->stack_levels_fast);
+    const TraceTune sec_tune = ctx->exact_secondary ? ctx->tune : (use_wide ? ctx->tune_wide : ctx->tune_fast);
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
     // (C_CUR_SHADOW must be 0)
@@ -303,11 +305,15 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
                 ctx->timed_end();
                 ctx->timed_begin(RM_KIND_SHADE);
                 k_surface<<<R->sm_count * kCtasSurface, kShadeBlock, 0, st>>>(ctx->scene, Fb, Ac, Qin, C, cur);
-                k_bounce<<<R->sm_count * kCtasBounce, kShadeBlock, 0, st>>>(seed, Qin, C + cur, Qout, C + (cur ^ 1), nq, C + C_NEE);
-                k_nee<<<R->sm_count * kCtasNee, kShadeBlock, 0, st>>>(ctx->scene, Fb, seed, Qin, nq, C + C_NEE, Qin.cap, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
+                k_decide<<<R->sm_count * RM_CTAS_DECIDE, kShadeBlock, 0, st>>>(seed, Qin, C + cur, C + C_BINS);
+                k_sort_offsets<<<1, kSortBins, 0, st>>>(C + C_BINS, C + C_OFFS);
+                k_sort_scatter<<<R->sm_count * 8, 256, 0, st>>>(Qin, C + cur, C + C_OFFS, sorted);
+                k_continue<false><<<R->sm_count * kCtasBounce, kShadeBlock, 0, st>>>(seed, Qin, Qout, C + (cur ^ 1), sorted, C + C_OFFS);
+                k_continue<true><<<R->sm_count * kCtasBounce, kShadeBlock, 0, st>>>(seed, Qin, Qout, C + (cur ^ 1), sorted, C + C_OFFS);
+                k_nee<<<R->sm_count * kCtasNee, kShadeBlock, 0, st>>>(ctx->scene, Fb, seed, Qin, sorted, C + C_OFFS, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
                 ctx->timed_end();
                 k_shadow_gate<<<1, 1, 0, st>>>(C, shadow_threshold, R->s_cap, 0);
-                ctx->launches += 7;
+                ctx->launches += 11;
                 trace_shadow(C + C_SQ_RUN, 0);
                 cur ^= 1;
             }

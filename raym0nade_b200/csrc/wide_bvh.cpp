@@ -152,3 +152,64 @@ int rm_build_wide_bvh(const std::vector<RmBvhNode> &bin, const std::vector<int32
     if (depth_out) *depth_out = C.max_depth + 1;
     return RM_OK;
 }
+
+// Host-only diagnostic behind the C ABI (no GPU needed): builds the secondary-ray tree for `positions`, collapses it and
+// checks the 4-wide form - every triangle in exactly one leaf, every child's DECODED box (o + s * q, evaluated in double)
+// encloses every triangle vertex beneath that child, links in range, leaves of 1..3 triangles - before it reports the shape.
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
+
+extern "C" int rm_wide_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t out[4]) {
+    std::vector<RmBvhNode> bin;
+    std::vector<int32_t> order, worder;
+    std::vector<RmWideNode> w;
+    int depth = 0, wdepth = 0;
+    int rc = rm_build_fast_bvh(positions, n, depth_cap, 3, bin, order, &depth);
+    if (rc) return rc;
+    if ((rc = rm_build_wide_bvh(bin, order, n, w, worder, &wdepth))) return rc;
+    std::vector<uint8_t> seen(size_t(n), 0);
+    struct Item { int node; double lo[3], hi[3]; };        // the decoded box every vertex beneath `node` must lie in
+    std::vector<Item> stack;
+    Item root{0, {-INFINITY, -INFINITY, -INFINITY}, {INFINITY, INFINITY, INFINITY}};
+    stack.push_back(root);
+    long long children = 0, leaves = 0;
+    bool ok = true;
+    while (ok && !stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.node < 0 || size_t(it.node) >= w.size()) { ok = false; break; }
+        const RmWideNode &nd = w[it.node];
+        for (int c = 0; c < 4 && ok; c++) {
+            const uint8_t m = nd.meta[c];
+            if (!m) continue;
+            children++;
+            Item ch;
+            for (int a = 0; a < 3; a++) {
+                ch.lo[a] = std::max(it.lo[a], double(nd.o[a]) + double(nd.s[a]) * nd.qlo[a][c]);
+                ch.hi[a] = std::min(it.hi[a], double(nd.o[a]) + double(nd.s[a]) * nd.qhi[a][c]);
+            }
+            if (m & 0x80) {
+                ch.node = nd.child_base + (m & 0x7f);
+                if (ch.node <= it.node) ok = false;            // children are emitted after their parent
+                stack.push_back(ch);
+            } else {
+                const int cnt = m & 3, first = nd.tri_base + (m >> 2);
+                if (cnt < 1 || first < 0 || first + cnt > n) { ok = false; break; }
+                leaves++;
+                for (int k = first; k < first + cnt && ok; k++) {
+                    const int t = worder[k];
+                    if (t < 0 || t >= n || seen[t]) { ok = false; break; }
+                    seen[t] = 1;
+                    for (int v = 0; v < 3 && ok; v++)
+                        for (int a = 0; a < 3; a++) {
+                            const double x = positions[size_t(t) * 9 + v * 3 + a];
+                            if (x == x && (x < ch.lo[a] || x > ch.hi[a])) ok = false;      // (a NaN vertex can never be hit)
+                        }
+                }
+            }
+        }
+    }
+    for (int i = 0; ok && i < n; i++) ok = seen[i] != 0;
+    if (!ok) return rm_fail(RM_ERR_STATE, "rm_wide_tree_stats: the 4-wide tree violates an invariant");
+    if (out) { out[0] = int32_t(w.size()); out[1] = wdepth; out[2] = int32_t(leaves); out[3] = int32_t(children * 100 / std::max<size_t>(w.size(), 1)); }
+    return RM_OK;
+}

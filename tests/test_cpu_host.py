@@ -220,6 +220,32 @@ def test_secondary_ray_tree_invariants(which):
         assert st["depth"] <= max(cap, min_depth) + 1, st
 
 
+@pytest.mark.parametrize("which", ["one", "cornell", "heightfield", "glossy", "flat"])
+def test_wide_secondary_tree_invariants(which):
+    """csrc/wide_bvh.cpp: the 4-wide collapse with 8-bit quantised child boxes keeps every triangle in exactly one leaf and
+    every decoded child box around the vertices beneath it (checked inside rm_wide_tree_stats, in double precision)"""
+    from raym0nade_b200 import api
+    if which == "one":
+        pos = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    elif which == "cornell":
+        pos = scenes.cornell_box(8, 8, 0)[0].positions
+    elif which == "heightfield":
+        pos = scenes.heightfield_scene(20_000)[0].positions
+    elif which == "flat":               # axis-aligned, zero-thickness geometry far from the origin: flat quantisation grids
+        g = np.stack(np.meshgrid(np.arange(40, dtype=np.float32), np.arange(40, dtype=np.float32)), -1).reshape(-1, 2)
+        z = np.full((g.shape[0], 1), 1000.25, np.float32)
+        a, b, c = np.concatenate([g, z], 1), np.concatenate([g + [1, 0], z], 1), np.concatenate([g + [0, 1], z], 1)
+        pos = np.concatenate([a, b, c], 1).astype(np.float32)
+    else:
+        pos = scenes.glossy_dielectric(120_000, 8, 8, 0)[0].positions
+    n = np.asarray(pos).reshape(-1, 9).shape[0]
+    st = api.wide_tree_stats(pos)
+    assert st["leaves"] >= (n + 2) // 3 and st["nodes"] >= 1
+    if n > 1000:
+        assert st["children_per_node"] > 2.5, st            # the collapse fills its nodes (2 = nothing gained over the binary tree)
+        assert 3 * st["levels"] <= 14 + 56, st              # deferred children fit the traversal stack (dev_trace.cuh)
+
+
 # --------------------------------------------------------------------------- static check of the compiled kernels
 def test_sass_has_the_fetch_widths_and_warp_primitives_the_design_states():
     """DESIGN.md section 4 in the machine code (cuobjdump -sass, no GPU): every traversal kernel fetches nodes and triangles
@@ -235,7 +261,7 @@ def test_sass_has_the_fetch_widths_and_warp_primitives_the_design_states():
     by_name = {sass_mix.short(names[k]): c for k, c in kernels.items()}
     assert len(by_name) >= 35
     trace = {n: c for n, c in by_name.items() if "k_trace<" in n}
-    assert len(trace) == 10                                   # 5 jobs x {reference tree, secondary-ray tree}
+    assert len(trace) == 20                                   # 5 jobs x {counting, plain} x {binary trees, 4-wide tree}
     for n, c in trace.items():
         assert c["LDG.128"] + c["LDG.256"] >= 8, (n, dict(c))     # node pairs and triangle records, 16 B or 32 B per load
         assert c["VOTE"] >= 3 and c["SHFL"] >= 8, (n, dict(c))    # ballot / shfl compaction of the ray queue

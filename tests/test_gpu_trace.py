@@ -154,10 +154,12 @@ def test_closest_and_occluded_random_rays(ref, which):
     ctx.close()
 
 
+@pytest.mark.parametrize("tree", [1, 2])
 @pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout", "glossy"])
-def test_secondary_ray_tree_finds_the_reference_hits(ref, which):
+def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree):
     """The estimator's bounce and shadow rays traverse a second tree over the same triangles (fast_bvh.cpp: binned SAH,
-    leaves <= 4) with the same box and triangle tests.  It must find the closest accepted triangle the reference finds:
+    leaves <= 3; tree = 1) - by default in its 4-wide form with 8-bit quantised child boxes and a conservative slab test
+    (wide_bvh.cpp; tree = 2) - with the reference's triangle test.  It must find the closest accepted triangle the reference finds:
     checked here ray by ray against the compiled reference through a test hook that sends the per-ray seam through that
     tree.  Equal-t ties between triangles (shared edges) are the only freedom a different visit order has: t is
     bit-equal on every ray (with alpha cut-outs: on all but <= 0.02 %), the triangle index and the occlusion booleans on all
@@ -173,7 +175,7 @@ def test_secondary_ray_tree_finds_the_reference_hits(ref, which):
     model = Model(scene)
     R = ref.RefScene(scene)
     ctx = Context(0).upload(model)
-    ctx.set_option("seam_secondary_tree", 1)
+    ctx.set_option("seam_secondary_tree", tree)
     org, d = _random_rays(scene, 50_000, 23)
     tri, t = ctx.trace_closest(org, d)
     rtri, rt = R.trace_closest(org, d)

@@ -146,6 +146,14 @@ template <class T> static inline T __shfl_up_sync(unsigned mask, T value, unsign
     const T from = __shfl_sync(mask, value, int(lane >= delta ? lane - delta : lane));
     return lane >= delta ? from : value;
 }
+// lanes holding the same value (full mask only): 32 broadcasts
+template <class T> static inline unsigned __match_any_sync(unsigned mask, T value) {
+    if (mask != 0xffffffffu) rm_gpu_only();
+    unsigned same = 0;
+    for (int src = 0; src < 32; src++)
+        if (__shfl_sync(mask, value, src) == value) same |= 1u << src;
+    return same;
+}
 static inline unsigned __activemask() { rm_gpu_only(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { rm_gpu_only(); }
 

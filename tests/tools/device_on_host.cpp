@@ -473,7 +473,7 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
     std::vector<float> sav(size_t(npix) * 3, 0.0f);
     std::vector<int> n_ind(npix, 0), dir_base(npix, -1), glass_list(npix, 0);
     FrameBuffers Fb{g.data(), sav.data(), n_ind.data(), dir_base.data()};
-    int C[C_COUNT] = {0};
+    int C[C_TOTAL] = {0};
     const int base = spp;                                                   // spp_direct = 0
     rm_host_launch(k_gbuffer, dim3((npix + 127) / 128), dim3(128), H.S, A, (const int *)tri.data(), (const float *)t.data(), Fb, 0, base, C + 4);
     rm_host_launch_blocks(k_glass_list_host, dim3((npix + 127) / 128), dim3(128), (const int *)n_ind.data(), npix, base, glass_list.data(), C + 5);
@@ -486,12 +486,12 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
     const int n_a = base, n_b_total = n_glass > 0 ? 16 * base : 0;
     const long long items_a = (long long)npix * n_a, items_b = n_b_total > n_a ? (long long)n_glass * (n_b_total - n_a) : 0, total_items = items_a + items_b;
     const int q_cap = int(std::max(1024LL, total_items)), s_cap = 6 * q_cap;
-    const size_t words[17] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6};
+    const size_t words[20] = {1, 1, 1, 3, 3, 12, 3, 3, 1, 1, 1, size_t(kMediumSlots), size_t(4 * kMediumSlots), 1, 1, 22, 6, 7, 1, 1};
     std::vector<std::vector<uint32_t>> store[2];
     PathQueue Q[2];
     for (int w = 0; w < 2; w++) {
-        store[w].resize(17);
-        for (int k = 0; k < 17; k++) store[w][k].assign(size_t(q_cap) * words[k], 0u);
+        store[w].resize(20);
+        for (int k = 0; k < 20; k++) store[w][k].assign(size_t(q_cap) * words[k], 0u);
         auto at = [&](int k) { return static_cast<void *>(store[w][k].data()); };
         PathQueue &q = Q[w];
         q.cap = q_cap;
@@ -501,8 +501,9 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
         q.flags = (int *)at(10); q.med_id = (int *)at(11); q.med = (float *)at(12);
         q.hit_t = (float *)at(13); q.hit_face = (int *)at(14);
         q.surf = (float *)at(15); q.hdP = (float *)at(16);
+        q.dec = (float *)at(17); q.skey = (int *)at(18); q.srank = (int *)at(19);
     }
-    std::vector<NeeRequest> nq(q_cap);
+    std::vector<int> sorted(q_cap);
     std::vector<ShadowItem> sq(size_t(s_cap) + 1);
     ItemSpace I;
     I.items_a = items_a; I.total = total_items; I.npix = npix; I.n_glass = std::max(n_glass, 1); I.n_a = n_a;
@@ -536,10 +537,14 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
             DOH_STEP("traced");
             rm_host_launch_blocks(k_surface, grid, block, H.S, Fb, Ac, Qin, C, cur);
             DOH_STEP("surfaced");
-            rm_host_launch_blocks(k_bounce, grid, block, seed, Qin, (const int *)(C + cur), Qout, C + (cur ^ 1), nq.data(), C + C_NEE);
-            DOH_STEP("bounced");
-            rm_host_launch_blocks(k_nee, grid, block, H.S, Fb, seed, Qin, (const NeeRequest *)nq.data(), (const int *)(C + C_NEE), Qin.cap, sq.data(), C + C_SQ, s_cap,
-                                  C + C_OVERFLOW);
+            rm_host_launch_blocks(k_decide, grid, block, seed, Qin, (const int *)(C + cur), C + C_BINS);
+            rm_host_launch_blocks(k_sort_offsets, dim3(1), dim3(kSortBins), (const int *)(C + C_BINS), C + C_OFFS);
+            rm_host_launch_blocks(k_sort_scatter, grid, dim3(256), Qin, (const int *)(C + cur), (const int *)(C + C_OFFS), sorted.data());
+            DOH_STEP("decided + sorted");
+            rm_host_launch_blocks(k_continue<false>, grid, block, seed, Qin, Qout, C + (cur ^ 1), (const int *)sorted.data(), (const int *)(C + C_OFFS));
+            rm_host_launch_blocks(k_continue<true>, grid, block, seed, Qin, Qout, C + (cur ^ 1), (const int *)sorted.data(), (const int *)(C + C_OFFS));
+            DOH_STEP("continued");
+            rm_host_launch_blocks(k_nee, grid, block, H.S, Fb, seed, Qin, (const int *)sorted.data(), (const int *)(C + C_OFFS), sq.data(), C + C_SQ, s_cap, C + C_OVERFLOW);
             DOH_STEP("nee drawn");
             rm_host_launch(k_shadow_gate, dim3(1), dim3(1), C, shadow_threshold, s_cap, 0);
             trace_shadow();
