@@ -172,6 +172,14 @@ int rm_comm_unique_id(uint8_t id[128]);
 int rm_comm_init(RmContext *ctx, const uint8_t id[128], int32_t rank, int32_t world);
 int rm_reduce(RmContext *ctx, int32_t root);
 int rm_comm_destroy(RmContext *ctx);
+/* The exchange with its last step scattered (ncclReduceScatter): afterwards rank r holds the summed frame for ITS slice of
+ * the pixels only - [r * per, (r + 1) * per), per = ceil(width * height / world) - and every rank finalises and downloads
+ * its own slice in parallel: rm_resolve_slice writes pixels [first, first + count) of the WHOLE-frame host arrays it is
+ * given (e.g. one shared pinned frame all ranks of a box map); rm_frame_slice reports the slice.  Without a preceding
+ * rm_reduce_scatter the slice is the whole frame. */
+int rm_reduce_scatter(RmContext *ctx);
+int rm_frame_slice(RmContext *ctx, int64_t *first_pixel, int64_t *pixels);
+int rm_resolve_slice(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is);
 
 /* Progressive checkpoint / resume (the reference has none): the un-finalised accumulators
  * of the current frame as one opaque blob of rm_checkpoint_bytes(args) bytes.  Save after any rm_render_samples call;

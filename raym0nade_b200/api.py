@@ -58,7 +58,7 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
-           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_reduce_scatter", "rm_frame_slice", "rm_resolve_slice", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -108,6 +108,9 @@ def lib():
     L.rm_comm_init.argtypes = [vp, vp, i32, i32]
     L.rm_reduce.argtypes = [vp, i32]
     L.rm_comm_destroy.argtypes = [vp]
+    L.rm_reduce_scatter.argtypes = [vp]
+    L.rm_frame_slice.argtypes = [vp, vp, vp]
+    L.rm_resolve_slice.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.rm_checkpoint_bytes.restype = i64
     L.rm_checkpoint_bytes.argtypes = [ARGS]
     L.rm_checkpoint_save.argtypes = [vp, vp, i64]
@@ -345,6 +348,21 @@ class Context:
     def reduce(self, root: int = 0):
         """the three-step frame reduction over the context's communicator, on the context's stream"""
         _check(lib().rm_reduce(self.h, root))
+
+    def reduce_scatter(self):
+        """the frame reduction with its last step scattered: this rank ends up holding its slice of the summed frame"""
+        _check(lib().rm_reduce_scatter(self.h))
+
+    def frame_slice(self):
+        """(first pixel, pixel count) of the frame this rank holds after reduce_scatter (the whole frame without one)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(lib().rm_frame_slice(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def resolve_slice(self, args: RenderArgs, gbuffer=None, planes=(None, None, None, None)):
+        """finalise this rank's slice and write it into the given WHOLE-frame host arrays (any may be None)"""
+        a = args.to_c()
+        _check(lib().rm_resolve_slice(self.h, C.byref(a), _p(gbuffer), *[_p(p) for p in planes]))
 
     def checkpoint_save(self, args: RenderArgs):
         """the un-finalised accumulators of the current frame as a byte blob"""

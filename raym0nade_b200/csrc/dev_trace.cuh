@@ -254,6 +254,27 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
     int face = -1, cur = kTraceDone, sp = 0, pass = 0, idx = 0, ti = -1, tend = 0;
 
     for (;;) {
+        // ---- report: the lanes whose BVH::rayHit ended since the last refill resolve cut-outs and hand their result over
+        // together - run per lane as soon as it ends, this block would execute on most iterations with one or two lanes in it
+        if (active && cur == kTraceDone) {
+            bool again = false;
+            if (!Job::kOcclusion) {
+                if (t != CUDART_INF_F && S.any_cutout && transparent_test(S, r, t, face)) {
+                    t_min = fadd(t, kEps); t = CUDART_INF_F; face = -1; pass++;
+                    again = pass < 8;
+                }
+                if (!again) job.hit(idx, t, (S.face_map && face >= 0) ? __ldg(S.face_map + face) : face);
+            } else {
+                bool occluded = !(t >= aim);
+                if (occluded && S.any_cutout && transparent_test(S, r, t, face)) {
+                    t_min = fadd(t, kEps); t = t_reset; face = -1; pass++;
+                    again = pass < 8;                 // 8 cut-outs in a row: the reference reports "blocked"
+                }
+                if (!again) job.visibility(idx, occluded);
+            }
+            if (again) { cur = root; sp = 0; ti = -1; cnt.rays++; }
+            else active = false;
+        }
         // ---- fetch: idle lanes take the next rays
         unsigned idle = __ballot_sync(FULL, !active);
         while (idle != 0u) {
@@ -293,8 +314,10 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
         // children, or every lane that holds a leaf tests its next triangle - whichever has more lanes
         // ready; the others wait a turn.  Lanes therefore never idle through a whole descent or a whole
         // leaf of their neighbours, and both step bodies run with most of their lanes busy.
+        live = __ballot_sync(FULL, active && cur != kTraceDone);
         do {
-            const bool wantI = active && cur >= 0;
+            const bool stepping = active && cur != kTraceDone;        // a lane whose ray has ended waits for the next report / refill
+            const bool wantI = stepping && cur >= 0;
             const int nI = __popc(__ballot_sync(FULL, wantI));
             const int nL = __popc(live) - nI;
             if (nI * tune.w_inner >= nL * tune.w_leaf) {
@@ -383,7 +406,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     }
                     ti = -1;
                 }
-            } else if (active && !wantI) {
+            } else if (stepping && !wantI) {
                 if (ti < 0) { const int x = ~cur; ti = x >> 4; tend = ti + (x & 15); }        // first visit of this leaf
 #if RM_LEAF_REPS > 1
 #pragma unroll 1
@@ -438,27 +461,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
               }
 #endif
             }
-            if (active && cur == kTraceDone) {
-                // one BVH::rayHit finished: resolve cut-outs, then report
-                bool again = false;
-                if (!Job::kOcclusion) {
-                    if (t != CUDART_INF_F && S.any_cutout && transparent_test(S, r, t, face)) {
-                        t_min = fadd(t, kEps); t = CUDART_INF_F; face = -1; pass++;
-                        again = pass < 8;
-                    }
-                    if (!again) job.hit(idx, t, (S.face_map && face >= 0) ? __ldg(S.face_map + face) : face);
-                } else {
-                    bool occluded = !(t >= aim);
-                    if (occluded && S.any_cutout && transparent_test(S, r, t, face)) {
-                        t_min = fadd(t, kEps); t = t_reset; face = -1; pass++;
-                        again = pass < 8;                 // 8 cut-outs in a row: the reference reports "blocked"
-                    }
-                    if (!again) job.visibility(idx, occluded);
-                }
-                if (again) { cur = root; sp = 0; ti = -1; cnt.rays++; }
-                else active = false;
-            }
-            live = __ballot_sync(FULL, active);
+            live = __ballot_sync(FULL, active && cur != kTraceDone);
         } while (__popc(live) >= need);
     }
 }

@@ -17,66 +17,101 @@ constexpr int kFxTileW = 32, kFxTileH = 8;
 RM_DI float min4(float a, float b, float c, float d) { float m = a; if (b < m) m = b; if (c < m) m = c; if (d < m) m = d; return m; }
 RM_DI float max4(float a, float b, float c, float d) { float m = a; if (m < b) m = b; if (m < c) m = c; if (m < d) m = d; return m; }
 
+// Data movement: the tile's rgb (12 B / pixel) comes in and goes out through shared memory as 16-byte vectors - a tile row is
+// 384 contiguous bytes, 24 float4 - instead of three stride-12 scalar accesses per pixel; the two halo columns are scalar.
+// Shared row layout: [32 interior pixels][right halo][left halo], so the interior starts 16-byte aligned.
+constexpr int kFxRow = kFxTileW * 3 + 8;          // floats per shared row (104: a multiple of 4)
+RM_DI int fx_col(int lx) { return lx >= 0 ? lx * 3 : kFxTileW * 3 + 3; }      // lx in [-1, 32]
+
 __global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__restrict__ in, float *__restrict__ out, int width, int height) {
+    __shared__ __align__(16) float rgb[kFxTileH + 2][kFxRow];
     __shared__ float luma[kFxTileH + 2][kFxTileW + 2];
     const int x0 = blockIdx.x * kFxTileW, y0 = blockIdx.y * kFxTileH;
     const int tid = threadIdx.y * kFxTileW + threadIdx.x;
-    for (int i = tid; i < (kFxTileH + 2) * (kFxTileW + 2); i += kFxTileW * kFxTileH) {
-        int ly = i / (kFxTileW + 2), lx = i % (kFxTileW + 2);
-        int gx = x0 + lx - 1, gy = y0 + ly - 1;
-        float l = 0.0f;
-        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
-            const float *p = in + (size_t(gy) * width + gx) * 3;
-            l = lum(mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)));
+    const bool vec = (width & 3) == 0 && x0 + kFxTileW <= width;       // every row segment of the tile is 16-byte aligned and inside the image
+    if (vec) {
+        for (int i = tid; i < (kFxTileH + 2) * (kFxTileW * 3 / 4); i += kFxTileW * kFxTileH) {
+            const int row = i / (kFxTileW * 3 / 4), q = i % (kFxTileW * 3 / 4), gy = y0 + row - 1;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (gy >= 0 && gy < height) v = __ldg(reinterpret_cast<const float4 *>(in + (size_t(gy) * width + x0) * 3) + q);
+            reinterpret_cast<float4 *>(rgb[row])[q] = v;
         }
-        luma[ly][lx] = l;
+        for (int i = tid; i < (kFxTileH + 2) * 6; i += kFxTileW * kFxTileH) {
+            const int row = i / 6, k = i % 6, gy = y0 + row - 1, gx = k < 3 ? x0 + kFxTileW : x0 - 1;
+            float v = 0.0f;
+            if (gy >= 0 && gy < height && gx >= 0 && gx < width) v = __ldg(in + (size_t(gy) * width + gx) * 3 + k % 3);
+            rgb[row][kFxTileW * 3 + k] = v;
+        }
+    } else {
+        for (int i = tid; i < (kFxTileH + 2) * (kFxTileW + 2) * 3; i += kFxTileW * kFxTileH) {
+            const int row = i / ((kFxTileW + 2) * 3), r = i % ((kFxTileW + 2) * 3), lx = r / 3 - 1, ch = r % 3;
+            const int gx = x0 + lx, gy = y0 + row - 1;
+            float v = 0.0f;
+            if (gx >= 0 && gx < width && gy >= 0 && gy < height) v = __ldg(in + (size_t(gy) * width + gx) * 3 + ch);
+            rgb[row][fx_col(lx) + ch] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (kFxTileH + 2) * (kFxTileW + 2); i += kFxTileW * kFxTileH) {
+        const int row = i / (kFxTileW + 2), lx = i % (kFxTileW + 2) - 1;
+        const float *p = rgb[row] + fx_col(lx);
+        luma[row][lx + 1] = lum(mk3(p[0], p[1], p[2]));
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= width || y >= height) return;
     const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
-    const float *pc = in + (size_t(y) * width + x) * 3;
-    const V3 center = mk3(__ldg(pc), __ldg(pc + 1), __ldg(pc + 2));
-    float *po = out + (size_t(y) * width + x) * 3;
-    const float M = luma[ly][lx];
-    const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
-    const float N = hasN ? luma[ly - 1][lx] : M, Sl = hasS ? luma[ly + 1][lx] : M;
-    const float E = hasE ? luma[ly][lx + 1] : M, Wl = hasW ? luma[ly][lx - 1] : M;
-    const float rangeMin = min4(N, Sl, E, Wl), rangeMax = max4(N, Sl, E, Wl);
-    const float range = fsub(rangeMax, rangeMin);
-    float thr = fmul(rangeMax, 0.125f);                 // EDGE_THRESHOLD_MAX
-    thr = (0.0312f < thr) ? thr : 0.0312f;              // std::max(EDGE_THRESHOLD_MIN, ...)
-    if (range < thr) { po[0] = center.x; po[1] = center.y; po[2] = center.z; return; }
-    const float NW = (hasN && hasW) ? luma[ly - 1][lx - 1] : M, NE = (hasN && hasE) ? luma[ly - 1][lx + 1] : M;
-    const float SW = (hasS && hasW) ? luma[ly + 1][lx - 1] : M, SE = (hasS && hasE) ? luma[ly + 1][lx + 1] : M;
-    const float third = fdiv(1.0f, 3.0f);
-    const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
-    const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
-    const bool isH = edgeHorz >= edgeVert;
-    const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
-    float g = fdiv(isH ? edgeHorz : edgeVert, range);
-    g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
-    const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
-    V3 finalColor = center;
-    float bestDelta = 0.0f;
-    const float gs = fmul(g, stepLength);
-    for (int i = 0; i < 12; i++) {                      // QUALITY
-        float off = fmul(gs, float(i + 1));
-        float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
-        if (su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f) continue;
-        int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
-        sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
-        sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
-        const float *ps = in + (size_t(sy) * width + sx) * 3;
-        V3 sc = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
-        float delta = fabsf(fsub(lum(sc), M));
-        if (delta > bestDelta) { bestDelta = delta; finalColor = sc; }
+    float *mine = rgb[ly] + threadIdx.x * 3;            // this pixel's slot: read as the centre, overwritten with the result
+    if (x < width && y < height) {
+        const V3 center = mk3(mine[0], mine[1], mine[2]);
+        V3 r = center;
+        const float M = luma[ly][lx];
+        const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
+        const float N = hasN ? luma[ly - 1][lx] : M, Sl = hasS ? luma[ly + 1][lx] : M;
+        const float E = hasE ? luma[ly][lx + 1] : M, Wl = hasW ? luma[ly][lx - 1] : M;
+        const float rangeMin = min4(N, Sl, E, Wl), rangeMax = max4(N, Sl, E, Wl);
+        const float range = fsub(rangeMax, rangeMin);
+        float thr = fmul(rangeMax, 0.125f);                 // EDGE_THRESHOLD_MAX
+        thr = (0.0312f < thr) ? thr : 0.0312f;              // std::max(EDGE_THRESHOLD_MIN, ...)
+        if (!(range < thr)) {
+            const float NW = (hasN && hasW) ? luma[ly - 1][lx - 1] : M, NE = (hasN && hasE) ? luma[ly - 1][lx + 1] : M;
+            const float SW = (hasS && hasW) ? luma[ly + 1][lx - 1] : M, SE = (hasS && hasE) ? luma[ly + 1][lx + 1] : M;
+            const float third = fdiv(1.0f, 3.0f);
+            const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
+            const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
+            const bool isH = edgeHorz >= edgeVert;
+            const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
+            float g = fdiv(isH ? edgeHorz : edgeVert, range);
+            g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
+            const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
+            V3 finalColor = center;
+            float bestDelta = 0.0f;
+            const float gs = fmul(g, stepLength);
+            for (int i = 0; i < 12; i++) {                      // QUALITY
+                float off = fmul(gs, float(i + 1));
+                float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
+                if (su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f) continue;
+                int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
+                sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
+                sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
+                const float *ps = in + (size_t(sy) * width + sx) * 3;
+                V3 sc = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
+                float delta = fabsf(fsub(lum(sc), M));
+                if (delta > bestDelta) { bestDelta = delta; finalColor = sc; }
+            }
+            float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
+            sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
+            const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
+            r = center * fsub(1.0f, a) + finalColor * a;        // glm::mix
+        }
+        if (vec) { mine[0] = r.x; mine[1] = r.y; mine[2] = r.z; }
+        else { float *po = out + (size_t(y) * width + x) * 3; po[0] = r.x; po[1] = r.y; po[2] = r.z; }
     }
-    float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
-    sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
-    const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
-    V3 r = center * fsub(1.0f, a) + finalColor * a;     // glm::mix
-    po[0] = r.x; po[1] = r.y; po[2] = r.z;
+    if (!vec) return;
+    __syncthreads();
+    for (int i = tid; i < kFxTileH * (kFxTileW * 3 / 4); i += kFxTileW * kFxTileH) {
+        const int row = i / (kFxTileW * 3 / 4), q = i % (kFxTileW * 3 / 4), gy = y0 + row;
+        if (gy < height) reinterpret_cast<float4 *>(out + (size_t(gy) * width + x0) * 3)[q] = reinterpret_cast<const float4 *>(rgb[row + 1])[q];
+    }
 }
 
 // Photo::ShadeOption bits (include/image.h:17-36)

@@ -129,10 +129,10 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
 enum { C_Q0 = 0, C_Q1 = 1, C_SQ = 2, C_OVERFLOW = 3, C_GLASS = 4, C_GLASS_LIST = 5, C_CUR_PATH = 6, C_CUR_SHADOW = 7,
        C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_SQ_RUN = 14, C_COUNT = 16 };
 
-// the sort of a round's live vertices by (mode, material), see k_decide
-constexpr int kSortClasses = 32;                      // material id modulo this
-constexpr int kKeyReflect = 0, kKeyRefract = kSortClasses, kKeyNee = 2 * kSortClasses;
-constexpr int kSortBins = 8 * kSortClasses;           // reflect | refract | NEE with 1..6 light samples
+// the sort of a round's live vertices by mode, see k_decide
+constexpr int kKeyReflect = 0;                        // 0: reflection off an opaque surface, 1: off a dielectric
+constexpr int kKeyRefract = 2, kKeyNee = 3;           // 3..8: NEE with 1..6 light samples
+constexpr int kSortBins = 16;
 // pipeline state beyond C_COUNT: per-bin counts of this round, then the exclusive offsets (kSortBins + 1)
 enum { C_BINS = C_COUNT, C_OFFS = C_COUNT + kSortBins, C_TOTAL = C_COUNT + 2 * kSortBins + 16 };
 
@@ -689,12 +689,15 @@ __constant__ int c_sampleCount[kMaxRayDepth + 1] = {0, 1, 2, 2, 3, 3, 3, 4, 4, 4
 // the level is split the way the reference branches (src/render.cpp:172-284):
 //   k_decide     roughness regularisation, medium scan + calcEta, Fresnel, Russian roulette -> the vertex's MODE, written
 //                with the few numbers the next stage needs (the decision record), and a sort key
-//   k_sort_*     counting sort of the live vertices by key = (mode, material) - NEE vertices also by their sample count
+//   k_sort_*     counting sort of the live vertices by key = mode (reflection split by opaque / dielectric surface, NEE by
+//                its number of light samples)
 //   k_continue   <reflect> and <refract>: dense over their segment of the sorted queue -> the next path queue
 //   k_nee        dense over the NEE segment -> shadow items
-// Every warp of the dense kernels then runs one mode on one material (full warps up to the rejection-loop tails), and
-// the surviving paths land in the next queue grouped by the object they left - the next closest-hit pass gets rays whose
-// origins are neighbours.
+// Every warp of the dense kernels then runs one mode (full warps up to the rejection-loop tails).  The sorted queue holds
+// path-queue slots, so the dense kernels gather: a bin is therefore filled in blocks - the vertices of one 1024-slot window
+// of the path queue that share a key sit next to each other in it - and a warp's gathers stay inside a few KB per SoA
+// array.  (Keys that also carried the material id, 256 bins, cut the blocks to a handful of vertices: ncu showed 14.6 GB
+// of DRAM reads per k_continue launch for 3.6 GB of records, profiles/r02d_*.)
 enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 };
 // PathQueue::flags: depth | exclude << 8 | n_medium << 16 | mode << 24 | doDirect << 26 | nee_pass_absorb << 27
 // decision record PathQueue::dec [7][cap]: P_reflect (NEE: the `scaling` factor), P_RR, F, absorb rgb, relative eta
@@ -705,13 +708,16 @@ enum { kBounceDead = 0, kBounceNee = 1, kBounceReflect = 2, kBounceRefract = 3 }
 __global__ void __launch_bounds__(kShadeBlock, RM_CTAS_DECIDE) k_decide(unsigned long long seed, PathQueue Q, const int *__restrict__ in_count, int *bins) {
     const int n = min(*in_count, Q.cap);
     const int c = Q.cap;
-    const int lane = threadIdx.x & 31;
     __shared__ int s_idx[kWindow];
     __shared__ int s_n;
+    __shared__ int s_cnt[kSortBins], s_base[kSortBins];
     for (int base = blockIdx.x * kWindow; base < n; base += gridDim.x * kWindow) {
+      if (threadIdx.x < kSortBins) s_cnt[threadIdx.x] = 0;
       // live here: a hit on a non-emissive surface (k_surface marked the others finished)
       const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Q.hit_t[i] != CUDART_INF_F; });
+#pragma unroll 1
       for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
+        RM_LOCKSTEP();
         const int j = j0 + threadIdx.x;
         const int i = j < n_live ? s_idx[j] : -1;
         int key = -1;
@@ -783,16 +789,17 @@ __global__ void __launch_bounds__(kShadeBlock, RM_CTAS_DECIDE) k_decide(unsigned
             Q.rough[i] = rough;
             float *d = Q.dec + i;
             d[0] = first; d[c] = P_RR; d[2 * c] = F; d[3 * c] = absorb.x; d[4 * c] = absorb.y; d[5 * c] = absorb.z; d[6 * c] = eta_rel;
-            const int cls = id & (kSortClasses - 1);
-            key = mode == kBounceReflect ? kKeyReflect + cls : (mode == kBounceRefract ? kKeyRefract + cls : kKeyNee + (c_sampleCount[depth] - 1) * kSortClasses + cls);
+            key = mode == kBounceReflect ? kKeyReflect + (opacity < kEps ? 1 : 0) : (mode == kBounceRefract ? kKeyRefract : kKeyNee + c_sampleCount[depth] - 1);
         }
-        // position inside the key's bin: the lanes of a warp that share a key share one atomic
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(grp) - 1;
-        int first_rank = 0;
-        if (key >= 0 && lane == leader) first_rank = atomicAdd(bins + key, __popc(grp));
-        first_rank = __shfl_sync(0xffffffffu, first_rank, leader);
-        if (key >= 0) { Q.skey[i] = key; Q.srank[i] = first_rank + __popc(grp & ((1u << lane) - 1u)); }
+        if (key >= 0) { Q.skey[i] = key; Q.srank[i] = atomicAdd(&s_cnt[key], 1); }      // position among the window's vertices of this key
+      }
+      // one block of each bin for this window
+      __syncthreads();
+      if (threadIdx.x < kSortBins) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(bins + threadIdx.x, s_cnt[threadIdx.x]) : 0;
+      __syncthreads();
+      for (int j = threadIdx.x; j < n_live; j += blockDim.x) {
+        const int i = s_idx[j];
+        Q.srank[i] += s_base[Q.skey[i]];
       }
     }
 }
@@ -1048,10 +1055,10 @@ __global__ void k_publish_max(Accum Ac, int npix) {
     if (p < npix) Ac.clum_max[p] = Ac.hold_clum[p];
 }
 
-__global__ void k_finalise(Accum Ac, FrameBuffers Fb, int npix, float exposure, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is,
+__global__ void k_finalise(Accum Ac, FrameBuffers Fb, int p_begin, int p_end, float exposure, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is,
                            RmHitInfo *g_out) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
+    int p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p_end) return;
     RmRadiance *planes[4] = {Dd, Ds, Id, Is};
 #pragma unroll
     for (int k = 0; k < 4; k++) {

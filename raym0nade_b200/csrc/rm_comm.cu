@@ -24,6 +24,7 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -44,10 +45,11 @@ Nccl &nccl() {
     N.CommDestroy = reinterpret_cast<decltype(N.CommDestroy)>(sym("ncclCommDestroy"));
     N.AllReduce = reinterpret_cast<decltype(N.AllReduce)>(sym("ncclAllReduce"));
     N.Reduce = reinterpret_cast<decltype(N.Reduce)>(sym("ncclReduce"));
+    N.ReduceScatter = reinterpret_cast<decltype(N.ReduceScatter)>(sym("ncclReduceScatter"));
     N.GroupStart = reinterpret_cast<decltype(N.GroupStart)>(sym("ncclGroupStart"));
     N.GroupEnd = reinterpret_cast<decltype(N.GroupEnd)>(sym("ncclGroupEnd"));
     N.GetErrorString = reinterpret_cast<decltype(N.GetErrorString)>(sym("ncclGetErrorString"));
-    N.ok = N.GetUniqueId && N.CommInitRank && N.CommDestroy && N.AllReduce && N.Reduce && N.GroupStart && N.GroupEnd && N.GetErrorString;
+    N.ok = N.GetUniqueId && N.CommInitRank && N.CommDestroy && N.AllReduce && N.Reduce && N.ReduceScatter && N.GroupStart && N.GroupEnd && N.GetErrorString;
     return N;
 }
 
@@ -127,6 +129,31 @@ int rm_reduce(RmContext *ctx, int32_t root) {
     if ((rc = rm_accum_radiance(ctx, &d_rad, &n_rad))) return rc;
     RM_NCCL(nccl().Reduce(d_rad, d_rad, size_t(n_rad), ncclFloat32, ncclSum, root, comm, ctx->stream));
     return RM_OK;
+}
+
+// The same exchange with the last step scattered: after it rank r holds the summed radiance of ITS slice of the frame -
+// pixels [r * per, (r + 1) * per), per = ceil(npix / world) - and nothing of the others'.  Every rank then finalises and
+// downloads its own slice (rm_resolve_slice) over its own PCIe link, instead of rank `root` finalising and downloading
+// the whole frame while the others wait.
+int rm_reduce_scatter(RmContext *ctx) {
+    if (!ctx) return rm_fail(RM_ERR_INVALID, "context is NULL");
+    if (!ctx->comm) return rm_fail(RM_ERR_STATE, "rm_reduce_scatter: call rm_comm_init first");
+    ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
+    float *d_sum = nullptr, *d_max = nullptr, *d_rad = nullptr;
+    int64_t n_sum = 0, n_max = 0, n_rad = 0;
+    int rc;
+    if ((rc = rm_accum_view(ctx, &d_sum, &n_sum, &d_max, &n_max))) return rc;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    RM_NCCL(nccl().GroupStart());
+    RM_NCCL(nccl().AllReduce(d_sum, d_sum, size_t(n_sum), ncclFloat32, ncclSum, comm, ctx->stream));
+    RM_NCCL(nccl().AllReduce(d_max, d_max, size_t(n_max), ncclFloat32, ncclMax, comm, ctx->stream));
+    RM_NCCL(nccl().GroupEnd());
+    if ((rc = rm_accum_after_reduce(ctx, ctx->comm_rank, ctx->comm_world))) return rc;
+    if ((rc = rm_accum_radiance(ctx, &d_rad, &n_rad))) return rc;
+    // in place: a rank's result lands where its slice already lies (the accumulators are padded to world * per pixels)
+    const int64_t per = (n_rad / 16 + ctx->comm_world - 1) / ctx->comm_world;
+    RM_NCCL(nccl().ReduceScatter(d_rad, d_rad + size_t(ctx->comm_rank) * size_t(per) * 16, size_t(per) * 16, ncclFloat32, ncclSum, comm, ctx->stream));
+    return rm_accum_mark_slice(ctx, ctx->comm_rank * per, per);
 }
 
 } // extern "C"

@@ -119,6 +119,7 @@ rm::DevArgs to_dev_args(const RmRenderArgs *a);
 int rm_check_args(const RmRenderArgs *a);
 // implemented in rm_render.cu
 void rm_render_state_free(RmContext *ctx);
+extern "C" int rm_accum_mark_slice(RmContext *ctx, int64_t first_pixel, int64_t pixels);       // after rm_reduce_scatter: only this slice of the accumulators holds the frame
 // implemented in fast_bvh.cpp
 int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
 // implemented in wide_bvh.cpp (declared in wide_bvh.h)

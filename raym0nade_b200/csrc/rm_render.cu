@@ -23,6 +23,7 @@ struct RenderState {
     // accumulators
     DevBuf rad, clum_sum, clum_max, hold_clum, hold, lock;
     bool accum_valid = false, hold_committed = false;
+    int64_t slice_first = 0, slice_pixels = -1;      // >= 0: after rm_reduce_scatter only these pixels of `rad` hold the frame's sums
     // queues
     int q_cap = 0, s_cap = 0;
     DevBuf q[2][20];
@@ -114,6 +115,8 @@ __global__ void k_glass_list(const int *__restrict__ n_ind, int npix, int base, 
     if (glass) list[slot] = p;
 }
 
+constexpr size_t kSlicePad = 64;         // pixels of padding behind the radiance accumulators: a reduce-scatter over <= 64 ranks needs world * ceil(npix / world)
+
 bool same_args(const RmRenderArgs &a, const RmRenderArgs &b) { return std::memcmp(&a, &b, sizeof(RmRenderArgs)) == 0; }
 
 int spp_direct_of(const RmRenderArgs *a) { return int(float(a->spp) * a->P_Direct); }        // src/render.cpp:500
@@ -176,11 +179,11 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
 static int reset_accum(RmContext *ctx, RenderState *R) {
     const size_t n = size_t(R->npix);
     int rc;
-    if ((rc = R->rad.alloc(n * 64)) || (rc = R->clum_sum.alloc(n * 8)) || (rc = R->clum_max.alloc(n * 4)) || (rc = R->hold_clum.alloc(n * 4)) ||
+    if ((rc = R->rad.alloc((n + kSlicePad) * 64)) || (rc = R->clum_sum.alloc(n * 8)) || (rc = R->clum_max.alloc(n * 4)) || (rc = R->hold_clum.alloc(n * 4)) ||
         (rc = R->hold.alloc(n * 32)) || (rc = R->lock.alloc(n * 4)))
         return rc;
     cudaStream_t st = ctx->stream;
-    RM_CUDA(cudaMemsetAsync(R->rad.p, 0, n * 64, st));
+    RM_CUDA(cudaMemsetAsync(R->rad.p, 0, (n + kSlicePad) * 64, st));       // the tail: padding of the reduce-scatter slices
     RM_CUDA(cudaMemsetAsync(R->clum_sum.p, 0, n * 8, st));
     RM_CUDA(cudaMemsetAsync(R->clum_max.p, 0, n * 4, st));
     RM_CUDA(cudaMemsetAsync(R->hold.p, 0, n * 32, st));
@@ -189,6 +192,7 @@ static int reset_accum(RmContext *ctx, RenderState *R) {
     ctx->launches++;
     R->accum_valid = true;
     R->hold_committed = false;
+    R->slice_first = 0; R->slice_pixels = -1;
     return RM_OK;
 }
 
@@ -457,6 +461,7 @@ int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadia
     if (rc) return rc;
     RenderState *R = state(ctx);
     if (!R->accum_valid || R->npix != args->width * args->height) return rm_fail(RM_ERR_STATE, "rm_resolve: accumulators do not match these args");
+    if (R->slice_pixels >= 0) return rm_fail(RM_ERR_STATE, "rm_resolve: after rm_reduce_scatter this rank holds a slice of the frame only; call rm_resolve_slice");
     RM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int npix = R->npix;
@@ -469,7 +474,7 @@ int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadia
     for (int k = 0; k < 4; k++)
         if ((rc = R->planes[k].alloc(size_t(npix) * sizeof(RmRadiance)))) return rc;
     if ((rc = R->g_out.alloc(size_t(npix) * sizeof(RmHitInfo)))) return rc;
-    k_finalise<<<(npix + 127) / 128, 128, 0, st>>>(accum(R), frame(R), npix, args->exposure, R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
+    k_finalise<<<(npix + 127) / 128, 128, 0, st>>>(accum(R), frame(R), 0, npix, args->exposure, R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
                                                    R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), R->g_out.as<RmHitInfo>());
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
@@ -481,6 +486,62 @@ int rm_resolve(RmContext *ctx, const RmRenderArgs *args, RmRadiance *Dd, RmRadia
     RM_CUDA(cudaStreamSynchronize(st));
     if (h[3]) return rm_fail(RM_ERR_STATE, "rm_resolve: a shadow queue overflowed during rendering (results incomplete)");
     ctx->have_resolved = true;
+    return RM_OK;
+}
+
+int rm_accum_mark_slice(RmContext *ctx, int64_t first_pixel, int64_t pixels) {
+    RenderState *R = state(ctx);
+    if (!R || !R->accum_valid) return rm_fail(RM_ERR_STATE, "rm_reduce_scatter: nothing rendered yet");
+    R->slice_first = std::min<int64_t>(first_pixel, R->npix);
+    R->slice_pixels = std::max<int64_t>(0, std::min<int64_t>(pixels, R->npix - R->slice_first));
+    return RM_OK;
+}
+
+int rm_frame_slice(RmContext *ctx, int64_t *first_pixel, int64_t *pixels) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_frame_slice: nothing rendered yet");
+    RenderState *R = state(ctx);
+    if (first_pixel) *first_pixel = R->slice_pixels >= 0 ? R->slice_first : 0;
+    if (pixels) *pixels = R->slice_pixels >= 0 ? R->slice_pixels : R->npix;
+    return RM_OK;
+}
+
+// rm_resolve for the slice of the frame this rank holds after rm_reduce_scatter (the whole frame when there was none): the
+// host pointers address WHOLE-frame arrays - e.g. one pinned / shared-memory frame every rank of the box maps - and only
+// this rank's pixels [first, first + count) of them are written; any may be NULL.
+int rm_resolve_slice(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer, RmRadiance *Dd, RmRadiance *Ds, RmRadiance *Id, RmRadiance *Is) {
+    if (!ctx || !ctx->render_state) return rm_fail(RM_ERR_STATE, "rm_resolve_slice: nothing rendered yet");
+    int rc = rm_check_args(args);
+    if (rc) return rc;
+    RenderState *R = state(ctx);
+    if (!R->accum_valid || R->npix != args->width * args->height) return rm_fail(RM_ERR_STATE, "rm_resolve_slice: accumulators do not match these args");
+    RM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int npix = R->npix;
+    if (!R->hold_committed) {          // no exchange happened: local totals are the global totals
+        k_publish_max<<<(npix + 255) / 256, 256, 0, st>>>(accum(R), npix);
+        k_commit_hold<<<(npix + 255) / 256, 256, 0, st>>>(accum(R), frame(R), npix, ctx->disable_clamp);
+        ctx->launches += 2;
+        R->hold_committed = true;
+    }
+    const int first = R->slice_pixels >= 0 ? int(R->slice_first) : 0, count = R->slice_pixels >= 0 ? int(R->slice_pixels) : npix;
+    for (int k = 0; k < 4; k++)
+        if ((rc = R->planes[k].alloc(size_t(npix) * sizeof(RmRadiance)))) return rc;
+    if ((rc = R->g_out.alloc(size_t(npix) * sizeof(RmHitInfo)))) return rc;
+    if (count > 0) {
+        k_finalise<<<(count + 127) / 128, 128, 0, st>>>(accum(R), frame(R), first, first + count, args->exposure, R->planes[0].as<RmRadiance>(), R->planes[1].as<RmRadiance>(),
+                                                        R->planes[2].as<RmRadiance>(), R->planes[3].as<RmRadiance>(), R->g_out.as<RmHitInfo>());
+        ctx->launches++;
+        RM_CUDA(cudaGetLastError());
+        RmRadiance *host[4] = {Dd, Ds, Id, Is};
+        for (int k = 0; k < 4; k++)
+            if (host[k]) RM_CUDA(cudaMemcpyAsync(host[k] + first, R->planes[k].as<RmRadiance>() + first, size_t(count) * sizeof(RmRadiance), cudaMemcpyDeviceToHost, st));
+        if (gbuffer) RM_CUDA(cudaMemcpyAsync(gbuffer + first, R->g_out.as<RmHitInfo>() + first, size_t(count) * sizeof(RmHitInfo), cudaMemcpyDeviceToHost, st));
+    }
+    int h[8];
+    RM_CUDA(cudaMemcpyAsync(h, R->counts.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RM_CUDA(cudaStreamSynchronize(st));
+    if (h[3]) return rm_fail(RM_ERR_STATE, "rm_resolve_slice: a shadow queue overflowed during rendering (results incomplete)");
+    ctx->have_resolved = R->slice_pixels < 0;         // the image-space passes need the whole frame on one device
     return RM_OK;
 }
 

@@ -27,11 +27,42 @@ for seed in (3, 4):                                  # twice: the communicator a
         combined = ctx.resolve(args)
         ctx.render_samples(args, 0, 1, seed=seed, reset=True)
         alone = ctx.resolve(args)
+        alone["gbuffer"] = ctx.resolved(args)["gbuffer"]
         for k in ("Dd", "Ds", "Id", "Is"):
             a, b = alone[k]["radiance"].astype(np.float64), combined[k]["radiance"].astype(np.float64)
             good = np.isfinite(b).all() and np.abs(a - b).max() <= 2e-4 * (1.0 + np.abs(a).max()) and abs(a.sum() - b.sum()) <= 1e-5 * abs(a.sum()) + 1e-6
             if not good: print("MISMATCH", k, np.abs(a - b).max(), a.sum(), b.sum())
             ok = ok and bool(good)
+    # the same frame through rm_reduce_scatter: every rank finalises its own slice and writes it into a whole-frame array;
+    # the slices of all ranks, gathered, must be the frame rank 0 renders alone
+    ctx.render_samples(args, rank, world, seed=seed, reset=True)
+    ctx.reduce_scatter()
+    first, count = ctx.frame_slice()
+    npix = args.width * args.height
+    from raym0nade_b200.ctypes_defs import HITINFO_DTYPE, RADIANCE_DTYPE
+    g = np.zeros(npix, HITINFO_DTYPE)
+    planes = [np.zeros(npix, RADIANCE_DTYPE) for _ in range(4)]
+    ctx.resolve_slice(args, g, planes)
+    mine = [(first, count, [p[first:first + count].copy() for p in planes], g[first:first + count].copy())]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine[0])
+    if rank == 0:
+        covered = np.zeros(npix, np.int32)
+        for k, name in enumerate(("Dd", "Ds", "Id", "Is")):
+            whole = np.zeros(npix, RADIANCE_DTYPE)
+            for (f, c, pl, gg) in gathered:
+                whole[f:f + c] = pl[k]
+                if k == 0: covered[f:f + c] += 1
+            a, b = alone[name]["radiance"].astype(np.float64), whole["radiance"].astype(np.float64)
+            good = np.isfinite(b).all() and np.abs(a - b).max() <= 2e-4 * (1.0 + np.abs(a).max()) and abs(a.sum() - b.sum()) <= 1e-5 * abs(a.sum()) + 1e-6
+            if not good: print("SCATTER MISMATCH", name, np.abs(a - b).max(), a.sum(), b.sum())
+            ok = ok and bool(good)
+        ok = ok and bool((covered == 1).all())
+        gw = np.zeros(npix, HITINFO_DTYPE)
+        for (f, c, pl, gg) in gathered: gw[f:f + c] = gg
+        same_g = np.array_equal(gw["baseColor"], alone["gbuffer"]["baseColor"], equal_nan=True) and np.array_equal(gw["position"], alone["gbuffer"]["position"], equal_nan=True)
+        if not same_g: print("SCATTER MISMATCH gbuffer")
+        ok = ok and bool(same_g)
     ctx.synchronize()
 verdict = [ok]
 dist.broadcast_object_list(verdict, src=0)

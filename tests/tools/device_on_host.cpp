@@ -438,7 +438,7 @@ int doh_direct_planes(const RmSceneDesc *sc, const RmRenderArgs *a, const RmHitI
     run_engine(H, job, s_count, nullptr, secondary_tree ? 14 : 0, secondary_tree ? 2 : 1);
     rm_host_launch(k_accum_direct, dim3((npix + 255) / 256), dim3(256), Fb, Ac, (const ShadowItem *)sq.data(), spp, npix);
     std::vector<RmRadiance> Id(npix), Is(npix);
-    rm_host_launch(k_finalise, dim3((npix + 255) / 256), dim3(256), Ac, Fb, npix, a->exposure, Dd, Ds, Id.data(), Is.data(), g_out.data());
+    rm_host_launch(k_finalise, dim3((npix + 255) / 256), dim3(256), Ac, Fb, 0, npix, a->exposure, Dd, Ds, Id.data(), Is.data(), g_out.data());
     return s_count;
 }
 
@@ -562,7 +562,7 @@ int doh_indirect_planes(const RmSceneDesc *sc, const RmRenderArgs *a, unsigned l
     rm_host_launch(k_publish_max, dim3((npix + 255) / 256), dim3(256), Ac, npix);
     rm_host_launch(k_commit_hold, dim3((npix + 255) / 256), dim3(256), Ac, Fb, npix, true);
     std::vector<RmRadiance> Dd(npix), Ds(npix);
-    rm_host_launch(k_finalise, dim3((npix + 127) / 128), dim3(128), Ac, Fb, npix, a->exposure, Dd.data(), Ds.data(), Id, Is, g_out);
+    rm_host_launch(k_finalise, dim3((npix + 127) / 128), dim3(128), Ac, Fb, 0, npix, a->exposure, Dd.data(), Ds.data(), Id, Is, g_out);
     if (rounds_out) *rounds_out = rounds;
     return n_glass;
 }
