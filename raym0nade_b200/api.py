@@ -58,7 +58,7 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
-           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_reduce_scatter", "rm_frame_slice", "rm_resolve_slice", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_reduce_scatter", "rm_frame_slice", "rm_resolve_slice", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_tree_info", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -104,6 +104,7 @@ def lib():
     L.rm_postprocess.argtypes = [vp, ARGS, i32, vp]
     L.rm_secondary_tree_stats.argtypes = [vp, i32, i32, i32, vp]
     L.rm_wide_tree_stats.argtypes = [vp, i32, i32, vp]
+    L.rm_tree_info.argtypes = [vp, vp]
     L.rm_comm_unique_id.argtypes = [vp]
     L.rm_comm_init.argtypes = [vp, vp, i32, i32]
     L.rm_reduce.argtypes = [vp, i32]
@@ -222,6 +223,12 @@ class Context:
         self.model = model
         return self
 
+    def tree_info(self):
+        """the 4-wide secondary-ray tree bounce / shadow rays currently traverse: dict(device_built, refined (the host builder's tree has been swapped in), nodes, levels, in_use)"""
+        out = np.zeros(4, np.int32)
+        _check(lib().rm_tree_info(self.h, _p(out)))
+        return dict(device_built=bool(out[0]), refined=int(out[0]) == 2, nodes=int(out[1]), levels=int(out[2]), in_use=bool(out[3]))
+
     def scene_bytes(self):
         return lib().rm_scene_device_bytes(self.h)
 
@@ -272,6 +279,11 @@ class Context:
         t = np.zeros(n, np.float32) if download else None
         _check(lib().rm_trace_primary(self.h, C.byref(a), _p(tri), _p(t)))
         return tri, t
+
+    def trace_primary_into(self, args: RenderArgs, tri_idx, t):
+        """rm_trace_primary with caller-owned (e.g. pinned) host arrays"""
+        a = args.to_c()
+        _check(lib().rm_trace_primary(self.h, C.byref(a), _p(tri_idx), _p(t)))
 
     def gbuffer(self, args: RenderArgs, download=True):
         a = args.to_c()

@@ -218,7 +218,7 @@ struct TraceTune {
     int smem_levels;     // stack entries per thread held in shared memory; deeper ones (rare) go to a small local array
 };
 constexpr int kStackSpill = 28;   // local spill entries: smem_levels + kStackSpill >= any tree depth we build (<= 40)
-constexpr int kStackSpillWide = 56; // the 4-wide tree defers up to three children per level (rm_scene_upload checks 3 * levels against it)
+constexpr int kStackSpillWide = 82; // the 4-wide tree defers up to three children per level (rm_scene_upload checks 3 * levels against it)
 
 template <class Job, bool COUNT, bool WIDE = false>
 RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, int2 *stack, const int stride, TraceCounters &cnt,
@@ -349,7 +349,7 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                         // sort key: the entry distance (positive, so its bit pattern orders like the float) with the slot in the low bits
                         key[c] = hitc ? ((__float_as_uint(tn) & ~3u) | unsigned(c)) : 0xffffffffu;
                     }
-                    if (COUNT) cnt.box += 4;
+                    if (COUNT) cnt.box += (meta & 0xffu ? 1 : 0) + (meta & 0xff00u ? 1 : 0) + (meta & 0xff0000u ? 1 : 0) + (meta & 0xff000000u ? 1 : 0);     // child boxes tested
                     // 5-comparator network: ascending by entry distance, misses last
 #define RM_CSWAP(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
                     RM_CSWAP(0, 1) RM_CSWAP(2, 3) RM_CSWAP(0, 2) RM_CSWAP(1, 3) RM_CSWAP(1, 2)

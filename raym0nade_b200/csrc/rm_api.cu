@@ -10,6 +10,7 @@
 #include "rm_context.cuh"
 #include "kernels_trace.cuh"
 #include "wide_bvh.h"
+#include "gpu_bvh.h"
 
 using namespace rm;
 
@@ -46,15 +47,14 @@ static int upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st, int
 
 // test hook "seam_secondary_tree": the per-ray seam through the binary (1) or the 4-wide (2) secondary-ray tree; the seam
 // itself (0) is the reference's tree in the reference's order
-static const DevScene &seam_scene(const RmContext *ctx) {
-    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->scene_wide : (ctx->seam_tree ? ctx->scene_fast : ctx->scene);
+static int seam_pick(const RmContext *ctx) {          // 0 the reference's tree, 1 the binary secondary-ray tree, 2 its 4-wide form
+    if (ctx->seam_tree == 2 && ctx->have_wide) return 2;
+    if (ctx->seam_tree && ctx->have_fast) return 1;
+    return ctx->seam_tree && ctx->have_wide ? 2 : 0;
 }
-static int seam_levels(const RmContext *ctx) {
-    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->stack_levels_wide : (ctx->seam_tree ? ctx->stack_levels_fast : ctx->stack_levels);
-}
-static TraceTune seam_tune(const RmContext *ctx) {
-    return ctx->seam_tree == 2 && ctx->have_wide ? ctx->tune_wide : (ctx->seam_tree ? ctx->tune_fast : ctx->tune);
-}
+static const DevScene &seam_scene(const RmContext *ctx) { const int k = seam_pick(ctx); return k == 2 ? ctx->scene_wide : (k ? ctx->scene_fast : ctx->scene); }
+static int seam_levels(const RmContext *ctx) { const int k = seam_pick(ctx); return k == 2 ? ctx->stack_levels_wide : (k ? ctx->stack_levels_fast : ctx->stack_levels); }
+static TraceTune seam_tune(const RmContext *ctx) { const int k = seam_pick(ctx); return k == 2 ? ctx->tune_wide : (k ? ctx->tune_fast : ctx->tune); }
 
 extern "C" {
 
@@ -195,43 +195,101 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
 
-    // the secondary-ray tree (fast_bvh.cpp): built on the host from the same positions, kept across uploads of the same
-    // geometry (a renderer re-stages materials and lights far more often than triangles)
+    // The secondary-ray tree.  Default: built on the device from the positions just uploaded (gpu_bvh.cu: Morton sort, PLOC
+    // clustering, 4-wide collapse - a few milliseconds, so every upload rebuilds it and nothing is cached).  The host
+    // builders (fast_bvh.cpp: binned SAH; wide_bvh.cpp: its collapse) remain for "tree_builder" 0, for the binary form of the
+    // tree ("secondary_tree" 1 / the seam test hook, asked for before the upload) and as the fallback should the device
+    // tree come out deeper than the traversal stack allows; they are cached by geometry hash.
     {
-        const uint64_t key = hash_words(sc->positions, size_t(n) * 36);
-        if (!(ctx->fast_key_valid && ctx->fast_key == key && ctx->fast_n == n)) {
-            std::vector<RmBvhNode> fnodes;
-            std::vector<int32_t> forder;
-            int fdepth = 0;
-            if ((rc = rm_build_fast_bvh(sc->positions, n, ctx->fast_depth_cap, ctx->fast_leaf_max, fnodes, forder, &fdepth))) return rc;
-            if ((rc = upload(ctx->b_nodes_fast, fnodes.data(), fnodes.size() * sizeof(RmBvhNode), st, total))) return rc;
-            if ((rc = upload(ctx->b_facemap, forder.data(), forder.size() * 4, st, total))) return rc;
-            RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die at scope exit
-            ctx->stack_levels_fast = std::min(std::max(fdepth, 2), 40);
-            ctx->fast_root_is_leaf = fnodes[1].faceR != 0;
-            // ... and its 4-wide, 8-bit quantised form (wide_bvh.cpp): what bounce and shadow rays traverse by default
-            ctx->have_wide = false;
-            if (ctx->fast_leaf_max <= 3) {
-                std::vector<RmWideNode> wnodes;
-                std::vector<int32_t> worder;
-                int wdepth = 0;
-                if ((rc = rm_build_wide_bvh(fnodes, forder, n, wnodes, worder, &wdepth))) return rc;
-                if (3 * wdepth <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {       // up to three deferred children per level
-                    if ((rc = upload(ctx->b_nodes_wide, wnodes.data(), wnodes.size() * sizeof(RmWideNode), st, total))) return rc;
-                    if ((rc = upload(ctx->b_facemap_wide, worder.data(), worder.size() * 4, st, total))) return rc;
-                    RM_CUDA(cudaStreamSynchronize(st));
-                    ctx->stack_levels_wide = std::max(3 * wdepth, 2);
-                    ctx->have_wide = true;
-                }
+        bool device_tree = false;
+        ctx->have_fast = false;
+        if (ctx->tree_builder_mode >= 1) {
+            int wlevels = 0, wnodes = 0;
+            const RmBvhNode &rootbox = sc->nodes[1];           // the reference tree's root box = the scene bounds
+            if ((rc = rm_gpu_build_wide(ctx, ctx->b_raw[0].as<float>(), n, rootbox.v0, rootbox.v1, &wlevels, &wnodes))) return rc;
+            if (3 * wlevels <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {
+                ctx->stack_levels_wide = std::max(3 * wlevels, 2);
+                ctx->have_wide = true;
+                ctx->wide_nodes = wnodes;
+                ctx->wide_levels = wlevels;
+                device_tree = true;
             }
-            ctx->fast_key = key; ctx->fast_n = n; ctx->fast_key_valid = true;
         }
-        if ((rc = ctx->b_tri_fast.alloc(size_t(n) * 16 * kTriStride))) return rc;
-        k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap.as<int>(), n, ctx->b_tri_fast.as<float4>());
-        ctx->launches++;
+        // "tree_builder" 2: the device tree serves at once; the host SAH builder refines it in the background
+        ctx->use_refined = false;
+        if (device_tree && ctx->tree_builder_mode == 2) {
+            const uint64_t key = hash_words(sc->positions, size_t(n) * 36);
+            if (ctx->refine && ctx->refine->th.joinable() && !(ctx->tree_cache && ctx->refine->key == key && ctx->refine->n == n)) {
+                ctx->refine->th.join();                        // a build for other geometry (or caching is off): let it end, drop it
+                ctx->refine.reset();
+            }
+            if (ctx->tree_cache && ctx->refined_installed && ctx->refined_key == key && ctx->refined_n == n) ctx->use_refined = true;
+            else if (!ctx->refine) {
+                ctx->refined_installed = false;
+                ctx->refine.reset(new RefineJob());
+                RefineJob *J = ctx->refine.get();
+                J->pos.assign(sc->positions, sc->positions + size_t(n) * 9);
+                J->n = n;
+                J->key = key;
+                J->state.store(1);
+                const int cap = ctx->fast_depth_cap, limit = ctx->tune_wide.smem_levels + rm::kStackSpillWide;
+                J->th = std::thread([J, cap, limit] {
+                    std::vector<RmBvhNode> fnodes;
+                    std::vector<int32_t> forder;
+                    int fdepth = 0;
+                    bool ok = rm_build_fast_bvh(J->pos.data(), J->n, cap, 3, fnodes, forder, &fdepth) == RM_OK &&
+                              rm_build_wide_bvh(fnodes, forder, J->n, J->wnodes, J->worder, &J->wdepth) == RM_OK && 3 * J->wdepth <= limit;
+                    J->pos = std::vector<float>();
+                    J->state.store(ok ? 2 : 3);
+                });
+            }
+        }
+        if (!device_tree || ctx->want_binary_tree) {
+            const uint64_t key = hash_words(sc->positions, size_t(n) * 36);
+            if (!(ctx->tree_cache && ctx->fast_key_valid && ctx->fast_key == key && ctx->fast_n == n && (device_tree || ctx->host_wide_valid))) {
+                std::vector<RmBvhNode> fnodes;
+                std::vector<int32_t> forder;
+                int fdepth = 0;
+                if ((rc = rm_build_fast_bvh(sc->positions, n, ctx->fast_depth_cap, ctx->fast_leaf_max, fnodes, forder, &fdepth))) return rc;
+                if ((rc = upload(ctx->b_nodes_fast, fnodes.data(), fnodes.size() * sizeof(RmBvhNode), st, total))) return rc;
+                if ((rc = upload(ctx->b_facemap, forder.data(), forder.size() * 4, st, total))) return rc;
+                RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die at scope exit
+                ctx->stack_levels_fast = std::min(std::max(fdepth, 2), 40);
+                ctx->fast_root_is_leaf = fnodes[1].faceR != 0;
+                ctx->host_wide_valid = false;
+                if (!device_tree) {
+                    ctx->have_wide = false;
+                    if (ctx->fast_leaf_max <= 3) {
+                        std::vector<RmWideNode> wnodes;
+                        std::vector<int32_t> worder;
+                        int wdepth = 0;
+                        if ((rc = rm_build_wide_bvh(fnodes, forder, n, wnodes, worder, &wdepth))) return rc;
+                        if (3 * wdepth <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {       // up to three deferred children per level
+                            if ((rc = upload(ctx->b_nodes_wide, wnodes.data(), wnodes.size() * sizeof(RmWideNode), st, total))) return rc;
+                            if ((rc = upload(ctx->b_facemap_wide, worder.data(), worder.size() * 4, st, total))) return rc;
+                            RM_CUDA(cudaStreamSynchronize(st));
+                            ctx->stack_levels_wide = std::max(3 * wdepth, 2);
+                            ctx->have_wide = true;
+                            ctx->host_wide_valid = true;
+                            ctx->wide_nodes = int(wnodes.size());
+                            ctx->wide_levels = wdepth;
+                        }
+                    }
+                }
+                ctx->fast_key = key; ctx->fast_n = n; ctx->fast_key_valid = true;
+            } else if (!device_tree) ctx->have_wide = ctx->host_wide_valid;
+            ctx->have_fast = true;
+            if ((rc = ctx->b_tri_fast.alloc(size_t(n) * 16 * kTriStride))) return rc;
+            k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap.as<int>(), n, ctx->b_tri_fast.as<float4>());
+            ctx->launches++;
+        }
         if (ctx->have_wide) {
             if ((rc = ctx->b_tri_wide.alloc(size_t(n) * 16 * kTriStride))) return rc;
             k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide.as<int>(), n, ctx->b_tri_wide.as<float4>());
+            ctx->launches++;
+        }
+        if (ctx->use_refined) {          // same geometry as the refined tree on the device: its triangle records follow the new materials
+            k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide2.as<int>(), n, ctx->b_tri_wide2.as<float4>());
             ctx->launches++;
         }
         RM_CUDA(cudaGetLastError());
@@ -344,6 +402,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     ctx->scene_fast.face_map = ctx->b_facemap.as<int32_t>();
     ctx->scene_fast.explicit_children = 1;
     ctx->scene_fast.root_is_leaf = ctx->fast_root_is_leaf ? 1 : 0;
+    if (!ctx->have_fast) ctx->scene_fast = S;        // not built: whoever asks for it gets the reference's tree
     ctx->scene_wide = S;
     if (ctx->have_wide) {
         ctx->scene_wide.nodes = ctx->b_nodes_wide.as<float4>();
@@ -351,6 +410,13 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         ctx->scene_wide.face_map = ctx->b_facemap_wide.as<int32_t>();
         ctx->scene_wide.root_is_leaf = 0;
         ctx->scene_wide.wide = 1;
+        ctx->scene_wide_first = ctx->scene_wide;
+        if (ctx->use_refined) {
+            ctx->scene_wide.nodes = ctx->b_nodes_wide2.as<float4>();
+            ctx->scene_wide.tri = ctx->b_tri_wide2.as<float4>();
+            ctx->scene_wide.face_map = ctx->b_facemap_wide2.as<int32_t>();
+            ctx->stack_levels_wide = std::max(3 * ctx->refined_levels, 2);
+        }
     }
     ctx->scene_h2d_bytes = total;
     ctx->scene_bytes = 0;
@@ -359,6 +425,52 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         ctx->scene_bytes += int64_t(b->bytes);
     ctx->has_scene = true;
     ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
+    return RM_OK;
+}
+
+// The background build has finished: stage its tree next to the device builder's and point bounce / shadow rays at it.
+// Called where the render loop waits for the device anyway (rm_render_samples: on entry and between batches of rounds).
+int rm_install_refined_tree(RmContext *ctx) {
+    if (!ctx || !ctx->refine || !ctx->has_scene) return RM_OK;
+    RefineJob *J = ctx->refine.get();
+    const int state = J->state.load();
+    if (state == 1) return RM_OK;
+    if (J->th.joinable()) J->th.join();
+    std::unique_ptr<RefineJob> job = std::move(ctx->refine);
+    if (state != 2 || job->n != ctx->scene.n_faces || !ctx->have_wide) return RM_OK;
+    RM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = job->n;
+    int rc;
+    int64_t total = 0;
+    if ((rc = upload(ctx->b_nodes_wide2, job->wnodes.data(), job->wnodes.size() * sizeof(RmWideNode), st, total))) return rc;
+    if ((rc = upload(ctx->b_facemap_wide2, job->worder.data(), job->worder.size() * 4, st, total))) return rc;
+    if ((rc = ctx->b_tri_wide2.alloc(size_t(n) * 16 * kTriStride))) return rc;
+    k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide2.as<int>(), n, ctx->b_tri_wide2.as<float4>());
+    ctx->launches++;
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaStreamSynchronize(st));            // the host vectors die with the job
+    ctx->scene_wide.nodes = ctx->b_nodes_wide2.as<float4>();
+    ctx->scene_wide.tri = ctx->b_tri_wide2.as<float4>();
+    ctx->scene_wide.face_map = ctx->b_facemap_wide2.as<int32_t>();
+    ctx->refined_levels = job->wdepth;
+    ctx->refined_nodes = int(job->wnodes.size());
+    ctx->stack_levels_wide = std::max(3 * job->wdepth, 2);
+    ctx->refined_installed = true;
+    ctx->use_refined = true;
+    ctx->refined_key = job->key;
+    ctx->refined_n = n;
+    return RM_OK;
+}
+
+// {1 when the 4-wide tree came from the device builder (0: host), its 64-byte records, its levels, 1 when bounce / shadow rays use it}
+int rm_tree_info(const RmContext *ctx, int32_t out[4]) {
+    if (!ctx || !out) return rm_fail(RM_ERR_INVALID, "rm_tree_info: null argument");
+    if (!ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_tree_info: no scene uploaded");
+    out[0] = ctx->have_wide && !ctx->host_wide_valid ? (ctx->use_refined ? 2 : 1) : 0;
+    out[1] = ctx->use_refined ? ctx->refined_nodes : ctx->wide_nodes;
+    out[2] = ctx->use_refined ? ctx->refined_levels : ctx->wide_levels;
+    out[3] = ctx->have_wide && !ctx->exact_secondary && (ctx->secondary_tree == 2 || !ctx->have_fast) ? 1 : 0;
     return RM_OK;
 }
 
@@ -494,9 +606,18 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return RM_OK; }
     if (!std::strcmp(name, "exact_secondary")) { ctx->exact_secondary = value != 0; return RM_OK; }
     // test hook: rm_trace_closest / rm_trace_occluded through the secondary-ray tree (the seam itself is the reference's tree)
-    if (!std::strcmp(name, "seam_secondary_tree")) { ctx->seam_tree = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); return RM_OK; }
-    // bounce and shadow rays: 1 = the binary secondary-ray tree, 2 = its 4-wide quantised form (default)
-    if (!std::strcmp(name, "secondary_tree")) { ctx->secondary_tree = value == 1 ? 1 : 2; return RM_OK; }
+    if (!std::strcmp(name, "seam_secondary_tree")) {
+        ctx->seam_tree = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2));
+        if (ctx->seam_tree == 1) ctx->want_binary_tree = true;           // takes effect at the next rm_scene_upload
+        return RM_OK;
+    }
+    // bounce and shadow rays: 1 = the binary secondary-ray tree (host-built; set before rm_scene_upload), 2 = the 4-wide quantised tree (default)
+    if (!std::strcmp(name, "secondary_tree")) { ctx->secondary_tree = value == 1 ? 1 : 2; if (value == 1) ctx->want_binary_tree = true; return RM_OK; }
+    // 0: on the host, cached by geometry hash; 1: on the device (gpu_bvh.cu) at every upload; 2 (default): on the device and
+    // then refined in the background by the host builder (the render loop swaps the better tree in when it is ready)
+    if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); ctx->fast_key_valid = false; return RM_OK; }
+    // 0: a tree built for earlier geometry is never reused (every upload rebuilds; what bench.py's end-to-end loop asks for)
+    if (!std::strcmp(name, "tree_cache")) { ctx->tree_cache = value != 0; if (!ctx->tree_cache) ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_leaf_max")) { ctx->fast_leaf_max = int(std::min<int64_t>(std::max<int64_t>(value, 1), 15)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_depth_cap")) { ctx->fast_depth_cap = int(std::min<int64_t>(std::max<int64_t>(value, 8), 26)); ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->ev_kind.clear(); return RM_OK; }

@@ -1,7 +1,10 @@
 // rm_context.cuh — the context object behind the C ABI (host side, CUDA runtime).
 #pragma once
 #include <cstdint>
+#include <atomic>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -9,6 +12,7 @@
 #include "rm_internal.h"
 #include "dev_scene.cuh"
 #include "dev_trace.cuh"
+#include "wide_bvh.h"
 
 #define RM_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -32,6 +36,20 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+// Background refinement of the secondary-ray tree ("tree_builder" 2): the device builder's tree serves from the first ray; a
+// host thread meanwhile runs the binned-SAH builder + collapse over a private copy of the positions, and the render loop
+// swaps its (better) tree in when it is ready.
+struct RefineJob {
+    std::thread th;
+    std::atomic<int> state{0};             // 1 running, 2 ready, 3 failed
+    std::vector<float> pos;
+    int n = 0;
+    uint64_t key = 0;
+    std::vector<RmWideNode> wnodes;
+    std::vector<int32_t> worder;
+    int wdepth = 0;
 };
 
 struct RmContext {
@@ -62,12 +80,23 @@ struct RmContext {
     // scene
     rm::DevScene scene{};
     rm::DevScene scene_fast{};             // the same scene with the secondary-ray tree (fast_bvh.cpp) in place of the reference's
+    rm::DevScene scene_wide_first{};       // the device builder's tree (what scene_wide points at until the refined one is installed)
+    bool use_refined = false;
     rm::DevScene scene_wide{};             // ... and with that tree collapsed to 4-wide quantised nodes (wide_bvh.cpp): what bounce and shadow rays traverse
     int stack_levels_fast = 24, stack_levels_wide = 42;
     int secondary_tree = 2;                // 1: the binary secondary-ray tree, 2: its 4-wide form (rm_set_option "secondary_tree")
-    bool have_wide = false;
+    bool have_wide = false, have_fast = false, host_wide_valid = false, want_binary_tree = false;
+    int wide_nodes = 0, wide_levels = 0;
     DevBuf b_nodes_fast, b_tri_fast, b_facemap;
     DevBuf b_nodes_wide, b_tri_wide, b_facemap_wide;
+    DevBuf b_nodes_wide2, b_tri_wide2, b_facemap_wide2;   // the refined tree (tree_builder 2)
+    std::unique_ptr<RefineJob> refine;
+    bool refined_installed = false, tree_cache = true;
+    uint64_t refined_key = 0;
+    int refined_n = 0, refined_levels = 0, refined_nodes = 0;
+    DevBuf b_build[16];                    // scratch of the device tree builder (gpu_bvh.cu), kept across uploads
+    int tree_builder_mode = 2;                  // 1: the secondary-ray tree is built on the device at every upload (gpu_bvh.cu); 0: on the host (fast_bvh.cpp +
+                                           // wide_bvh.cpp), cached by geometry hash; 2 (default): on the device, then refined by the host builder in the background
     int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
     int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
     bool fast_root_is_leaf = false, fast_key_valid = false;
@@ -111,6 +140,9 @@ struct RmContext {
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
                           &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_nodes_wide, &b_tri_wide, &b_facemap_wide, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
+        if (refine && refine->th.joinable()) refine->th.join();
+        for (DevBuf &b : b_build) b.release();
+        for (DevBuf *b : {&b_nodes_wide2, &b_tri_wide2, &b_facemap_wide2}) b->release();
     }
 };
 
@@ -123,5 +155,7 @@ extern "C" int rm_accum_mark_slice(RmContext *ctx, int64_t first_pixel, int64_t 
 // implemented in fast_bvh.cpp
 int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
 // implemented in wide_bvh.cpp (declared in wide_bvh.h)
+// implemented in rm_api.cu: swaps the background-refined secondary-ray tree in once it is ready (no-op otherwise)
+extern "C" int rm_install_refined_tree(RmContext *ctx);
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);

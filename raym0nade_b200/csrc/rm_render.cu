@@ -242,10 +242,12 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const int tgrid = R->sm_count * kTraceCtasPerSm;
     const bool ct = ctx->count_tests;
     // bounce and shadow rays: the secondary-ray tree unless the caller asked for the reference's traversal order throughout
-    const bool use_wide = !ctx->exact_secondary && ctx->secondary_tree == 2 && ctx->have_wide;
-    const DevScene &sec_scene = ctx->exact_secondary ? ctx->scene : (use_wide ? ctx->scene_wide : ctx->scene_fast);
-    const int sec_levels = ctx->exact_secondary ? ctx->stack_levels : (use_wide ? ctx->stack_levels_wide : ctx->stack_levels_fast);
-    const TraceTune sec_tune = ctx->exact_secondary ? ctx->tune : (use_wide ? ctx->tune_wide : ctx->tune_fast);
+    if ((rc = rm_install_refined_tree(ctx))) return rc;          // a background-refined tree that became ready since the last call
+    const bool use_wide = !ctx->exact_secondary && ctx->have_wide && (ctx->secondary_tree == 2 || !ctx->have_fast);
+    const bool use_ref = ctx->exact_secondary || (!use_wide && !ctx->have_fast);
+    const DevScene &sec_scene = use_ref ? ctx->scene : (use_wide ? ctx->scene_wide : ctx->scene_fast);     // (a member: follows a later install)
+    int sec_levels = use_ref ? ctx->stack_levels : (use_wide ? ctx->stack_levels_wide : ctx->stack_levels_fast);
+    const TraceTune sec_tune = use_ref ? ctx->tune : (use_wide ? ctx->tune_wide : ctx->tune_fast);
 
     // rayHit_test over the first *n_dev items of the shadow queue, then the coalesced accumulation pass
     // (C_CUR_SHADOW must be 0)
@@ -323,6 +325,10 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
             }
             RM_CUDA(cudaMemcpyAsync(R->h_counts, C, C_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
             RM_CUDA(cudaStreamSynchronize(st));
+            if (use_wide && ctx->refine) {                  // the host waits here anyway: swap the refined tree in if it has arrived
+                if ((rc = rm_install_refined_tree(ctx))) return rc;
+                sec_levels = ctx->stack_levels_wide;
+            }
             const long long handed = (long long)(unsigned)R->h_counts[C_ITEM_LO] | ((long long)R->h_counts[C_ITEM_HI] << 32);
             done = (handed >= total_items && R->h_counts[cur] == 0) || rounds >= max_rounds;
         }

@@ -76,17 +76,10 @@ struct Collapser {
     void fill(int self, const RmBvhNode *const *ch, int n, int depth) {
         RmWideNode w;
         std::memset(&w, 0, sizeof(w));
-        Box3 u = box_of(*ch[0]);
-        for (int i = 1; i < n; i++)
-            for (int a = 0; a < 3; a++) { u.lo[a] = std::min(u.lo[a], ch[i]->v0[a]); u.hi[a] = std::max(u.hi[a], ch[i]->v1[a]); }
-        for (int a = 0; a < 3; a++) {
-            w.o[a] = u.lo[a];
-            // grid step: o + 255 s must reach the upper corner (in exact arithmetic: o, s are floats, the check is in double)
-            float s = float((double(u.hi[a]) - double(u.lo[a])) / 255.0);
-            if (!(s > 0.0f)) s = 0.0f;
-            while (double(u.lo[a]) + 255.0 * double(s) < double(u.hi[a])) s = std::nextafter(s, INFINITY);
-            w.s[a] = s;
-        }
+        float lo[4][3], hi[4][3];
+        for (int i = 0; i < n; i++)
+            for (int a = 0; a < 3; a++) { lo[i][a] = ch[i]->v0[a]; hi[i][a] = ch[i]->v1[a]; }
+        if (!wide_quantise(lo, hi, n, w)) ok = false;
         int n_inner = 0, n_tris = 0;
         for (int i = 0; i < n; i++) (ch[i]->faceR == 0 ? n_inner : n_tris) += ch[i]->faceR == 0 ? 1 : ch[i]->faceR - ch[i]->faceL;
         w.child_base = n_inner ? int32_t(out.size()) : 0;
@@ -96,24 +89,6 @@ struct Collapser {
         const RmBvhNode *inner[4];
         for (int i = 0; i < n; i++) {
             const RmBvhNode &c = *ch[i];
-            for (int a = 0; a < 3; a++) {
-                const double o = w.o[a], s = w.s[a];
-                int lo = 0, hi = 255;
-                if (s > 0.0) {
-                    lo = int(std::floor((double(c.v0[a]) - o) / s));
-                    hi = int(std::ceil((double(c.v1[a]) - o) / s));
-                    lo = std::min(std::max(lo, 0), 255);
-                    hi = std::min(std::max(hi, 0), 255);
-                    while (lo > 0 && o + s * lo > double(c.v0[a])) lo--;
-                    while (hi < 255 && o + s * hi < double(c.v1[a])) hi++;
-                    if (o + s * lo > double(c.v0[a]) || o + s * hi < double(c.v1[a])) ok = false;
-                } else {
-                    lo = hi = 0;                                // flat node along this axis: every child plane is o itself
-                    if (double(c.v0[a]) < o || double(c.v1[a]) > o) ok = false;
-                }
-                w.qlo[a][i] = uint8_t(lo);
-                w.qhi[a][i] = uint8_t(hi);
-            }
             if (c.faceR == 0) {
                 w.meta[i] = uint8_t(0x80 | k_inner);
                 inner[k_inner++] = &c;

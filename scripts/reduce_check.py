@@ -14,7 +14,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("gloo")                      # only carries the unique id and the verdict: the data path is rm_reduce
 scene, args = scenes.cornell_box(128, 128, 48)
-ctx = Context(local).upload(Model(scene))
+ctx = Context(local)
+ctx.set_option("tree_builder", 1)           # the same tree on every rank and in the single-GPU render it is compared with
+ctx.upload(Model(scene))
 uid = [Context.comm_unique_id().tobytes() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(np.frombuffer(uid[0], np.uint8), rank, world)

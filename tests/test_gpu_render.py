@@ -310,7 +310,9 @@ def test_interleaved_sample_shards_sum_to_the_single_pass(which):
         scene, args = scenes.cornell_box(128, 128, 24)
     else:
         scene, args = scenes.glossy_dielectric(1_000_000, 1920, 1080, 6)
-    ctx = Context(0).upload(Model(scene))
+    ctx = Context(0)
+    ctx.set_option("tree_builder", 1)        # one tree for all four renders: the default swaps a refined tree in when it is ready, and two
+    ctx.upload(Model(scene))                 # valid trees may name different triangles where a ray hits a shared edge exactly
     ctx.render_samples(args, 0, 1, seed=5, reset=True)
     one = ctx.resolve(args)
     for r in range(3):
@@ -368,13 +370,17 @@ def test_checkpoint_resume_in_a_fresh_context_equals_one_render():
     from raym0nade_b200.api import RmError
     scene, args = scenes.cornell_box(96, 96, 24)
     model = Model(scene)
-    ctx = Context(0).upload(model)
+    ctx = Context(0)
+    ctx.set_option("tree_builder", 1)        # the same tree in both contexts (see the sharding test)
+    ctx.upload(model)
     ctx.render_samples(args, 0, 1, seed=8, reset=True)
     whole = ctx.resolve(args)
     ctx.render_samples(args, 0, 2, seed=8, reset=True)
     blob = ctx.checkpoint_save(args)
     ctx.close()
-    ctx = Context(0).upload(model)
+    ctx = Context(0)
+    ctx.set_option("tree_builder", 1)
+    ctx.upload(model)
     with pytest.raises(RmError):
         ctx.checkpoint_load(args.replace(spp=args.spp + 1), blob)          # a checkpoint only fits the args it was made for
     ctx.checkpoint_load(args, blob)

@@ -154,12 +154,13 @@ def test_closest_and_occluded_random_rays(ref, which):
     ctx.close()
 
 
-@pytest.mark.parametrize("tree", [1, 2])
+@pytest.mark.parametrize("tree,builder", [(1, 0), (2, 0), (2, 1)])
 @pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout", "glossy"])
-def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree):
+def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree, builder):
     """The estimator's bounce and shadow rays traverse a second tree over the same triangles (fast_bvh.cpp: binned SAH,
     leaves <= 3; tree = 1) - by default in its 4-wide form with 8-bit quantised child boxes and a conservative slab test
-    (wide_bvh.cpp; tree = 2) - with the reference's triangle test.  It must find the closest accepted triangle the reference finds:
+    (wide_bvh.cpp; tree = 2), built on the host (builder = 0) or, the default, on the device by Morton sort + PLOC clustering
+    + collapse (gpu_bvh.cu; builder = 1) - with the reference's triangle test.  It must find the closest accepted triangle the reference finds:
     checked here ray by ray against the compiled reference through a test hook that sends the per-ray seam through that
     tree.  Equal-t ties between triangles (shared edges) are the only freedom a different visit order has: t is
     bit-equal on every ray (with alpha cut-outs: on all but <= 0.02 %), the triangle index and the occlusion booleans on all
@@ -174,8 +175,10 @@ def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree):
         scene, _ = scenes.glossy_dielectric(200_000, 64, 36, 0)
     model = Model(scene)
     R = ref.RefScene(scene)
-    ctx = Context(0).upload(model)
-    ctx.set_option("seam_secondary_tree", tree)
+    ctx = Context(0)
+    ctx.set_option("seam_secondary_tree", tree)          # before the upload: the binary form is only built when asked for
+    ctx.set_option("tree_builder", builder)
+    ctx.upload(model)
     org, d = _random_rays(scene, 50_000, 23)
     tri, t = ctx.trace_closest(org, d)
     rtri, rt = R.trace_closest(org, d)
