@@ -395,6 +395,23 @@ __global__ void k_bloom_pass(const float *__restrict__ prev, float *__restrict__
 constexpr int kDofTile = 32;
 constexpr float kDofMaxCoC = 96.0f;
 
+// [0] number of NaN distances, [1] the largest circle of confusion in whole pixels (how far a source reaches)
+__global__ void k_dof_stats(const float *__restrict__ depth, const float2 *__restrict__ src, int npix, int *stat) {
+    int nans = 0, reach = 0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        if (depth[p] != depth[p]) nans++;
+        const float c0 = src[p].x;
+        if (c0 == c0) reach = max(reach, int(c0));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nans += __shfl_xor_sync(0xffffffffu, nans, o); reach = max(reach, __shfl_xor_sync(0xffffffffu, reach, o)); }
+    if ((threadIdx.x & 31) == 0) { if (nans) atomicAdd(stat, nans); if (reach) atomicMax(stat + 1, reach); }
+}
+
+__global__ void k_iota(int *p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+
 // per source pixel: depth, CoC0 and the disc's total weight (the first pair of loops of the reference)
 __global__ void k_dof_prepare(const RmHitInfo *__restrict__ G, V3 cam, float focus, float CoC, int npix, float *__restrict__ depth,
                               float2 *__restrict__ src) {

@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "rm_context.cuh"
 #include "kernels_render.cuh"
 #include "kernels_post.cuh"
@@ -35,7 +37,7 @@ struct RenderState {
     DevBuf planes_alt[4];     // second set of planes: every image-space pass reads one set and writes the other
     DevBuf f_pm, f_ns, f_op;  // packed neighbour fields of the G-buffer for the edge-stopping filter
     DevBuf glow[2];           // bloom
-    DevBuf dof_depth, dof_src, dof_sorted, dof_lists, dof_counts;      // depth of field
+    DevBuf dof_depth, dof_src, dof_sorted, dof_lists, dof_counts, dof_keys, dof_iota, dof_temp, dof_stat;      // depth of field
     int n_glass = 0;
     int sm_count = 148;
 };
@@ -128,7 +130,7 @@ void rm_render_state_free(RmContext *ctx) {
     if (!R) return;
     for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
-                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts})
+                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts, &R->dof_keys, &R->dof_iota, &R->dof_temp, &R->dof_stat})
         b->release();
     for (int w = 0; w < 2; w++)
         for (int k = 0; k < 20; k++) R->q[w][k].release();
@@ -674,23 +676,42 @@ static int dof_device(RmContext *ctx, RenderState *R, const RmRenderArgs *args, 
     if ((rc = R->dof_depth.alloc(size_t(npix) * 4)) || (rc = R->dof_src.alloc(size_t(npix) * 8)) || (rc = R->dof_sorted.alloc(size_t(npix) * 4))) return rc;
     const V3 cam = {args->position[0], args->position[1], args->position[2]};
     k_dof_prepare<<<(npix + 127) / 128, 128, 0, st>>>(R->g_out.as<RmHitInfo>(), cam, args->focus, args->CoC, npix, R->dof_depth.as<float>(), R->dof_src.as<float2>());
-    std::vector<float> depth(npix);
-    std::vector<float2> src(npix);
-    RM_CUDA(cudaMemcpyAsync(depth.data(), R->dof_depth.p, size_t(npix) * 4, cudaMemcpyDeviceToHost, st));
-    RM_CUDA(cudaMemcpyAsync(src.data(), R->dof_src.p, size_t(npix) * 8, cudaMemcpyDeviceToHost, st));
+    // The visiting order is the reference's stable sort of the pixels by camera distance (src/image.cpp:300-303).  Distances are
+    // >= +0, so their bit patterns order like the floats and a stable LSD radix sort of (bits, pixel) gives that very order -
+    // as long as no distance is NaN.  A pixel without a hit has a NaN distance, and with NaNs in the range the reference's
+    // comparator is no ordering at all: where the other pixels end up is then a property of libstdc++'s merge sort, which only
+    // that routine reproduces - such frames take the host path below (same comparator, same library routine).
+    if ((rc = R->dof_stat.alloc(64))) return rc;
+    int *stat = R->dof_stat.as<int>();              // [0] NaN distances, [1] largest circle of confusion (whole pixels)
+    RM_CUDA(cudaMemsetAsync(stat, 0, 8, st));
+    k_dof_stats<<<R->sm_count * 4, 256, 0, st>>>(R->dof_depth.as<float>(), R->dof_src.as<float2>(), npix, stat);
+    int h_stat[2] = {0, 0};
+    RM_CUDA(cudaMemcpyAsync(h_stat, stat, 8, cudaMemcpyDeviceToHost, st));
     RM_CUDA(cudaStreamSynchronize(st));
-    // the visiting order: the reference's own stable sort by camera distance (same comparator, same library routine)
-    struct Px { int idx; float depth; };
-    std::vector<Px> px(npix);
-    int reach = 0;
-    for (int i = 0; i < npix; i++) {
-        px[i] = {i, depth[i]};
-        if (src[i].x == src[i].x) reach = std::max(reach, int(src[i].x));
+    ctx->launches += 2;
+    const int reach = h_stat[1];
+    if (h_stat[0] == 0) {
+        if ((rc = R->dof_keys.alloc(size_t(npix) * 4)) || (rc = R->dof_iota.alloc(size_t(npix) * 4))) return rc;
+        k_iota<<<R->sm_count * 4, 256, 0, st>>>(R->dof_iota.as<int>(), npix);
+        size_t temp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, temp, R->dof_depth.as<unsigned>(), R->dof_keys.as<unsigned>(), R->dof_iota.as<int>(), R->dof_sorted.as<int>(), npix, 0, 32, st);
+        if ((rc = R->dof_temp.alloc(temp))) return rc;
+        RM_CUDA(cub::DeviceRadixSort::SortPairs(R->dof_temp.p, temp, R->dof_depth.as<unsigned>(), R->dof_keys.as<unsigned>(), R->dof_iota.as<int>(), R->dof_sorted.as<int>(), npix,
+                                                0, 32, st));
+        ctx->launches += 2;
+    } else {
+        std::vector<float> depth(npix);
+        RM_CUDA(cudaMemcpyAsync(depth.data(), R->dof_depth.p, size_t(npix) * 4, cudaMemcpyDeviceToHost, st));
+        RM_CUDA(cudaStreamSynchronize(st));
+        struct Px { int idx; float depth; };
+        std::vector<Px> px(npix);
+        for (int i = 0; i < npix; i++) px[i] = {i, depth[i]};
+        std::stable_sort(px.begin(), px.end(), [](const Px &a, const Px &b) { return a.depth < b.depth; });
+        std::vector<int> sorted(npix);
+        for (int i = 0; i < npix; i++) sorted[i] = px[i].idx;
+        RM_CUDA(cudaMemcpyAsync(R->dof_sorted.p, sorted.data(), size_t(npix) * 4, cudaMemcpyHostToDevice, st));
+        RM_CUDA(cudaStreamSynchronize(st));        // `sorted` dies at scope exit
     }
-    std::stable_sort(px.begin(), px.end(), [](const Px &a, const Px &b) { return a.depth < b.depth; });
-    std::vector<int> sorted(npix);
-    for (int i = 0; i < npix; i++) sorted[i] = px[i].idx;
-    RM_CUDA(cudaMemcpyAsync(R->dof_sorted.p, sorted.data(), size_t(npix) * 4, cudaMemcpyHostToDevice, st));
     const int tiles_x = (w + kDofTile - 1) / kDofTile, tiles_y = (h + kDofTile - 1) / kDofTile, tiles = tiles_x * tiles_y;
     const long long side = kDofTile + 2LL * reach;
     const long long cap = std::min<long long>(npix, side * side);
@@ -700,7 +721,6 @@ static int dof_device(RmContext *ctx, RenderState *R, const RmRenderArgs *args, 
     k_dof_gather<<<tiles, dim3(kDofTile, kDofTile), 0, st>>>(d_in, R->dof_src.as<float2>(), R->dof_lists.as<int>(), R->dof_counts.as<int>(), int(cap), w, h, tiles_x, d_out);
     ctx->launches += 3;
     RM_CUDA(cudaGetLastError());
-    RM_CUDA(cudaStreamSynchronize(st));        // `sorted` dies at scope exit
     return RM_OK;
 }
 
