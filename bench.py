@@ -192,6 +192,11 @@ class SharedFrame:
         barrier()
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:                                        # rank 0 owns the segment: the attaching ranks must not unlink it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.buf = np.frombuffer(self.shm.buf, np.uint8, self.bytes)
         self.rt = torch.cuda.cudart()
         err = self.rt.cudaHostRegister(self.buf.ctypes.data, self.bytes, 0)

@@ -23,7 +23,15 @@ RM_DI float max4(float a, float b, float c, float d) { float m = a; if (m < b) m
 constexpr int kFxRow = kFxTileW * 3 + 8;          // floats per shared row (104: a multiple of 4)
 RM_DI int fx_col(int lx) { return lx >= 0 ? lx * 3 : kFxTileW * 3 + 3; }      // lx in [-1, 32]
 
-__global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__restrict__ in, float *__restrict__ out, int width, int height) {
+// Two passes.  Only a few percent of a frame's pixels sit on an edge (range >= threshold), but they carry the expensive part -
+// five divisions and the 12 gather taps - and in one kernel a warp runs that part with the two or three lanes that need it
+// (ncu, round 2: the tap loop held 45 % of k_fxaa's instructions at 4.7 of 32 lanes).  So:
+//   k_fxaa        every pixel: luminance tile, 4-neighbour range test; writes the centre through unchanged (what a pixel below the
+//                 threshold gets) and appends the pixels at or above it to a list
+//   k_fxaa_edges  one thread per listed pixel, dense warps: 3x3 luminances, edge direction, the 12 taps, sub-pixel blend
+// Same operations on the same values in the same order as Photo::FXAA, so the result is bit-equal.
+__global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__restrict__ in, float *__restrict__ out, int width, int height,
+                                                               int *__restrict__ edge_list, int *edge_count) {
     __shared__ __align__(16) float rgb[kFxTileH + 2][kFxRow];
     __shared__ float luma[kFxTileH + 2][kFxTileW + 2];
     const int x0 = blockIdx.x * kFxTileW, y0 = blockIdx.y * kFxTileH;
@@ -33,7 +41,11 @@ __global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__res
         for (int i = tid; i < (kFxTileH + 2) * (kFxTileW * 3 / 4); i += kFxTileW * kFxTileH) {
             const int row = i / (kFxTileW * 3 / 4), q = i % (kFxTileW * 3 / 4), gy = y0 + row - 1;
             float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (gy >= 0 && gy < height) v = __ldg(reinterpret_cast<const float4 *>(in + (size_t(gy) * width + x0) * 3) + q);
+            if (gy >= 0 && gy < height) {
+                v = __ldg(reinterpret_cast<const float4 *>(in + (size_t(gy) * width + x0) * 3) + q);
+                // the interior rows go straight out again: a pixel below the threshold keeps its colour, the others are rewritten by k_fxaa_edges
+                if (row >= 1 && row <= kFxTileH) reinterpret_cast<float4 *>(out + (size_t(gy) * width + x0) * 3)[q] = v;
+            }
             reinterpret_cast<float4 *>(rgb[row])[q] = v;
         }
         for (int i = tid; i < (kFxTileH + 2) * 6; i += kFxTileW * kFxTileH) {
@@ -47,7 +59,10 @@ __global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__res
             const int row = i / ((kFxTileW + 2) * 3), r = i % ((kFxTileW + 2) * 3), lx = r / 3 - 1, ch = r % 3;
             const int gx = x0 + lx, gy = y0 + row - 1;
             float v = 0.0f;
-            if (gx >= 0 && gx < width && gy >= 0 && gy < height) v = __ldg(in + (size_t(gy) * width + gx) * 3 + ch);
+            if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
+                v = __ldg(in + (size_t(gy) * width + gx) * 3 + ch);
+                if (row >= 1 && row <= kFxTileH && lx >= 0 && lx < kFxTileW) out[(size_t(gy) * width + gx) * 3 + ch] = v;
+            }
             rgb[row][fx_col(lx) + ch] = v;
         }
     }
@@ -60,57 +75,78 @@ __global__ void __launch_bounds__(kFxTileW * kFxTileH) k_fxaa(const float *__res
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
-    float *mine = rgb[ly] + threadIdx.x * 3;            // this pixel's slot: read as the centre, overwritten with the result
+    bool edge = false;
     if (x < width && y < height) {
-        const V3 center = mk3(mine[0], mine[1], mine[2]);
-        V3 r = center;
         const float M = luma[ly][lx];
-        const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
-        const float N = hasN ? luma[ly - 1][lx] : M, Sl = hasS ? luma[ly + 1][lx] : M;
-        const float E = hasE ? luma[ly][lx + 1] : M, Wl = hasW ? luma[ly][lx - 1] : M;
-        const float rangeMin = min4(N, Sl, E, Wl), rangeMax = max4(N, Sl, E, Wl);
-        const float range = fsub(rangeMax, rangeMin);
+        const float N = y > 0 ? luma[ly - 1][lx] : M, Sl = y < height - 1 ? luma[ly + 1][lx] : M;
+        const float E = x < width - 1 ? luma[ly][lx + 1] : M, Wl = x > 0 ? luma[ly][lx - 1] : M;
+        const float rangeMax = max4(N, Sl, E, Wl);
+        const float range = fsub(rangeMax, min4(N, Sl, E, Wl));
         float thr = fmul(rangeMax, 0.125f);                 // EDGE_THRESHOLD_MAX
         thr = (0.0312f < thr) ? thr : 0.0312f;              // std::max(EDGE_THRESHOLD_MIN, ...)
-        if (!(range < thr)) {
-            const float NW = (hasN && hasW) ? luma[ly - 1][lx - 1] : M, NE = (hasN && hasE) ? luma[ly - 1][lx + 1] : M;
-            const float SW = (hasS && hasW) ? luma[ly + 1][lx - 1] : M, SE = (hasS && hasE) ? luma[ly + 1][lx + 1] : M;
-            const float third = fdiv(1.0f, 3.0f);
-            const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
-            const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
-            const bool isH = edgeHorz >= edgeVert;
-            const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
-            float g = fdiv(isH ? edgeHorz : edgeVert, range);
-            g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
-            const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
-            V3 finalColor = center;
-            float bestDelta = 0.0f;
-            const float gs = fmul(g, stepLength);
-            for (int i = 0; i < 12; i++) {                      // QUALITY
-                float off = fmul(gs, float(i + 1));
-                float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
-                if (su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f) continue;
-                int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
-                sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
-                sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
-                const float *ps = in + (size_t(sy) * width + sx) * 3;
-                V3 sc = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
-                float delta = fabsf(fsub(lum(sc), M));
-                if (delta > bestDelta) { bestDelta = delta; finalColor = sc; }
-            }
-            float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
-            sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
-            const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
-            r = center * fsub(1.0f, a) + finalColor * a;        // glm::mix
-        }
-        if (vec) { mine[0] = r.x; mine[1] = r.y; mine[2] = r.z; }
-        else { float *po = out + (size_t(y) * width + x) * 3; po[0] = r.x; po[1] = r.y; po[2] = r.z; }
+        edge = !(range < thr);
     }
-    if (!vec) return;
-    __syncthreads();
-    for (int i = tid; i < kFxTileH * (kFxTileW * 3 / 4); i += kFxTileW * kFxTileH) {
-        const int row = i / (kFxTileW * 3 / 4), q = i % (kFxTileW * 3 / 4), gy = y0 + row;
-        if (gy < height) reinterpret_cast<float4 *>(out + (size_t(gy) * width + x0) * 3)[q] = reinterpret_cast<const float4 *>(rgb[row + 1])[q];
+    // append the edge pixels: one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, edge);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(edge_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (edge) edge_list[base + __popc(m & ((1u << lane) - 1u))] = y * width + x;
+    }
+}
+
+RM_DI float fx_luma_at(const float *__restrict__ in, int width, int x, int y) {
+    const float *p = in + (size_t(y) * width + x) * 3;
+    return lum(mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)));
+}
+
+__global__ void __launch_bounds__(256) k_fxaa_edges(const float *__restrict__ in, float *__restrict__ out, int width, int height,
+                                                    const int *__restrict__ edge_list, const int *__restrict__ edge_count) {
+    const int n = *edge_count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int pix = edge_list[e];
+        const int x = pix % width, y = pix / width;
+        const float *pc = in + size_t(pix) * 3;
+        const V3 center = mk3(__ldg(pc), __ldg(pc + 1), __ldg(pc + 2));
+        const float M = lum(center);
+        const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
+        const float N = hasN ? fx_luma_at(in, width, x, y - 1) : M, Sl = hasS ? fx_luma_at(in, width, x, y + 1) : M;
+        const float E = hasE ? fx_luma_at(in, width, x + 1, y) : M, Wl = hasW ? fx_luma_at(in, width, x - 1, y) : M;
+        const float range = fsub(max4(N, Sl, E, Wl), min4(N, Sl, E, Wl));
+        const float NW = (hasN && hasW) ? fx_luma_at(in, width, x - 1, y - 1) : M, NE = (hasN && hasE) ? fx_luma_at(in, width, x + 1, y - 1) : M;
+        const float SW = (hasS && hasW) ? fx_luma_at(in, width, x - 1, y + 1) : M, SE = (hasS && hasE) ? fx_luma_at(in, width, x + 1, y + 1) : M;
+        const float third = fdiv(1.0f, 3.0f);
+        const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
+        const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
+        const bool isH = edgeHorz >= edgeVert;
+        const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
+        float g = fdiv(isH ? edgeHorz : edgeVert, range);
+        g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
+        const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
+        V3 finalColor = center;
+        float bestDelta = 0.0f;
+        const float gs = fmul(g, stepLength);
+#pragma unroll 4
+        for (int i = 0; i < 12; i++) {                      // QUALITY
+            float off = fmul(gs, float(i + 1));
+            float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
+            if (su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f) continue;
+            int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
+            sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
+            sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
+            const float *ps = in + (size_t(sy) * width + sx) * 3;
+            V3 sc = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
+            float delta = fabsf(fsub(lum(sc), M));
+            if (delta > bestDelta) { bestDelta = delta; finalColor = sc; }
+        }
+        float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
+        sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
+        const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
+        const V3 r = center * fsub(1.0f, a) + finalColor * a;        // glm::mix
+        float *po = out + size_t(pix) * 3;
+        po[0] = r.x; po[1] = r.y; po[2] = r.z;
     }
 }
 

@@ -38,6 +38,7 @@ struct RenderState {
     DevBuf f_pm, f_ns, f_op;  // packed neighbour fields of the G-buffer for the edge-stopping filter
     DevBuf glow[2];           // bloom
     DevBuf dof_depth, dof_src, dof_sorted, dof_lists, dof_counts, dof_keys, dof_iota, dof_temp, dof_stat;      // depth of field
+    DevBuf fx_list;           // FXAA: the edge pixels of the frame (count + indices)
     int n_glass = 0;
     int sm_count = 148;
 };
@@ -130,7 +131,7 @@ void rm_render_state_free(RmContext *ctx) {
     if (!R) return;
     for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
-                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts, &R->dof_keys, &R->dof_iota, &R->dof_temp, &R->dof_stat})
+                      &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts, &R->dof_keys, &R->dof_iota, &R->dof_temp, &R->dof_stat, &R->fx_list})
         b->release();
     for (int w = 0; w < 2; w++)
         for (int k = 0; k < 20; k++) R->q[w][k].release();
@@ -730,9 +731,16 @@ int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int3
     if (!d_rgb_in || !d_rgb_out || width <= 0 || height <= 0) return rm_fail(RM_ERR_INVALID, "rm_fxaa_device: bad arguments");
     if (d_rgb_in == d_rgb_out) return rm_fail(RM_ERR_INVALID, "rm_fxaa_device: in-place operation is not supported");
     RM_CUDA(cudaSetDevice(ctx->device));
+    RenderState *R = state(ctx);
+    if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    int rc;
+    if ((rc = R->fx_list.alloc(size_t(width) * height * 4 + 16))) return rc;
+    int *list = R->fx_list.as<int>() + 4, *count = R->fx_list.as<int>();           // [0] the number of edge pixels, [4..] their indices
+    RM_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
     dim3 grid((width + kFxTileW - 1) / kFxTileW, (height + kFxTileH - 1) / kFxTileH), block(kFxTileW, kFxTileH);
-    k_fxaa<<<grid, block, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height);
-    ctx->launches++;
+    k_fxaa<<<grid, block, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, list, count);
+    k_fxaa_edges<<<R->sm_count * 4, 256, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, list, count);
+    ctx->launches += 2;
     RM_CUDA(cudaGetLastError());
     return RM_OK;
 }

@@ -239,7 +239,10 @@ void doh_sky_get(const RmSceneDesc *sc, int64_t n, const float *dirs, float *out
 // ---- whole kernels, launched on the host thread by thread (cuda_on_host.h) with the launch shapes of rm_render.cu
 
 void doh_fxaa(const float *in, float *out, int w, int h) {                 // rm_fxaa_device
-    rm_host_launch_blocks(k_fxaa, dim3((w + kFxTileW - 1) / kFxTileW, (h + kFxTileH - 1) / kFxTileH), dim3(kFxTileW, kFxTileH), in, out, w, h);
+    std::vector<int> list(size_t(w) * h + 1, 0);
+    int count = 0;
+    rm_host_launch_blocks(k_fxaa, dim3((w + kFxTileW - 1) / kFxTileW, (h + kFxTileH - 1) / kFxTileH), dim3(kFxTileW, kFxTileH), in, out, w, h, list.data(), &count);
+    rm_host_launch(k_fxaa_edges, dim3(2), dim3(256), in, out, w, h, (const int *)list.data(), (const int *)&count);
 }
 
 // stages: bit 0 Photo::spatialClamp (rm_spatial_clamp), bit 1 Photo::filter (rm_filter), in the reference's order; planes in place
