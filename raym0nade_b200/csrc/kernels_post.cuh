@@ -128,18 +128,25 @@ __global__ void __launch_bounds__(256) k_fxaa_edges(const float *__restrict__ in
         V3 finalColor = center;
         float bestDelta = 0.0f;
         const float gs = fmul(g, stepLength);
-#pragma unroll 4
+        // the 12 taps: every fetch is issued up front (coordinates are clamped, so a tap outside [0, 1] may be read and is then
+        // ignored, as the reference's `continue` ignores it); the running maximum is taken in tap order
+        V3 tapc[12];
+        bool tapv[12];
+#pragma unroll
         for (int i = 0; i < 12; i++) {                      // QUALITY
-            float off = fmul(gs, float(i + 1));
-            float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
-            if (su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f) continue;
+            const float off = fmul(gs, float(i + 1));
+            const float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
+            tapv[i] = !(su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f);
             int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
             sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
             sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
             const float *ps = in + (size_t(sy) * width + sx) * 3;
-            V3 sc = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
-            float delta = fabsf(fsub(lum(sc), M));
-            if (delta > bestDelta) { bestDelta = delta; finalColor = sc; }
+            tapc[i] = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const float delta = fabsf(fsub(lum(tapc[i]), M));
+            if (tapv[i] && delta > bestDelta) { bestDelta = delta; finalColor = tapc[i]; }
         }
         float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
         sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
@@ -304,7 +311,27 @@ __global__ void k_filter_pack(const RmHitInfo *__restrict__ G, FilterG F, int np
 // (normal power, grazing-angle term, material distance) are shared by the planes, the radiance-distance term and
 // exp() are per plane.  powf / expf are CUDA's (<= 2 ulp from glibc's): results agree with the reference to ~1e-6
 // relative, not bit for bit - the tolerance is stated in tests/test_gpu_post.py.
-__global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G, FilterG F, Planes4 in, Planes4 out, int width, int height, int step) {
+// The edge-stopping weight is an exp() of distances: it tolerates approximate square roots and quotients (MUFU.SQRT / MUFU.RCP,
+// ~2 ulp) where the rest of the library insists on the correctly rounded ones - the pass already differs from the reference by
+// the ulps of powf / expf, and the weight's relative error stays below 2e-6 (|k| <= 7.5), far inside the test's 2e-4.  The
+// IEEE sequences were a third of the kernel's instructions (ncu, profiles/r02k_ncu_source_k_atrous.txt).
+RM_DI float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return sqrtf(x);
+#endif
+}
+RM_DI float div_fast(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+RM_DI float length_fast(V3 v) { return sqrt_fast(dot(v, v)); }
+
+__global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__ G, FilterG F, Planes4 in, Planes4 out, int width, int height, int step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= width || y >= height) return;
     const size_t p = size_t(y) * width + x;
@@ -323,12 +350,13 @@ __global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G,
     const float rough = __ldg(gp + 16);
     const float spec_scale = (rough < 4e-2f) ? 4e-2f : rough;          // std::max(Gp.roughness, eps_r)
     float4 Lp[4];
-    float sig[4], wsum[4], var[4];
+    float sig[4], rsig[4], wsum[4], var[4];
     V3 acc[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         Lp[j] = ld_rad(in.p[j] + p);
         sig[j] = fadd(fsqrt(Lp[j].w), 1e-2f);                          // sigma_l * sqrt(Lp.Var) + eps
+        rsig[j] = div_fast(1.0f, sig[j]);
         wsum[j] = 0.0f; var[j] = 0.0f; acc[j] = splat3(0.0f);
     }
     const float tap[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
@@ -341,8 +369,6 @@ __global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G,
             const size_t q = size_t(ny) * width + nx;
             const float base = fmul(tap[dx + 2], tap[dy + 2]);
             float4 Lq[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) Lq[j] = ld_rad(in.p[j] + q);
             float w[4] = {base, base, base, base};
             if (dx != 0 || dy != 0) {
                 const float4 Aq = __ldg(F.pm + q);
@@ -351,18 +377,22 @@ __global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G,
                 if (isfinite_any(posq)) {
                     const float4 Bq = __ldg(F.ns + q);
                     const float d = dot(snp, mk3(Bq.x, Bq.y, Bq.z));
-                    wn = powf((0.0f < d) ? d : 0.0f, 1024.0f);
+                    // the reference drops a neighbour whose normal weight d^1024 is below 1e-6, i.e. d < 0.98660: for d <= 0.98
+                    // (d^1024 <= 1.1e-9) that is known without the power
+                    if (d > 0.98f) wn = powf(d, 1024.0f);
                     if (wn < 1e-6f) wn = 0.0f;
                     else {
-                        const V3 dir = normalize(posq - posp);
-                        const float sn = fabsf(dot(shp, dir));
-                        const float tanT = fdiv(sn, fadd(fsqrt(fsub(1.0f, fmul(sn, sn))), kEps));
-                        const float dm = length(mk3(fsub(Ap.w, Aq.w), fsub(Bp.w, Bq.w), fsub(opp, __ldg(F.opacity + q))));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) Lq[j] = ld_rad(in.p[j] + q);
+                        const V3 dpos = posq - posp;
+                        const float sn = fabsf(div_fast(dot(shp, dpos), length_fast(dpos)));          // |dot(shapeNormal, normalize(dpos))|
+                        const float tanT = div_fast(sn, fadd(sqrt_fast(fsub(1.0f, fmul(sn, sn))), kEps));
+                        const float dm = length_fast(mk3(fsub(Ap.w, Aq.w), fsub(Bp.w, Bq.w), fsub(opp, __ldg(F.opacity + q))));
                         // k = ((0 - tan/sigma_z) - radianceDiff) - materialDiff/sigma_m; the middle term is per plane
                         kg = -tanT;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const float dr = fdiv(length(mk3(fsub(Lp[j].x, Lq[j].x), fsub(Lp[j].y, Lq[j].y), fsub(Lp[j].z, Lq[j].z))), sig[j]);
+                            const float dr = fmul(length_fast(mk3(fsub(Lp[j].x, Lq[j].x), fsub(Lp[j].y, Lq[j].y), fsub(Lp[j].z, Lq[j].z))), rsig[j]);
                             const float k = fadd(fadd(kg, -dr), -dm);
                             float wj = 0.0f;
                             if (!(k < -7.5f)) {
@@ -374,7 +404,12 @@ __global__ void __launch_bounds__(128) k_atrous(const RmHitInfo *__restrict__ G,
                         }
                     }
                 }
-                if (wn == 0.0f) { w[0] = w[1] = w[2] = w[3] = fmul(base, 0.0f); }
+                // a dropped neighbour enters every sum with weight base * 0 = +0: with finite planes (accumulateInwardRadiance admits
+                // nothing else) it changes no sum, so its radiance is not even fetched
+                if (wn == 0.0f) continue;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) Lq[j] = Lp[j];
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {

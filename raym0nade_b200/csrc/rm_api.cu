@@ -616,6 +616,11 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     // 0: on the host, cached by geometry hash; 1: on the device (gpu_bvh.cu) at every upload; 2 (default): on the device and
     // then refined in the background by the host builder (the render loop swaps the better tree in when it is ready)
     if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); ctx->fast_key_valid = false; return RM_OK; }
+    // block until the background refinement (if any) has finished and install its tree
+    if (!std::strcmp(name, "tree_wait")) {
+        if (ctx->refine && ctx->refine->th.joinable()) ctx->refine->th.join();
+        return rm_install_refined_tree(ctx);
+    }
     // 0: a tree built for earlier geometry is never reused (every upload rebuilds; what bench.py's end-to-end loop asks for)
     if (!std::strcmp(name, "tree_cache")) { ctx->tree_cache = value != 0; if (!ctx->tree_cache) ctx->fast_key_valid = false; return RM_OK; }
     if (!std::strcmp(name, "fast_leaf_max")) { ctx->fast_leaf_max = int(std::min<int64_t>(std::max<int64_t>(value, 1), 15)); ctx->fast_key_valid = false; return RM_OK; }

@@ -739,7 +739,9 @@ int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int3
     RM_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
     dim3 grid((width + kFxTileW - 1) / kFxTileW, (height + kFxTileH - 1) / kFxTileH), block(kFxTileW, kFxTileH);
     k_fxaa<<<grid, block, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, list, count);
-    k_fxaa_edges<<<R->sm_count * 4, 256, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, list, count);
+    // one thread per edge pixel for up to ~1.2 M of them (a 4K frame has 0.4 - 1 M): the pass is a chain of dependent gathers per
+    // pixel, so it wants all of them in flight at once; blocks beyond the list's length exit at once
+    k_fxaa_edges<<<R->sm_count * 32, 256, 0, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, list, count);
     ctx->launches += 2;
     RM_CUDA(cudaGetLastError());
     return RM_OK;
