@@ -37,6 +37,32 @@ def reduce_frame(acc, dist, rank: int, world: int, as_tensor, dst: int = 0):
     dist.reduce(as_tensor(acc.accum_radiance()), dst=dst, op=dist.ReduceOp.SUM)
 
 
+def frame_slice(npix: int, rank: int, world: int):
+    """(first pixel, pixel count) of the frame rank `rank` owns after the scattered exchange: slices of
+    per = ceil(npix / world) pixels, the last ones clipped to the frame (rm_frame_slice)"""
+    per = (npix + world - 1) // world
+    first = min(rank * per, npix)
+    return first, max(0, min(per, npix - first))
+
+
+def reduce_frame_scatter(acc, dist, rank: int, world: int, as_tensor, npix: int):
+    """The same exchange with its last step scattered (rm_reduce_scatter): afterwards the radiance buffer of rank r holds
+    the frame's sums in ITS slice of the pixels only; returns that slice.  With a backend that has no reduce-scatter
+    (gloo) every slice is reduced to its owner."""
+    if world <= 1:
+        return 0, npix
+    sum_buf, max_buf = acc.accum_view()
+    dist.all_reduce(as_tensor(sum_buf), op=dist.ReduceOp.SUM)
+    dist.all_reduce(as_tensor(max_buf), op=dist.ReduceOp.MAX)
+    acc.accum_after_reduce(rank, world)
+    rad = as_tensor(acc.accum_radiance()).view(-1)
+    for owner in range(world):
+        first, count = frame_slice(npix, owner, world)
+        if count:
+            dist.reduce(rad[first * 16:(first + count) * 16], dst=owner, op=dist.ReduceOp.SUM)
+    return frame_slice(npix, rank, world)
+
+
 class ContextAccum:
     """adapter: raym0nade_b200.api.Context -> the protocol above (device pointers + lengths)"""
 

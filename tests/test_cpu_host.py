@@ -167,8 +167,17 @@ def _gloo_worker(rank, world, port, q):
 
     acc = Acc()
     multi_gpu.reduce_frame(acc, dist, rank, world, torch.from_numpy)
+    # the scattered form on fresh accumulators: every rank ends up with the frame's sums in its own slice of the pixels
+    acc2 = Acc()
+    first, count = multi_gpu.reduce_frame_scatter(acc2, dist, rank, world, torch.from_numpy, npix)
+    mine = [None] * world
+    dist.all_gather_object(mine, (first, count, acc2.rad[first:first + count, 8].copy()))
     if rank == 0:
-        q.put(acc.rad[:, 8].copy())
+        whole = np.full(npix, np.nan, np.float32)
+        for f, c, v in mine:
+            assert np.isnan(whole[f:f + c]).all()              # slices do not overlap
+            whole[f:f + c] = v
+        q.put((acc.rad[:, 8].copy(), whole))
     dist.destroy_process_group()
 
 
@@ -180,7 +189,7 @@ def test_two_rank_reduction_equals_single_process_clamp():
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got, got_scattered = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -194,6 +203,23 @@ def test_two_rank_reduction_equals_single_process_clamp():
     want = (clum * keep).sum(0)
     assert keep[3, ::4].sum() == 0 and keep[8].all()
     assert np.allclose(got, want, rtol=1e-5)
+    assert np.allclose(got_scattered, want, rtol=1e-5)          # the slices of the scattered exchange, put together, are the same frame
+
+
+def test_frame_slices_cover_every_pixel_once():
+    """rm_frame_slice's partition: ceil(npix / world) pixels per rank, the tail clipped - also when world does not divide npix"""
+    for npix in [1, 7, 64, 1920 * 1080, 3840 * 2160 + 5]:
+        for world in [1, 2, 3, 8, 64]:
+            cover = np.zeros(npix, np.int8) if npix < 10000 else None
+            total, end = 0, 0
+            for r in range(world):
+                first, count = multi_gpu.frame_slice(npix, r, world)
+                assert first == min(end, npix) or count == 0
+                end = first + count
+                total += count
+                if cover is not None:
+                    cover[first:first + count] += 1
+            assert total == npix and (cover is None or (cover == 1).all())
 
 
 @pytest.mark.parametrize("which", ["one", "cornell", "heightfield", "glossy"])
