@@ -118,6 +118,27 @@ int64_t rm_scene_device_bytes(const RmContext *ctx);
 int64_t rm_scene_h2d_bytes(const RmContext *ctx);
 
 /* ---------------------------------------------------------------------------------
+ * The reference's tree built and refitted on the device (csrc/gpu_ref_bvh.cu)
+ * ------------------------------------------------------------------------------- */
+/* nodeCount(1, n) + 1 (src/bvh.cpp:44-49): the length of BVH::node for n faces. */
+int32_t rm_tree_node_count(int32_t n_faces);
+/* BVH::build (src/bvh.cpp:18-54) on the device: the reference's rule - leaves of at most 10 faces, split at the median of the
+ * face centres along the axis of their largest variance, heap-indexed nodes - applied level by level (prefix sums for the
+ * variances, one radix sort per level).  positions: raw faces [n_faces][3][3] (host).  nodes (host, n_nodes =
+ * rm_tree_node_count(n_faces) records) receives BVH::node; perm[i] (host) = the raw face that the build moves to slot i, i.e.
+ * what BVH::build does to Model::faces in place (bvh.cpp:38).  Same tree shape and boxes as the reference's; which of two faces
+ * with equal centre coordinates lands left of a median, and the order inside a leaf, are std::nth_element's in the reference
+ * and a sort's here. */
+int rm_tree_build(RmContext *ctx, const float *positions, int32_t n_faces, RmBvhNode *nodes, int32_t n_nodes, int32_t *perm);
+/* rm_prepare_scene with the tree built by rm_tree_build on `ctx`'s device; everything else is the same host code. */
+int rm_prepare_scene_device(RmContext *ctx, const RmRawScene *raw, RmPrepared **out);
+/* Vertices moved, topology kept: positions [n_faces][3][3] (host) in the uploaded scene's POST-BUILD order replace the staged
+ * ones; the boxes of the reference's tree are recomputed on the device (leaf boxes from their faces, inner boxes bottom-up:
+ * dfs_build's box arithmetic, bvh.cpp:21-24,41) and the secondary-ray tree is refitted and re-quantised bottom-up.  uvs, normals,
+ * materials, lights and sky stay as uploaded (a moved emissive face keeps its old light-object entry). */
+int rm_scene_refit(RmContext *ctx, const float *positions);
+
+/* ---------------------------------------------------------------------------------
  * Per-ray seam: Model::rayHit / Model::rayHit_test (include/model.h:41-42,
  * src/model.cpp:332-354) over batches of rays.
  * ------------------------------------------------------------------------------- */

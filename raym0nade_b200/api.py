@@ -58,7 +58,8 @@ EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "r
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
            "rm_fxaa_device", "rm_postprocess", "rm_spatial_clamp", "rm_filter", "rm_upload_resolved", "rm_depth_field_blur",
            "rm_checkpoint_bytes", "rm_checkpoint_save", "rm_checkpoint_load",
-           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_reduce_scatter", "rm_frame_slice", "rm_resolve_slice", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_tree_info", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
+           "rm_comm_unique_id", "rm_comm_init", "rm_reduce", "rm_comm_destroy", "rm_reduce_scatter", "rm_frame_slice", "rm_resolve_slice", "rm_secondary_tree_stats", "rm_wide_tree_stats", "rm_tree_info",
+           "rm_tree_node_count", "rm_tree_build", "rm_prepare_scene_device", "rm_scene_refit", "rm_stats_reset", "rm_stats_read", "rm_stats_kernels", "rm_set_option"]
 
 
 def lib():
@@ -105,6 +106,11 @@ def lib():
     L.rm_secondary_tree_stats.argtypes = [vp, i32, i32, i32, vp]
     L.rm_wide_tree_stats.argtypes = [vp, i32, i32, vp]
     L.rm_tree_info.argtypes = [vp, vp]
+    L.rm_tree_node_count.argtypes = [i32]
+    L.rm_tree_node_count.restype = i32
+    L.rm_tree_build.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.rm_prepare_scene_device.argtypes = [vp, C.POINTER(RmRawScene), C.POINTER(vp)]
+    L.rm_scene_refit.argtypes = [vp, vp]
     L.rm_comm_unique_id.argtypes = [vp]
     L.rm_comm_init.argtypes = [vp, vp, i32, i32]
     L.rm_reduce.argtypes = [vp, i32]
@@ -144,11 +150,15 @@ def _f32(a):
 class Model:
     """Host-side prepared scene = the reference's loaded `Model` (include/model.h:25-43)."""
 
-    def __init__(self, raw: RawScene):
+    def __init__(self, raw: RawScene, ctx: "Optional[Context]" = None):
+        """ctx given: the reference's tree is built on that context's device (rm_prepare_scene_device) instead of by the host recursion"""
         self.raw = raw
         self._c = raw.to_c()
         h = C.c_void_p()
-        _check(lib().rm_prepare_scene(C.byref(self._c), C.byref(h)))
+        if ctx is None:
+            _check(lib().rm_prepare_scene(C.byref(self._c), C.byref(h)))
+        else:
+            _check(lib().rm_prepare_scene_device(ctx.h, C.byref(self._c), C.byref(h)))
         self.h = h
         self.desc = lib().rm_prepared_desc(h).contents
 
@@ -222,6 +232,21 @@ class Context:
         _check(lib().rm_scene_upload(self.h, C.byref(model.desc)))
         self.model = model
         return self
+
+    def tree_build(self, positions):
+        """BVH::build on the device: (nodes, perm) for raw positions [n][3][3]"""
+        pos = _f32(positions).reshape(-1, 9)
+        n = pos.shape[0]
+        nn = lib().rm_tree_node_count(n)
+        nodes, perm = np.zeros(nn, BVHNODE_DTYPE), np.zeros(n, np.int32)
+        _check(lib().rm_tree_build(self.h, _p(pos), n, _p(nodes), nn, _p(perm)))
+        return nodes, perm
+
+    def refit(self, positions):
+        """moved vertices (post-build order, [n][3][3]): both trees of the uploaded scene are refitted on the device"""
+        pos = _f32(positions).reshape(-1, 9)
+        assert self.model is not None and pos.shape[0] == self.model.n_faces
+        _check(lib().rm_scene_refit(self.h, _p(pos)))
 
     def tree_info(self):
         """the 4-wide secondary-ray tree bounce / shadow rays currently traverse: dict(device_built, refined (the host builder's tree has been swapped in), nodes, levels, in_use)"""

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <string>
@@ -195,9 +196,11 @@ struct RmPrepared {
     std::vector<RmLightDesc> light_descs;
 };
 
-extern "C" {
+// `tree`: who builds the reference's tree over the raw positions - nullptr = the host recursion above; rm_prepare_scene_device
+// (gpu_ref_bvh.cu) passes the device builder.  Everything else is the same host code either way.
+using RmTreeFn = std::function<int(const float *, int, std::vector<RmBvhNode> &, std::vector<int32_t> &)>;
 
-int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out) {
+int rm_prepare_scene_impl(const RmRawScene *raw, RmPrepared **out, const RmTreeFn *tree) {
     if (!raw || !out) return rm_fail(RM_ERR_INVALID, "rm_prepare_scene: null argument");
     if (raw->n_faces <= 0) return rm_fail(RM_ERR_INVALID, "rm_prepare_scene: scene has no faces");
     for (int k = 0; k < raw->n_meshes; k++) {
@@ -312,10 +315,16 @@ int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out) {
             }
     }
     // BVH + permuted face streams
-    BvhBuilder B;
-    B.run(raw->positions, n);
-    P->nodes = std::move(B.nodes);
-    P->perm = std::move(B.order);
+    if (tree) {
+        const int rc = (*tree)(raw->positions, n, P->nodes, P->perm);
+        if (rc) return rc;
+        if (P->perm.size() != size_t(n) || P->nodes.size() < 2) return rm_fail(RM_ERR_STATE, "rm_prepare_scene: the tree builder returned no tree");
+    } else {
+        BvhBuilder B;
+        B.run(raw->positions, n);
+        P->nodes = std::move(B.nodes);
+        P->perm = std::move(B.order);
+    }
     P->positions.resize(size_t(n) * 9);
     P->uvs.resize(size_t(n) * 6);
     P->normals.resize(size_t(n) * 9);
@@ -368,6 +377,10 @@ int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out) {
     *out = P.release();
     return RM_OK;
 }
+
+extern "C" {
+
+int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out) { return rm_prepare_scene_impl(raw, out, nullptr); }
 
 const RmSceneDesc *rm_prepared_desc(const RmPrepared *p) { return p ? &p->desc : nullptr; }
 const int32_t *rm_prepared_permutation(const RmPrepared *p) { return p ? p->perm.data() : nullptr; }

@@ -102,60 +102,237 @@ RM_DI float fx_luma_at(const float *__restrict__ in, int width, int x, int y) {
     return lum(mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)));
 }
 
+// The expensive part of Photo::FXAA for one pixel at or above the threshold (src/image.cpp:384-446): 3x3 luminances, edge
+// direction, the 12 taps, sub-pixel blend.  Shared by both forms of the pass below.
+RM_DI void fx_edge_pixel(const float *__restrict__ in, float *__restrict__ out, int width, int height, int x, int y) {
+    const size_t pix = size_t(y) * width + x;
+    const float *pc = in + pix * 3;
+    const V3 center = mk3(__ldg(pc), __ldg(pc + 1), __ldg(pc + 2));
+    const float M = lum(center);
+    const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
+    const float N = hasN ? fx_luma_at(in, width, x, y - 1) : M, Sl = hasS ? fx_luma_at(in, width, x, y + 1) : M;
+    const float E = hasE ? fx_luma_at(in, width, x + 1, y) : M, Wl = hasW ? fx_luma_at(in, width, x - 1, y) : M;
+    const float range = fsub(max4(N, Sl, E, Wl), min4(N, Sl, E, Wl));
+    const float NW = (hasN && hasW) ? fx_luma_at(in, width, x - 1, y - 1) : M, NE = (hasN && hasE) ? fx_luma_at(in, width, x + 1, y - 1) : M;
+    const float SW = (hasS && hasW) ? fx_luma_at(in, width, x - 1, y + 1) : M, SE = (hasS && hasE) ? fx_luma_at(in, width, x + 1, y + 1) : M;
+    const float third = fdiv(1.0f, 3.0f);
+    const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
+    const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
+    const bool isH = edgeHorz >= edgeVert;
+    const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
+    float g = fdiv(isH ? edgeHorz : edgeVert, range);
+    g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
+    const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
+    V3 finalColor = center;
+    float bestDelta = 0.0f;
+    const float gs = fmul(g, stepLength);
+    // the 12 taps: every fetch is issued up front (coordinates are clamped, so a tap outside [0, 1] may be read and is then
+    // ignored, as the reference's `continue` ignores it); the running maximum is taken in tap order
+    V3 tapc[12];
+    bool tapv[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {                      // QUALITY
+        const float off = fmul(gs, float(i + 1));
+        const float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
+        tapv[i] = !(su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f);
+        int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
+        sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
+        sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
+        const float *ps = in + (size_t(sy) * width + sx) * 3;
+        tapc[i] = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const float delta = fabsf(fsub(lum(tapc[i]), M));
+        if (tapv[i] && delta > bestDelta) { bestDelta = delta; finalColor = tapc[i]; }
+    }
+    float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
+    sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
+    const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
+    const V3 r = center * fsub(1.0f, a) + finalColor * a;        // glm::mix
+    float *po = out + pix * 3;
+    po[0] = r.x; po[1] = r.y; po[2] = r.z;
+}
+
 __global__ void __launch_bounds__(256) k_fxaa_edges(const float *__restrict__ in, float *__restrict__ out, int width, int height,
                                                     const int *__restrict__ edge_list, const int *__restrict__ edge_count) {
     const int n = *edge_count;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int pix = edge_list[e];
-        const int x = pix % width, y = pix / width;
-        const float *pc = in + size_t(pix) * 3;
-        const V3 center = mk3(__ldg(pc), __ldg(pc + 1), __ldg(pc + 2));
-        const float M = lum(center);
-        const bool hasN = y > 0, hasS = y < height - 1, hasE = x < width - 1, hasW = x > 0;
-        const float N = hasN ? fx_luma_at(in, width, x, y - 1) : M, Sl = hasS ? fx_luma_at(in, width, x, y + 1) : M;
-        const float E = hasE ? fx_luma_at(in, width, x + 1, y) : M, Wl = hasW ? fx_luma_at(in, width, x - 1, y) : M;
-        const float range = fsub(max4(N, Sl, E, Wl), min4(N, Sl, E, Wl));
-        const float NW = (hasN && hasW) ? fx_luma_at(in, width, x - 1, y - 1) : M, NE = (hasN && hasE) ? fx_luma_at(in, width, x + 1, y - 1) : M;
-        const float SW = (hasS && hasW) ? fx_luma_at(in, width, x - 1, y + 1) : M, SE = (hasS && hasE) ? fx_luma_at(in, width, x + 1, y + 1) : M;
-        const float third = fdiv(1.0f, 3.0f);
-        const float edgeHorz = fmul(fabsf(fsub(fadd(fadd(NW, Wl), SW), fadd(fadd(NE, E), SE))), third);
-        const float edgeVert = fmul(fabsf(fsub(fadd(fadd(NW, N), NE), fadd(fadd(SW, Sl), SE))), third);
-        const bool isH = edgeHorz >= edgeVert;
-        const float stepLength = isH ? fdiv(1.0f, float(width)) : fdiv(1.0f, float(height));
-        float g = fdiv(isH ? edgeHorz : edgeVert, range);
-        g = (g < -2.0f) ? -2.0f : ((2.0f < g) ? 2.0f : g);  // std::clamp
-        const float u = fdiv(float(x), float(width)), v = fdiv(float(y), float(height));
-        V3 finalColor = center;
-        float bestDelta = 0.0f;
-        const float gs = fmul(g, stepLength);
-        // the 12 taps: every fetch is issued up front (coordinates are clamped, so a tap outside [0, 1] may be read and is then
-        // ignored, as the reference's `continue` ignores it); the running maximum is taken in tap order
-        V3 tapc[12];
-        bool tapv[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {                      // QUALITY
-            const float off = fmul(gs, float(i + 1));
-            const float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
-            tapv[i] = !(su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f);
-            int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
-            sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
-            sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
-            const float *ps = in + (size_t(sy) * width + sx) * 3;
-            tapc[i] = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
-        }
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const float delta = fabsf(fsub(lum(tapc[i]), M));
-            if (tapv[i] && delta > bestDelta) { bestDelta = delta; finalColor = tapc[i]; }
-        }
-        float sub = fmul(fadd(fmul(fabsf(fsub(fadd(N, Sl), fmul(2.0f, M))), 2.0f), fabsf(fsub(fadd(E, Wl), fmul(2.0f, M)))), 0.25f);
-        sub = (1.0f < sub) ? 1.0f : sub;                    // std::min(..., 1.0f)
-        const float a = fmul(sub, 0.75f);                   // SUBPIXEL_QUALITY
-        const V3 r = center * fsub(1.0f, a) + finalColor * a;        // glm::mix
-        float *po = out + size_t(pix) * 3;
-        po[0] = r.x; po[1] = r.y; po[2] = r.z;
+        fx_edge_pixel(in, out, width, height, pix % width, pix / width);
     }
 }
+
+// ---- FXAA in one launch, for frames whose width is a multiple of four (every row is then a whole number of 16-byte vectors).
+// The tiled kernel above spends ~200 warp instructions per 32 pixels on index arithmetic around 12-byte pixels and is bound by
+// instruction issue at a quarter of the HBM roofline.  Here a warp owns a strip of 128 x ROWS pixels and walks it top to bottom:
+//   * rows travel by the bulk-copy engine (TMA, cp.async.bulk): lane 0 asks for a row of the strip - its 128 pixels plus four
+//     on either side, 1632 contiguous bytes - to be dropped into one of the warp's STAGES shared-memory buffers and signalled on
+//     an mbarrier, up to kFxStages rows ahead of the row being worked on; the copy-through every pixel below the threshold gets is
+//     one bulk store from that same buffer back to the output frame.  No LDG / STG, no register staging, the loads of several
+//     rows in flight per warp;
+//   * a lane owns FOUR consecutive pixels of a row = 48 bytes = three 16-byte shared-memory loads -> four luminances; the rows
+//     above / at / below the current row stay in registers (a rolling window), left / right neighbours come across lanes by
+//     shuffle, the two pixels beside the warp's span from the buffer's margins;
+//   * the 4-neighbour range test appends the strip's edge pixels (ballot + popc) to a per-warp list in shared memory as 16-bit
+//     strip coordinates; when the strip is done - or the list may overflow - the warp runs the expensive part, fx_edge_pixel,
+//     for them in dense lanes, while the strip's pixels are still in L1 / L2.  No global list, no atomics, no second launch.
+// The range test uses FMNMX; std::min / std::max chains (what the reference evaluates) agree with it unless a luminance is NaN,
+// which a per-row check routes to the exact chains.  Same operations on the same values in the same order as Photo::FXAA:
+// bit-equal.
+#ifdef __CUDACC__
+constexpr int kFxStripWarps = 4, kFxStages = 4;
+constexpr int kFxRowBytes = 136 * 12;               // 4 + 128 + 4 pixels
+constexpr int kFxRowStride = 1664;                  // ... padded to a multiple of 128 bytes
+constexpr int kFxListCap = 1024;                    // edge pixels a warp gathers before it works them off
+constexpr int kFxWarpBytes = kFxStages * kFxRowStride + kFxListCap * 2 + 128;      // row buffers, edge list, mbarriers: a multiple of 128
+static_assert(kFxWarpBytes % 128 == 0 && kFxRowStride >= kFxRowBytes, "shared-memory layout of k_fxaa_strip");
+
+RM_DI unsigned fx_smem(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+RM_DI void fx_bar_init(unsigned bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
+RM_DI void fx_bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+RM_DI void fx_bar_wait(unsigned bar, unsigned parity) {
+    unsigned ok, spins = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();          // a copy that never lands is an error, not a hang
+    } while (!ok);
+}
+RM_DI void fx_bulk_store(void *dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32 * kFxStripWarps) k_fxaa_strip(const float *__restrict__ in, float *__restrict__ out, int width, int height, int ROWS) {
+    extern __shared__ __align__(128) unsigned char fx_dyn[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *mine = fx_dyn + size_t(wid) * kFxWarpBytes;
+    float *rows = reinterpret_cast<float *>(mine);                                                   // [kFxStages][kFxRowStride / 4]
+    unsigned short *s_edges = reinterpret_cast<unsigned short *>(mine + kFxStages * kFxRowStride);    // [kFxListCap]
+    const unsigned bar0 = fx_smem(mine + kFxStages * kFxRowStride + kFxListCap * 2);                  // kFxStages mbarriers
+    const int spans = (width + 127) >> 7, bands = (height + ROWS - 1) / ROWS;
+    const int strip = blockIdx.x * kFxStripWarps + wid;
+    if (strip >= spans * bands) return;                 // whole warps leave; the kernel has no CTA-wide barrier
+    const int span_x = (strip % spans) << 7, y0 = (strip / spans) * ROWS;
+    const int y1 = min(y0 + ROWS, height);
+    const int x0 = span_x + lane * 4;
+    const bool active = x0 < width;                     // width % 4 == 0: a lane's four pixels are all inside or all outside
+    const bool first = x0 == 0, last = x0 + 4 == width;
+    // the rows this strip reads: [ylo, yhi]; the columns a row copy covers: [xb, xe)
+    const int ylo = max(y0 - 1, 0), yhi = min(y1, height - 1), nrows = yhi - ylo + 1;
+    const int xb = max(span_x - 4, 0), xe = min(span_x + 132, width);
+    const unsigned row_bytes = unsigned(xe - xb) * 12u, own_bytes = unsigned(min(128, width - span_x)) * 12u;
+    const unsigned dst_off = unsigned(xb - (span_x - 4)) * 12u;           // pixel span_x always lands 48 bytes into the buffer
+
+    auto issue = [&](int k) {                           // lane 0: ask for row k of the strip's sequence
+        const int st = k % kFxStages;
+        fx_bulk_load(fx_smem(rows) + st * kFxRowStride + dst_off, in + (size_t(ylo + k) * width + xb) * 3, row_bytes, bar0 + st * 8);
+    };
+    if (lane == 0) {
+        for (int st = 0; st < kFxStages; st++) fx_bar_init(bar0 + st * 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < kFxStages && k < nrows; k++) issue(k);
+    }
+    __syncwarp();
+
+    int n_list = 0;                                     // warp-uniform
+    auto flush = [&]() {
+        // every copy-through this warp has issued must have landed before an edge pixel is rewritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        for (int e = lane; e < n_list; e += 32) {
+            const int c = s_edges[e];
+            fx_edge_pixel(in, out, width, height, span_x + (c & 127), y0 + (c >> 7));
+        }
+        __syncwarp();
+        n_list = 0;
+    };
+
+    float prv[6], cur[6], nxt[6];
+    bool nan_prv = false, nan_cur = false, nan_nxt = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) prv[k] = cur[k] = nxt[k] = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k <= nrows; k++) {
+        if (k < nrows) {                                // warp-uniform
+            const int st = k % kFxStages, y = ylo + k;
+            fx_bar_wait(bar0 + st * 8, unsigned(k / kFxStages) & 1u);
+            const float *buf = rows + st * (kFxRowStride / 4);
+            if (lane == 0 && y >= y0 && y < y1) fx_bulk_store(out + (size_t(y) * width + span_x) * 3, fx_smem(buf) + 48, own_bytes);
+            const float4 a = reinterpret_cast<const float4 *>(buf + 12)[lane * 3], b = reinterpret_cast<const float4 *>(buf + 12)[lane * 3 + 1],
+                         c = reinterpret_cast<const float4 *>(buf + 12)[lane * 3 + 2];
+            const float *hp = buf + (lane == 0 ? 9 : 12 + 128 * 3);      // the pixel left of the span / right of it
+            const float h = lum(mk3(hp[0], hp[1], hp[2]));
+            nxt[1] = lum(mk3(a.x, a.y, a.z));
+            nxt[2] = lum(mk3(a.w, b.x, b.y));
+            nxt[3] = lum(mk3(b.z, b.w, c.x));
+            nxt[4] = lum(mk3(c.y, c.z, c.w));
+            const float up = __shfl_up_sync(0xffffffffu, nxt[4], 1), dn = __shfl_down_sync(0xffffffffu, nxt[1], 1);
+            nxt[0] = first ? nxt[1] : (lane == 0 ? h : up);              // x == 0: lumaW = lumaM
+            nxt[5] = last ? nxt[4] : (lane == 31 ? h : dn);              // x == width - 1: lumaE = lumaM
+            const float chk = fadd(fadd(fadd(nxt[0], nxt[1]), fadd(nxt[2], nxt[3])), fadd(nxt[4], nxt[5]));
+            nan_nxt = __any_sync(0xffffffffu, active && !(fabsf(chk) <= 3.0e38f));      // a NaN (or an infinity) somewhere in this row
+            __syncwarp();                               // every lane has its row in registers: the buffer before this one is free
+            // refill the buffer of row k - 1 with row k - 1 + STAGES once the copy-through issued from it has read it
+            if (lane == 0 && k >= 1 && k - 1 + kFxStages < nrows) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue(k - 1 + kFxStages);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 6; j++) nxt[j] = cur[j];                // y == height - 1: lumaS = lumaM
+            nan_nxt = nan_cur;
+        }
+        const int y = ylo + k - 1;                      // the row under test: cur, between prv and nxt
+        if (k >= 1 && y >= y0 && y < y1) {
+            if (y == 0) {                               // lumaN = lumaM
+#pragma unroll
+                for (int j = 0; j < 6; j++) prv[j] = cur[j];
+                nan_prv = nan_cur;
+            }
+            bool edge[4];
+            if (!(nan_prv || nan_cur || nan_nxt)) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float N = prv[1 + j], Sl = nxt[1 + j], E = cur[2 + j], Wl = cur[j];
+                    const float rangeMax = fmaxf(fmaxf(N, Sl), fmaxf(E, Wl));
+                    const float range = fsub(rangeMax, fminf(fminf(N, Sl), fminf(E, Wl)));
+                    const float thr = fmaxf(fmul(rangeMax, 0.125f), 0.0312f);
+                    edge[j] = active && !(range < thr);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float N = prv[1 + j], Sl = nxt[1 + j], E = cur[2 + j], Wl = cur[j];
+                    const float rangeMax = max4(N, Sl, E, Wl);
+                    const float range = fsub(rangeMax, min4(N, Sl, E, Wl));
+                    float thr = fmul(rangeMax, 0.125f);                 // EDGE_THRESHOLD_MAX
+                    thr = (0.0312f < thr) ? thr : 0.0312f;              // std::max(EDGE_THRESHOLD_MIN, ...)
+                    edge[j] = active && !(range < thr);
+                }
+            }
+            if (n_list + 128 > kFxListCap) flush();
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned m = __ballot_sync(0xffffffffu, edge[j]);
+                if (edge[j]) s_edges[n_list + __popc(m & lt)] = static_cast<unsigned short>(((y - y0) << 7) | (lane * 4 + j));
+                n_list += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) { prv[j] = cur[j]; cur[j] = nxt[j]; }
+        nan_prv = nan_cur; nan_cur = nan_nxt;
+    }
+    if (n_list) flush();
+    // a CTA's shared memory must outlive the bulk stores that read it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif  // __CUDACC__
 
 // Photo::ShadeOption bits (include/image.h:17-36)
 enum { kBaseColor = 1, kEmission = 2, kDirect = 4, kIndirect = 8, kDiffuse = 16, kSpecular = 32, kShapeNormal = 64, kSurfaceNormal = 128 };

@@ -428,6 +428,30 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     return RM_OK;
 }
 
+// After rm_scene_refit (gpu_ref_bvh.cu) has put new positions into b_raw[0]: the traversal and shading records are formed anew and
+// re-permuted for the 4-wide tree(s).  The binary form of the secondary-ray tree is not refitted: whoever asks for it afterwards
+// gets the reference's tree.
+int rm_repack_faces(RmContext *ctx) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->scene.n_faces;
+    k_pack_faces<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_raw[0].as<float>(), ctx->b_raw[1].as<float>(), ctx->b_raw[2].as<float>(), ctx->b_raw[3].as<int>(),
+                                                  ctx->b_mats.as<DevMaterial>(), n, ctx->b_tri.as<float4>(), ctx->b_shade.as<float4>());
+    ctx->launches++;
+    if (ctx->have_wide) {
+        k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide.as<int>(), n, ctx->b_tri_wide.as<float4>());
+        ctx->launches++;
+        if (ctx->refined_installed) {
+            k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide2.as<int>(), n, ctx->b_tri_wide2.as<float4>());
+            ctx->launches++;
+        }
+    }
+    ctx->have_fast = false;
+    ctx->scene_fast = ctx->scene;
+    RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaStreamSynchronize(st));
+    return RM_OK;
+}
+
 // The background build has finished: stage its tree next to the device builder's and point bounce / shadow rays at it.
 // Called where the render loop waits for the device anyway (rm_render_samples: on entry and between batches of rounds).
 int rm_install_refined_tree(RmContext *ctx) {
@@ -437,7 +461,7 @@ int rm_install_refined_tree(RmContext *ctx) {
     if (state == 1) return RM_OK;
     if (J->th.joinable()) J->th.join();
     std::unique_ptr<RefineJob> job = std::move(ctx->refine);
-    if (state != 2 || job->n != ctx->scene.n_faces || !ctx->have_wide) return RM_OK;
+    if (state != 2 || job->discard || job->n != ctx->scene.n_faces || !ctx->have_wide) return RM_OK;
     RM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = job->n;
@@ -639,6 +663,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     }
     if (!std::strcmp(name, "wave_paths")) { ctx->wave_paths = int(std::min<int64_t>(std::max<int64_t>(value, 1 << 16), 1 << 25)); return RM_OK; }
     if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
+    if (!std::strcmp(name, "fxaa_rows")) { ctx->fxaa_rows = int(std::min<int64_t>(std::max<int64_t>(value, 0), 256)); return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
 }

@@ -50,6 +50,7 @@ struct RefineJob {
     std::vector<RmWideNode> wnodes;
     std::vector<int32_t> worder;
     int wdepth = 0;
+    bool discard = false;                  // the vertices moved while it ran (rm_scene_refit): its tree is not installed
 };
 
 struct RmContext {
@@ -121,6 +122,7 @@ struct RmContext {
                                            // launch long enough that kernel tails and launch gaps stay ~1 % (4 M: -10 %, 16 M: -1 %,
                                            // profiles/r01c_ab7_wave_size.txt, r01d_ab8_wave_size.txt) for 38 GB of queues out of 180 GB
     int max_depth = 16;                    // perf experiments only: bounce limit of the wavefront loop (16 = the reference's maxRayDepth)
+    int fxaa_rows = 16;                    // rows per warp strip of k_fxaa_strip; 0 = the two-pass tiled form (what frames with width % 4 != 0 always get)
 
     // per-frame state
     int width = 0, height = 0;
@@ -157,5 +159,7 @@ int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max
 // implemented in wide_bvh.cpp (declared in wide_bvh.h)
 // implemented in rm_api.cu: swaps the background-refined secondary-ray tree in once it is ready (no-op otherwise)
 extern "C" int rm_install_refined_tree(RmContext *ctx);
+// implemented in rm_api.cu: after rm_scene_refit (gpu_ref_bvh.cu) - the traversal and shading records formed anew from ctx->b_raw[0] and re-permuted for the 4-wide tree(s)
+extern "C" int rm_repack_faces(RmContext *ctx);
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);

@@ -733,6 +733,16 @@ int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int3
     RM_CUDA(cudaSetDevice(ctx->device));
     RenderState *R = state(ctx);
     if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
+    // one launch when every row is a whole number of 16-byte vectors (kernels_post.cuh: k_fxaa_strip)
+    if (ctx->fxaa_rows && (width & 3) == 0 && ((reinterpret_cast<uintptr_t>(d_rgb_in) | reinterpret_cast<uintptr_t>(d_rgb_out)) & 15) == 0) {
+        const int rows = ctx->fxaa_rows;
+        const int strips = ((width + 127) / 128) * ((height + rows - 1) / rows);
+        const int grid = (strips + kFxStripWarps - 1) / kFxStripWarps;
+        k_fxaa_strip<<<grid, 32 * kFxStripWarps, kFxStripWarps * kFxWarpBytes, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, rows);
+        ctx->launches += 1;
+        RM_CUDA(cudaGetLastError());
+        return RM_OK;
+    }
     int rc;
     if ((rc = R->fx_list.alloc(size_t(width) * height * 4 + 16))) return rc;
     int *list = R->fx_list.as<int>() + 4, *count = R->fx_list.as<int>();           // [0] the number of edge pixels, [4..] their indices

@@ -1,4 +1,4 @@
-"""k_fxaa timed alone on the device (24 B/pixel algorithmic -> 199 MB at 4K, ~31 us at the HBM peak).
+"""FXAA timed alone on the device (24 B/pixel algorithmic -> 199 MB at 4K, ~31 us at the HBM peak).
 
     python scripts/post_bench.py [width height]
 
@@ -25,27 +25,37 @@ for k in range(8):
     img = torch.stack([base + blocks, base * 0.8 + blocks, base * 0.6 + 0.3 * blocks], -1) + 0.02 * torch.rand((h, w, 3), device=dev, generator=g)
     frames.append(img.clamp(0, 1).float().contiguous())
 out = torch.empty_like(frames[0])
-for f in frames[:3]:
-    ctx.fxaa_device(f.data_ptr(), out.data_ptr(), w, h)
-torch.cuda.synchronize()
-changed = float((out != frames[2]).any(-1).float().mean())
-reps = 40
-evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-for i, (a, b) in enumerate(evs):
-    a.record()
-    ctx.fxaa_device(frames[i % 8].data_ptr(), out.data_ptr(), w, h)
-    b.record()
-torch.cuda.synchronize()
-ms = sorted(a.elapsed_time(b) for a, b in evs)
 peak = 6650.0
 try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
 alg = 24.0 * w * h
-med = ms[len(ms) // 2]
-print(json.dumps({"kernel": "k_fxaa", "frame": "%dx%d" % (w, h), "launches": reps, "us_median": med * 1e3, "us_min": ms[0] * 1e3,
-                  "algorithmic_bytes": alg, "achieved_gbs": alg / (med * 1e-3) / 1e9, "peak_gbs": peak, "frac": alg / (med * 1e-3) / 1e9 / peak,
+reps = 40
+
+
+def timed(rows):
+    """median / min microseconds of rm_fxaa_device with "fxaa_rows" = rows (16 | 8: one-launch strip kernel, 0: two passes)"""
+    ctx.set_option("fxaa_rows", rows)
+    for f in frames[:3]:
+        ctx.fxaa_device(f.data_ptr(), out.data_ptr(), w, h)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        ctx.fxaa_device(frames[i % 8].data_ptr(), out.data_ptr(), w, h)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    return ms[len(ms) // 2] * 1e3, ms[0] * 1e3
+
+
+variants = {("strip%d" % r if r else "two_pass"): timed(r) for r in (0, 8, 12, 24, 16)}
+med, best = variants["strip16"]           # the default form
+changed = float((out != frames[(reps - 1) % 8]).any(-1).float().mean())
+print(json.dumps({"kernel": "k_fxaa_strip, 16 rows per warp", "frame": "%dx%d" % (w, h), "launches": reps, "us_median": med, "us_min": best,
+                  "algorithmic_bytes": alg, "achieved_gbs": alg / (med * 1e-6) / 1e9, "peak_gbs": peak, "frac": alg / (med * 1e-6) / 1e9 / peak,
                   "roofline_us": alg / peak / 1e3, "pixels_changed_share": changed,
+                  "variants_us_median_min": {k: [round(v[0], 2), round(v[1], 2)] for k, v in variants.items()},
                   "l2_policy": "8 distinct 4K inputs rotated (800 MB > 126 MB L2)"}))
 ctx.close()

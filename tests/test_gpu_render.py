@@ -395,17 +395,37 @@ def test_checkpoint_resume_in_a_fresh_context_equals_one_render():
 
 # --------------------------------------------------------------------------- FXAA + post pass
 def test_fxaa_bit_exact_random_and_edges(ref):
+    """Photo::FXAA (src/image.cpp:358-452), bit for bit, through every form of the pass: the one-launch strip kernel that frames
+    with width % 4 == 0 get (rows travel by bulk copies; several strip heights; spans of 128 pixels - sizes straddle one, two and three spans and strips
+    that end short of the frame) and the two-pass tiled form (any width; "fxaa_rows" 0 forces it)."""
     ctx = Context(0)
     rs = np.random.default_rng(0)
-    for (h, w) in [(37, 53), (64, 64), (1, 40), (40, 1), (8, 32)]:
+    cases = []
+    for (h, w) in [(37, 53), (64, 64), (1, 40), (40, 1), (8, 32), (5, 4), (17, 128), (19, 132), (33, 256), (50, 260), (16, 384), (47, 400)]:
         img = rs.random((h, w, 3), dtype=np.float32)
         img[h // 3: h // 2, :, :] *= 0.05          # strong horizontal edges
         img[:, w // 3: w // 2, :] *= 0.2
-        got = ctx.fxaa(img)
-        want = ref.fxaa(img)
-        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (h, w)
-    flat = np.full((16, 16, 3), 0.5, np.float32)
-    assert np.array_equal(ctx.fxaa(flat), flat)    # below the edge threshold: identity
+        cases.append((img, ref.fxaa(img)))
+    smooth = (0.5 + 0.01 * rs.random((70, 300, 3), dtype=np.float32)).astype(np.float32)       # few pixels above the threshold
+    smooth[30:33, 100:200] = 0.9
+    cases.append((smooth, ref.fxaa(smooth)))
+    # NaN / infinite / huge pixels: std::min / std::max chains are order-dependent around a NaN (the strip kernel's FMNMX fast path
+    # must hand such rows to the exact chains)
+    odd = rs.random((40, 264, 3), dtype=np.float32)
+    odd[5, 7] = np.nan; odd[6, 130, 1] = np.nan; odd[20, 0] = np.inf; odd[21, 263, 2] = -np.inf; odd[30, 128] = 3e38; odd[39, 100, 0] = np.nan
+    cases.append((odd, ref.fxaa(odd)))
+
+    def same_bits(a, b):                            # bit-equal; a NaN only has to be a NaN (its sign / payload is the FPU's choice)
+        na, nb = np.isnan(a), np.isnan(b)
+        return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+    for rows in (16, 8, 3, 64, 0):
+        ctx.set_option("fxaa_rows", rows)
+        for img, want in cases:
+            got = ctx.fxaa(img)
+            assert same_bits(got, want), (rows, img.shape)
+        flat = np.full((16, 16, 3), 0.5, np.float32)
+        assert np.array_equal(ctx.fxaa(flat), flat)    # below the edge threshold: identity
     ctx.close()
 
 

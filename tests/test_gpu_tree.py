@@ -1,0 +1,256 @@
+"""GPU parity, SURVEY.md section 8f row 3: the reference's tree built on the device (rm_tree_build: BVH::build, src/bvh.cpp:18-54)
+and the refit of an uploaded scene's trees for moved vertices (rm_scene_refit).
+
+What is held to the reference bit for bit: the tree's shape (node count, heap layout, every leaf range - they follow from the
+face count alone), every box given the faces beneath it (Face::aabb + Box::operator+ are min / max), and the hits rays find in
+it.  What the reference itself does not define - which of several equal keys std::nth_element leaves left of a median, the order
+inside a range, the axis where two fp32 running sums tie - is checked as a property instead: every split separates its two
+halves along the axis the rule names for the faces actually in the node."""
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import pytest
+
+from raym0nade_b200 import scenes
+from raym0nade_b200.api import Context, Model, RmSceneDesc, lib, _check, _p
+
+pytestmark = pytest.mark.gpu
+
+
+def _centres(pos):
+    """Face::center(): (v0 + v1 + v2) * (1 / 3) in fp32, glm's operation order"""
+    return ((pos[:, 0] + pos[:, 1]) + pos[:, 2]) * np.float32(np.float32(1.0) / np.float32(3.0))
+
+
+def _check_tree(raw_pos, nodes, perm, n_ref_nodes=None):
+    """every property of BVH::dfs_build the reference defines, for the tree (nodes, perm) over raw_pos [n][3][3]"""
+    n = raw_pos.shape[0]
+    assert sorted(perm.tolist()) == list(range(n)), "perm is not a permutation"
+    pos = raw_pos[perm]
+    cen = _centres(pos).astype(np.float64)
+    fmin = pos.min(axis=1)
+    fmax = pos.max(axis=1)
+    if n_ref_nodes is not None:
+        assert nodes.shape[0] == n_ref_nodes
+    stack = [(1, 0, n)]
+    leaves = inner = near_ties = 0
+    box = {}
+    order = []
+    while stack:                      # ranges as dfs_build hands them down
+        u, L, R = stack.pop()
+        order.append((u, L, R))
+        if R - L <= 10:
+            assert (nodes["faceL"][u], nodes["faceR"][u]) == (L, R), (u, L, R)
+            leaves += 1
+            continue
+        assert nodes["faceR"][u] == 0 and nodes["faceL"][u] == 0, u
+        inner += 1
+        c = cen[L:R]
+        D = (c * c).sum(0) - c.sum(0) ** 2 / (R - L)
+        axis = 0
+        if D[1] > D[0]:
+            axis = 1
+        if D[2] > D[0] and D[2] > D[1]:
+            axis = 2
+        M = (L + R) // 2
+        sep = [cen[L:M, a].max() <= cen[M:R, a].min() for a in range(3)]
+        if not sep[axis]:
+            # the rule's axis is decided by sums in another order on the device (prefix sums): only a near-tie may flip it
+            alt = [a for a in range(3) if sep[a]]
+            assert alt, "node %d [%d, %d) is not split along any axis" % (u, L, R)
+            assert abs(D[alt[0]] - D[axis]) <= 1e-9 * max(abs(D).max(), 1e-30), (u, D, alt)
+            near_ties += 1
+        stack.append((u << 1, L, M))
+        stack.append((u << 1 | 1, M, R))
+    for u, L, R in reversed(order):   # children before parents
+        if R - L <= 10:
+            lo, hi = fmin[L:R].min(0), fmax[L:R].max(0)
+        else:
+            lo = np.minimum(box[u << 1][0], box[u << 1 | 1][0])
+            hi = np.maximum(box[u << 1][1], box[u << 1 | 1][1])
+        box[u] = (lo, hi)
+        assert np.array_equal(nodes["v0"][u], lo) and np.array_equal(nodes["v1"][u], hi), u
+    used = np.zeros(nodes.shape[0], bool)
+    used[[u for u, _, _ in order]] = True
+    rest = nodes[~used]
+    assert not rest["faceL"].any() and not rest["faceR"].any() and not rest["v0"].any() and not rest["v1"].any(), "never-written slots must be zero"
+    return leaves, inner, near_ties
+
+
+@pytest.mark.parametrize("which", ["tiny", "cornell", "heightfield", "cutout", "duplicates"])
+def test_device_built_reference_tree_follows_the_rule(which):
+    """rm_tree_build against BVH::dfs_build's definition, node by node (numpy, double precision)"""
+    if which == "tiny":
+        scene, _ = scenes.cornell_box()
+        scene.positions = scene.positions[:7].copy()
+    elif which == "cornell":
+        scene, _ = scenes.cornell_box()
+    elif which == "heightfield":
+        scene, _ = scenes.heightfield_scene(20_000)
+    elif which == "cutout":
+        scene, _ = scenes.texture_heavy(40_000, tex_size=64, n_materials=8)
+    else:
+        scene, _ = scenes.heightfield_scene(3_000)
+        scene.positions = np.concatenate([scene.positions] * 3)       # every face three times: ties across every median
+    raw = np.ascontiguousarray(scene.positions, np.float32).reshape(-1, 3, 3)
+    ctx = Context(0)
+    nodes, perm = ctx.tree_build(raw)
+    leaves, inner, ties = _check_tree(raw, nodes, perm, lib().rm_tree_node_count(raw.shape[0]))
+    assert leaves == inner + 1
+    if which in ("heightfield", "cutout"):
+        assert ties <= inner // 100
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout", "glossy"])
+def test_device_built_reference_tree_against_the_reference(ref, which):
+    """Model(raw, ctx): the scene prepared with the device-built tree.  Same shape as the reference's own tree (every leaf range),
+    the same face sets per leaf wherever no tie exists (all of them on these scenes but a sliver), and primary rays find the
+    reference's hits: t bit-equal, the raw face equal (ties at shared edges aside)."""
+    if which == "cornell":
+        scene, args = scenes.cornell_box(256, 256, 0)
+    elif which == "heightfield":
+        scene, args = scenes.heightfield_scene(20_000, 480, 270)
+    elif which == "cutout":
+        scene, args = scenes.texture_heavy(40_000, 320, 180, tex_size=64, n_materials=8)
+    else:
+        scene, args = scenes.glossy_dielectric(200_000, 480, 270, 0)
+    ctx = Context(0)
+    host = Model(scene)
+    dev = Model(scene, ctx)
+    dev.validate()
+    hn, dn = host.nodes(), dev.nodes()
+    assert hn.shape == dn.shape
+    assert np.array_equal(hn["faceL"], dn["faceL"]) and np.array_equal(hn["faceR"], dn["faceR"])
+    hp, dp = host.permutation(), dev.permutation()
+    leaf = np.nonzero(hn["faceR"])[0]
+    same = sum(set(hp[hn["faceL"][u]:hn["faceR"][u]].tolist()) == set(dp[dn["faceL"][u]:dn["faceR"][u]].tolist()) for u in leaf)
+    assert same >= 0.98 * leaf.size, (same, leaf.size)
+    # boxes of nodes holding the same faces are the reference's bits
+    root_same = np.array_equal(hn["v0"][1], dn["v0"][1]) and np.array_equal(hn["v1"][1], dn["v1"][1])
+    assert root_same
+    ctx.upload(dev)
+    tri, t = ctx.trace_primary(args)
+    R = ref.RefScene(scene)
+    rtri, rt = R.trace_primary(args, threads=8)
+    t_differs = t.view(np.uint32) != rt.view(np.uint32)
+    assert t_differs.mean() <= (2e-4 if which == "cutout" else 1e-5), t_differs.sum()
+    hit = (tri >= 0) & (rtri >= 0)
+    assert np.array_equal(tri >= 0, rtri >= 0) or t_differs.any()
+    raw_dev, raw_ref = dp[tri[hit]], hp[rtri[hit]]
+    assert (raw_dev != raw_ref).mean() <= 1e-3, (raw_dev != raw_ref).mean()
+    # the per-ray seam and the estimator run on the device-prepared scene like on any other
+    out = ctx.render(args.replace(spp=2), seed=1)
+    assert np.isfinite(out["Id"]["radiance"]).all()
+    ctx.close()
+
+
+def test_device_built_tree_one_million(ref):
+    """configs[2]'s scene: the build on the device, the rule checked per node, and the primary hits of the full 1080p frame"""
+    import os
+    scene, args = scenes.glossy_dielectric(1_000_000, 1920, 1080, 0)
+    raw = np.ascontiguousarray(scene.positions, np.float32).reshape(-1, 3, 3)
+    ctx = Context(0)
+    dev = Model(scene, ctx)
+    _check_tree(raw, dev.nodes(), dev.permutation(), lib().rm_tree_node_count(raw.shape[0]))
+    ctx.upload(dev)
+    tri, t = ctx.trace_primary(args)
+    host = Model(scene)
+    rtri, rt = ref.RefScene(scene).trace_primary(args, threads=os.cpu_count() or 8)
+    assert (t.view(np.uint32) != rt.view(np.uint32)).mean() <= 1e-5
+    hit = (tri >= 0) & (rtri >= 0)
+    assert (dev.permutation()[tri[hit]] != host.permutation()[rtri[hit]]).mean() <= 1e-3
+    ctx.close()
+
+
+def _upload_desc(ctx, model, nodes, positions):
+    """rm_scene_upload of `model`'s prepared scene with another node array and other (post-build order) positions"""
+    d = RmSceneDesc()
+    C.memmove(C.byref(d), C.byref(model.desc), C.sizeof(RmSceneDesc))
+    d.nodes = nodes.ctypes.data
+    d.positions = positions.ctypes.data
+    _check(lib().rm_scene_upload(ctx.h, C.byref(d)))
+    ctx.model = model
+
+
+def _host_refit(nodes, pos):
+    """dfs_build's box arithmetic over a fixed topology (numpy): leaf boxes from their faces, inner boxes from their children"""
+    out = nodes.copy()
+    fmin, fmax = pos.min(axis=1), pos.max(axis=1)
+    order, stack = [], [1]
+    while stack:
+        u = stack.pop()
+        order.append(u)
+        if not nodes["faceR"][u]:
+            stack += [u << 1, u << 1 | 1]
+    for u in reversed(order):
+        if nodes["faceR"][u]:
+            L, R = nodes["faceL"][u], nodes["faceR"][u]
+            out["v0"][u], out["v1"][u] = fmin[L:R].min(0), fmax[L:R].max(0)
+        else:
+            out["v0"][u] = np.minimum(out["v0"][u << 1], out["v0"][u << 1 | 1])
+            out["v1"][u] = np.maximum(out["v1"][u << 1], out["v1"][u << 1 | 1])
+    return out
+
+
+@pytest.mark.parametrize("builder", [1, 0])
+@pytest.mark.parametrize("which", ["heightfield", "glossy"])
+def test_refit_for_moved_vertices(ref, which, builder):
+    """rm_scene_refit: the vertices of an uploaded scene move (a travelling wave, amplitude ~ a few triangle sizes).  Afterwards
+      * primary rays - the reference's tree, refitted in place - return bit for bit what a fresh upload of the same topology
+        with host-recomputed boxes returns, and the reference's own answers for the moved scene (its own new tree) in t;
+      * the refitted secondary-ray tree (device-built, builder = 1, or host-built, builder = 0) finds the same closest hits and
+        occlusion answers as the reference does on the moved scene."""
+    if which == "heightfield":
+        scene, args = scenes.heightfield_scene(20_000, 320, 180)
+    else:
+        scene, args = scenes.glossy_dielectric(200_000, 320, 180, 0)
+    model = Model(scene)
+    ctx = Context(0)
+    ctx.set_option("tree_builder", builder)
+    ctx.upload(model)
+    n = model.n_faces
+    old = np.frombuffer((C.c_char * (36 * n)).from_address(model.desc.positions), np.float32).reshape(n, 3, 3).copy()
+    ext = old.reshape(-1, 3).max(0) - old.reshape(-1, 3).min(0)
+    new = old.copy()
+    new[..., 1] += (0.02 * ext[1] * np.sin(old[..., 0] * (12.0 / ext[0])) * np.cos(old[..., 2] * (9.0 / max(ext[2], 1e-6)))).astype(np.float32)
+    new[..., 0] += (0.01 * ext[0] * np.sin(old[..., 2] * (7.0 / max(ext[2], 1e-6)))).astype(np.float32)
+    new = np.ascontiguousarray(new, np.float32)
+    ctx.refit(new)
+    tri, t = ctx.trace_primary(args)
+    # (a) the same topology with boxes recomputed on the host, uploaded afresh
+    ctx2 = Context(0)
+    ctx2.set_option("tree_builder", builder)
+    _upload_desc(ctx2, model, _host_refit(model.nodes(), new), new)
+    tri2, t2 = ctx2.trace_primary(args)
+    assert np.array_equal(tri, tri2) and np.array_equal(t.view(np.uint32), t2.view(np.uint32))
+    # (b) the reference on the moved scene (raw order restored; it builds its own tree)
+    raw_new = np.empty_like(new)
+    raw_new[model.permutation()] = new
+    moved = dataclasses.replace(scene, positions=raw_new.reshape(np.asarray(scene.positions).shape))
+    R = ref.RefScene(moved)
+    rtri, rt = R.trace_primary(args, threads=8)
+    assert (t.view(np.uint32) != rt.view(np.uint32)).mean() <= 1e-5
+    assert 0.2 < (rtri >= 0).mean()
+    # (c) the refitted secondary-ray tree through the per-ray seam
+    from test_gpu_trace import _random_rays
+    org, d = _random_rays(moved, 50_000, 5)
+    rtri, rt = R.trace_closest(org, d)
+    for c in (ctx, ctx2):
+        c.set_option("seam_secondary_tree", 2)
+        stri, st = c.trace_closest(org, d)
+        assert not (st.view(np.uint32) != rt.view(np.uint32)).any(), (st.view(np.uint32) != rt.view(np.uint32)).sum()
+        hit = rtri >= 0
+        aim = np.full(org.shape[0], np.inf, np.float32)
+        aim[hit] = rt[hit] * np.where(np.arange(hit.sum()) % 3 == 0, 0.5, np.where(np.arange(hit.sum()) % 3 == 1, 1.0, 1.5)).astype(np.float32)
+        assert (c.trace_occluded(org, d, aim) != R.trace_occluded(org, d, aim)).mean() <= 1e-3
+    info = ctx.tree_info()
+    assert info["in_use"] and info["device_built"] == bool(builder)
+    # and the estimator runs on the refitted scene
+    out = ctx.render(args.replace(spp=2), seed=3)
+    out2 = ctx2.render(args.replace(spp=2), seed=3)
+    a, b = out["Id"]["radiance"].astype(np.float64), out2["Id"]["radiance"].astype(np.float64)
+    assert np.isfinite(a).all() and abs(a.sum() - b.sum()) <= 0.05 * abs(b.sum()) + 1e-6
+    ctx.close()
+    ctx2.close()
