@@ -126,19 +126,28 @@ RM_DI void fx_edge_pixel(const float *__restrict__ in, float *__restrict__ out, 
     V3 finalColor = center;
     float bestDelta = 0.0f;
     const float gs = fmul(g, stepLength);
-    // the 12 taps: every fetch is issued up front (coordinates are clamped, so a tap outside [0, 1] may be read and is then
-    // ignored, as the reference's `continue` ignores it); the running maximum is taken in tap order
+    // The 12 taps step along ONE axis: sampleUv = uv + (0, off) on a horizontal edge, uv + (off, 0) on a vertical one
+    // (src/image.cpp:412-418; the other offset is 0.0f and uv + 0.0f = uv, both being >= 0).  So one coordinate - texel, validity,
+    // address - is formed once per pixel and only the other per tap.  Every fetch is issued up front (coordinates are clamped, so
+    // a tap outside [0, 1] may be read and is then ignored, as the reference's `continue` ignores it); the running maximum is
+    // taken in tap order.
+    const float fw = float(width), fh = float(height);
+    const float c_fix = isH ? u : v, c_var = isH ? v : u, n_fix = isH ? fw : fh, n_var = isH ? fh : fw;
+    const int m_fix = (isH ? width : height) - 1, m_var = (isH ? height : width) - 1;
+    const bool fix_ok = !(c_fix < 0.0f || c_fix > 1.0f);
+    int i_fix = int(fmul(c_fix, n_fix));
+    i_fix = i_fix < 0 ? 0 : (m_fix < i_fix ? m_fix : i_fix);
+    const float *tap_base = in + (isH ? size_t(i_fix) * 3 : size_t(i_fix) * width * 3);
+    const size_t tap_stride = isH ? size_t(width) * 3 : size_t(3);
     V3 tapc[12];
     bool tapv[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {                      // QUALITY
-        const float off = fmul(gs, float(i + 1));
-        const float su = fadd(u, isH ? 0.0f : off), sv = fadd(v, isH ? off : 0.0f);
-        tapv[i] = !(su < 0.0f || su > 1.0f || sv < 0.0f || sv > 1.0f);
-        int sx = int(fmul(su, float(width))), sy = int(fmul(sv, float(height)));
-        sx = sx < 0 ? 0 : (width - 1 < sx ? width - 1 : sx);
-        sy = sy < 0 ? 0 : (height - 1 < sy ? height - 1 : sy);
-        const float *ps = in + (size_t(sy) * width + sx) * 3;
+        const float sc = fadd(c_var, fmul(gs, float(i + 1)));
+        tapv[i] = fix_ok && !(sc < 0.0f || sc > 1.0f);
+        int si = int(fmul(sc, n_var));
+        si = si < 0 ? 0 : (m_var < si ? m_var : si);
+        const float *ps = tap_base + size_t(si) * tap_stride;
         tapc[i] = mk3(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2));
     }
 #pragma unroll
@@ -181,10 +190,10 @@ __global__ void __launch_bounds__(256) k_fxaa_edges(const float *__restrict__ in
 // which a per-row check routes to the exact chains.  Same operations on the same values in the same order as Photo::FXAA:
 // bit-equal.
 #ifdef __CUDACC__
-constexpr int kFxStripWarps = 4, kFxStages = 4;
+constexpr int kFxStripWarps = 1, kFxStages = 3;       // one warp per CTA: the block scheduler hands out strips as warps finish
 constexpr int kFxRowBytes = 136 * 12;               // 4 + 128 + 4 pixels
 constexpr int kFxRowStride = 1664;                  // ... padded to a multiple of 128 bytes
-constexpr int kFxListCap = 1024;                    // edge pixels a warp gathers before it works them off
+constexpr int kFxListCap = 512;                     // edge pixels a warp gathers before it works them off
 constexpr int kFxWarpBytes = kFxStages * kFxRowStride + kFxListCap * 2 + 128;      // row buffers, edge list, mbarriers: a multiple of 128
 static_assert(kFxWarpBytes % 128 == 0 && kFxRowStride >= kFxRowBytes, "shared-memory layout of k_fxaa_strip");
 
@@ -206,7 +215,7 @@ RM_DI void fx_bulk_store(void *dst, unsigned src, unsigned bytes) {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(32 * kFxStripWarps) k_fxaa_strip(const float *__restrict__ in, float *__restrict__ out, int width, int height, int ROWS) {
+__global__ void __launch_bounds__(32 * kFxStripWarps, 32 / kFxStripWarps) k_fxaa_strip(const float *__restrict__ in, float *__restrict__ out, int width, int height, int ROWS) {
     extern __shared__ __align__(128) unsigned char fx_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned char *mine = fx_dyn + size_t(wid) * kFxWarpBytes;
@@ -227,9 +236,14 @@ __global__ void __launch_bounds__(32 * kFxStripWarps) k_fxaa_strip(const float *
     const unsigned row_bytes = unsigned(xe - xb) * 12u, own_bytes = unsigned(min(128, width - span_x)) * 12u;
     const unsigned dst_off = unsigned(xb - (span_x - 4)) * 12u;           // pixel span_x always lands 48 bytes into the buffer
 
-    auto issue = [&](int k) {                           // lane 0: ask for row k of the strip's sequence
+    const size_t row_floats = size_t(width) * 3;
+    const float *src_row = in + (size_t(ylo) * width + xb) * 3;          // lane 0: the next row to ask for ...
+    float *dst_row = out + (size_t(y0) * width + span_x) * 3;             // ... and the next owned row to write through
+    const unsigned rows_s = fx_smem(rows) + dst_off;
+    auto issue = [&](int k) {                           // lane 0: ask for row k of the strip's sequence (called with k = 0, 1, 2, ...)
         const int st = k % kFxStages;
-        fx_bulk_load(fx_smem(rows) + st * kFxRowStride + dst_off, in + (size_t(ylo + k) * width + xb) * 3, row_bytes, bar0 + st * 8);
+        fx_bulk_load(rows_s + st * kFxRowStride, src_row, row_bytes, bar0 + st * 8);
+        src_row += row_floats;
     };
     if (lane == 0) {
         for (int st = 0; st < kFxStages; st++) fx_bar_init(bar0 + st * 8);
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(32 * kFxStripWarps) k_fxaa_strip(const float *
             const int st = k % kFxStages, y = ylo + k;
             fx_bar_wait(bar0 + st * 8, unsigned(k / kFxStages) & 1u);
             const float *buf = rows + st * (kFxRowStride / 4);
-            if (lane == 0 && y >= y0 && y < y1) fx_bulk_store(out + (size_t(y) * width + span_x) * 3, fx_smem(buf) + 48, own_bytes);
+            if (lane == 0 && y >= y0 && y < y1) { fx_bulk_store(dst_row, fx_smem(buf) + 48, own_bytes); dst_row += row_floats; }
             const float4 a = reinterpret_cast<const float4 *>(buf + 12)[lane * 3], b = reinterpret_cast<const float4 *>(buf + 12)[lane * 3 + 1],
                          c = reinterpret_cast<const float4 *>(buf + 12)[lane * 3 + 2];
             const float *hp = buf + (lane == 0 ? 9 : 12 + 128 * 3);      // the pixel left of the span / right of it
@@ -486,8 +500,9 @@ __global__ void k_filter_pack(const RmHitInfo *__restrict__ G, FilterG F, int np
 
 // One a-trous pass of filterRadiance (src/image.cpp:160-191) for all four planes: the geometric factors of getWeight
 // (normal power, grazing-angle term, material distance) are shared by the planes, the radiance-distance term and
-// exp() are per plane.  powf / expf are CUDA's (<= 2 ulp from glibc's): results agree with the reference to ~1e-6
-// relative, not bit for bit - the tolerance is stated in tests/test_gpu_post.py.
+// exp() are per plane.  The weight is exp() of distances times the 1024th power of a normal dot product: it is evaluated with
+// the SFU's exp2 (pow1024_near_one, exp2_fast: ~1e-6 relative) and the sums are contracted to FMAs, so results agree with the
+// reference to a few 1e-6 relative, not bit for bit - the tolerance is stated in tests/test_gpu_post.py.
 // The edge-stopping weight is an exp() of distances: it tolerates approximate square roots and quotients (MUFU.SQRT / MUFU.RCP,
 // ~2 ulp) where the rest of the library insists on the correctly rounded ones - the pass already differs from the reference by
 // the ulps of powf / expf, and the weight's relative error stays below 2e-6 (|k| <= 7.5), far inside the test's 2e-4.  The
@@ -506,7 +521,25 @@ RM_DI float div_fast(float a, float b) {
     return a / b;
 #endif
 }
-RM_DI float length_fast(V3 v) { return sqrt_fast(dot(v, v)); }
+RM_DI float exp2_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return exp2f(x);
+#endif
+}
+// contracted dot product / length: for the DISTANCE terms of the weight only (sensitivity ~1); the normal dot product that is
+// raised to the 1024th power keeps the reference's own rounding sequence (one ulp of it is 6e-5 of the weight)
+RM_DI float dot_fma(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+RM_DI float length_fast(V3 v) { return sqrt_fast(dot_fma(v, v)); }
+// d^1024 for d in (0.98, 1 + a few ulps]: exp2(1024 * log2(d)) with ln(d) = -(e + e^2/2 + ... + e^6/6), e = 1 - d (exact by
+// Sterbenz; the next term, e^7/7, is below 1e-11 of the sum) - six FMAs and one MUFU.EX2 instead of powf's ~45 instructions,
+// relative error ~1e-6 (the rounding of an exponent of magnitude <= 30, and ex2.approx's 2^-22)
+RM_DI float pow1024_near_one(float d) {
+    const float e = 1.0f - d;
+    const float p = e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, fmaf(e, 1.0f / 6.0f, 0.2f), 0.25f), 1.0f / 3.0f), 0.5f), 1.0f);
+    return exp2_fast(-1477.3196798378912f * p);            // 1024 / ln 2
+}
 
 __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__ G, FilterG F, Planes4 in, Planes4 out, int width, int height, int step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -556,28 +589,28 @@ __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__
                     const float d = dot(snp, mk3(Bq.x, Bq.y, Bq.z));
                     // the reference drops a neighbour whose normal weight d^1024 is below 1e-6, i.e. d < 0.98660: for d <= 0.98
                     // (d^1024 <= 1.1e-9) that is known without the power
-                    if (d > 0.98f) wn = powf(d, 1024.0f);
+                    if (d > 0.98f) wn = pow1024_near_one(d);
                     if (wn < 1e-6f) wn = 0.0f;
                     else {
 #pragma unroll
                         for (int j = 0; j < 4; j++) Lq[j] = ld_rad(in.p[j] + q);
                         const V3 dpos = posq - posp;
-                        const float sn = fabsf(div_fast(dot(shp, dpos), length_fast(dpos)));          // |dot(shapeNormal, normalize(dpos))|
-                        const float tanT = div_fast(sn, fadd(sqrt_fast(fsub(1.0f, fmul(sn, sn))), kEps));
+                        const float sn = fabsf(div_fast(dot_fma(shp, dpos), length_fast(dpos)));          // |dot(shapeNormal, normalize(dpos))|
+                        const float tanT = div_fast(sn, sqrt_fast(fmaf(-sn, sn, 1.0f)) + kEps);
                         const float dm = length_fast(mk3(fsub(Ap.w, Aq.w), fsub(Bp.w, Bq.w), fsub(opp, __ldg(F.opacity + q))));
                         // k = ((0 - tan/sigma_z) - radianceDiff) - materialDiff/sigma_m; the middle term is per plane
                         kg = -tanT;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const float dr = fmul(length_fast(mk3(fsub(Lp[j].x, Lq[j].x), fsub(Lp[j].y, Lq[j].y), fsub(Lp[j].z, Lq[j].z))), rsig[j]);
-                            const float k = fadd(fadd(kg, -dr), -dm);
+                            const float k = (kg - dr) - dm;
                             float wj = 0.0f;
                             if (!(k < -7.5f)) {
-                                wj = fmul(wn, expf(k));
-                                if (j & 1) wj = fmul(wj, spec_scale);
+                                wj = wn * exp2_fast(k * 1.4426950408889634f);
+                                if (j & 1) wj *= spec_scale;
                                 if (!isfinite(wj)) wj = 0.0f;
                             }
-                            w[j] = fmul(base, wj);
+                            w[j] = base * wj;
                         }
                     }
                 }
@@ -590,9 +623,9 @@ __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                wsum[j] = fadd(wsum[j], w[j]);
-                acc[j] = acc[j] + mk3(Lq[j].x, Lq[j].y, Lq[j].z) * w[j];
-                var[j] = fadd(var[j], fmul(fmul(Lq[j].w, w[j]), w[j]));
+                wsum[j] += w[j];
+                acc[j] = mk3(fmaf(Lq[j].x, w[j], acc[j].x), fmaf(Lq[j].y, w[j], acc[j].y), fmaf(Lq[j].z, w[j], acc[j].z));
+                var[j] = fmaf(Lq[j].w * w[j], w[j], var[j]);
             }
         }
 #pragma unroll

@@ -663,7 +663,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     }
     if (!std::strcmp(name, "wave_paths")) { ctx->wave_paths = int(std::min<int64_t>(std::max<int64_t>(value, 1 << 16), 1 << 25)); return RM_OK; }
     if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
-    if (!std::strcmp(name, "fxaa_rows")) { ctx->fxaa_rows = int(std::min<int64_t>(std::max<int64_t>(value, 0), 256)); return RM_OK; }
+    if (!std::strcmp(name, "fxaa_rows")) { ctx->fxaa_rows = int(std::min<int64_t>(std::max<int64_t>(value < 0 ? 16 : value, 0), 256)); ctx->fxaa_auto = value < 0; return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);
 }

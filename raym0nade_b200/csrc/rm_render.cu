@@ -735,8 +735,23 @@ int rm_fxaa_device(RmContext *ctx, const float *d_rgb_in, float *d_rgb_out, int3
     if (!R) return rm_fail(RM_ERR_INVALID, "out of host memory");
     // one launch when every row is a whole number of 16-byte vectors (kernels_post.cuh: k_fxaa_strip)
     if (ctx->fxaa_rows && (width & 3) == 0 && ((reinterpret_cast<uintptr_t>(d_rgb_in) | reinterpret_cast<uintptr_t>(d_rgb_out)) & 15) == 0) {
-        const int rows = ctx->fxaa_rows;
-        const int strips = ((width + 127) / 128) * ((height + rows - 1) / rows);
+        // A warp (= a CTA) walks one strip of 128 x rows pixels: first the rows (bulk copies in and out, bound by memory), then its
+        // edge pixels (dependent gathers, bound by latency).  Short strips, several per resident warp, so that the two phases of
+        // different warps overlap on an SM and the block scheduler evens out the finish; at least 4 rows (a strip re-reads two
+        // halo rows).  "fxaa_rows" pins the height.
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            RM_CUDA(cudaFuncSetAttribute(k_fxaa_strip, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            RM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fxaa_strip, 32 * kFxStripWarps, kFxStripWarps * kFxWarpBytes));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+        const int spans = (width + 127) / 128, slots = ctas_per_sm * R->sm_count * kFxStripWarps;
+        int rows = ctx->fxaa_rows;
+        if (ctx->fxaa_auto) {
+            rows = 8;
+            while (rows > 4 && int64_t(spans) * ((height + rows - 1) / rows) < 2 * int64_t(slots)) rows--;
+        }
+        const int strips = spans * ((height + rows - 1) / rows);
         const int grid = (strips + kFxStripWarps - 1) / kFxStripWarps;
         k_fxaa_strip<<<grid, 32 * kFxStripWarps, kFxStripWarps * kFxWarpBytes, ctx->stream>>>(d_rgb_in, d_rgb_out, width, height, rows);
         ctx->launches += 1;

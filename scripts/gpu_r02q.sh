@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, call q: FXAA strips as one-warp CTAs (dynamic hand-out by the block scheduler), strip heights 4..16; refit tests
+mkdir -p gpurun_out
+( timeout 150 python -m pytest tests/test_gpu_render.py -m gpu -x -q -k "fxaa" ) > gpurun_out/r02q_pytest_fxaa.log 2>&1
+FX=$?
+tail -5 gpurun_out/r02q_pytest_fxaa.log
+if [ $FX -eq 0 ]; then
+  timeout 100 python scripts/post_bench.py 3840 2160 | tee gpurun_out/r02q_fxaa_4k.json
+  timeout 100 python scripts/post_bench.py 1920 1080 | tee gpurun_out/r02q_fxaa_1080p.json
+  timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_fxaa_strip' -s 220 -c 2 \
+      -f -o gpurun_out/r02q_prof_fxaa python scripts/post_bench.py 3840 2160 > gpurun_out/r02q_prof_fxaa.log 2>&1
+  python scripts/ncu_summary.py gpurun_out/r02q_prof_fxaa.ncu-rep | cut -c 1-420 | tee gpurun_out/r02q_ncu_fxaa.txt
+fi
+( timeout 600 python -m pytest tests/test_gpu_tree.py -m gpu -x -q -k "refit" ) > gpurun_out/r02q_pytest_tree.log 2>&1
+tail -25 gpurun_out/r02q_pytest_tree.log

@@ -50,10 +50,10 @@ def timed(rows):
     return ms[len(ms) // 2] * 1e3, ms[0] * 1e3
 
 
-variants = {("strip%d" % r if r else "two_pass"): timed(r) for r in (0, 8, 12, 24, 16)}
-med, best = variants["strip16"]           # the default form
+variants = {("strip%d" % r if r > 0 else ("two_pass" if r == 0 else "strip_auto")): timed(r) for r in (0, 4, 6, 8, 12, 16, -1)}
+med, best = variants["strip_auto"]        # the default form: strip height chosen so that every strip is resident at once
 changed = float((out != frames[(reps - 1) % 8]).any(-1).float().mean())
-print(json.dumps({"kernel": "k_fxaa_strip, 16 rows per warp", "frame": "%dx%d" % (w, h), "launches": reps, "us_median": med, "us_min": best,
+print(json.dumps({"kernel": "k_fxaa_strip", "frame": "%dx%d" % (w, h), "launches": reps, "us_median": med, "us_min": best,
                   "algorithmic_bytes": alg, "achieved_gbs": alg / (med * 1e-6) / 1e9, "peak_gbs": peak, "frac": alg / (med * 1e-6) / 1e9 / peak,
                   "roofline_us": alg / peak / 1e3, "pixels_changed_share": changed,
                   "variants_us_median_min": {k: [round(v[0], 2), round(v[1], 2)] for k, v in variants.items()},

@@ -179,12 +179,14 @@ def test_clamp_and_filter_kernels(doh, name, stages):
         want = GP["%s_s%d_%s" % (name, stages, k)]
         if stages == 1:
             assert same(got["radiance"], want["radiance"]) and same(got["Var"], want["Var"]), k       # + - * / only: to the bit
-        else:                                                  # powf(x, 1024) and expf in the weights: libm's on the host
+        else:                                                  # the weights go through exp2 approximations (k_atrous): the bar of tests/test_gpu_post.py
             for f in ("radiance", "Var"):
                 a, b = got[f].astype(np.float64), want[f].astype(np.float64)
                 assert np.array_equal(np.isnan(a), np.isnan(b)), (k, f)
                 ok = np.isfinite(b)
-                assert (np.abs(a[ok] - b[ok]) <= 2e-6 * (1.0 + np.abs(b[ok]))).all(), (k, f, np.abs(a[ok] - b[ok]).max())
+                bad = np.abs(a[ok] - b[ok]) > 2e-4 * (1.0 + np.abs(b[ok]))
+                assert bad.mean() <= 2e-3, (k, f, bad.mean(), np.abs(a[ok] - b[ok]).max())
+                assert np.median(np.abs(a[ok] - b[ok]) / (1.0 + np.abs(b[ok]))) <= 2e-6, (k, f)
     assert any(not same(p["radiance"], GP["%s_in_%s" % (name, k)]["radiance"]) for k, p in zip(PLANES, planes))
 
 

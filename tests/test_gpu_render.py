@@ -419,7 +419,7 @@ def test_fxaa_bit_exact_random_and_edges(ref):
         na, nb = np.isnan(a), np.isnan(b)
         return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
 
-    for rows in (16, 8, 3, 64, 0):
+    for rows in (-1, 16, 8, 3, 64, 0):             # -1: the library picks the strip height (the default)
         ctx.set_option("fxaa_rows", rows)
         for img, want in cases:
             got = ctx.fxaa(img)
