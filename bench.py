@@ -18,7 +18,7 @@ pixel-samples/s and time-to-spp are reported beside it.
   value           : device-resident - scene already in HBM, no host copies in the timed region
   e2e             : through the C ABI the reference would bind, with HOST buffers, nothing cached between steps: per step
                     rm_scene_upload (scene H2D + the secondary-ray tree rebuilt on the device) + the render + the frame D2H
-  e2e_first_frame : the first frame of a fresh process on the host clock, host scene preparation and context creation included
+  e2e_first_frame : the first frame of a fresh process on the host clock, context creation and scene preparation (reference tree built on the device) included
 Multi-GPU: samples are sharded by interleaved index (rank, world) with no data-path collective
 during sampling; per step the fp32 accumulators are exchanged over NCCL inside the timed region
 (rm_reduce_scatter: every rank ends up with, finalises and - end to end - downloads its own slice of
@@ -251,10 +251,11 @@ def run_ours(opt, rank, world, local_rank):
     stream = torch.cuda.current_stream().cuda_stream
     out_bytes = npix * (HITINFO_DTYPE.itemsize + 4 * RADIANCE_DTYPE.itemsize)
 
-    # --- the first frame of a fresh process, timed on the host clock, everything included: the host-side preparation of the
-    # scene (rm_prepare_scene: the reference-topology tree, mip chains, light tables - the "model loading" the north star
-    # keeps on the host), context creation, rm_scene_upload (H2D + the secondary-ray tree built on the device), the render
-    # with cold caches and first-touch allocations, and the download of the frame.  Single rank only (N > 1 adds nothing to it).
+    # --- the first frame of a fresh process, timed on the host clock, everything included: context creation, the preparation of
+    # the scene (rm_prepare_scene_device: the reference-topology tree built on the device; mip chains, light tables and the permuted
+    # face streams on the host - the "model loading" the north star keeps there), rm_scene_upload (H2D + the secondary-ray tree
+    # built on the device), the render with cold caches and first-touch allocations, and the download of the frame.  Single rank
+    # only (N > 1 adds nothing to it).
     first_frame = None
     t0 = time.perf_counter()
     model = Model(scene)
@@ -267,17 +268,23 @@ def run_ours(opt, rank, world, local_rank):
         t1 = time.perf_counter()
         c0 = Context(local_rank, stream=stream)
         t2 = time.perf_counter()
-        c0.upload(model)
+        m0 = Model(scene, c0)              # rm_prepare_scene_device: the reference's tree built on the device (gpu_ref_bvh.cu), the rest on the host
+        t2b = time.perf_counter()
+        c0.upload(m0)
         c0.synchronize()
         t3 = time.perf_counter()
         c0.render_into(a_ff, 1, g_host, p_host)
         t4 = time.perf_counter()
         tree = c0.tree_info()
         c0.close()
-        first_frame = {"spp": ff_spp, "total_s": t_prepare + (t4 - t1), "prepare_scene_host_s": t_prepare, "context_create_s": t2 - t1,
-                       "scene_upload_and_tree_build_s": t3 - t2, "render_and_download_s": t4 - t3, "secondary_tree": tree,
-                       "note": "fresh context, nothing cached: host scene preparation + rm_context_create + rm_scene_upload (secondary-ray tree built on the "
-                               "device) + rm_render into pageable host arrays, at %d spp" % ff_spp}
+        m0.close()
+        first_frame = {"spp": ff_spp, "total_s": t4 - t1, "context_create_s": t2 - t1, "prepare_scene_device_tree_s": t2b - t2,
+                       "scene_upload_and_tree_build_s": t3 - t2b, "render_and_download_s": t4 - t3, "secondary_tree": tree,
+                       "prepare_scene_host_s": t_prepare,
+                       "note": "fresh context, nothing cached: rm_context_create + rm_prepare_scene_device (reference tree built on the device; mips, lights, "
+                               "permuted face streams on the host) + rm_scene_upload (secondary-ray tree built on the device) + rm_render into pageable "
+                               "host arrays, at %d spp; prepare_scene_host_s = the all-host rm_prepare_scene of the same scene, for comparison (not in "
+                               "total_s)" % ff_spp}
         del g_host, p_host
 
     ctx = Context(local_rank, stream=stream)

@@ -541,6 +541,8 @@ RM_DI float pow1024_near_one(float d) {
     return exp2_fast(-1477.3196798378912f * p);            // 1024 / ln 2
 }
 
+__constant__ float c_tap5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+
 __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__ G, FilterG F, Planes4 in, Planes4 out, int width, int height, int step) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= width || y >= height) return;
@@ -569,15 +571,14 @@ __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__
         rsig[j] = div_fast(1.0f, sig[j]);
         wsum[j] = 0.0f; var[j] = 0.0f; acc[j] = splat3(0.0f);
     }
-    const float tap[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
 #pragma unroll 1
-    for (int dy = -2; dy <= 2; dy++)
+    for (int dy = -2; dy <= 2; dy++) {
 #pragma unroll 1
         for (int dx = -2; dx <= 2; dx++) {
             const int nx = x + dx * step, ny = y + dy * step;
             if (nx < 0 || nx >= width || ny < 0 || ny >= height) continue;
             const size_t q = size_t(ny) * width + nx;
-            const float base = fmul(tap[dx + 2], tap[dy + 2]);
+            const float base = fmul(c_tap5[dx + 2], c_tap5[dy + 2]);
             float4 Lq[4];
             float w[4] = {base, base, base, base};
             if (dx != 0 || dy != 0) {
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(128, 5) k_atrous(const RmHitInfo *__restrict__
                 var[j] = fmaf(Lq[j].w * w[j], w[j], var[j]);
             }
         }
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) st_rad(out.p[j] + p, div_true(acc[j], wsum[j]), fdiv(var[j], fmul(wsum[j], wsum[j])));
 }

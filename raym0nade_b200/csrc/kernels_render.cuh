@@ -107,6 +107,11 @@ struct FrameBuffers {
     float *sav_base;         // [npix][3] un-nudged baseColor (restored at resolve, src/render.cpp:550)
     int *n_ind;              // [npix] spp_indirect of the pixel (0 when nothing is sampled)
     int *dir_base;           // [npix] first shadow-queue slot of the pixel's direct samples in the current direct wave (-1: none)
+    // The pixels that are sampled at all - a primary hit on a non-emissive surface - in pixel order (rm_gbuffer); the per-pixel
+    // stages (k_direct_gen, k_accum_direct, the first path vertices of k_regen) run over this list, so that a frame that is
+    // 40 % background does not leave 40 % of their lanes idle.  nullptr: every pixel (the per-pixel checks stay in place).
+    const int *active_list;
+    int n_active;
 };
 
 // pow_s (src/geometry.cpp:22-28): there `pow` resolves to the double version.  Out of line: one copy of the (large)
@@ -356,9 +361,11 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasDirect) k_direct_gen(DevScen
                                                     ShadowItem *sq, int *s_count, int s_cap, int *overflow) {
     const int lane = threadIdx.x & 31;
     const int per_cta = WARP ? (blockDim.x >> 5) : blockDim.x;          // pixels a CTA takes per batch
-    for (int base = blockIdx.x * per_cta; base < npix; base += gridDim.x * per_cta) {
+    const int n_loop = Fb.active_list ? Fb.n_active : npix;
+    for (int base = blockIdx.x * per_cta; base < n_loop; base += gridDim.x * per_cta) {
         RM_LOCKSTEP();                       // CTA-wide lock step per batch: shared instruction-cache lines (see k_bounce)
-        const int p = base + (WARP ? (threadIdx.x >> 5) : threadIdx.x);
+        const int at = base + (WARP ? (threadIdx.x >> 5) : threadIdx.x);
+        const int p = at < n_loop ? (Fb.active_list ? Fb.active_list[at] : at) : npix;
         bool go = false;
         Bsdf B;
         B.s = default_surface();
@@ -411,8 +418,9 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasDirect) k_direct_gen(DevScen
 // running sums it owns and folds them into the pixel's Dd / Ds accumulators once (the same pixel is touched by no
 // other thread while this kernel runs) - 8 read-modify-writes per pixel and wave instead of 8 atomics per sample.
 __global__ void __launch_bounds__(256) k_accum_direct(FrameBuffers Fb, Accum Ac, const ShadowItem *__restrict__ sq, int n_samples, int npix) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
+    const int at = blockIdx.x * blockDim.x + threadIdx.x;
+    if (at >= (Fb.active_list ? Fb.n_active : npix)) return;
+    const int p = Fb.active_list ? Fb.active_list[at] : at;
     const int first = Fb.dir_base[p];
     if (first < 0) return;
     const float *gf = reinterpret_cast<const float *>(Fb.gbuffer + p);
@@ -448,7 +456,8 @@ RM_DI void store_path(const PathQueue &Q, int i, int pixel, unsigned sample, uns
 }
 
 // ------------------------------------------------------------------ work items of the indirect sample loop
-// item j in [0, items_a): sample k = j / npix of pixel j % npix                      (every pixel, k < n_a)
+// item j in [0, items_a): sample k = j / npix of pixel j % npix                      (every pixel, k < n_a; with
+//                        FrameBuffers::active_list: sample j / n_active of pixel active_list[j % n_active])
 // item j in [items_a, total): j' = j - items_a, sample n_a + j' / n_glass of glass pixel list[j' % n_glass]
 // (glass pixels take 16x the indirect samples, src/render.cpp:498-501); local sample k is the global
 // sample index s_begin + k * s_stride (interleaved over GPUs).
@@ -508,7 +517,12 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasRegen) k_regen(DevScene S, D
         if (i < n_items) {
             const long long j = first + i;
             int k;
-            if (j < I.items_a) { k = int(j / I.npix); p = int(j % I.npix); }
+            if (j < I.items_a) {
+                const int per = Fb.active_list ? Fb.n_active : I.npix;
+                k = int(j / per);
+                p = int(j % per);
+                if (Fb.active_list) p = Fb.active_list[p];
+            }
             else { const long long jj = j - I.items_a; k = I.n_a + int(jj / I.n_glass); p = I.glass_list[int(jj % I.n_glass)]; }
             s = unsigned(I.s_begin + k * I.s_stride);
             int n_ind = Fb.n_ind[p];

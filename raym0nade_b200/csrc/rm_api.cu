@@ -3,7 +3,10 @@
 // No CPU fallback: every entry point that computes needs an sm_100 device and fails with
 // RM_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <new>
 
@@ -155,6 +158,17 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     cudaStream_t st = ctx->stream;
     int64_t total = 0;
     const int n = sc->n_faces;
+    // RM_TIMING=1: wall-clock per phase of the upload on stderr (synchronises the stream at every mark)
+    static const bool timing = std::getenv("RM_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "rm_scene_upload: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    mark("validate");
     // the buffers of the previous scene are reused (and reallocated on growth) from here on: until this upload has
     // finished there is no scene, so a failure half-way cannot leave a later call traversing freed or half-written memory
     ctx->has_scene = ctx->have_primary = ctx->have_gbuffer = ctx->have_resolved = false;
@@ -194,6 +208,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
                                                   ctx->b_mats.as<DevMaterial>(), n, ctx->b_tri.as<float4>(), ctx->b_shade.as<float4>());
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
+    mark("faces: H2D + records");
 
     // The secondary-ray tree.  Default: built on the device from the positions just uploaded (gpu_bvh.cu: Morton sort, PLOC
     // clustering, 4-wide collapse - a few milliseconds, so every upload rebuilds it and nothing is cached).  The host
@@ -207,6 +222,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
             int wlevels = 0, wnodes = 0;
             const RmBvhNode &rootbox = sc->nodes[1];           // the reference tree's root box = the scene bounds
             if ((rc = rm_gpu_build_wide(ctx, ctx->b_raw[0].as<float>(), n, rootbox.v0, rootbox.v1, &wlevels, &wnodes))) return rc;
+            mark("device tree build");
             if (3 * wlevels <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {
                 ctx->stack_levels_wide = std::max(3 * wlevels, 2);
                 ctx->have_wide = true;
@@ -293,6 +309,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
             ctx->launches++;
         }
         RM_CUDA(cudaGetLastError());
+        mark("refine job / host trees");
     }
 
     // textures: one blob, each level 16-byte aligned, copied level by level straight from the caller's memory
@@ -365,6 +382,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     for (int k = 0; k < 256; k++) lut[k] = float(k) / 255.0f;
     if ((rc = upload(ctx->b_lut, lut, sizeof(lut), st, total))) return rc;
     RM_CUDA(cudaStreamSynchronize(st));    // host staging vectors die at scope exit
+    mark("textures, lights, sky");
 
     DevScene &S = ctx->scene;
     S.nodes = ctx->b_nodes.as<float4>();
@@ -663,6 +681,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     }
     if (!std::strcmp(name, "wave_paths")) { ctx->wave_paths = int(std::min<int64_t>(std::max<int64_t>(value, 1 << 16), 1 << 25)); return RM_OK; }
     if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
+    if (!std::strcmp(name, "compact_pixels")) { ctx->compact_pixels = value != 0; ctx->have_gbuffer = false; return RM_OK; }
     if (!std::strcmp(name, "fxaa_rows")) { ctx->fxaa_rows = int(std::min<int64_t>(std::max<int64_t>(value < 0 ? 16 : value, 0), 256)); ctx->fxaa_auto = value < 0; return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }
     return rm_fail(RM_ERR_INVALID, "rm_set_option: unknown option '%s'", name);

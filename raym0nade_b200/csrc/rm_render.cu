@@ -9,6 +9,8 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "rm_context.cuh"
 #include "kernels_render.cuh"
@@ -21,7 +23,8 @@ namespace {
 struct RenderState {
     int npix = 0;
     // frame
-    DevBuf gbuffer, sav_base, n_ind, glass_list, dir_base;
+    DevBuf gbuffer, sav_base, n_ind, glass_list, dir_base, active_list, active_tmp;
+    int n_active = 0;                   // pixels with a primary hit on a non-emissive surface (FrameBuffers::active_list)
     // accumulators
     DevBuf rad, clum_sum, clum_max, hold_clum, hold, lock;
     bool accum_valid = false, hold_committed = false;
@@ -93,6 +96,8 @@ FrameBuffers frame(RenderState *R) {
     F.sav_base = R->sav_base.as<float>();
     F.n_ind = R->n_ind.as<int>();
     F.dir_base = R->dir_base.as<int>();
+    F.active_list = R->n_active >= 0 ? R->active_list.as<int>() : nullptr;
+    F.n_active = R->n_active;
     return F;
 }
 
@@ -118,6 +123,18 @@ __global__ void k_glass_list(const int *__restrict__ n_ind, int npix, int base, 
     if (glass) list[slot] = p;
 }
 
+// what k_direct_gen / k_regen ask of a pixel before they sample it (src/render.cpp:480-489): a hit, and not on a light
+struct IsSampledPixel {
+    const RmHitInfo *g;
+    __host__ __device__ bool operator()(int p) const {
+        const float *f = reinterpret_cast<const float *>(g + p);
+        const bool hit = isfinite(f[12]) || isfinite(f[13]) || isfinite(f[14]);         // position
+        // length(emission) > 0  <=>  its squared length, summed in glm's order, > 0 (a correctly rounded root is positive iff its argument is)
+        const float e2 = (f[6] * f[6] + f[7] * f[7]) + f[8] * f[8];
+        return hit && !(e2 > 0.0f);
+    }
+};
+
 constexpr size_t kSlicePad = 64;         // pixels of padding behind the radiance accumulators: a reduce-scatter over <= 64 ranks needs world * ceil(npix / world)
 
 bool same_args(const RmRenderArgs &a, const RmRenderArgs &b) { return std::memcmp(&a, &b, sizeof(RmRenderArgs)) == 0; }
@@ -129,7 +146,7 @@ int spp_direct_of(const RmRenderArgs *a) { return int(float(a->spp) * a->P_Direc
 void rm_render_state_free(RmContext *ctx) {
     auto *R = static_cast<RenderState *>(ctx->render_state);
     if (!R) return;
-    for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
+    for (DevBuf *b : {&R->gbuffer, &R->sav_base, &R->n_ind, &R->glass_list, &R->dir_base, &R->active_list, &R->active_tmp, &R->rad, &R->clum_sum, &R->clum_max, &R->hold_clum, &R->hold,
                       &R->lock, &R->shadow, &R->counts, &R->planes[0], &R->planes[1], &R->planes[2], &R->planes[3], &R->g_out, &R->rgb[0], &R->rgb[1],
                       &R->planes_alt[0], &R->planes_alt[1], &R->planes_alt[2], &R->planes_alt[3], &R->f_pm, &R->f_ns, &R->f_op, &R->glow[0], &R->glow[1], &R->dof_depth, &R->dof_src, &R->dof_sorted, &R->dof_lists, &R->dof_counts, &R->dof_keys, &R->dof_iota, &R->dof_temp, &R->dof_stat, &R->fx_list})
         b->release();
@@ -156,8 +173,12 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     const int npix = args->width * args->height;
     if ((rc = R->gbuffer.alloc(size_t(npix) * sizeof(RmHitInfo))) || (rc = R->sav_base.alloc(size_t(npix) * 12)) ||
         (rc = R->n_ind.alloc(size_t(npix) * 4)) || (rc = R->glass_list.alloc(size_t(npix) * 4)) || (rc = R->dir_base.alloc(size_t(npix) * 4)) ||
-        (rc = R->counts.alloc(C_TOTAL * 4)))
+        (rc = R->active_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(C_TOTAL * 4)))
         return rc;
+    size_t sel_bytes = 0;
+    cub::DeviceSelect::If(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), R->active_list.as<int>(), R->counts.as<int>() + (C_TOTAL - 1), npix,
+                          IsSampledPixel{R->gbuffer.as<RmHitInfo>()}, ctx->stream);
+    if ((rc = R->active_tmp.alloc(sel_bytes))) return rc;
     R->npix = npix;
     cudaStream_t st = ctx->stream;
     RM_CUDA(cudaMemsetAsync(R->counts.p, 0, C_TOTAL * 4, st));
@@ -165,13 +186,20 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     int *counts = R->counts.as<int>();
     k_gbuffer<<<(npix + 127) / 128, 128, 0, st>>>(ctx->scene, to_dev_args(args), ctx->b_tri_idx.as<int>(), ctx->b_t.as<float>(), frame(R), spp_d, base, counts + 4);
     k_glass_list<<<(npix + 127) / 128, 128, 0, st>>>(R->n_ind.as<int>(), npix, base, R->glass_list.as<int>(), counts + 5);
+    // the sampled pixels in pixel order (an ordered stream compaction: neighbouring pixels stay neighbours in the item space);
+    // a pixel outside the list keeps dir_base = -1 for good
+    RM_CUDA(cub::DeviceSelect::If(R->active_tmp.p, sel_bytes, cub::CountingInputIterator<int>(0), R->active_list.as<int>(), counts + (C_TOTAL - 1), npix,
+                                  IsSampledPixel{R->gbuffer.as<RmHitInfo>()}, st));
+    RM_CUDA(cudaMemsetAsync(R->dir_base.p, 0xff, size_t(npix) * 4, st));
     ctx->launches += 2;
     RM_CUDA(cudaGetLastError());
-    int h[8];
+    int h[8], h_active = 0;
+    RM_CUDA(cudaMemcpyAsync(&h_active, counts + (C_TOTAL - 1), 4, cudaMemcpyDeviceToHost, st));
     RM_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     if (gbuffer) RM_CUDA(cudaMemcpyAsync(gbuffer, R->gbuffer.p, size_t(npix) * sizeof(RmHitInfo), cudaMemcpyDeviceToHost, st));
     RM_CUDA(cudaStreamSynchronize(st));
     R->n_glass = h[5];
+    R->n_active = ctx->compact_pixels ? h_active : -1;
     ctx->have_gbuffer = true;
     ctx->have_resolved = false;
     R->accum_valid = false;
@@ -223,7 +251,8 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     // terminates emits at most 6 shadow rays; a direct wave is one shadow item per (pixel, sample)
     const long long target = ctx->wave_paths;
     const int S_all = int(std::max(1LL, target / npix));
-    const long long items_a = (long long)npix * n_a;
+    const int n_first = R->n_active >= 0 ? R->n_active : npix;          // pixels of the per-pixel stages
+    const long long items_a = (long long)n_first * n_a;
     const long long items_b = n_b_total > n_a ? (long long)R->n_glass * (n_b_total - n_a) : 0;
     const long long total_items = items_a + items_b;
     const long long q_cap = std::max(1024LL, std::min(target, total_items));
@@ -260,7 +289,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         ctx->timed_begin(RM_KIND_SHADOW);
         launch_trace(sec_scene, sec_levels, ct, tgrid, st, job, R->s_cap, n_dev, C + C_CUR_SHADOW, cnt + 6, sec_tune);
         ctx->timed_end();
-        if (direct_samples > 0) k_accum_direct<<<(npix + 255) / 256, 256, 0, st>>>(Fb, Ac, sq, direct_samples, npix);
+        if (direct_samples > 0) k_accum_direct<<<(std::max(n_first, 1) + 255) / 256, 256, 0, st>>>(Fb, Ac, sq, direct_samples, npix);
         else k_accum_shadow<<<grid, 256, 0, st>>>(Fb, Ac, sq, n_dev, R->s_cap);
         ctx->launches += 2;
     };
