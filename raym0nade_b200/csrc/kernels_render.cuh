@@ -32,9 +32,12 @@ namespace rm {
 #ifndef RM_SHADE_CTAS
 #define RM_SHADE_CTAS 3
 #endif
-// CTA-wide lock step per batch / per phase of the shading stages: the warps of a CTA then run the same stretch of
-// these large, branchy kernels together and share its instruction-cache lines (see k_bounce)
-#ifdef RM_NO_LOCKSTEP
+// CTA-wide lock step per batch / per phase of the shading stages: the warps of a CTA then run the same stretch of a large,
+// branchy kernel together and share its instruction-cache lines.  It paid while one sampleRay level was a single kernel (round 1,
+// k_bounce: 234 KB of SASS); with the level split into k_decide / k_continue / k_nee the barriers cost more than they save (17 - 20 %
+// of the stall samples of k_surface / k_direct_gen sat on them; shade 103.1 -> 101.4 ms per 128 spp without, profiles/r02x_*), so it
+// is off unless RM_LOCKSTEP_ON is defined.
+#ifndef RM_LOCKSTEP_ON
 #define RM_LOCKSTEP() ((void)0)
 #else
 #define RM_LOCKSTEP() __syncthreads()

@@ -681,6 +681,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     }
     if (!std::strcmp(name, "wave_paths")) { ctx->wave_paths = int(std::min<int64_t>(std::max<int64_t>(value, 1 << 16), 1 << 25)); return RM_OK; }
     if (!std::strcmp(name, "max_depth")) { ctx->max_depth = int(std::min<int64_t>(std::max<int64_t>(value, 1), 16)); return RM_OK; }
+    if (!std::strcmp(name, "direct_warp")) { ctx->direct_warp = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); return RM_OK; }
     if (!std::strcmp(name, "compact_pixels")) { ctx->compact_pixels = value != 0; ctx->have_gbuffer = false; return RM_OK; }
     if (!std::strcmp(name, "fxaa_rows")) { ctx->fxaa_rows = int(std::min<int64_t>(std::max<int64_t>(value < 0 ? 16 : value, 0), 256)); ctx->fxaa_auto = value < 0; return RM_OK; }
     if (!std::strcmp(name, "disable_clamp")) { ctx->disable_clamp = value != 0; return RM_OK; }

@@ -122,6 +122,7 @@ struct RmContext {
                                            // launch long enough that kernel tails and launch gaps stay ~1 % (4 M: -10 %, 16 M: -1 %,
                                            // profiles/r01c_ab7_wave_size.txt, r01d_ab8_wave_size.txt) for 38 GB of queues out of 180 GB
     int max_depth = 16;                    // perf experiments only: bounce limit of the wavefront loop (16 = the reference's maxRayDepth)
+    int direct_warp = 0;                   // k_direct_gen mapping: 0 = a warp per pixel for environment-lit scenes, a thread per pixel otherwise; 1 / 2 force one (A/B)
     bool compact_pixels = true;            // the per-pixel stages run over the list of sampled pixels (rm_gbuffer); 0: over every pixel (A/B, rm_set_option "compact_pixels")
     bool fxaa_auto = true;                 // the strip height is chosen per frame so that all strips are resident at once; rm_set_option("fxaa_rows", n) pins it
     int fxaa_rows = 16;                    // rows per warp strip of k_fxaa_strip; 0 = the two-pass tiled form (what frames with width % 4 != 0 always get)

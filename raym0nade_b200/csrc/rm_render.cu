@@ -10,7 +10,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "rm_context.cuh"
 #include "kernels_render.cuh"
@@ -176,7 +176,7 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
         (rc = R->active_list.alloc(size_t(npix) * 4)) || (rc = R->counts.alloc(C_TOTAL * 4)))
         return rc;
     size_t sel_bytes = 0;
-    cub::DeviceSelect::If(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), R->active_list.as<int>(), R->counts.as<int>() + (C_TOTAL - 1), npix,
+    cub::DeviceSelect::If(nullptr, sel_bytes, thrust::counting_iterator<int>(0), R->active_list.as<int>(), R->counts.as<int>() + (C_TOTAL - 1), npix,
                           IsSampledPixel{R->gbuffer.as<RmHitInfo>()}, ctx->stream);
     if ((rc = R->active_tmp.alloc(sel_bytes))) return rc;
     R->npix = npix;
@@ -188,7 +188,7 @@ int rm_gbuffer(RmContext *ctx, const RmRenderArgs *args, RmHitInfo *gbuffer) {
     k_glass_list<<<(npix + 127) / 128, 128, 0, st>>>(R->n_ind.as<int>(), npix, base, R->glass_list.as<int>(), counts + 5);
     // the sampled pixels in pixel order (an ordered stream compaction: neighbouring pixels stay neighbours in the item space);
     // a pixel outside the list keeps dir_base = -1 for good
-    RM_CUDA(cub::DeviceSelect::If(R->active_tmp.p, sel_bytes, cub::CountingInputIterator<int>(0), R->active_list.as<int>(), counts + (C_TOTAL - 1), npix,
+    RM_CUDA(cub::DeviceSelect::If(R->active_tmp.p, sel_bytes, thrust::counting_iterator<int>(0), R->active_list.as<int>(), counts + (C_TOTAL - 1), npix,
                                   IsSampledPixel{R->gbuffer.as<RmHitInfo>()}, st));
     RM_CUDA(cudaMemsetAsync(R->dir_base.p, 0xff, size_t(npix) * 4, st));
     ctx->launches += 2;
@@ -303,7 +303,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
         // environment-lit scenes: a warp per pixel (the sky CDF search dominates and the lanes share the surface);
         // light objects: a thread per pixel (the per-light weights - one BSDF evaluation each - are formed once per pixel);
         // A/B in profiles/r01e_ab15_direct_gen_mapping.txt
-        if (S >= 16 && ctx->scene.sky_width != 0)
+        if (S >= 16 && (ctx->direct_warp == 1 || (ctx->direct_warp == 0 && ctx->scene.sky_width != 0)))
             k_direct_gen<true><<<R->sm_count * kCtasDirect, kShadeBlock, 0, st>>>(ctx->scene, A, Fb, S, npix, sample_begin + k0 * sample_stride, sample_stride, spp_d,
                                                                                  seed, sq, C + C_SQ, R->s_cap, C + C_OVERFLOW);
         else
