@@ -79,10 +79,14 @@ struct PathQueue {
     int *med_id;             // [kMediumSlots][cap]   the medium stack lives here, in insertion order; the kernels walk it in place
     float *med;              // [4][kMediumSlots][cap]  ior, absorb rgb
     float *hit_t;            // INF = this entry is finished (miss, emissive hit) - the later stages skip it
-    int *hit_face;
-    float *surf;             // [22][cap]  the vertex's HitInfo (written by k_surface), field order of RmHitInfo
-    float *hdP;              // [6][cap]   dPdx, dPdy at the hit (calc_dPdxy)
-    float *dec;              // [7][cap]   decision record of k_decide: P_reflect | NEE scaling, P_RR, F, absorb rgb, relative eta
+    int *hit_face;           // k_trace: the face hit; from k_surface on: the vertex's DENSE index v (below)
+    // Per-vertex records of one round.  Most of a queue's slots are dead by the time they are shaded (in the bench scene 60 % of
+    // a round's rays leave the scene), so these are not indexed by queue slot but by a dense vertex index v that k_surface hands
+    // out window by window (one atomic per 1024-slot window; the live slots of a window get consecutive v): written and read
+    // as whole sectors instead of 40 %-full ones.
+    float *surf;             // [22][cap]  the vertex's HitInfo (written by k_surface), field order of RmHitInfo; at [k * cap + v]
+    float *hdP;              // [6][cap]   dPdx, dPdy at the hit (calc_dPdxy); at v
+    float *dec;              // [7][cap]   decision record of k_decide: P_reflect | NEE scaling, P_RR, F, absorb rgb, relative eta; at v
     int *skey, *srank;       // sort key of the vertex and its position inside the key's bin
 };
 
@@ -135,7 +139,7 @@ RM_DI V3 get_absorb(V3 absorb, float dis) {
 
 // device-side pipeline state (ints): queue lengths, cursors
 enum { C_Q0 = 0, C_Q1 = 1, C_SQ = 2, C_OVERFLOW = 3, C_GLASS = 4, C_GLASS_LIST = 5, C_CUR_PATH = 6, C_CUR_SHADOW = 7,
-       C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_SQ_RUN = 14, C_COUNT = 16 };
+       C_NEE = 8, C_PLAN_TAKE = 9, C_ITEM_LO = 10, C_ITEM_HI = 11, C_PLAN_LO = 12, C_PLAN_HI = 13, C_SQ_RUN = 14, C_VERT = 15, C_COUNT = 16 };
 
 // the sort of a round's live vertices by mode, see k_decide
 constexpr int kKeyReflect = 0;                        // 0: reflection off an opaque surface, 1: off a dielectric
@@ -486,6 +490,7 @@ __global__ void k_plan(int *C, int q_slot, int cap, long long total) {
     C[C_ITEM_LO] = (int)(unsigned)(cur & 0xffffffffLL);
     C[C_ITEM_HI] = (int)(cur >> 32);
     C[C_CUR_PATH] = 0;
+    C[C_VERT] = 0;                                           // dense vertex indices of this round (k_surface)
     if (C[C_SQ_RUN]) { C[C_SQ] = 0; C[C_SQ_RUN] = 0; }       // the shadow queue was traced last round: start it afresh
 }
 
@@ -647,11 +652,14 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene 
     }
     const int c = Q.cap;
     __shared__ int s_idx[kWindow];
-    __shared__ int s_n;
+    __shared__ int s_n, s_vbase;
     const bool sky = S.sky_width != 0;
     for (int base = blockIdx.x * kWindow; base < n; base += gridDim.x * kWindow) {
       // live here: a hit, or a miss that returns the sky (src/render.cpp:129-133)
       const int n_live = cta_compact(base, n, s_idx, &s_n, [&](int i) { return Q.hit_t[i] != CUDART_INF_F || (sky && !(Q.flags[i] & 256)); });
+      if (threadIdx.x == 0) s_vbase = n_live ? atomicAdd(C + C_VERT, n_live) : 0;       // this window's block of dense vertex indices
+      __syncthreads();
+      const int vbase = s_vbase;
       for (int j0 = 0; j0 < n_live; j0 += blockDim.x) {
         RM_LOCKSTEP();                       // CTA-wide lock step per batch (see k_bounce)
         const int j = j0 + threadIdx.x;
@@ -685,7 +693,10 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasSurface) k_surface(DevScene 
                     add = true;
                 }
                 Q.hit_t[i] = CUDART_INF_F;
-            } else store_surface(Q, i, sf, dPdx, dPdy);
+            } else {
+                store_surface(Q, vbase + j, sf, dPdx, dPdy);
+                Q.hit_face[i] = vbase + j;
+            }
         }
         if (add) {
             const V3 T = mk3(Q.T[i], Q.T[c + i], Q.T[2 * c + i]), B0 = mk3(Q.B0[i], Q.B0[c + i], Q.B0[2 * c + i]);
@@ -745,7 +756,8 @@ __global__ void __launch_bounds__(kShadeBlock, RM_CTAS_DECIDE) k_decide(unsigned
             const float t = Q.hit_t[i];
             Rng gen;
             gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, Q.drawn[i]);
-            const float *f = Q.surf + i;
+            const int v = Q.hit_face[i];                        // dense vertex index (k_surface)
+            const float *f = Q.surf + v;
             const float s_rough = f[16 * c], opacity = f[18 * c], s_eta = f[19 * c];
             const int id = __float_as_int(f[20 * c]);
             const bool entering = __float_as_int(f[21 * c]) != 0;
@@ -804,7 +816,7 @@ __global__ void __launch_bounds__(kShadeBlock, RM_CTAS_DECIDE) k_decide(unsigned
             Q.flags[i] = (fl & 0x00ffffff) | (mode << 24) | (doDirect ? 1 << 26 : 0) | (pass_absorb ? 1 << 27 : 0);
             Q.drawn[i] = gen.drawn;
             Q.rough[i] = rough;
-            float *d = Q.dec + i;
+            float *d = Q.dec + v;
             d[0] = first; d[c] = P_RR; d[2 * c] = F; d[3 * c] = absorb.x; d[4 * c] = absorb.y; d[5 * c] = absorb.z; d[6 * c] = eta_rel;
             key = mode == kBounceReflect ? kKeyReflect + (opacity < kEps ? 1 : 0) : (mode == kBounceRefract ? kKeyRefract : kKeyNee + c_sampleCount[depth] - 1);
         }
@@ -877,11 +889,12 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasBounce) k_continue(unsigned 
             W = Qin.W[i];
             rough = Qin.rough[i];
             gen.init(seed, (unsigned)p, sample, kStreamIndirect, Qin.drawn[i]);
-            const float *d = Qin.dec + i;
+            const int v = Qin.hit_face[i];                      // dense vertex index: surface, hdP and decision records
+            const float *d = Qin.dec + v;
             const float P_reflect = d[0], P_RR = d[c], F = d[2 * c];
             const V3 absorb = mk3(d[3 * c], d[4 * c], d[5 * c]);
             B.inDir = -dir;
-            B.s = load_surface(Qin, i);
+            B.s = load_surface(Qin, v);
             ior = B.s.eta;
             B.s.roughness = rough;
             B.s.eta = d[6 * c];
@@ -897,8 +910,8 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasBounce) k_continue(unsigned 
                 bd.dDdy = mk3(Qin.diff[9 * c + i], Qin.diff[10 * c + i], Qin.diff[11 * c + i]);
                 V3 dDdx, dDdy;
                 calc_dDdxy(dir, B.s.surfaceNormal, bd, dDdx, dDdy);
-                next.dPdx = mk3(Qin.hdP[i], Qin.hdP[c + i], Qin.hdP[2 * c + i]);
-                next.dPdy = mk3(Qin.hdP[3 * c + i], Qin.hdP[4 * c + i], Qin.hdP[5 * c + i]);
+                next.dPdx = mk3(Qin.hdP[v], Qin.hdP[c + v], Qin.hdP[2 * c + v]);
+                next.dPdy = mk3(Qin.hdP[3 * c + v], Qin.hdP[4 * c + v], Qin.hdP[5 * c + v]);
                 next.dDdx = dDdx; next.dDdy = dDdy;
             } else {
                 // the incoming differentials pass through a refraction unchanged (src/render.cpp:268,273)
@@ -974,7 +987,8 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, Frame
         first = __shfl_sync(0xffffffffu, first, 31) + incl - cnt;
         if (cnt == 0) continue;
         const bool pass_absorb = (fl >> 27) & 1;
-        const float *d = Q.dec + i;
+        const int v = Q.hit_face[i];                            // dense vertex index: surface and decision records
+        const float *d = Q.dec + v;
         const float nee_factor = d[0];
         const V3 absorb = mk3(d[3 * c], d[4 * c], d[5 * c]);
         const int p = Q.pixel[i];
@@ -982,7 +996,7 @@ __global__ void __launch_bounds__(kShadeBlock, kCtasNee) k_nee(DevScene S, Frame
         gen.init(seed, (unsigned)p, Q.sample[i], kStreamIndirect, Q.drawn[i]);
         Bsdf B;
         B.inDir = -mk3(Q.d[i], Q.d[c + i], Q.d[2 * c + i]);
-        B.s = load_surface(Q, i);
+        B.s = load_surface(Q, v);
         // the light samples see the regularised roughness and the relative eta of this vertex
         B.s.roughness = Q.rough[i];
         B.s.eta = d[6 * c];
