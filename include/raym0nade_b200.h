@@ -133,10 +133,10 @@ int rm_tree_build(RmContext *ctx, const float *positions, int32_t n_faces, RmBvh
 /* rm_prepare_scene with the tree built by rm_tree_build on `ctx`'s device; everything else is the same host code. */
 int rm_prepare_scene_device(RmContext *ctx, const RmRawScene *raw, RmPrepared **out);
 /* Vertices moved, topology kept: positions [n_faces][3][3] (host) in the uploaded scene's POST-BUILD order replace the staged
- * ones; the boxes of the reference's tree are recomputed on the device (leaf boxes from their faces, inner boxes bottom-up:
+ * ones (n_faces must be the uploaded scene's); the boxes of the reference's tree are recomputed on the device (leaf boxes from their faces, inner boxes bottom-up:
  * dfs_build's box arithmetic, bvh.cpp:21-24,41) and the secondary-ray tree is refitted and re-quantised bottom-up.  uvs, normals,
  * materials, lights and sky stay as uploaded (a moved emissive face keeps its old light-object entry). */
-int rm_scene_refit(RmContext *ctx, const float *positions);
+int rm_scene_refit(RmContext *ctx, const float *positions, int32_t n_faces);
 
 /* ---------------------------------------------------------------------------------
  * Per-ray seam: Model::rayHit / Model::rayHit_test (include/model.h:41-42,

@@ -110,7 +110,7 @@ def lib():
     L.rm_tree_node_count.restype = i32
     L.rm_tree_build.argtypes = [vp, vp, i32, vp, i32, vp]
     L.rm_prepare_scene_device.argtypes = [vp, C.POINTER(RmRawScene), C.POINTER(vp)]
-    L.rm_scene_refit.argtypes = [vp, vp]
+    L.rm_scene_refit.argtypes = [vp, vp, i32]
     L.rm_comm_unique_id.argtypes = [vp]
     L.rm_comm_init.argtypes = [vp, vp, i32, i32]
     L.rm_reduce.argtypes = [vp, i32]
@@ -245,8 +245,7 @@ class Context:
     def refit(self, positions):
         """moved vertices (post-build order, [n][3][3]): both trees of the uploaded scene are refitted on the device"""
         pos = _f32(positions).reshape(-1, 9)
-        assert self.model is not None and pos.shape[0] == self.model.n_faces
-        _check(lib().rm_scene_refit(self.h, _p(pos)))
+        _check(lib().rm_scene_refit(self.h, _p(pos), pos.shape[0]))
 
     def tree_info(self):
         """the 4-wide secondary-ray tree bounce / shadow rays currently traverse: dict(device_built, refined (the host builder's tree has been swapped in), nodes, levels, in_use)"""

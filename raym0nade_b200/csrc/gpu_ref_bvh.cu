@@ -413,9 +413,10 @@ int rm_prepare_scene_device(RmContext *ctx, const RmRawScene *raw, RmPrepared **
     return rm_prepare_scene_impl(raw, out, &tree);
 }
 
-int rm_scene_refit(RmContext *ctx, const float *positions) {
+int rm_scene_refit(RmContext *ctx, const float *positions, int32_t n_faces) {
     if (!ctx || !positions) return rm_fail(RM_ERR_INVALID, "rm_scene_refit: null argument");
     if (!ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_scene_refit: no scene uploaded");
+    if (n_faces != ctx->scene.n_faces) return rm_fail(RM_ERR_INVALID, "rm_scene_refit: %d faces given, the uploaded scene has %d", n_faces, ctx->scene.n_faces);
     RM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = ctx->scene.n_faces, n_nodes = ctx->scene.n_nodes;

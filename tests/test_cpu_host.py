@@ -35,6 +35,40 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert "no CPU path" in str(e.value) or "CUDA" in str(e.value)
 
 
+def test_tree_node_count_is_the_reference_node_array_length():
+    """rm_tree_node_count = nodeCount(1, n) + 1 (src/bvh.cpp:44-49): SURVEY.md's figures (8 @ 40 faces, 65 536 @ 260 K, 262 144 @ 1 M,
+    1 048 576 @ 5 M), the golden trees' lengths, and the host builder's own array for a spread of sizes"""
+    L = api.lib()
+    for n, want in [(40, 8), (260_000, 65_536), (1_000_000, 262_144), (5_000_000, 1_048_576), (10, 2), (11, 4), (1, 2), (0, 0), (-3, 0)]:
+        assert L.rm_tree_node_count(n) == want, (n, L.rm_tree_node_count(n))
+    for name in ("cornell", "hf", "tex"):
+        assert L.rm_tree_node_count(G[name + "_perm"].shape[0]) == G[name + "_nodes"].shape[0]
+    for n in (12, 21, 22, 23, 100, 1000, 2999):
+        scene, _ = scenes.heightfield_scene(n)
+        m = Model(scene)
+        assert L.rm_tree_node_count(m.n_faces) == m.desc.n_nodes, (n, m.n_faces)
+
+
+def test_device_tree_entry_points_fail_loudly_without_a_gpu():
+    """rm_tree_build / rm_prepare_scene_device / rm_scene_refit need a context, and there is none without a device: no host fallback"""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = api.lib()
+    pos = np.zeros((12, 9), np.float32)
+    nodes, perm = np.zeros(4, api.BVHNODE_DTYPE), np.zeros(12, np.int32)
+    assert L.rm_tree_build(None, api._p(pos), 12, api._p(nodes), 4, api._p(perm)) != 0
+    assert b"null" in L.rm_last_error()
+    assert L.rm_scene_refit(None, api._p(pos), 12) != 0
+    scene, _ = scenes.cornell_box()
+    raw = scene.to_c()
+    h = C.c_void_p()
+    assert L.rm_prepare_scene_device(None, C.byref(raw), C.byref(h)) != 0 and not h.value
+    with pytest.raises(RmError):
+        Model(scene, api.Context(0))
+
+
 @pytest.mark.parametrize("name", ["cornell", "hf", "tex"])
 def test_host_prepare_matches_reference_vectors(name):
     scene, _ = {"cornell": lambda: scenes.cornell_box(64, 64, 0), "hf": lambda: scenes.heightfield_scene(3000, 96, 54, 0, with_sky=True),

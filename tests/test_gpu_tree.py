@@ -215,6 +215,8 @@ def test_refit_for_moved_vertices(ref, which, builder):
     new[..., 1] += (0.02 * ext[1] * np.sin(old[..., 0] * (12.0 / ext[0])) * np.cos(old[..., 2] * (9.0 / max(ext[2], 1e-6)))).astype(np.float32)
     new[..., 0] += (0.01 * ext[0] * np.sin(old[..., 2] * (7.0 / max(ext[2], 1e-6)))).astype(np.float32)
     new = np.ascontiguousarray(new, np.float32)
+    with pytest.raises(Exception):
+        ctx.refit(new[:-1])                  # a face count other than the uploaded scene's is refused
     ctx.refit(new)
     tri, t = ctx.trace_primary(args)
     # (a) the same topology with boxes recomputed on the host, uploaded afresh
