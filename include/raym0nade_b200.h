@@ -86,6 +86,10 @@ int rm_prepare_scene(const RmRawScene *raw, RmPrepared **out);
 const RmSceneDesc *rm_prepared_desc(const RmPrepared *p);
 const int32_t *rm_prepared_permutation(const RmPrepared *p); /* perm[i] = raw face index stored at post-build slot i */
 void rm_prepared_free(RmPrepared *p);
+/* Page-lock (on = 1) or release (on = 0) the arrays of a prepared scene (cudaHostRegister; needs a CUDA device): every later
+ * rm_scene_upload of it is then a DMA straight out of them.  For scenes uploaded more than once, or by several ranks of one host
+ * at a time.  Release before rm_prepared_free.  Nothing like it in the reference (no device). */
+int rm_prepared_pin(RmPrepared *p, int32_t on);
 
 /* ---------------------------------------------------------------------------------
  * Context and scene upload

@@ -52,7 +52,7 @@ class RmSceneDesc(C.Structure):
 
 
 # every symbol include/raym0nade_b200.h declares
-EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_last_error",
+EXPORTS = ["rm_prepare_scene", "rm_prepared_desc", "rm_prepared_permutation", "rm_prepared_free", "rm_prepared_pin", "rm_last_error",
            "rm_version", "rm_context_create", "rm_context_destroy", "rm_context_synchronize", "rm_scene_validate", "rm_scene_upload",
            "rm_scene_device_bytes", "rm_scene_h2d_bytes", "rm_trace_closest", "rm_trace_occluded", "rm_trace_primary", "rm_gbuffer",
            "rm_render_samples", "rm_accum_view", "rm_accum_after_reduce", "rm_accum_radiance", "rm_resolve", "rm_download_resolved", "rm_render", "rm_fxaa",
@@ -80,6 +80,7 @@ def lib():
     L.rm_prepared_permutation.restype = C.POINTER(C.c_int32)
     L.rm_prepared_permutation.argtypes = [vp]
     L.rm_prepared_free.argtypes = [vp]
+    L.rm_prepared_pin.argtypes = [vp, i32]
     L.rm_context_create.argtypes = [i32, vp, C.POINTER(vp)]
     L.rm_context_destroy.argtypes = [vp]
     L.rm_context_synchronize.argtypes = [vp]
@@ -207,8 +208,15 @@ class Model:
         """rm_scene_validate on the prepared scene (host only); raises RmError naming the first inconsistency"""
         _check(lib().rm_scene_validate(C.byref(self.desc)))
 
+    def pin(self, on=True):
+        """page-lock (or release) the prepared arrays: later uploads of this model are DMAs straight out of them"""
+        _check(lib().rm_prepared_pin(self.h, 1 if on else 0))
+        self._pinned = bool(on)
+
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self, "_pinned", False):
+                lib().rm_prepared_pin(self.h, 0)
             lib().rm_prepared_free(self.h)
             self.h = None
 

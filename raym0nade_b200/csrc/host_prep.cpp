@@ -194,6 +194,7 @@ struct RmPrepared {
     std::vector<RmMaterialDesc> materials;
     std::vector<HostLight> lights;
     std::vector<RmLightDesc> light_descs;
+    std::vector<void *> pinned;       // arrays page-locked by rm_prepared_pin
 };
 
 // `tree`: who builds the reference's tree over the raw positions - nullptr = the host recursion above; rm_prepare_scene_device
@@ -377,6 +378,22 @@ int rm_prepare_scene_impl(const RmRawScene *raw, RmPrepared **out, const RmTreeF
     *out = P.release();
     return RM_OK;
 }
+
+// The arrays a prepared scene hands to rm_scene_upload, for rm_prepared_pin (rm_api.cu: page-locking needs the CUDA runtime, which
+// this file stays clear of)
+void rm_prepared_spans(RmPrepared *P, std::vector<std::pair<void *, size_t>> &out) {
+    auto add = [&](void *p, size_t bytes) { if (p && bytes) out.emplace_back(p, bytes); };
+    add(P->nodes.data(), P->nodes.size() * sizeof(RmBvhNode));
+    add(P->positions.data(), P->positions.size() * 4);
+    add(P->uvs.data(), P->uvs.size() * 4);
+    add(P->normals.data(), P->normals.size() * 4);
+    add(P->face_material.data(), P->face_material.size() * 4);
+    add(P->sky_data.data(), P->sky_data.size() * 4);
+    add(P->sky_cdf.data(), P->sky_cdf.size() * 4);
+    for (HostTexture &t : P->textures)
+        for (int l = 0; l < t.map_depth; l++) add(t.level[l].data(), t.level[l].size());
+}
+std::vector<void *> &rm_prepared_pinned(RmPrepared *P) { return P->pinned; }
 
 extern "C" {
 

@@ -234,7 +234,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         // "tree_builder" 2: the device tree serves at once; the host SAH builder refines it in the background
         ctx->use_refined = false;
         if (device_tree && ctx->tree_builder_mode == 2) {
-            const uint64_t key = hash_words(sc->positions, size_t(n) * 36);
+            const uint64_t key = ctx->tree_cache ? hash_words(sc->positions, size_t(n) * 36) : 0;      // (only ever compared while caching is on)
             if (ctx->refine && ctx->refine->th.joinable() && !(ctx->tree_cache && ctx->refine->key == key && ctx->refine->n == n)) {
                 ctx->refine->th.join();                        // a build for other geometry (or caching is off): let it end, drop it
                 ctx->refine.reset();
@@ -513,6 +513,32 @@ int rm_tree_info(const RmContext *ctx, int32_t out[4]) {
     out[1] = ctx->use_refined ? ctx->refined_nodes : ctx->wide_nodes;
     out[2] = ctx->use_refined ? ctx->refined_levels : ctx->wide_levels;
     out[3] = ctx->have_wide && !ctx->exact_secondary && (ctx->secondary_tree == 2 || !ctx->have_fast) ? 1 : 0;
+    return RM_OK;
+}
+
+// Page-lock (on = 1) / release (on = 0) the arrays of a prepared scene, so that every later rm_scene_upload of it is a DMA
+// straight out of them instead of a staged copy of pageable memory.  A few tens of milliseconds once; worth it for a scene
+// that is uploaded more than once (an animation, the end-to-end loop of bench.py) or by several ranks of one host at the same
+// time (eight staged 100 MB copies share the host's memory bandwidth).  Release before rm_prepared_free.
+int rm_prepared_pin(RmPrepared *p, int32_t on) {
+    if (!p) return rm_fail(RM_ERR_INVALID, "rm_prepared_pin: null argument");
+    std::vector<void *> &pinned = rm_prepared_pinned(p);
+    if (!on) {
+        for (void *q : pinned) cudaHostUnregister(q);
+        pinned.clear();
+        return RM_OK;
+    }
+    if (!pinned.empty()) return RM_OK;
+    std::vector<std::pair<void *, size_t>> spans;
+    rm_prepared_spans(p, spans);
+    for (auto &sp : spans) {
+        if (sp.second < (size_t(1) << 16)) continue;             // small arrays are not worth a registration
+        const cudaError_t e = cudaHostRegister(sp.first, sp.second, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+        if (e == cudaSuccess) pinned.push_back(sp.first);
+        else if (cudaHostRegister(sp.first, sp.second, cudaHostRegisterPortable) == cudaSuccess) pinned.push_back(sp.first);
+        else { cudaGetLastError(); return rm_fail(RM_ERR_CUDA, "rm_prepared_pin: cudaHostRegister(%zu bytes) failed: %s", sp.second, cudaGetErrorString(e)); }
+    }
+    cudaGetLastError();
     return RM_OK;
 }
 

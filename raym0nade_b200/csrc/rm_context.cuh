@@ -166,3 +166,6 @@ extern "C" int rm_install_refined_tree(RmContext *ctx);
 extern "C" int rm_repack_faces(RmContext *ctx);
 // implemented in rm_comm.cu
 void rm_comm_state_free(RmContext *ctx);
+// implemented in host_prep.cpp: the arrays of a prepared scene / the ones currently page-locked (rm_prepared_pin)
+void rm_prepared_spans(RmPrepared *P, std::vector<std::pair<void *, size_t>> &out);
+std::vector<void *> &rm_prepared_pinned(RmPrepared *P);

@@ -198,6 +198,28 @@ def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree, builder):
     ctx.close()
 
 
+def test_upload_from_a_page_locked_prepared_scene():
+    """rm_prepared_pin: the same scene uploaded from page-locked arrays (a DMA out of them) gives the same hits; pinning twice and
+    releasing are harmless"""
+    scene, args = scenes.texture_heavy(40_000, 160, 90, tex_size=64, n_materials=8)
+    model = Model(scene)
+    ctx = Context(0).upload(model)
+    tri, t = ctx.trace_primary(args)
+    model.pin()
+    model.pin()
+    ctx.upload(model)
+    tri2, t2 = ctx.trace_primary(args)
+    assert np.array_equal(tri, tri2) and np.array_equal(t.view(np.uint32), t2.view(np.uint32))
+    out = ctx.render(args.replace(spp=2), seed=1)
+    assert np.isfinite(out["Id"]["radiance"]).all()
+    model.pin(False)
+    ctx.upload(model)
+    tri3, _ = ctx.trace_primary(args)
+    assert np.array_equal(tri, tri3)
+    ctx.close()
+    model.close()
+
+
 def test_work_counters_match_reference_traversal(ref):
     """box / triangle test counts come out identical because the traversal order is identical
     (these are the B and T of the bytes-per-ray roofline figure)"""
