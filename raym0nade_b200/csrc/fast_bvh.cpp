@@ -47,6 +47,7 @@ struct Builder {
     std::atomic<int> next_block{2};   // block 0 = {unused, whole-tree record}, block 1 = the root's children
     std::atomic<int> max_depth{0};
     int depth_cap, kLeafMax;
+    const std::atomic<bool> *cancel = nullptr;        // set by the owner of a background build: unwind, the tree is not wanted any more
 
     Builder(const float *p, int n, std::vector<int32_t> &o, std::vector<RmBvhNode> &nd, int cap, int leaf_max)
         : pos(p), order(o), nodes(nd), depth_cap(cap), kLeafMax(leaf_max) {
@@ -70,6 +71,7 @@ struct Builder {
 
     // fills `rec` for the triangles order[L, R); its children go into pair block `block` (-1: a freshly allocated one)
     void build(RmBvhNode &rec, int L, int R, int depth, int spawn_levels, int block = -1) {
+        if (cancel && cancel->load(std::memory_order_relaxed)) return;
         int seen = max_depth.load();
         while (depth > seen && !max_depth.compare_exchange_weak(seen, depth)) {}
         // big nodes (the top few levels) split their two passes over the triangles across threads
@@ -176,7 +178,9 @@ struct Builder {
 } // namespace
 
 // positions [n][9]; returns the node records (pairs), the triangle order and the tree depth (levels of inner nodes + 1)
-int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out) {
+// (cancel: set by the owner of a background build to make it unwind; the result is then RM_ERR_STATE and no tree)
+int rm_build_fast_bvh_cancellable(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out,
+                                  const std::atomic<bool> *cancel) {
     const int kLeafMax = std::min(std::max(leaf_max, 1), 15);          // a leaf reference holds its count in 4 bits (dev_trace.cuh)
     if (!positions || n <= 0) return rm_fail(RM_ERR_INVALID, "rm_build_fast_bvh: no triangles");
     order.resize(n);
@@ -184,12 +188,18 @@ int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max
     nodes.assign(size_t(n + 2) * 2, RmBvhNode{});
     const int min_cap = int(std::ceil(std::log2(std::max(1.0, double(n) / kLeafMax)))) + 1;
     Builder B(positions, n, order, nodes, std::max(depth_cap, min_cap), kLeafMax);
+    B.cancel = cancel;
     RmBvhNode whole{};
     B.build(whole, 0, n, 0, 4, /*the root's children are block 1, where the engine starts*/ 1);
     nodes[1] = whole;          // only read when the whole scene is one leaf (root_is_leaf)
     nodes.resize(size_t(B.next_block.load()) * 2);
     if (depth_out) *depth_out = B.max_depth.load() + 1;
+    if (cancel && cancel->load()) return rm_fail(RM_ERR_STATE, "rm_build_fast_bvh: cancelled");
     return RM_OK;
+}
+
+int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out) {
+    return rm_build_fast_bvh_cancellable(positions, n, depth_cap, leaf_max, nodes, order, depth_out, nullptr);
 }
 
 // Host-only diagnostic behind the C ABI (no GPU needed): builds the secondary-ray tree for `positions` and checks its

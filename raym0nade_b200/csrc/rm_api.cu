@@ -235,8 +235,8 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         ctx->use_refined = false;
         if (device_tree && ctx->tree_builder_mode == 2) {
             const uint64_t key = ctx->tree_cache ? hash_words(sc->positions, size_t(n) * 36) : 0;      // (only ever compared while caching is on)
-            if (ctx->refine && ctx->refine->th.joinable() && !(ctx->tree_cache && ctx->refine->key == key && ctx->refine->n == n)) {
-                ctx->refine->th.join();                        // a build for other geometry (or caching is off): let it end, drop it
+            if (ctx->refine && !(ctx->tree_cache && ctx->refine->started && ctx->refine->key == key && ctx->refine->n == n)) {
+                ctx->refine->stop();                           // a build for other geometry (or caching is off): it unwinds within milliseconds
                 ctx->refine.reset();
             }
             if (ctx->tree_cache && ctx->refined_installed && ctx->refined_key == key && ctx->refined_n == n) ctx->use_refined = true;
@@ -247,17 +247,9 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
                 J->pos.assign(sc->positions, sc->positions + size_t(n) * 9);
                 J->n = n;
                 J->key = key;
-                J->state.store(1);
-                const int cap = ctx->fast_depth_cap, limit = ctx->tune_wide.smem_levels + rm::kStackSpillWide;
-                J->th = std::thread([J, cap, limit] {
-                    std::vector<RmBvhNode> fnodes;
-                    std::vector<int32_t> forder;
-                    int fdepth = 0;
-                    bool ok = rm_build_fast_bvh(J->pos.data(), J->n, cap, 3, fnodes, forder, &fdepth) == RM_OK &&
-                              rm_build_wide_bvh(fnodes, forder, J->n, J->wnodes, J->worder, &J->wdepth) == RM_OK && 3 * J->wdepth <= limit;
-                    J->pos = std::vector<float>();
-                    J->state.store(ok ? 2 : 3);
-                });
+                J->limit = ctx->tune_wide.smem_levels + rm::kStackSpillWide;
+                J->depth_cap = ctx->fast_depth_cap;
+                // (the thread itself is launched by rm_start_refinement, from the first render that is long enough to profit)
             }
         }
         if (!device_tree || ctx->want_binary_tree) {
@@ -470,11 +462,35 @@ int rm_repack_faces(RmContext *ctx) {
     return RM_OK;
 }
 
+// The pending refinement of the secondary-ray tree starts here, not in rm_scene_upload: a build costs ~0.4 s of several host threads
+// and pays back ~1.5 % of the traversal that follows it, so it is only worth starting when the scene is going to be rendered for
+// longer than that - always when trees are cached across uploads (a static scene re-rendered), and with the cache off (a scene that
+// changes every frame) only for a frame of at least kRefineMinSamples pixel-samples (~0.6 s on a B200).  Eight ranks of a host
+// rendering 0.3 s frames used to spend each frame waiting for the previous frame's useless build to end.
+constexpr int64_t kRefineMinSamples = 500000000;
+void rm_start_refinement(RmContext *ctx, int64_t pixel_samples) {
+    if (!ctx->refine || ctx->refine->started) return;
+    if (!ctx->tree_cache && pixel_samples < kRefineMinSamples) { ctx->refine.reset(); return; }
+    RefineJob *J = ctx->refine.get();
+    J->started = true;
+    J->state.store(1);
+    J->th = std::thread([J] {
+        std::vector<RmBvhNode> fnodes;
+        std::vector<int32_t> forder;
+        int fdepth = 0;
+        bool ok = rm_build_fast_bvh_cancellable(J->pos.data(), J->n, J->depth_cap, 3, fnodes, forder, &fdepth, &J->cancel) == RM_OK && !J->cancel.load() &&
+                  rm_build_wide_bvh(fnodes, forder, J->n, J->wnodes, J->worder, &J->wdepth) == RM_OK && 3 * J->wdepth <= J->limit;
+        J->pos = std::vector<float>();
+        J->state.store(ok && !J->cancel.load() ? 2 : 3);
+    });
+}
+
 // The background build has finished: stage its tree next to the device builder's and point bounce / shadow rays at it.
 // Called where the render loop waits for the device anyway (rm_render_samples: on entry and between batches of rounds).
 int rm_install_refined_tree(RmContext *ctx) {
     if (!ctx || !ctx->refine || !ctx->has_scene) return RM_OK;
     RefineJob *J = ctx->refine.get();
+    if (!J->started) return RM_OK;
     const int state = J->state.load();
     if (state == 1) return RM_OK;
     if (J->th.joinable()) J->th.join();
@@ -686,6 +702,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); ctx->fast_key_valid = false; return RM_OK; }
     // block until the background refinement (if any) has finished and install its tree
     if (!std::strcmp(name, "tree_wait")) {
+        rm_start_refinement(ctx, kRefineMinSamples);
         if (ctx->refine && ctx->refine->th.joinable()) ctx->refine->th.join();
         return rm_install_refined_tree(ctx);
     }

@@ -51,6 +51,10 @@ struct RefineJob {
     std::vector<int32_t> worder;
     int wdepth = 0;
     bool discard = false;                  // the vertices moved while it ran (rm_scene_refit): its tree is not installed
+    bool started = false;                  // the thread is launched by the first render that is long enough to profit (rm_start_refinement)
+    std::atomic<bool> cancel{false};       // asks a running build to unwind (a new scene arrived, the context goes away)
+    int limit = 0, depth_cap = 22;         // stack entries the traversal allows; depth cap of the binary tree
+    void stop() { cancel.store(true); if (th.joinable()) th.join(); }
 };
 
 struct RmContext {
@@ -145,7 +149,7 @@ struct RmContext {
         for (DevBuf *b : {&b_nodes, &b_tri, &b_shade, &b_mats, &b_texs, &b_texels, &b_lights, &b_lpos, &b_lnrm, &b_lcdf,
                           &b_sky, &b_skycdf, &b_skyguide, &b_lut, &b_nodes_fast, &b_tri_fast, &b_facemap, &b_nodes_wide, &b_tri_wide, &b_facemap_wide, &b_raw[0], &b_raw[1], &b_raw[2], &b_raw[3], &b_counters, &b_cursor, &b_tri_idx, &b_t, &b_gbuffer, &b_io[0], &b_io[1], &b_io[2], &b_io[3]})
             b->release();
-        if (refine && refine->th.joinable()) refine->th.join();
+        if (refine) refine->stop();
         for (DevBuf &b : b_build) b.release();
         for (DevBuf *b : {&b_nodes_wide2, &b_tri_wide2, &b_facemap_wide2}) b->release();
     }
@@ -159,9 +163,14 @@ void rm_render_state_free(RmContext *ctx);
 extern "C" int rm_accum_mark_slice(RmContext *ctx, int64_t first_pixel, int64_t pixels);       // after rm_reduce_scatter: only this slice of the accumulators holds the frame
 // implemented in fast_bvh.cpp
 int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out);
+int rm_build_fast_bvh_cancellable(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out,
+                                  const std::atomic<bool> *cancel);
 // implemented in wide_bvh.cpp (declared in wide_bvh.h)
 // implemented in rm_api.cu: swaps the background-refined secondary-ray tree in once it is ready (no-op otherwise)
 extern "C" int rm_install_refined_tree(RmContext *ctx);
+// implemented in rm_api.cu: launches the pending background refinement if `pixel_samples` of rendering are about to follow that make
+// it worth its host time (always when trees are cached across uploads), drops it otherwise
+extern "C" void rm_start_refinement(RmContext *ctx, int64_t pixel_samples);
 // implemented in rm_api.cu: after rm_scene_refit (gpu_ref_bvh.cu) - the traversal and shading records formed anew from ctx->b_raw[0] and re-permuted for the 4-wide tree(s)
 extern "C" int rm_repack_faces(RmContext *ctx);
 // implemented in rm_comm.cu

@@ -22,6 +22,29 @@ static uint64_t spread21(uint32_t v) { uint64_t x = v & 0x1fffffu; x = (x | x <<
 struct Bin { std::vector<B3> box; std::vector<int> left, right, count; int root; };
 static int gLeafMax = 3;
 static int METRIC = 0;     // 0 area of union
+static int TOPK = 0;       // > 0: clustering stops at <= TOPK clusters, a top-down sweep-SAH tree over the clusters finishes the job
+static int TOPW = 0;       // weight of a cluster in the top SAH: 0 triangles beneath, 1 one per cluster, 2 its own SAH cost estimate (area-independent: count^0.5?)
+static int top_sah(Bin &T, std::vector<int> &ids, int L, int R, int &next) {
+    if (R - L == 1) return ids[L];
+    int n = R - L; float best = INFINITY; int bax = -1, bk = -1;
+    std::vector<float> la(n); std::vector<double> lw(n);
+    auto wt = [&](int c) { return TOPW == 0 ? double(T.count[c]) : TOPW == 1 ? 1.0 : std::sqrt(double(T.count[c])); };
+    for (int ax = 0; ax < 3; ax++) {
+        std::sort(ids.begin() + L, ids.begin() + R, [&](int a, int b) { return T.box[a].lo[ax] + T.box[a].hi[ax] < T.box[b].lo[ax] + T.box[b].hi[ax]; });
+        B3 acc{{1e30f,1e30f,1e30f},{-1e30f,-1e30f,-1e30f}}; double w = 0;
+        for (int i = 0; i < n - 1; i++) { const B3 &b = T.box[ids[L + i]]; for (int q = 0; q < 3; q++) { acc.lo[q] = std::min(acc.lo[q], b.lo[q]); acc.hi[q] = std::max(acc.hi[q], b.hi[q]); } w += wt(ids[L + i]); la[i] = area(acc); lw[i] = w; }
+        acc = B3{{1e30f,1e30f,1e30f},{-1e30f,-1e30f,-1e30f}}; w = 0;
+        for (int i = n - 1; i >= 1; i--) { const B3 &b = T.box[ids[L + i]]; for (int q = 0; q < 3; q++) { acc.lo[q] = std::min(acc.lo[q], b.lo[q]); acc.hi[q] = std::max(acc.hi[q], b.hi[q]); } w += wt(ids[L + i]);
+            float cost = float(la[i - 1] * lw[i - 1] + area(acc) * w); if (cost < best) { best = cost; bax = ax; bk = i; } }
+    }
+    std::sort(ids.begin() + L, ids.begin() + R, [&](int a, int b) { return T.box[a].lo[bax] + T.box[a].hi[bax] < T.box[b].lo[bax] + T.box[b].hi[bax]; });
+    int M = L + bk;
+    int l = top_sah(T, ids, L, M, next), r = top_sah(T, ids, M, R, next);
+    int id = next++;
+    for (int q = 0; q < 3; q++) { T.box[id].lo[q] = std::min(T.box[l].lo[q], T.box[r].lo[q]); T.box[id].hi[q] = std::max(T.box[l].hi[q], T.box[r].hi[q]); }
+    T.left[id] = l; T.right[id] = r; T.count[id] = T.count[l] + T.count[r];
+    return id;
+}
 static Bin ploc(int n, int R) {
     Bin T; T.box.resize(2 * n); T.left.resize(2 * n); T.right.resize(2 * n); T.count.resize(2 * n);
     B3 sb{{1e30f,1e30f,1e30f},{-1e30f,-1e30f,-1e30f}};
@@ -33,12 +56,13 @@ static Bin ploc(int n, int R) {
     std::vector<int> cl(n), nn(n), out(n);
     for (int k = 0; k < n; k++) { int t = keys[k].second; T.box[k] = tb[t]; T.left[k] = ~t; T.right[k] = -1; T.count[k] = 1; cl[k] = k; }
     int next = n, m = n, rounds = 0;
-    while (m > 1) {
+    while (m > 1 && !(TOPK > 0 && m <= TOPK)) {
         for (int i = 0; i < m; i++) { float best = INFINITY; int bj = -1; for (int j = std::max(i - R, 0); j <= std::min(i + R, m - 1); j++) { if (j == i) continue; float a = uarea(T.box[cl[i]], T.box[cl[j]]); if (METRIC == 1) a = a - area(T.box[cl[i]]) - area(T.box[cl[j]]); if (METRIC == 2) a *= float(T.count[cl[i]] + T.count[cl[j]]); if (METRIC == 3) a *= std::sqrt(float(T.count[cl[i]] + T.count[cl[j]])); if (a < best || bj < 0) { best = a; bj = j; } } nn[i] = bj; }
         int k = 0;
         for (int i = 0; i < m; i++) { int j = nn[i]; if (nn[j] != i) { out[k++] = cl[i]; continue; } if (i > j) continue; int id = next++; const B3 &a = T.box[cl[i]], &b = T.box[cl[j]]; for (int q = 0; q < 3; q++) { T.box[id].lo[q] = std::min(a.lo[q], b.lo[q]); T.box[id].hi[q] = std::max(a.hi[q], b.hi[q]); } T.left[id] = cl[i]; T.right[id] = cl[j]; T.count[id] = T.count[cl[i]] + T.count[cl[j]]; out[k++] = id; }
         m = k; std::swap(cl, out); rounds++;
     }
+    if (m > 1) { fprintf(stderr, "  top SAH over %d clusters\n", m); std::vector<int> ids(cl.begin(), cl.begin() + m); auto t0 = std::chrono::steady_clock::now(); T.root = top_sah(T, ids, 0, m, next); fprintf(stderr, "  top build %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } else
     T.root = cl[0];
     { double ci = 0, cl_ = 0; float ra = area(T.box[T.root]); std::vector<int> stk{T.root}; int maxd = 0; std::vector<int> dep{0};
       while (!stk.empty()) { int b = stk.back(); stk.pop_back(); int dd = dep.back(); dep.pop_back(); maxd = std::max(maxd, dd); if (T.count[b] <= gLeafMax) { cl_ += area(T.box[b]) / ra * T.count[b]; continue; } ci += area(T.box[b]) / ra; stk.push_back(T.left[b]); dep.push_back(dd + 1); stk.push_back(T.right[b]); dep.push_back(dd + 1); }
@@ -106,5 +130,5 @@ int main(int argc, char **argv) {
         fprintf(stderr, "host binary SAH cost: inner %.2f leaf %.2f depth %d\n", ci, cl_, d); }
       rm_build_wide_bvh(bin, order, n, w, worder, &wd);
       std::vector<int> o2(worder.begin(), worder.end()); char nm[64]; snprintf(nm, 64, "host SAH (levels %d)", wd); trace(w, o2, nm); }
-    for (int i = 1; i < argc; i++) { int R = 16, lm = 3, om = 0, mt = 0; sscanf(argv[i], "%d:%d:%d:%d", &R, &lm, &om, &mt); gLeafMax = lm; COLLAPSE_MODE = om; METRIC = mt; Bin T = ploc(n, R); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "PLOC R=%d leaf%d open%d m%d (lv %d)", R, lm, om, mt, lv); trace(W, order, nm); }
+    for (int i = 1; i < argc; i++) { int R = 16, lm = 3, om = 0, mt = 0, tk = 0, tw = 0; sscanf(argv[i], "%d:%d:%d:%d:%d:%d", &R, &lm, &om, &mt, &tk, &tw); TOPK = tk; TOPW = tw; gLeafMax = lm; COLLAPSE_MODE = om; METRIC = mt; Bin T = ploc(n, R); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "PLOC R=%d l%d o%d m%d top%d w%d (lv %d)", R, lm, om, mt, tk, tw, lv); trace(W, order, nm); }
 }
