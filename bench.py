@@ -329,8 +329,8 @@ def run_ours(opt, rank, world, local_rank):
 
     for i in range(opt.warmup):
         step(100 + i)
-    # the device-resident figure is for a scene that has been on the device for a while: let the background refinement of the
-    # secondary-ray tree finish (it normally has, during the warm-up) so that the counted and the timed steps traverse the same tree
+    # ("tree_builder" 2 only: the device-resident figure is for a scene that has been on the device for a while - let the background
+    # refinement of the secondary-ray tree finish so that the counted and the timed steps traverse the same tree)
     ctx.set_option("tree_wait", 1)
     barrier()
 
@@ -379,7 +379,7 @@ def run_ours(opt, rank, world, local_rank):
     frame = SharedFrame(npix, rank, world, os.environ.get("MASTER_PORT", str(os.getpid())), barrier)
     e2e_steps = max(1, min(opt.steps, 3))
 
-    ctx.set_option("tree_cache", 0)             # every upload builds its trees anew (device build + background refinement from scratch)
+    ctx.set_option("tree_cache", 0)             # every upload builds its trees anew (nothing keyed by geometry hash survives an upload)
     if not opt.pageable_scene:
         model.pin()                             # the prepared scene is page-locked once (outside the timed loop): each step's upload is a DMA out of it
 
@@ -461,8 +461,9 @@ def run_ours(opt, rank, world, local_rank):
             pass
         sec_tree = "reference tree, reference visit order" if opt.exact_secondary else (
             "4-wide secondary-ray tree over the same triangles (%s, %d records of 64 B, %d levels; 8-bit quantised child boxes, conservative slab test, "
-            "the reference's triangle test)" % (("built on the device (Morton sort + PLOC + collapse), then replaced by the host binned-SAH tree built in the background" if tree_info["refined"]
-                                                 else "built on the device: Morton sort + PLOC + collapse") if tree_info["device_built"] else "host binned SAH + collapse",
+            "the reference's triangle test)" % ({"sweep_sah": "built on the device at every upload: top-down sweep SAH (gpu_sah_bvh.cu) + collapse",
+                                                 "ploc+host refinement": "built on the device (Morton sort + PLOC + collapse), then replaced by the host binned-SAH tree built in the background",
+                                                 "ploc": "built on the device: Morton sort + PLOC + collapse", "host": "host binned SAH + collapse"}[tree_info["builder"]],
                                                 tree_info["nodes"], tree_info["levels"]))
         roofline = {"bound": "hbm", "kernel": {"primary": "k_trace<PrimaryJob>", "paths": "k_trace<PathJob>", "shadow": "k_trace<ShadowJob>"}[dom],
                     "achieved": per_kind[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kind[dom]["achieved_gbs"] / peak,
@@ -642,7 +643,7 @@ def main():
     ap.add_argument("--exact-secondary", action="store_true", help="bounce and shadow rays through the reference's own tree in the reference's order (default: the secondary-ray tree)")
     ap.add_argument("--reduce", default="scatter", choices=["scatter", "root", "torch"],
                     help="N > 1: rm_reduce_scatter (default: every rank resolves and downloads its slice), rm_reduce to rank 0, or torch.distributed collectives")
-    ap.add_argument("--tree-builder", type=int, default=-1, help="secondary-ray tree: 0 host binned SAH, 1 device PLOC, 2 device + background refinement (library default)")
+    ap.add_argument("--tree-builder", type=int, default=-1, help="secondary-ray tree: 0 host binned SAH, 1 device PLOC, 2 device PLOC + background refinement by the host builder, 3 device sweep SAH (library default)")
     ap.add_argument("--no-first-frame", action="store_true", help="skip the e2e_first_frame measurement")
     ap.add_argument("--pageable-scene", action="store_true", help="end-to-end loop: upload the scene from pageable host memory (round-2 behaviour) instead of page-locking it once")
     ap.add_argument("--first-frame-spp", type=int, default=1 << 30, help="spp of the first-frame measurement (default: the step's)")

@@ -268,8 +268,10 @@ int rm_secondary_tree_stats(const float *positions, int32_t n, int32_t depth_cap
  * (csrc/wide_bvh.cpp): every triangle in one leaf, every decoded child box encloses the vertices beneath it;
  * out = {nodes (64-byte records), levels, leaves, children per node x 100}. */
 int rm_wide_tree_stats(const float *positions, int32_t n, int32_t depth_cap, int32_t out[4]);
-/* The 4-wide tree of the uploaded scene: out = {1 if it was built on the device (csrc/gpu_bvh.cu: Morton sort + PLOC clustering
- * + collapse, the default - "tree_builder" 1) / 0 if on the host, records, levels, 1 if bounce and shadow rays traverse it}. */
+/* The 4-wide tree of the uploaded scene: out = {its builder - 3: on the device by the top-down sweep SAH of csrc/gpu_sah_bvh.cu
+ * (the default, "tree_builder" 3), 1: on the device by Morton sort + PLOC clustering (csrc/gpu_bvh.cu, "tree_builder" 1), 2: the
+ * PLOC tree replaced by the host builder's in the background ("tree_builder" 2), 0: on the host -, records, levels, 1 if bounce
+ * and shadow rays traverse it}. */
 int rm_tree_info(const RmContext *ctx, int32_t out[4]);
 /* Options (integers).  "exact_secondary" 0|1 (default 0): 1 sends the estimator's bounce and shadow rays through the
  * reference's own BVH in the reference's visit order, like primary rays and the per-ray seam always are; 0 lets them use the

@@ -256,10 +256,12 @@ class Context:
         _check(lib().rm_scene_refit(self.h, _p(pos), pos.shape[0]))
 
     def tree_info(self):
-        """the 4-wide secondary-ray tree bounce / shadow rays currently traverse: dict(device_built, refined (the host builder's tree has been swapped in), nodes, levels, in_use)"""
+        """the 4-wide secondary-ray tree bounce / shadow rays currently traverse: dict(device_built, builder ("host" | "ploc" | "ploc+host refinement" |
+        "sweep_sah"), refined (the host builder's tree has been swapped in), nodes, levels, in_use)"""
         out = np.zeros(4, np.int32)
         _check(lib().rm_tree_info(self.h, _p(out)))
-        return dict(device_built=bool(out[0]), refined=int(out[0]) == 2, nodes=int(out[1]), levels=int(out[2]), in_use=bool(out[3]))
+        return dict(device_built=bool(out[0]), builder=("host", "ploc", "ploc+host refinement", "sweep_sah")[int(out[0])], refined=int(out[0]) == 2, nodes=int(out[1]), levels=int(out[2]),
+                    in_use=bool(out[3]))
 
     def scene_bytes(self):
         return lib().rm_scene_device_bytes(self.h)

@@ -34,11 +34,7 @@ namespace {
 constexpr int kPlocRadius = 16;
 constexpr int kPlocBlock = 256;
 
-struct BNodes {            // the binary tree under construction: nodes [0, n) are the triangles in Morton order, [n, 2n-1) merges
-    float4 *lo, *hi;       // box; lo.w / hi.w unused
-    int *left, *right;     // children; a triangle node has left = ~triangle, right = -1
-    int *count;            // triangles beneath
-};
+using BNodes = RmBinTree;   // the binary tree under construction: nodes [0, n) are the triangles in Morton order, [n, 2n-1) merges
 
 __device__ __forceinline__ unsigned long long spread21(unsigned v) {      // 21 bits -> every third bit of 63
     unsigned long long x = v & 0x1fffffu;
@@ -297,7 +293,18 @@ int rm_gpu_build_wide(RmContext *ctx, const float *d_pos, int n, const float sce
     RM_CUDA(cudaMemcpyAsync(&root, cl_a, 4, cudaMemcpyDeviceToHost, st));
     RM_CUDA(cudaStreamSynchronize(st));
 
-    // ---- collapse, one launch per level; the queues hold at most n items each
+    return rm_gpu_collapse_wide(ctx, N, root, n, levels_out, nodes_out);
+}
+
+// The binary tree N (root `root`, n triangles) collapsed into ctx->b_nodes_wide / b_facemap_wide, one launch per level; the
+// queues hold at most n items each.  Shared by the PLOC builder above and the sweep-SAH builder (gpu_sah_bvh.cu).
+int rm_gpu_collapse_wide(RmContext *ctx, const RmBinTree &N, int root, int n, int *levels_out, int *nodes_out) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    DevBuf *B = ctx->b_build;
+    if ((rc = B[13].alloc(size_t(n + 1) * 2 * sizeof(LevelItem))) || (rc = B[14].alloc(64))) return rc;
+    if ((rc = ctx->b_nodes_wide.alloc(size_t(n + 1) * sizeof(RmWideNode))) || (rc = ctx->b_facemap_wide.alloc(size_t(n) * 4))) return rc;
+    int *counters = B[14].as<int>();
     LevelItem *q[2] = {B[13].as<LevelItem>(), B[13].as<LevelItem>() + (n + 1)};
     k_collapse_start<<<1, 1, 0, st>>>(root, q[0], counters);
     const int cgrid = std::max(1, std::min(ctx->sm_count * 8, (n + 127) / 128));
@@ -316,8 +323,8 @@ int rm_gpu_build_wide(RmContext *ctx, const float *d_pos, int n, const float sce
     RM_CUDA(cudaGetLastError());
     RM_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
     RM_CUDA(cudaStreamSynchronize(st));
-    if (h[0] != 0 || h[1] != 0) return rm_fail(RM_ERR_STATE, "rm_gpu_build_wide: the tree is deeper than 96 wide levels");
-    if (h[3] != n) return rm_fail(RM_ERR_STATE, "rm_gpu_build_wide: the collapse placed %d of %d triangles", h[3], n);
+    if (h[0] != 0 || h[1] != 0) return rm_fail(RM_ERR_STATE, "rm_gpu_collapse_wide: the tree is deeper than 96 wide levels");
+    if (h[3] != n) return rm_fail(RM_ERR_STATE, "rm_gpu_collapse_wide: the collapse placed %d of %d triangles", h[3], n);
     if (levels_out) *levels_out = h[4];
     if (nodes_out) *nodes_out = h[2];
     return RM_OK;

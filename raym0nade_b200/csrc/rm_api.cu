@@ -210,8 +210,9 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     RM_CUDA(cudaGetLastError());
     mark("faces: H2D + records");
 
-    // The secondary-ray tree.  Default: built on the device from the positions just uploaded (gpu_bvh.cu: Morton sort, PLOC
-    // clustering, 4-wide collapse - a few milliseconds, so every upload rebuilds it and nothing is cached).  The host
+    // The secondary-ray tree.  Default: built on the device from the positions just uploaded (gpu_sah_bvh.cu: top-down sweep
+    // SAH, every level a few scans over all triangles, then the 4-wide collapse - ~8 ms per million triangles, so every upload
+    // rebuilds it and nothing is cached; gpu_bvh.cu: Morton sort + PLOC clustering, 3 ms for a tree of ~14 % more visits).  The host
     // builders (fast_bvh.cpp: binned SAH; wide_bvh.cpp: its collapse) remain for "tree_builder" 0, for the binary form of the
     // tree ("secondary_tree" 1 / the seam test hook, asked for before the upload) and as the fallback should the device
     // tree come out deeper than the traversal stack allows; they are cached by geometry hash.
@@ -221,13 +222,16 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
         if (ctx->tree_builder_mode >= 1) {
             int wlevels = 0, wnodes = 0;
             const RmBvhNode &rootbox = sc->nodes[1];           // the reference tree's root box = the scene bounds
-            if ((rc = rm_gpu_build_wide(ctx, ctx->b_raw[0].as<float>(), n, rootbox.v0, rootbox.v1, &wlevels, &wnodes))) return rc;
+            if (ctx->tree_builder_mode == 3) rc = rm_gpu_build_wide_sah(ctx, ctx->b_raw[0].as<float>(), n, ctx->fast_depth_cap, rootbox.v0, &wlevels, &wnodes);
+            else rc = rm_gpu_build_wide(ctx, ctx->b_raw[0].as<float>(), n, rootbox.v0, rootbox.v1, &wlevels, &wnodes);
+            if (rc) return rc;
             mark("device tree build");
             if (3 * wlevels <= ctx->tune_wide.smem_levels + rm::kStackSpillWide) {
                 ctx->stack_levels_wide = std::max(3 * wlevels, 2);
                 ctx->have_wide = true;
                 ctx->wide_nodes = wnodes;
                 ctx->wide_levels = wlevels;
+                ctx->wide_built_by = ctx->tree_builder_mode == 3 ? 3 : 1;
                 device_tree = true;
             }
         }
@@ -525,7 +529,7 @@ int rm_install_refined_tree(RmContext *ctx) {
 int rm_tree_info(const RmContext *ctx, int32_t out[4]) {
     if (!ctx || !out) return rm_fail(RM_ERR_INVALID, "rm_tree_info: null argument");
     if (!ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_tree_info: no scene uploaded");
-    out[0] = ctx->have_wide && !ctx->host_wide_valid ? (ctx->use_refined ? 2 : 1) : 0;
+    out[0] = ctx->have_wide && !ctx->host_wide_valid ? (ctx->use_refined ? 2 : ctx->wide_built_by == 3 ? 3 : 1) : 0;
     out[1] = ctx->use_refined ? ctx->refined_nodes : ctx->wide_nodes;
     out[2] = ctx->use_refined ? ctx->refined_levels : ctx->wide_levels;
     out[3] = ctx->have_wide && !ctx->exact_secondary && (ctx->secondary_tree == 2 || !ctx->have_fast) ? 1 : 0;
@@ -697,9 +701,10 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     }
     // bounce and shadow rays: 1 = the binary secondary-ray tree (host-built; set before rm_scene_upload), 2 = the 4-wide quantised tree (default)
     if (!std::strcmp(name, "secondary_tree")) { ctx->secondary_tree = value == 1 ? 1 : 2; if (value == 1) ctx->want_binary_tree = true; return RM_OK; }
-    // 0: on the host, cached by geometry hash; 1: on the device (gpu_bvh.cu) at every upload; 2 (default): on the device and
-    // then refined in the background by the host builder (the render loop swaps the better tree in when it is ready)
-    if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2)); ctx->fast_key_valid = false; return RM_OK; }
+    // 3 (default): on the device at every upload by the sweep-SAH builder (gpu_sah_bvh.cu); 1: on the device by PLOC (gpu_bvh.cu);
+    // 2: PLOC, then refined in the background by the host builder (the render loop swaps the better tree in when it is ready);
+    // 0: on the host, cached by geometry hash
+    if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 3)); ctx->fast_key_valid = false; return RM_OK; }
     // block until the background refinement (if any) has finished and install its tree
     if (!std::strcmp(name, "tree_wait")) {
         rm_start_refinement(ctx, kRefineMinSamples);

@@ -100,8 +100,10 @@ struct RmContext {
     uint64_t refined_key = 0;
     int refined_n = 0, refined_levels = 0, refined_nodes = 0;
     DevBuf b_build[16];                    // scratch of the device tree builder (gpu_bvh.cu), kept across uploads
-    int tree_builder_mode = 2;                  // 1: the secondary-ray tree is built on the device at every upload (gpu_bvh.cu); 0: on the host (fast_bvh.cpp +
-                                           // wide_bvh.cpp), cached by geometry hash; 2 (default): on the device, then refined by the host builder in the background
+    int tree_builder_mode = 3;             // the secondary-ray tree: 3 (default) built on the device at every upload by the sweep-SAH builder (gpu_sah_bvh.cu);
+                                           // 1: on the device by Morton sort + PLOC (gpu_bvh.cu; a 3 ms build, ~14 % more node visits per ray); 2: PLOC, then
+                                           // refined by the host builder in the background; 0: on the host (fast_bvh.cpp + wide_bvh.cpp), cached by geometry hash
+    int wide_built_by = 0;                 // the builder mode that made the tree in b_nodes_wide
     int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
     int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
     bool fast_root_is_leaf = false, fast_key_valid = false;

@@ -121,6 +121,16 @@ static void trace(const std::vector<RmWideNode> &W, const std::vector<int> &orde
     printf("%-28s nodes %7zu | visits/ray %6.2f boxes/ray %6.2f tris/ray %5.2f pushes/ray %5.2f | est cost %7.0f | hit %.3f maxsp %d\n", name, W.size(), visits / m, boxes / m, tris / m, pushes / m, (visits * 300 + tris * 110) / m, hits / m, maxsp);
 }
 static std::vector<float> readf(const char *p) { FILE *f = fopen(p, "rb"); fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET); std::vector<float> v(n / 4); fread(v.data(), 4, v.size(), f); fclose(f); return v; }
+extern "C" int sah_sweep_host(const float *pos, int n, int depth_cap, float *lo_out, float *hi_out, int *left, int *right, int *count, int *root_out);
+static Bin sweep_tree(int n, int cap) {          // the host mirror of the device's sweep-SAH builder (tests/tools/sah_sweep_host.cpp)
+    Bin T; T.box.resize(2 * n); T.left.resize(2 * n); T.right.resize(2 * n); T.count.resize(2 * n);
+    std::vector<float> lo(size_t(8) * n), hi(size_t(8) * n);
+    auto t0 = std::chrono::steady_clock::now();
+    int lv = sah_sweep_host(pos.data(), n, cap, lo.data(), hi.data(), T.left.data(), T.right.data(), T.count.data(), &T.root);
+    fprintf(stderr, "sweep mirror: %d levels, %.0f ms\n", lv, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    for (int b = 0; b < 2 * n - 1; b++) for (int a = 0; a < 3; a++) { T.box[b].lo[a] = lo[size_t(b) * 4 + a]; T.box[b].hi[a] = hi[size_t(b) * 4 + a]; }
+    return T;
+}
 int main(int argc, char **argv) {
     pos = readf("/tmp/ploc/tris.bin"); rays = readf("/tmp/ploc/rays.bin"); int n = int(pos.size() / 9);
     { std::vector<RmBvhNode> bin; std::vector<int32_t> order, worder; std::vector<RmWideNode> w; int d = 0, wd = 0;
@@ -130,5 +140,6 @@ int main(int argc, char **argv) {
         fprintf(stderr, "host binary SAH cost: inner %.2f leaf %.2f depth %d\n", ci, cl_, d); }
       rm_build_wide_bvh(bin, order, n, w, worder, &wd);
       std::vector<int> o2(worder.begin(), worder.end()); char nm[64]; snprintf(nm, 64, "host SAH (levels %d)", wd); trace(w, o2, nm); }
-    for (int i = 1; i < argc; i++) { int R = 16, lm = 3, om = 0, mt = 0, tk = 0, tw = 0; sscanf(argv[i], "%d:%d:%d:%d:%d:%d", &R, &lm, &om, &mt, &tk, &tw); TOPK = tk; TOPW = tw; gLeafMax = lm; COLLAPSE_MODE = om; METRIC = mt; Bin T = ploc(n, R); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "PLOC R=%d l%d o%d m%d top%d w%d (lv %d)", R, lm, om, mt, tk, tw, lv); trace(W, order, nm); }
+    for (int i = 1; i < argc; i++) { if (!strncmp(argv[i], "sweep", 5)) { int cap = 22; sscanf(argv[i], "sweep:%d", &cap); gLeafMax = 3; COLLAPSE_MODE = 0; Bin T = sweep_tree(n, cap); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "sweep SAH mirror cap%d (lv %d)", cap, lv); trace(W, order, nm); continue; }
+      int R = 16, lm = 3, om = 0, mt = 0, tk = 0, tw = 0; sscanf(argv[i], "%d:%d:%d:%d:%d:%d", &R, &lm, &om, &mt, &tk, &tw); TOPK = tk; TOPW = tw; gLeafMax = lm; COLLAPSE_MODE = om; METRIC = mt; Bin T = ploc(n, R); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "PLOC R=%d l%d o%d m%d top%d w%d (lv %d)", R, lm, om, mt, tk, tw, lv); trace(W, order, nm); }
 }

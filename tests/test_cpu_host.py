@@ -2,6 +2,7 @@
 host-side scene preparation reproduces the reference's load-time derivations bit for bit,
 argument parsing follows the reference console, errors are loud, and the multi-GPU reduction
 protocol is exact (world_size 2 over gloo)."""
+import ctypes as C
 import os
 import re
 import sys
@@ -537,3 +538,89 @@ def test_reference_tree_binding_without_a_gpu_leaves_the_photo_alone():
     assert R.L.ref_bridge_render(R.h, C.byref(a), 63, rgb.ctypes.data_as(C.c_void_p), None) == -1
     assert not rgb.any()
     R.close()
+
+
+@pytest.fixture(scope="module")
+def sweep_mirror(tmp_path_factory):
+    """tests/tools/sah_sweep_host.cpp: the level loop of the device's sweep-SAH builder on the CPU, around csrc/sah_sweep.h"""
+    import subprocess
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "vector_types.h")):
+        pytest.skip("no CUDA headers")
+    so = str(tmp_path_factory.mktemp("sweep") / "sah_sweep_host.so")
+    r = subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-I", cuda_inc, "-I", os.path.join(ROOT, "raym0nade_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "tools", "sah_sweep_host.cpp"), "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = C.CDLL(so)
+    L.sah_sweep_host.restype = C.c_int
+    L.sah_sweep_host.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    return L
+
+
+def _half_area(lo, hi):
+    d = hi - lo
+    return d[..., 0] * d[..., 1] + d[..., 1] * d[..., 2] + d[..., 2] * d[..., 0]
+
+
+@pytest.mark.parametrize("which", ["one", "two", "three", "cornell", "heightfield", "duplicates", "glossy"])
+def test_sweep_sah_builder_steps(sweep_mirror, which):
+    """csrc/sah_sweep.h - the per-element code of the device's sweep-SAH builder (gpu_sah_bvh.cu) - driven level by level on the
+    CPU: a binary tree over every triangle exactly once, counts and boxes consistent, depth within the cap's reach, and a SAH
+    cost no worse than the object-median tree's over the same lists (the depth-cap fallback alone)"""
+    tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    if which in ("one", "two", "three"):
+        k = {"one": 1, "two": 2, "three": 3}[which]
+        pos = np.concatenate([tri + 2.0 * i for i in range(k)])
+    elif which == "cornell":
+        pos = np.asarray(scenes.cornell_box(8, 8, 0)[0].positions, np.float32).reshape(-1, 9)
+    elif which == "heightfield":
+        pos = np.asarray(scenes.heightfield_scene(20_000)[0].positions, np.float32).reshape(-1, 9)
+    elif which == "duplicates":       # coincident triangles: every split costs the same; the tie-break and the depth rule must still end the build
+        pos = np.concatenate([np.repeat(tri, 500, axis=0), np.asarray(scenes.cornell_box(8, 8, 0)[0].positions, np.float32).reshape(-1, 9)])
+    else:
+        pos = np.asarray(scenes.glossy_dielectric(60_000, 8, 8, 0)[0].positions, np.float32).reshape(-1, 9)
+    pos = np.ascontiguousarray(pos)
+    n = pos.shape[0]
+
+    def build(cap):
+        lo, hi = np.zeros((2 * n, 4), np.float32), np.zeros((2 * n, 4), np.float32)
+        left, right, count = (np.zeros(2 * n, np.int32) for _ in range(3))
+        root = C.c_int(-1)
+        levels = sweep_mirror.sah_sweep_host(pos.ctypes.data, n, cap, lo.ctypes.data, hi.ctypes.data, left.ctypes.data, right.ctypes.data, count.ctypes.data, C.byref(root))
+        assert levels >= 0, levels
+        return lo[:, :3], hi[:, :3], left, right, count, root.value, levels
+
+    def walk(tree):
+        lo, hi, left, right, count, root, _ = tree
+        seen = np.zeros(n, np.int32)
+        cost, depth_wide, stack = 0.0, 0, [(root, 0)]
+        root_area = max(float(_half_area(lo[root], hi[root])), 1e-30)
+        while stack:
+            b, d = stack.pop()
+            if right[b] < 0:
+                t = ~left[b]
+                assert 0 <= t < n and b == t and count[b] == 1
+                seen[t] += 1
+                v = pos[t].reshape(3, 3)
+                assert (v.min(0) >= lo[b]).all() and (v.max(0) <= hi[b]).all()
+                continue
+            l, r = left[b], right[b]
+            assert n <= b < 2 * n - 1 and count[b] == count[l] + count[r]
+            assert (np.minimum(lo[l], lo[r]) == lo[b]).all() and (np.maximum(hi[l], hi[r]) == hi[b]).all()
+            if count[b] > 3:
+                depth_wide = max(depth_wide, d + 1)
+                cost += float(_half_area(lo[b], hi[b])) / root_area
+            stack += [(l, d + 1), (r, d + 1)]
+        assert (seen == 1).all()
+        return cost, depth_wide
+
+    sah = build(22)
+    assert sah[4][sah[5]] == n
+    cost, depth = walk(sah)
+    need = int(np.ceil(np.log2(max(1.0, n / 3)))) + 1
+    assert depth <= max(22, need) + 1, depth
+    if n > 3:
+        median_cost, _ = walk(build(0))          # cap 0: every node takes the median fallback
+        assert cost <= median_cost * 1.0001, (cost, median_cost)
+        if which in ("heightfield", "glossy"):
+            assert cost <= 0.9 * median_cost, (cost, median_cost)

@@ -154,7 +154,7 @@ def test_closest_and_occluded_random_rays(ref, which):
     ctx.close()
 
 
-@pytest.mark.parametrize("tree,builder", [(1, 0), (2, 0), (2, 1)])
+@pytest.mark.parametrize("tree,builder", [(1, 0), (2, 0), (2, 1), (2, 3)])
 @pytest.mark.parametrize("which", ["cornell", "heightfield", "cutout", "glossy"])
 def test_secondary_ray_tree_finds_the_reference_hits(ref, which, tree, builder):
     """The estimator's bounce and shadow rays traverse a second tree over the same triangles (fast_bvh.cpp: binned SAH,

@@ -192,7 +192,7 @@ def _host_refit(nodes, pos):
     return out
 
 
-@pytest.mark.parametrize("builder", [1, 0])
+@pytest.mark.parametrize("builder", [3, 1, 0])
 @pytest.mark.parametrize("which", ["heightfield", "glossy"])
 def test_refit_for_moved_vertices(ref, which, builder):
     """rm_scene_refit: the vertices of an uploaded scene move (a travelling wave, amplitude ~ a few triangle sizes).  Afterwards
