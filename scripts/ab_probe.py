@@ -24,7 +24,7 @@ for k, v in opts.items(): ctx.set_option(k, int(v))         # before the upload:
 t0 = time.time(); ctx.upload(model); ctx.synchronize(); up1 = time.time() - t0
 t0 = time.time(); ctx.upload(model); ctx.synchronize(); up2 = time.time() - t0
 print("%-22s upload %.1f ms, again %.1f ms (host tree cache cleared: " % (label, up1 * 1e3, up2 * 1e3), end="")
-ctx.set_option("tree_builder", int(opts.get("tree_builder", 1)))      # clears the host-tree cache
+ctx.set_option("tree_builder", int(opts.get("tree_builder", 3)))      # clears the host-tree cache (3 = the library default)
 t0 = time.time(); ctx.upload(model); ctx.synchronize(); print("%.1f ms)  tree %s" % ((time.time() - t0) * 1e3, ctx.tree_info()), flush=True)
 ctx.trace_primary(args, download=False); ctx.gbuffer(args, download=False)
 ctx.render_samples(args, seed=1); ctx.synchronize()          # warm-up

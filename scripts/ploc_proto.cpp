@@ -72,6 +72,8 @@ static Bin ploc(int n, int R) {
 }
 static int small_sub(const Bin &N, int b, int tri[8]) { if (N.right[b] < 0) { tri[0] = ~N.left[b]; return 1; } int n = 0; n += small_sub(N, N.left[b], tri + n); n += small_sub(N, N.right[b], tri + n); return n; }
 static int COLLAPSE_MODE = 0;
+static int EXACT_BOXES = 0;          // 1: the traversal tests the children's true boxes instead of the decoded 8-bit ones (what does the grid cost?)
+static std::vector<float> gExact;    // [node][child][6]
 static void collapse(const Bin &N, std::vector<RmWideNode> &W, std::vector<int> &order, int *levels) {
     struct It { int bin, slot; };
     std::vector<It> cur{{N.root, 0}}, nxt; W.assign(1, RmWideNode{}); order.clear(); int lv = 0;
@@ -79,6 +81,51 @@ static void collapse(const Bin &N, std::vector<RmWideNode> &W, std::vector<int> 
         for (auto it : cur) { int ch[4], n = 0;
             if (N.count[it.bin] <= gLeafMax) ch[n++] = it.bin; else { ch[n++] = N.left[it.bin]; ch[n++] = N.right[it.bin];
                 while (n < 4) { int open = -1; float oa = -1; for (int k = 0; k < n; k++) if (N.count[ch[k]] > gLeafMax) { float a = area(N.box[ch[k]]); if (COLLAPSE_MODE == 1) a *= float(N.count[ch[k]]); if (COLLAPSE_MODE == 2) a = float(N.count[ch[k]]); if (open < 0 || a > oa) { open = k; oa = a; } } if (open < 0) break; int b = ch[open]; ch[open] = N.left[b]; ch[n++] = N.right[b]; } }
+            float lo[4][3], hi[4][3]; int ni = 0, nt = 0;
+            for (int k = 0; k < n; k++) { for (int a = 0; a < 3; a++) { lo[k][a] = N.box[ch[k]].lo[a]; hi[k][a] = N.box[ch[k]].hi[a]; } if (N.count[ch[k]] > gLeafMax) ni++; else nt += N.count[ch[k]]; }
+            RmWideNode w; memset(&w, 0, sizeof(w)); wide_quantise(lo, hi, n, w);
+            if (gExact.size() < (size_t(it.slot) + 1) * 24) gExact.resize((size_t(it.slot) + 1) * 24 * 2); for (int k = 0; k < n; k++) for (int a = 0; a < 3; a++) { gExact[size_t(it.slot) * 24 + k * 6 + a] = lo[k][a]; gExact[size_t(it.slot) * 24 + k * 6 + 3 + a] = hi[k][a]; }
+            w.child_base = ni ? int(W.size()) : 0; w.tri_base = int(order.size()); if (ni) W.resize(W.size() + ni);
+            int ki = 0, toff = 0;
+            for (int k = 0; k < n; k++) { if (N.count[ch[k]] > gLeafMax) { w.meta[k] = uint8_t(0x80 | ki); nxt.push_back({ch[k], w.child_base + ki}); ki++; } else { int tri[8]; int c = small_sub(N, ch[k], tri); w.meta[k] = uint8_t((toff << 2) | c); for (int t = 0; t < c; t++) order.push_back(tri[t]); toff += c; } }
+            W[it.slot] = w; }
+        cur.swap(nxt); }
+    *levels = lv;
+}
+// SAH-optimal collapse (after Ylitie et al. 2017): T[b][k] = cheapest way to hand subtree b to its wide parent as <= k+1 children
+static float C_NODE = 1.0f, C_TRI = 0.37f;
+static void dp_collapse(const Bin &N, std::vector<RmWideNode> &W, std::vector<int> &order, int *levels) {
+    const int total = int(N.box.size());
+    std::vector<float> T(size_t(total) * 4, 0.0f); std::vector<uint8_t> J(size_t(total) * 4, 0);     // J[b][k]: children given to the left subtree (0 = b stays whole)
+    // post-order
+    std::vector<int> post; post.reserve(total); { std::vector<std::pair<int,int>> st{{N.root, 0}}; while (!st.empty()) { auto [b, ph] = st.back(); st.pop_back(); if (N.count[b] <= gLeafMax) { post.push_back(b); continue; } if (ph == 0) { st.push_back({b, 1}); st.push_back({N.left[b], 0}); st.push_back({N.right[b], 0}); } else post.push_back(b); } }
+    float ra = area(N.box[N.root]);
+    for (int b : post) {
+        float *t = &T[size_t(b) * 4]; uint8_t *j = &J[size_t(b) * 4];
+        if (N.count[b] <= gLeafMax) { float c = area(N.box[b]) / ra * N.count[b] * C_TRI; for (int k = 0; k < 4; k++) { t[k] = c; j[k] = 0; } continue; }
+        const float *tl = &T[size_t(N.left[b]) * 4], *tr = &T[size_t(N.right[b]) * 4];
+        // opened into k+1 pieces (k >= 1): left gets a pieces, right k+1-a
+        float open[4]; uint8_t oj[4]; open[0] = INFINITY; oj[0] = 0;
+        for (int k = 1; k < 4; k++) { open[k] = INFINITY; oj[k] = 0; for (int a = 1; a <= k; a++) { float c = tl[a - 1] + tr[k - a]; if (c < open[k]) { open[k] = c; oj[k] = uint8_t(a); } } }
+        const float whole = area(N.box[b]) / ra * C_NODE + open[3];      // b as a wide node of its own: always worth all four slots
+        t[0] = whole; j[0] = 0;
+        for (int k = 1; k < 4; k++) { t[k] = whole; j[k] = 0; if (open[k] < t[k]) { t[k] = open[k]; j[k] = oj[k]; } if (t[k - 1] < t[k]) { t[k] = t[k - 1]; j[k] = j[k - 1]; /* fewer pieces */ } }
+        // remember the opening of b itself in slot 3 of a side table: reuse J[b][.] only for 'as a child'; the node's own split is oj[3]
+        J[size_t(b) * 4 + 0] = oj[3];      // (slot 0 as a child is always 'whole', so its J is free)
+    }
+    struct It { int bin, slot; };
+    std::vector<It> cur{{N.root, 0}}, nxt; W.assign(1, RmWideNode{}); order.clear(); int lv = 0;
+    while (!cur.empty()) { lv++; nxt.clear();
+        for (auto it : cur) { int ch[4], n = 0;
+            if (N.count[it.bin] <= gLeafMax) ch[n++] = it.bin; else {
+                // expand: (node, pieces-1 budget)
+                struct E { int b, k; }; std::vector<E> st; int a = J[size_t(it.bin) * 4 + 0]; st.push_back({N.right[it.bin], 3 - a}); st.push_back({N.left[it.bin], a - 1});
+                while (!st.empty()) { E e = st.back(); st.pop_back(); int jj = (N.count[e.b] <= gLeafMax || e.k == 0) ? 0 : J[size_t(e.b) * 4 + e.k];
+                    // J[b][k] with k>=1: 0 = whole (or fewer pieces chain) ; we stored fewer-pieces by copying j, so jj is final
+                    if (jj == 0) { ch[n++] = e.b; continue; }
+                    // find the k' actually used: pieces = largest k' <= e.k with T equal; simpler: recompute
+                    int kk = e.k; while (kk > 1 && T[size_t(e.b) * 4 + kk] == T[size_t(e.b) * 4 + kk - 1]) kk--; jj = J[size_t(e.b) * 4 + kk]; if (jj == 0) { ch[n++] = e.b; continue; }
+                    st.push_back({N.right[e.b], kk - jj}); st.push_back({N.left[e.b], jj - 1}); } }
             float lo[4][3], hi[4][3]; int ni = 0, nt = 0;
             for (int k = 0; k < n; k++) { for (int a = 0; a < 3; a++) { lo[k][a] = N.box[ch[k]].lo[a]; hi[k][a] = N.box[ch[k]].hi[a]; } if (N.count[ch[k]] > gLeafMax) ni++; else nt += N.count[ch[k]]; }
             RmWideNode w; memset(&w, 0, sizeof(w)); wide_quantise(lo, hi, n, w);
@@ -100,7 +147,7 @@ static void trace(const std::vector<RmWideNode> &W, const std::vector<int> &orde
             if (cur >= 0) { const RmWideNode &nd = W[cur]; visits++;
                 struct K { float tn; int ref; } ks[4]; int nk = 0;
                 for (int c = 0; c < 4; c++) { if (!nd.meta[c]) continue; boxes++; float tn = tmin, tf = t;
-                    for (int a = 0; a < 3; a++) { float ax = nd.s[a] * inv[a], bx = (nd.o[a] - o[a]) * inv[a]; float t0 = nd.qlo[a][c] * ax + bx, t1 = nd.qhi[a][c] * ax + bx; if (inv[a] < 0) std::swap(t0, t1); tn = std::max(tn, t0); tf = std::min(tf, t1); }
+                    for (int a = 0; a < 3; a++) { float ax = nd.s[a] * inv[a], bx = (nd.o[a] - o[a]) * inv[a]; float t0 = nd.qlo[a][c] * ax + bx, t1 = nd.qhi[a][c] * ax + bx; if (EXACT_BOXES) { t0 = (gExact[size_t(cur) * 24 + c * 6 + a] - o[a]) * inv[a]; t1 = (gExact[size_t(cur) * 24 + c * 6 + 3 + a] - o[a]) * inv[a]; } if (inv[a] < 0) std::swap(t0, t1); tn = std::max(tn, t0); tf = std::min(tf, t1); }
                     if (tn * 0.999998f <= tf * 1.000002f + 1e-4f) { uint8_t mm = nd.meta[c]; int ref = (mm & 0x80) ? nd.child_base + (mm & 0x7f) : ~(((nd.tri_base + (mm >> 2)) << 4) | (mm & 3)); ks[nk++] = {tn, ref}; } }
                 std::sort(ks, ks + nk, [](const K &a, const K &b) { return a.tn < b.tn; });
                 for (int c = nk - 1; c >= 1; c--) { st[sp++] = {ks[c].ref, ks[c].tn}; pushes++; } maxsp = std::max(maxsp, sp);
@@ -140,6 +187,8 @@ int main(int argc, char **argv) {
         fprintf(stderr, "host binary SAH cost: inner %.2f leaf %.2f depth %d\n", ci, cl_, d); }
       rm_build_wide_bvh(bin, order, n, w, worder, &wd);
       std::vector<int> o2(worder.begin(), worder.end()); char nm[64]; snprintf(nm, 64, "host SAH (levels %d)", wd); trace(w, o2, nm); }
-    for (int i = 1; i < argc; i++) { if (!strncmp(argv[i], "sweep", 5)) { int cap = 22; sscanf(argv[i], "sweep:%d", &cap); gLeafMax = 3; COLLAPSE_MODE = 0; Bin T = sweep_tree(n, cap); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "sweep SAH mirror cap%d (lv %d)", cap, lv); trace(W, order, nm); continue; }
+    for (int i = 1; i < argc; i++) { if (!strcmp(argv[i], "exact")) { EXACT_BOXES = 1; continue; } if (!strcmp(argv[i], "quant")) { EXACT_BOXES = 0; continue; }
+      if (!strncmp(argv[i], "sweep", 5)) { int cap = 22; sscanf(argv[i], "sweep:%d", &cap); gLeafMax = 3; COLLAPSE_MODE = 0; Bin T = sweep_tree(n, cap); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "sweep SAH mirror cap%d (lv %d)", cap, lv); trace(W, order, nm);
+        for (float ct : {0.2f, 0.37f, 0.6f, 1.0f}) { C_TRI = ct; dp_collapse(T, W, order, &lv); snprintf(nm, 64, "  + DP collapse c_tri %.2f (lv %d)", ct, lv); trace(W, order, nm); } continue; }
       int R = 16, lm = 3, om = 0, mt = 0, tk = 0, tw = 0; sscanf(argv[i], "%d:%d:%d:%d:%d:%d", &R, &lm, &om, &mt, &tk, &tw); TOPK = tk; TOPW = tw; gLeafMax = lm; COLLAPSE_MODE = om; METRIC = mt; Bin T = ploc(n, R); std::vector<RmWideNode> W; std::vector<int> order; int lv; collapse(T, W, order, &lv); char nm[64]; snprintf(nm, 64, "PLOC R=%d l%d o%d m%d top%d w%d (lv %d)", R, lm, om, mt, tk, tw, lv); trace(W, order, nm); }
 }
