@@ -277,7 +277,11 @@ int rm_tree_info(const RmContext *ctx, int32_t out[4]);
  * reference's own BVH in the reference's visit order, like primary rays and the per-ray seam always are; 0 lets them use the
  * library's second tree over the same triangles (same box / triangle tests, binned-SAH topology - the closest accepted hit is
  * the same, far fewer tests per ray) - "secondary_tree" 1: as the binary tree, 2 (default): collapsed to 4-wide nodes with
- * quantised child boxes and a conservative slab test.  "count_tests", "time_kernels": counters / per-kind device timing.  The others
+ * quantised child boxes and a conservative slab test.  "tree_builder" 3 (default) | 1 | 2 | 0: who builds that tree - the
+ * device by a top-down sweep SAH at every upload, the device by PLOC clustering, PLOC followed by a background refinement on
+ * the host, the host; "lazy_tree" 1 (default) | 0: the sweep-SAH build waits for the first call that needs the tree
+ * (rm_render_samples with samples to draw, rm_tree_info) instead of running inside rm_scene_upload.
+ * "count_tests", "time_kernels": counters / per-kind device timing.  The others
  * ("trace_refill", "wave_paths", "stack_levels", ...) are tuning and test hooks, see rm_api.cu. */
 int rm_set_option(RmContext *ctx, const char *name, int64_t value);
 /* Per-kernel-kind breakdown.  Kinds: 0 primary / batched per-ray kernels, 1 closest hit over the

@@ -209,6 +209,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     ctx->launches++;
     RM_CUDA(cudaGetLastError());
     mark("faces: H2D + records");
+    for (int a = 0; a < 3; a++) ctx->scene_lo[a] = sc->nodes[1].v0[a];
 
     // The secondary-ray tree.  Default: built on the device from the positions just uploaded (gpu_sah_bvh.cu: top-down sweep
     // SAH, every level a few scans over all triangles, then the 4-wide collapse - ~8 ms per million triangles, so every upload
@@ -219,7 +220,14 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     {
         bool device_tree = false;
         ctx->have_fast = false;
-        if (ctx->tree_builder_mode >= 1) {
+        // The sweep-SAH build is deferred to the first call that needs the tree (rm_ensure_secondary_tree: rm_render_samples with
+        // samples to draw, rm_tree_info): a scene that is only ever hit by primary rays (previews, G-buffers, BASELINE's configs[4])
+        // never pays for it, and the positions it works from stay on the device anyway (b_raw[0], what rm_scene_refit replaces).
+        ctx->wide_pending = ctx->tree_builder_mode == 3 && ctx->lazy_tree && ctx->seam_tree == 0 && !ctx->want_binary_tree;
+        if (ctx->wide_pending) {
+            ctx->have_wide = false;
+            device_tree = true;
+        } else if (ctx->tree_builder_mode >= 1) {
             int wlevels = 0, wnodes = 0;
             const RmBvhNode &rootbox = sc->nodes[1];           // the reference tree's root box = the scene bounds
             if (ctx->tree_builder_mode == 3) rc = rm_gpu_build_wide_sah(ctx, ctx->b_raw[0].as<float>(), n, ctx->fast_depth_cap, rootbox.v0, &wlevels, &wnodes);
@@ -442,6 +450,38 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
     return RM_OK;
 }
 
+// The deferred build of the secondary-ray tree (see rm_scene_upload): from the positions on the device, whatever rm_scene_refit
+// has made of them since.
+int rm_ensure_secondary_tree(RmContext *ctx) {
+    if (!ctx || !ctx->wide_pending || !ctx->has_scene) return RM_OK;
+    ctx->wide_pending = false;
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->scene.n_faces;
+    int rc, wlevels = 0, wnodes = 0;
+    if ((rc = rm_gpu_build_wide_sah(ctx, ctx->b_raw[0].as<float>(), n, ctx->fast_depth_cap, ctx->scene_lo, &wlevels, &wnodes))) return rc;
+    // (the builder's depth rule keeps the binary tree within the cap + 2 levels, and a wide level spans at least one binary level)
+    if (3 * wlevels > ctx->tune_wide.smem_levels + rm::kStackSpillWide)
+        return rm_fail(RM_ERR_STATE, "rm_ensure_secondary_tree: %d levels exceed the traversal stack", wlevels);
+    ctx->stack_levels_wide = std::max(3 * wlevels, 2);
+    ctx->wide_nodes = wnodes;
+    ctx->wide_levels = wlevels;
+    ctx->wide_built_by = 3;
+    ctx->host_wide_valid = false;
+    if ((rc = ctx->b_tri_wide.alloc(size_t(n) * 16 * kTriStride))) return rc;
+    k_permute_tris<<<(n + 255) / 256, 256, 0, st>>>(ctx->b_tri.as<float4>(), ctx->b_facemap_wide.as<int>(), n, ctx->b_tri_wide.as<float4>());
+    ctx->launches += 2;
+    RM_CUDA(cudaGetLastError());
+    ctx->have_wide = true;
+    ctx->scene_wide = ctx->scene;
+    ctx->scene_wide.nodes = ctx->b_nodes_wide.as<float4>();
+    ctx->scene_wide.tri = ctx->b_tri_wide.as<float4>();
+    ctx->scene_wide.face_map = ctx->b_facemap_wide.as<int32_t>();
+    ctx->scene_wide.root_is_leaf = 0;
+    ctx->scene_wide.wide = 1;
+    ctx->scene_wide_first = ctx->scene_wide;
+    return RM_OK;
+}
+
 // After rm_scene_refit (gpu_ref_bvh.cu) has put new positions into b_raw[0]: the traversal and shading records are formed anew and
 // re-permuted for the 4-wide tree(s).  The binary form of the secondary-ray tree is not refitted: whoever asks for it afterwards
 // gets the reference's tree.
@@ -526,9 +566,12 @@ int rm_install_refined_tree(RmContext *ctx) {
 }
 
 // {1 when the 4-wide tree came from the device builder (0: host), its 64-byte records, its levels, 1 when bounce / shadow rays use it}
-int rm_tree_info(const RmContext *ctx, int32_t out[4]) {
-    if (!ctx || !out) return rm_fail(RM_ERR_INVALID, "rm_tree_info: null argument");
-    if (!ctx->has_scene) return rm_fail(RM_ERR_STATE, "rm_tree_info: no scene uploaded");
+int rm_tree_info(const RmContext *ctx_in, int32_t out[4]) {
+    if (!ctx_in || !out) return rm_fail(RM_ERR_INVALID, "rm_tree_info: null argument");
+    if (!ctx_in->has_scene) return rm_fail(RM_ERR_STATE, "rm_tree_info: no scene uploaded");
+    RmContext *ctx = const_cast<RmContext *>(ctx_in);          // a deferred build happens now: the caller asks what the rays will traverse
+    const int rc_build = rm_ensure_secondary_tree(ctx);
+    if (rc_build) return rc_build;
     out[0] = ctx->have_wide && !ctx->host_wide_valid ? (ctx->use_refined ? 2 : ctx->wide_built_by == 3 ? 3 : 1) : 0;
     out[1] = ctx->use_refined ? ctx->refined_nodes : ctx->wide_nodes;
     out[2] = ctx->use_refined ? ctx->refined_levels : ctx->wide_levels;
@@ -697,7 +740,7 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     if (!std::strcmp(name, "seam_secondary_tree")) {
         ctx->seam_tree = int(std::min<int64_t>(std::max<int64_t>(value, 0), 2));
         if (ctx->seam_tree == 1) ctx->want_binary_tree = true;           // takes effect at the next rm_scene_upload
-        return RM_OK;
+        return ctx->seam_tree ? rm_ensure_secondary_tree(ctx) : RM_OK;   // a deferred build of the 4-wide tree happens now
     }
     // bounce and shadow rays: 1 = the binary secondary-ray tree (host-built; set before rm_scene_upload), 2 = the 4-wide quantised tree (default)
     if (!std::strcmp(name, "secondary_tree")) { ctx->secondary_tree = value == 1 ? 1 : 2; if (value == 1) ctx->want_binary_tree = true; return RM_OK; }
@@ -705,8 +748,12 @@ int rm_set_option(RmContext *ctx, const char *name, int64_t value) {
     // 2: PLOC, then refined in the background by the host builder (the render loop swaps the better tree in when it is ready);
     // 0: on the host, cached by geometry hash
     if (!std::strcmp(name, "tree_builder")) { ctx->tree_builder_mode = int(std::min<int64_t>(std::max<int64_t>(value, 0), 3)); ctx->fast_key_valid = false; return RM_OK; }
-    // block until the background refinement (if any) has finished and install its tree
+    // 1 (default): the sweep-SAH build of the secondary-ray tree waits for the first call that needs the tree; 0: rm_scene_upload builds it
+    if (!std::strcmp(name, "lazy_tree")) { ctx->lazy_tree = value != 0; return RM_OK; }
+    // block until the secondary-ray tree is in place: a deferred build runs, a background refinement (if any) finishes and its tree is installed
     if (!std::strcmp(name, "tree_wait")) {
+        const int rc_build = rm_ensure_secondary_tree(ctx);
+        if (rc_build) return rc_build;
         rm_start_refinement(ctx, kRefineMinSamples);
         if (ctx->refine && ctx->refine->th.joinable()) ctx->refine->th.join();
         return rm_install_refined_tree(ctx);

@@ -104,6 +104,8 @@ struct RmContext {
                                            // 1: on the device by Morton sort + PLOC (gpu_bvh.cu; a 3 ms build, ~14 % more node visits per ray); 2: PLOC, then
                                            // refined by the host builder in the background; 0: on the host (fast_bvh.cpp + wide_bvh.cpp), cached by geometry hash
     int wide_built_by = 0;                 // the builder mode that made the tree in b_nodes_wide
+    bool lazy_tree = true, wide_pending = false;      // the sweep-SAH build waits for the first call that needs the tree (rm_ensure_secondary_tree)
+    float scene_lo[3] = {0, 0, 0};         // lower corner of the scene bounds (the reference tree's root box)
     int fast_depth_cap = 22;               // depth cap of the secondary-ray tree = its traversal stack entries (8 CTAs x 128 threads x 8 B x depth of shared memory per SM)
     int fast_leaf_max = 3;                 // triangles per leaf of the secondary-ray tree (A/B of 2..8 and caps 20..24: profiles/r01f_ab16_secondary_tree.txt)
     bool fast_root_is_leaf = false, fast_key_valid = false;
@@ -168,6 +170,8 @@ int rm_build_fast_bvh(const float *positions, int n, int depth_cap, int leaf_max
 int rm_build_fast_bvh_cancellable(const float *positions, int n, int depth_cap, int leaf_max, std::vector<RmBvhNode> &nodes, std::vector<int32_t> &order, int *depth_out,
                                   const std::atomic<bool> *cancel);
 // implemented in wide_bvh.cpp (declared in wide_bvh.h)
+// implemented in rm_api.cu: the deferred build of the secondary-ray tree, if one is pending
+extern "C" int rm_ensure_secondary_tree(RmContext *ctx);
 // implemented in rm_api.cu: swaps the background-refined secondary-ray tree in once it is ready (no-op otherwise)
 extern "C" int rm_install_refined_tree(RmContext *ctx);
 // implemented in rm_api.cu: launches the pending background refinement if `pixel_samples` of rendering are about to follow that make

@@ -274,6 +274,7 @@ int rm_render_samples(RmContext *ctx, const RmRenderArgs *args, int32_t sample_b
     const int tgrid = R->sm_count * kTraceCtasPerSm;
     const bool ct = ctx->count_tests;
     // bounce and shadow rays: the secondary-ray tree unless the caller asked for the reference's traversal order throughout
+    if (n_d + n_a > 0 && !ctx->exact_secondary && (rc = rm_ensure_secondary_tree(ctx))) return rc;          // a deferred build of that tree happens now
     rm_start_refinement(ctx, int64_t(npix) * std::max(n_d + n_a, 1));          // a pending background refinement: worth it for this much rendering?
     if ((rc = rm_install_refined_tree(ctx))) return rc;          // a background-refined tree that became ready since the last call
     const bool use_wide = !ctx->exact_secondary && ctx->have_wide && (ctx->secondary_tree == 2 || !ctx->have_fast);

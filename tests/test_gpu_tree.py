@@ -207,6 +207,7 @@ def test_refit_for_moved_vertices(ref, which, builder):
     model = Model(scene)
     ctx = Context(0)
     ctx.set_option("tree_builder", builder)
+    ctx.set_option("lazy_tree", 0)           # the tree is built by the upload, so that it is there to be refitted
     ctx.upload(model)
     n = model.n_faces
     old = np.frombuffer((C.c_char * (36 * n)).from_address(model.desc.positions), np.float32).reshape(n, 3, 3).copy()
@@ -259,3 +260,44 @@ def test_refit_for_moved_vertices(ref, which, builder):
     assert np.isfinite(a).all() and abs(a.sum() - b.sum()) <= 0.05 * abs(b.sum()) + 1e-6
     ctx.close()
     ctx2.close()
+
+
+def test_secondary_tree_is_built_when_first_needed():
+    """The sweep-SAH build of the secondary-ray tree is deferred to the first call that needs the tree (rm_ensure_secondary_tree):
+    an upload followed by primary rays and a G-buffer launches no builder kernel, the first render builds the tree, and the frame
+    is the frame of a context whose upload built it ("lazy_tree" 0); vertices moved in between are what it is built from."""
+    scene, args = scenes.glossy_dielectric(60_000, 160, 90, 4)
+    model = Model(scene)
+    lazy, eager = Context(0), Context(0)
+    eager.set_option("lazy_tree", 0)
+    for c in (lazy, eager):
+        c.stats_reset()
+        c.upload(model)
+    l0, e0 = lazy.stats()["launches"], eager.stats()["launches"]
+    assert l0 + 50 < e0, (l0, e0)                      # 20-odd levels of the builder at a handful of launches each
+    lazy.trace_primary(args)
+    lazy.gbuffer(args)
+    assert lazy.stats()["launches"] <= l0 + 4
+    a, b = lazy.render(args, seed=9), eager.render(args, seed=9)
+    for plane in ("Dd", "Ds", "Id", "Is"):              # (same tree, same draws; float atomics sum in their own order)
+        x, y = a[plane]["radiance"].astype(np.float64), b[plane]["radiance"].astype(np.float64)
+        assert np.abs(x - y).max() <= 2e-4 * (1.0 + np.abs(x).max()), plane
+        assert abs(x.sum() - y.sum()) <= 1e-5 * abs(x.sum()) + 1e-6, plane
+    ia, ib = lazy.tree_info(), eager.tree_info()
+    assert ia == ib and ia["builder"] == "sweep_sah" and ia["in_use"]
+    # moved vertices before the first render: the deferred build sees the new positions (the refit has nothing to refit yet)
+    n = model.n_faces
+    old = np.frombuffer((C.c_char * (36 * n)).from_address(model.desc.positions), np.float32).reshape(n, 3, 3).copy()
+    new = old.copy()
+    new[..., 1] += (0.05 * np.sin(old[..., 0] * 3.0)).astype(np.float32)
+    new = np.ascontiguousarray(new, np.float32)
+    c1, c2 = Context(0), Context(0)
+    c2.set_option("lazy_tree", 0)
+    for c in (c1, c2):
+        c.upload(model)
+        c.refit(new)
+    r1, r2 = c1.render(args, seed=11), c2.render(args, seed=11)
+    s1, s2 = float(r1["Id"]["radiance"].astype(np.float64).sum()), float(r2["Id"]["radiance"].astype(np.float64).sum())
+    assert np.isfinite(r1["Id"]["radiance"]).all() and abs(s1 - s2) <= 0.05 * abs(s2) + 1e-6
+    for c in (lazy, eager, c1, c2):
+        c.close()
