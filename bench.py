@@ -17,7 +17,7 @@ metric = Mrays/s (one ray = one BVH::rayHit invocation, closest-hit or occlusion
 pixel-samples/s and time-to-spp are reported beside it.
   value           : device-resident - scene already in HBM, no host copies in the timed region
   e2e             : through the C ABI the reference would bind, with HOST buffers, nothing cached between steps: per step
-                    rm_scene_upload (scene H2D + the secondary-ray tree rebuilt on the device) + the render + the frame D2H
+                    rm_scene_upload (scene H2D) + the render (which first rebuilds the secondary-ray tree on the device) + the frame D2H
   e2e_first_frame : the first frame of a fresh process on the host clock, context creation and scene preparation (reference tree built on the device) included
 Multi-GPU: samples are sharded by interleaved index (rank, world) with no data-path collective
 during sampling; per step the fp32 accumulators are exchanged over NCCL inside the timed region
@@ -279,10 +279,10 @@ def run_ours(opt, rank, world, local_rank):
         c0.close()
         m0.close()
         first_frame = {"spp": ff_spp, "total_s": t4 - t1, "context_create_s": t2 - t1, "prepare_scene_device_tree_s": t2b - t2,
-                       "scene_upload_and_tree_build_s": t3 - t2b, "render_and_download_s": t4 - t3, "secondary_tree": tree,
+                       "scene_upload_s": t3 - t2b, "render_incl_secondary_tree_build_and_download_s": t4 - t3, "secondary_tree": tree,
                        "prepare_scene_host_s": t_prepare,
                        "note": "fresh context, nothing cached: rm_context_create + rm_prepare_scene_device (reference tree built on the device; mips, lights, "
-                               "permuted face streams on the host) + rm_scene_upload (secondary-ray tree built on the device) + rm_render into pageable "
+                               "permuted face streams on the host) + rm_scene_upload + rm_render (its first call builds the secondary-ray tree on the device: sweep SAH) into pageable "
                                "host arrays, at %d spp; prepare_scene_host_s = the all-host rm_prepare_scene of the same scene, for comparison (not in "
                                "total_s)" % ff_spp}
         del g_host, p_host
@@ -373,7 +373,7 @@ def run_ours(opt, rank, world, local_rank):
     tree_info = ctx.tree_info()                 # the tree the timed steps traversed
 
     # --- end to end through the C ABI with HOST buffers: every step stages the scene again (rm_scene_upload: H2D of the
-    # prepared scene + the secondary-ray tree rebuilt on the device - nothing is cached between steps), renders, and brings
+    # prepared scene; the secondary-ray tree is rebuilt on the device by the render that follows - nothing is cached between steps), renders, and brings
     # the frame to host memory.  N > 1: the frame lands in one pinned shared-memory frame every rank maps; each rank writes
     # its slice of it (rm_reduce_scatter + rm_resolve_slice), rank 0 owns the whole frame after the closing barrier.
     frame = SharedFrame(npix, rank, world, os.environ.get("MASTER_PORT", str(os.getpid())), barrier)
@@ -505,7 +505,7 @@ def run_ours(opt, rank, world, local_rank):
                         "time_to_spp_s": {str(args.spp): float(e2e_s.item()) / e2e_steps},
                         "scene_upload_ms": upload_s * 1e3, "frame_finite": frame_ok, "frame_pinned": frame_pinned,
                         "scene_pinned": not opt.pageable_scene,
-                        "note": "per step and per rank: rm_scene_upload (prepared scene from " + ("pageable" if opt.pageable_scene else "page-locked") + " host memory + the secondary-ray tree rebuilt on the device, "
+                        "note": "per step and per rank: rm_scene_upload (prepared scene from " + ("pageable" if opt.pageable_scene else "page-locked") + " host memory; the secondary-ray tree is rebuilt on the device by the render that follows, "
                                 "nothing cached) + primary + G-buffer + the rank's sample shard + exchange + resolve + download into a pinned host frame"
                                 + ("" if world == 1 else " shared by the ranks (each DMAs its 1/%d slice)" % world)},
                 "e2e_first_frame": first_frame,
