@@ -175,9 +175,14 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
 
     // nodes: same 32-byte images, heap-indexed; the array is padded to an even count so that
     // every child pair (2u, 2u+1) is a whole 64-byte block
-    std::vector<RmBvhNode> nodes(size_t(sc->n_nodes + 2) & ~size_t(1));
-    std::memcpy(nodes.data(), sc->nodes, sizeof(RmBvhNode) * sc->n_nodes);
-    if ((rc = upload(ctx->b_nodes, nodes.data(), nodes.size() * sizeof(RmBvhNode), st, total))) return rc;
+    // (straight from the caller's array - a DMA when it is page-locked, rm_prepared_pin -, the padding record or two zeroed on the device)
+    {
+        const size_t padded = size_t(sc->n_nodes + 2) & ~size_t(1);
+        if ((rc = ctx->b_nodes.alloc(padded * sizeof(RmBvhNode)))) return rc;
+        RM_CUDA(cudaMemcpyAsync(ctx->b_nodes.p, sc->nodes, sizeof(RmBvhNode) * size_t(sc->n_nodes), cudaMemcpyHostToDevice, st));
+        RM_CUDA(cudaMemsetAsync(ctx->b_nodes.as<RmBvhNode>() + sc->n_nodes, 0, (padded - size_t(sc->n_nodes)) * sizeof(RmBvhNode), st));
+        total += int64_t(sizeof(RmBvhNode) * size_t(sc->n_nodes));
+    }
 
     // materials (needed first for the per-triangle cut-out flag)
     std::vector<DevMaterial> mats(std::max(sc->n_materials, 1));

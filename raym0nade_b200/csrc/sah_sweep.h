@@ -79,11 +79,16 @@ RM_SHD SweepItem sweep_item(const Level &V, int idx) {
     const int n = V.n, a = idx / (2 * n), r = idx - a * 2 * n;
     const bool rev = r >= n;
     const int i = rev ? r - n : r, pos = rev ? n - 1 - i : i;
-    const int t = list_of(V, a)[pos], nd = V.nodeid[pos];
-    int flag = 1;
-    if (i > 0 && nd >= 0) flag = V.nodeid[rev ? pos + 1 : pos - 1] != nd;
-    const float4 lo = V.tlo[t], hi = V.thi[t];
+    const int nd = V.nodeid[pos];
     SweepItem it;
+    if (nd < 0) {               // a finished position is a segment of its own whose prefix nobody reads: no need to fetch its box
+        it.lx = it.ly = it.lz = it.hx = it.hy = it.hz = 0.0f; it.flag = 1; it.pad = 0;
+        return it;
+    }
+    const int t = list_of(V, a)[pos];
+    int flag = 1;
+    if (i > 0) flag = V.nodeid[rev ? pos + 1 : pos - 1] != nd;
+    const float4 lo = V.tlo[t], hi = V.thi[t];
     it.lx = lo.x; it.ly = lo.y; it.lz = lo.z; it.flag = flag;
     it.hx = hi.x; it.hy = hi.y; it.hz = hi.z; it.pad = 0;
     return it;
