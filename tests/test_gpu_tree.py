@@ -301,3 +301,33 @@ def test_secondary_tree_is_built_when_first_needed():
     assert np.isfinite(r1["Id"]["radiance"]).all() and abs(s1 - s2) <= 0.05 * abs(s2) + 1e-6
     for c in (lazy, eager, c1, c2):
         c.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+def test_sweep_sah_tree_of_a_handful_of_triangles(ref, k):
+    """the device's sweep-SAH builder on scenes of 1, 2, 3 and 5 triangles (no level loop at all; one split; one leaf; the first
+    real collapse): the seam through its 4-wide tree finds the reference's hits, and a render comes back finite"""
+    from test_gpu_trace import _random_rays
+    b = scenes.SceneBuilder("handful")
+    light, grey = b.emissive(255), b.diffuse(180, 180, 180)
+    rng = np.random.default_rng(k)
+    for i in range(k):
+        c = np.array([1.5 * i, 0.0, 0.3 * i])
+        tri = c + rng.uniform(-1.0, 1.0, (3, 3))
+        b.add(tri[None], None, None, light if i == 0 else grey)
+    scene = b.build()
+    args = scenes.camera((0.5 * k, 0.5, 6.0), (0.5 * k, 0.0, 0.0), 64, 48, hfov_tan=0.8, exposure=1.0, P_Direct=0.5, spp=4)
+    model = Model(scene)
+    ctx = Context(0)
+    ctx.set_option("seam_secondary_tree", 2)
+    ctx.upload(model)
+    info = ctx.tree_info()
+    assert info["builder"] == "sweep_sah" and info["in_use"] and info["levels"] >= 1
+    org, d = _random_rays(scene, 5_000, 3)
+    tri, t = ctx.trace_closest(org, d)
+    rtri, rt = ref.RefScene(scene).trace_closest(org, d)
+    assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)) and np.array_equal(tri, rtri)
+    out = ctx.render(args, seed=2)
+    for plane in ("Dd", "Ds", "Id", "Is"):
+        assert np.isfinite(out[plane]["radiance"]).all()
+    ctx.close()
