@@ -41,7 +41,8 @@ using namespace rm_sah;
 
 constexpr int kBlock = 256;
 
-__global__ void __launch_bounds__(kBlock) k_tri_boxes(const float *__restrict__ pos, int n, float3 fallback, Tree T, float *__restrict__ keys, int *__restrict__ ids) {
+__global__ void __launch_bounds__(kBlock) k_tri_boxes(const float *__restrict__ pos, int n, float3 fallback, Tree T, float4 *__restrict__ tbox, float *__restrict__ keys,
+                                                      int *__restrict__ ids) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float *p = pos + size_t(t) * 9;
@@ -57,6 +58,8 @@ __global__ void __launch_bounds__(kBlock) k_tri_boxes(const float *__restrict__ 
     const float4 l = make_float4(lo[0], lo[1], lo[2], 0.0f), h = make_float4(hi[0], hi[1], hi[2], 0.0f);
     T.lo[t] = l;
     T.hi[t] = h;
+    tbox[2 * size_t(t)] = l;
+    tbox[2 * size_t(t) + 1] = h;
     T.left[t] = ~t;
     T.right[t] = -1;
     T.count[t] = 1;
@@ -144,16 +147,19 @@ __device__ __forceinline__ SweepItem cta_exclusive(const SweepItem &mine, SweepI
     return op(s_warp[warp], excl);
 }
 
-__global__ void __launch_bounds__(kBlock) k_union_fold(Level V, int total, SweepItem *__restrict__ tile_agg) {
+// grid = (tiles per row, 6 rows): a tile never straddles two rows, and nobody divides by n
+__global__ void __launch_bounds__(kBlock) k_union_fold(Level V, SweepItem *__restrict__ tile_agg) {
     __shared__ SweepItem s_warp[kBlock / 32 + 1];
     const SweepUnion op;
-    const int base = blockIdx.x * kTile + threadIdx.x * kPerThread;
+    const int row = blockIdx.y, base = blockIdx.x * kTile + threadIdx.x * kPerThread;
+    const int *list = list_of(V, row >> 1);
+    const bool rev = row & 1;
     SweepItem acc = scan_identity();
 #pragma unroll
     for (int k = 0; k < kPerThread; k++)
-        if (base + k < total) acc = op(acc, sweep_item(V, base + k));
+        if (base + k < V.n) acc = op(acc, sweep_item_at(V, list, rev, base + k));
     cta_exclusive(acc, s_warp);
-    if (threadIdx.x == 0) tile_agg[blockIdx.x] = s_warp[kBlock / 32];
+    if (threadIdx.x == 0) tile_agg[row * gridDim.x + blockIdx.x] = s_warp[kBlock / 32];
 }
 
 // one CTA: tile_agg[t] becomes the exclusive prefix of the aggregates (the carry into tile t)
@@ -167,21 +173,24 @@ __global__ void __launch_bounds__(kBlock) k_union_carries(SweepItem *tile_agg, i
     for (int t = first; t < last; t++) { const SweepItem mine = tile_agg[t]; tile_agg[t] = carry; carry = op(carry, mine); }
 }
 
-__global__ void __launch_bounds__(kBlock) k_union_scan(Level V, int total, const SweepItem *__restrict__ tile_carry, float *__restrict__ areas) {
+__global__ void __launch_bounds__(kBlock) k_union_scan(Level V, const SweepItem *__restrict__ tile_carry, float *__restrict__ areas) {
     __shared__ SweepItem s_warp[kBlock / 32 + 1];
     const SweepUnion op;
-    const int base = blockIdx.x * kTile + threadIdx.x * kPerThread;
+    const int row = blockIdx.y, base = blockIdx.x * kTile + threadIdx.x * kPerThread;
+    const int *list = list_of(V, row >> 1);
+    const bool rev = row & 1;
     SweepItem out[kPerThread];
     SweepItem acc = scan_identity();
 #pragma unroll
     for (int k = 0; k < kPerThread; k++) {
-        if (base + k < total) acc = op(acc, sweep_item(V, base + k));
+        if (base + k < V.n) acc = op(acc, sweep_item_at(V, list, rev, base + k));
         out[k] = acc;
     }
-    const SweepItem carry = op(tile_carry[blockIdx.x], cta_exclusive(acc, s_warp));
+    const SweepItem carry = op(tile_carry[row * gridDim.x + blockIdx.x], cta_exclusive(acc, s_warp));
+    float *dst = areas + size_t(row) * V.n;
 #pragma unroll
     for (int k = 0; k < kPerThread; k++)
-        if (base + k < total) areas[base + k] = sweep_area(op(carry, out[k]));
+        if (base + k < V.n) dst[base + k] = sweep_area(op(carry, out[k]));
 }
 
 __global__ void __launch_bounds__(kBlock) k_compare(const float *__restrict__ a, const float *__restrict__ b, int total, int *mismatches) {
@@ -271,11 +280,12 @@ int rm_gpu_build_wide_sah(RmContext *ctx, const float *d_pos, int n, int depth_c
     size_t o_aL[2], o_aR[2], o_aB[2], o_best[2];
     for (int k = 0; k < 2; k++) { o_aL[k] = take(nn); o_aR[k] = take(nn); o_aB[k] = take(nn); o_best[k] = take(2 * nn); }
     const size_t o_axis = take(nn), o_M = take(nn), o_cl = take(nn), o_cr = take(nn);
-    const int total = 6 * n, tiles = (total + kTile - 1) / kTile;
+    const int total = 6 * n, row_tiles = (n + kTile - 1) / kTile, tiles = 6 * row_tiles;
     // RM_SAH_SCAN=cub: the box-union scan through cub::DeviceScan (the first form of this builder); =check: both, compared bit for bit
     const char *senv = getenv("RM_SAH_SCAN");
     const bool scan_cub = senv && !strcmp(senv, "cub"), scan_check = senv && !strcmp(senv, "check");
     const size_t o_side = take((nn + 3) / 4), o_areas = take(6 * nn), o_zeros = take(3 * nn), o_counters = take(64);
+    const size_t o_tbox = take(8 * nn);
     const size_t o_tiles = take(size_t(tiles) * 8), o_areas2 = take(scan_check ? 6 * nn : 0);
     if ((rc = B[0].alloc(words * 4))) return rc;
     int *W = B[0].as<int>();
@@ -285,7 +295,7 @@ int rm_gpu_build_wide_sah(RmContext *ctx, const float *d_pos, int n, int depth_c
     Split S{W + o_axis, W + o_M, W + o_cl, W + o_cr};
 
     Level V0{};
-    V0.n = n; V0.tlo = T.lo; V0.thi = T.hi;
+    V0.n = n; V0.tlo = T.lo; V0.thi = T.hi; V0.tbox = reinterpret_cast<const float4 *>(W + o_tbox);
     for (int a = 0; a < 3; a++) V0.list[a] = W + o_list[0] + size_t(a) * n;
     V0.nodeid = W + o_nodeid[0]; V0.aL = W + o_aL[0]; V0.aR = W + o_aR[0];
     auto items_in = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), ItemOp{V0});
@@ -299,7 +309,7 @@ int rm_gpu_build_wide_sah(RmContext *ctx, const float *d_pos, int n, int depth_c
     if ((rc = B[15].alloc(temp_bytes))) return rc;
 
     const int grid_n = (n + kBlock - 1) / kBlock, grid_3n = int((3ll * n + kBlock - 1) / kBlock);
-    k_tri_boxes<<<grid_n, kBlock, 0, st>>>(d_pos, n, make_float3(fallback_point[0], fallback_point[1], fallback_point[2]), T, keys, ids);
+    k_tri_boxes<<<grid_n, kBlock, 0, st>>>(d_pos, n, make_float3(fallback_point[0], fallback_point[1], fallback_point[2]), T, reinterpret_cast<float4 *>(W + o_tbox), keys, ids);
     for (int a = 0; a < 3; a++)
         RM_CUDA(cub::DeviceRadixSort::SortPairs(B[15].p, temp_bytes, keys + size_t(a) * n, keys_tmp, ids, W + o_list[0] + size_t(a) * n, n, 0, 32, st));
     ctx->launches += 1;
@@ -331,9 +341,9 @@ int rm_gpu_build_wide_sah(RmContext *ctx, const float *d_pos, int n, int depth_c
             if (scan_cub) RM_CUDA(cub::DeviceScan::InclusiveScan(B[15].p, temp_bytes, in, areas_out, SweepUnion(), total, st));
             else {
                 SweepItem *tile_agg = reinterpret_cast<SweepItem *>(W + o_tiles);
-                k_union_fold<<<tiles, kBlock, 0, st>>>(V, total, tile_agg);
+                k_union_fold<<<dim3(row_tiles, 6), kBlock, 0, st>>>(V, tile_agg);
                 k_union_carries<<<1, kBlock, 0, st>>>(tile_agg, tiles);
-                k_union_scan<<<tiles, kBlock, 0, st>>>(V, total, tile_agg, areas);
+                k_union_scan<<<dim3(row_tiles, 6), kBlock, 0, st>>>(V, tile_agg, areas);
             }
             if (scan_check) {
                 float *areas2 = reinterpret_cast<float *>(W + o_areas2);

@@ -61,6 +61,7 @@ RM_SHD float sweep_area(const SweepItem &b) {
 struct Level {
     int n;                      // triangles
     const float4 *tlo, *thi;    // triangle boxes, by triangle
+    const float4 *tbox;         // the same boxes as {lo, hi} pairs, 32 bytes per triangle: one 256-bit load on the device
     const int *list[3];         // per axis: triangles sorted by box centre inside every node's range
     const int *nodeid;          // per position: the slot of the active node whose range holds it, -1 = finished (a single triangle)
     const int *aL, *aR;         // per slot: the node's range
@@ -73,25 +74,43 @@ RM_SHD float centre_key(const float4 &lo, const float4 &hi, int axis) {
     return axis == 0 ? lo.x + hi.x : axis == 1 ? lo.y + hi.y : lo.z + hi.z;
 }
 
-// item `idx` of the scan input, idx in [0, 6 n): axis a = idx / 2n; within an axis first the n positions forwards, then the
-// n positions backwards (scan index j of the backward half is position n - 1 - j)
-RM_SHD SweepItem sweep_item(const Level &V, int idx) {
-    const int n = V.n, a = idx / (2 * n), r = idx - a * 2 * n;
-    const bool rev = r >= n;
-    const int i = rev ? r - n : r, pos = rev ? n - 1 - i : i;
+// the box of triangle t as one 32-byte record
+RM_SHD void load_box(const Level &V, int t, float4 &lo, float4 &hi) {
+#ifdef __CUDA_ARCH__
+    const float4 *p = V.tbox + 2 * size_t(t);
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+#else
+    lo = V.tbox[2 * size_t(t)];
+    hi = V.tbox[2 * size_t(t) + 1];
+#endif
+}
+
+// The scan input is six rows of n items: row = 2 * axis + direction, item i of a forward row is position i of the axis's list, item
+// i of a backward row is position n - 1 - i.  `list` = list_of(V, axis).
+RM_SHD SweepItem sweep_item_at(const Level &V, const int *list, bool rev, int i) {
+    const int pos = rev ? V.n - 1 - i : i;
     const int nd = V.nodeid[pos];
     SweepItem it;
     if (nd < 0) {               // a finished position is a segment of its own whose prefix nobody reads: no need to fetch its box
         it.lx = it.ly = it.lz = it.hx = it.hy = it.hz = 0.0f; it.flag = 1; it.pad = 0;
         return it;
     }
-    const int t = list_of(V, a)[pos];
+    const int t = list[pos];
     int flag = 1;
     if (i > 0) flag = V.nodeid[rev ? pos + 1 : pos - 1] != nd;
-    const float4 lo = V.tlo[t], hi = V.thi[t];
+    float4 lo, hi;
+    load_box(V, t, lo, hi);
     it.lx = lo.x; it.ly = lo.y; it.lz = lo.z; it.flag = flag;
     it.hx = hi.x; it.hy = hi.y; it.hz = hi.z; it.pad = 0;
     return it;
+}
+
+// item `idx` of the scan input as one sequence, idx in [0, 6 n): the rows one after the other
+RM_SHD SweepItem sweep_item(const Level &V, int idx) {
+    const int row = idx / V.n;
+    return sweep_item_at(V, list_of(V, row >> 1), (row & 1) != 0, idx - row * V.n);
 }
 
 // candidate c in [0, 3 n): axis a = c / n, split after position i = c % n.  `areas` = sweep_area of the scan's output, same

@@ -32,6 +32,8 @@ extern "C" int sah_sweep_host(const float *pos, int n, int depth_cap, float *lo_
         thi[t] = float4{hi[0], hi[1], hi[2], 0.0f};
         left[t] = ~t; right[t] = -1; count[t] = 1;
     }
+    std::vector<float4> tbox(size_t(2) * n);
+    for (int t = 0; t < n; t++) { tbox[2 * size_t(t)] = tlo[t]; tbox[2 * size_t(t) + 1] = thi[t]; }
     std::vector<int> list[2][3], nodeid[2];
     for (int k = 0; k < 2; k++) { for (int a = 0; a < 3; a++) list[k][a].resize(n); nodeid[k].assign(n, 0); }
     for (int a = 0; a < 3; a++) {
@@ -55,7 +57,7 @@ extern "C" int sah_sweep_host(const float *pos, int n, int depth_cap, float *lo_
         for (int level = 0; n_slots > 0; level++, cur ^= 1) {
             if (level > 200) return -2;
             levels = level + 1;
-            Level V{n, tlo.data(), thi.data(), {list[cur][0].data(), list[cur][1].data(), list[cur][2].data()}, nodeid[cur].data(), aL[cur].data(), aR[cur].data()};
+            Level V{n, tlo.data(), thi.data(), tbox.data(), {list[cur][0].data(), list[cur][1].data(), list[cur][2].data()}, nodeid[cur].data(), aL[cur].data(), aR[cur].data()};
             for (int idx = 0; idx < 6 * n; idx++) items[idx] = sweep_item(V, idx);
             {
                 SweepUnion op;
