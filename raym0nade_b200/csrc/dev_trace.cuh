@@ -106,12 +106,18 @@ RM_DI WideRay setup_wide_ray(V3 d) {
     w.inv[0] = __frcp_rn(dx); w.inv[1] = __frcp_rn(dy); w.inv[2] = __frcp_rn(dz);
     return w;
 }
-// byte c of w as a float: the byte is dropped into the mantissa of 2^23 (one PRMT), then 2^23 is subtracted (exact)
-RM_DI float q8(unsigned w, int c) {
+// byte C of w as a float: the byte is dropped into the mantissa of 2^23 (one PRMT), then 2^23 is subtracted (exact).  The PRMT is
+// spelled out so that the SELECTOR is its immediate and 2^23's bit pattern comes from the kernel's parameters (TraceTune::q8_magic -
+// a value ptxas cannot see): given two constants, ptxas makes 2^23 the immediate and moves every one of the 24 selectors of a node
+// step into a register first (IMAD.U32 Rx, RZ, RZ, URy before each PRMT - a tenth of the step's instructions, cuobjdump -sass).
+template <int C> RM_DI float q8(unsigned w, unsigned magic) {
 #ifdef __CUDA_ARCH__
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | unsigned(c))) - 8388608.0f;
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7440 | C));
+    return __uint_as_float(r) - 8388608.0f;
 #else
-    return float((w >> (8 * c)) & 0xffu);
+    (void)magic;
+    return float((w >> (8 * C)) & 0xffu);
 #endif
 }
 
@@ -216,6 +222,7 @@ struct TraceTune {
     int refill_live;     // refill idle lanes once fewer than this many lanes are busy
     int w_inner, w_leaf; // vote weights: the inner step runs when n_inner * w_inner >= n_leaf * w_leaf
     int smem_levels;     // stack entries per thread held in shared memory; deeper ones (rare) go to a small local array
+    unsigned q8_magic = 0x4B000000u;      // the bit pattern of 2^23, handed over as a kernel parameter so that ptxas cannot fold it (see q8)
 };
 constexpr int kStackSpill = 28;   // local spill entries: smem_levels + kStackSpill >= any tree depth we build (<= 40)
 constexpr int kStackSpillWide = 82; // the 4-wide tree defers up to three children per level (rm_scene_upload checks 3 * levels against it)
@@ -341,14 +348,18 @@ RM_DI void trace_engine(const DevScene &S, Job &job, const int n, int *cursor, i
                     const unsigned meta = __float_as_uint(h3.z);
                     const int child_base = __float_as_int(h3.x), tri_base = __float_as_int(h3.y);
                     unsigned key[4];
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float tn = fmaxf(fmaxf(fmaf(q8(nx, c), ax, bx), fmaf(q8(ny, c), ay, by)), fmaxf(fmaf(q8(nz, c), az, bz), t_min));
-                        const float tf = fminf(fminf(fmaf(q8(fx, c), ax, bx), fmaf(q8(fy, c), ay, by)), fminf(fmaf(q8(fz, c), az, bz), t));
-                        const bool hitc = ((meta >> (8 * c)) & 0xffu) != 0u && tn * 0.999998f <= tf * 1.000002f + kEps;      // a few ulps, and the slack rayInBox gives its far plane
-                        // sort key: the entry distance (positive, so its bit pattern orders like the float) with the slot in the low bits
-                        key[c] = hitc ? ((__float_as_uint(tn) & ~3u) | unsigned(c)) : 0xffffffffu;
+                    const unsigned magic = tune.q8_magic;
+#define RM_WIDE_CHILD(c)                                                                                                                                          \
+                    {                                                                                                                                             \
+                        const float tn = fmaxf(fmaxf(fmaf(q8<c>(nx, magic), ax, bx), fmaf(q8<c>(ny, magic), ay, by)), fmaxf(fmaf(q8<c>(nz, magic), az, bz), t_min)); \
+                        const float tf = fminf(fminf(fmaf(q8<c>(fx, magic), ax, bx), fmaf(q8<c>(fy, magic), ay, by)), fminf(fmaf(q8<c>(fz, magic), az, bz), t));     \
+                        /* a few ulps, and the slack rayInBox gives its far plane */                                                                             \
+                        const bool hitc = ((meta >> (8 * c)) & 0xffu) != 0u && tn * 0.999998f <= tf * 1.000002f + kEps;                                           \
+                        /* sort key: the entry distance (positive, so its bit pattern orders like the float) with the slot in the low bits */                    \
+                        key[c] = hitc ? ((__float_as_uint(tn) & ~3u) | unsigned(c)) : 0xffffffffu;                                                                \
                     }
+                    RM_WIDE_CHILD(0) RM_WIDE_CHILD(1) RM_WIDE_CHILD(2) RM_WIDE_CHILD(3)
+#undef RM_WIDE_CHILD
                     if (COUNT) cnt.box += (meta & 0xffu ? 1 : 0) + (meta & 0xff00u ? 1 : 0) + (meta & 0xff0000u ? 1 : 0) + (meta & 0xff000000u ? 1 : 0);     // child boxes tested
                     // 5-comparator network: ascending by entry distance, misses last
 #define RM_CSWAP(a, b) { const unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
