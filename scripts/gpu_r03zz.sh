@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, last call: the final state of the code (sweep-SAH builder with its row-wise tile scan, deferred build, nodes uploaded in place,
+# PRMT selectors as immediates): whole GPU suite + smoke, the default bench line, the ncu launch list, the ncu capture of the traversal kernels
+TAG=${1:-r03zz}
+mkdir -p gpurun_out
+( timeout 1800 python -m pytest tests -m gpu -x -q; echo "pytest exit $?"; python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/${TAG}_pytest_gpu_and_smoke.log 2>&1
+grep -v "Light object\|BVH has" gpurun_out/${TAG}_pytest_gpu_and_smoke.log | tail -6
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > gpurun_out/${TAG}_clocks.csv &
+SMI=$!
+timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench rc $?"
+kill $SMI
+python - <<PY
+import json
+d = json.load(open("gpurun_out/${TAG}_bench.json"))
+print({k: d[k] for k in ("value", "ms_per_step")}, "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "first", d["e2e_first_frame"]["total_s"], "frac", d["roofline"]["frac"], d["roofline"]["achieved"])
+print({k: (round(v.get("ms_per_step", 0), 1), round(v.get("mrays_per_s_kernel_only", 0)), round(v.get("box_tests_per_ray", 0), 1)) for k, v in d["kernels"].items()})
+PY
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 3 --spp 64 --no-cpu --no-first-frame > gpurun_out/${TAG}_launches.log 2>&1
+python scripts/summarize_launches.py gpurun_out/${TAG}_launches.csv | tee gpurun_out/${TAG}_launches_summary.txt | head -14
+bash scripts/gpu_traffic.sh ${TAG} 2>&1 | grep -v "^[0246] "
