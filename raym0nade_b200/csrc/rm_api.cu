@@ -459,6 +459,7 @@ int rm_scene_upload(RmContext *ctx, const RmSceneDesc *sc) {
 // has made of them since.
 int rm_ensure_secondary_tree(RmContext *ctx) {
     if (!ctx || !ctx->wide_pending || !ctx->has_scene) return RM_OK;
+    RM_CUDA(cudaSetDevice(ctx->device));          // (rm_tree_info and rm_set_option reach this without having done so)
     ctx->wide_pending = false;
     cudaStream_t st = ctx->stream;
     const int n = ctx->scene.n_faces;
