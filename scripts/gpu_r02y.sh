@@ -20,7 +20,7 @@ PY
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; cut -c 1-400 gpurun_out/${TAG}_bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --spp 64 --no-cpu --no-first-frame > gpurun_out/${TAG}_launches.log 2>&1
-python scripts/summarize_launches.py gpurun_out/${TAG}_launches.csv | tee gpurun_out/${TAG}_launches_summary.txt | head -24
+python scripts/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt; head -24 gpurun_out/${TAG}_launches_summary.txt
 timeout 200 python scripts/post_bench.py 3840 2160 | tee gpurun_out/${TAG}_fxaa_4k.json
 timeout 300 python tests/tools/post_probe.py 8 2>/dev/null | tee gpurun_out/${TAG}_post_passes_1080p.json | cut -c 1-600
 timeout 200 python scripts/tree_bench.py 2>/dev/null | tee gpurun_out/${TAG}_tree_bench.json

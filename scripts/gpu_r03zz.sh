@@ -18,5 +18,5 @@ print({k: (round(v.get("ms_per_step", 0), 1), round(v.get("mrays_per_s_kernel_on
 PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --spp 64 --no-cpu --no-first-frame > gpurun_out/${TAG}_launches.log 2>&1
-python scripts/summarize_launches.py gpurun_out/${TAG}_launches.csv | tee gpurun_out/${TAG}_launches_summary.txt | head -14
+python scripts/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt; head -14 gpurun_out/${TAG}_launches_summary.txt
 bash scripts/gpu_traffic.sh ${TAG} 2>&1 | grep -v "^[0246] "
